@@ -1,0 +1,1170 @@
+// C ABI of libcomms_b200.so (see include/comms_b200.h): handles, buffers, streams,
+// host-pointer pipelines.  No torch, no C++ types in any signature, no CPU fallback.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "chain_kernels.cuh"
+#include "common.cuh"
+#include "fft_kernels.cuh"
+#include "fir_kernels.cuh"
+#include "misc_kernels.cuh"
+
+namespace cb {
+
+static thread_local char g_err[512] = "";
+static thread_local int g_dev = 0;
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return CB_ERR_NO_DEVICE;
+    if (e == cudaErrorMemoryAllocation) return CB_ERR_OOM;
+    return CB_ERR_CUDA;
+}
+
+int current_device() { return g_dev; }
+
+static int use_device(int dev)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        (void)cudaGetLastError();
+        set_error("no CUDA device available (%s); libcomms_b200 has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return CB_ERR_NO_DEVICE;
+    }
+    CB_REQUIRE(dev >= 0 && dev < count, CB_ERR_INVALID_ARG, "device %d out of range (0..%d)", dev, count - 1);
+    CB_CUDA(cudaSetDevice(dev));
+    return CB_OK;
+}
+
+int ensure_device() { return use_device(g_dev); }
+
+// Two copy/compute lanes used by the host-pointer entry points: chunk i runs
+// H2D -> kernel -> D2H on lane i%2, so the copy engines and the SMs overlap.
+struct HostPipe {
+    cudaStream_t lane[2] = {nullptr, nullptr};
+    void *in[2] = {nullptr, nullptr};
+    void *out[2] = {nullptr, nullptr};
+    size_t in_cap = 0, out_cap = 0;
+
+    int init(cudaStream_t first)
+    {
+        lane[0] = first;
+        CB_CUDA(cudaStreamCreateWithFlags(&lane[1], cudaStreamNonBlocking));
+        return CB_OK;
+    }
+    int reserve(size_t in_bytes, size_t out_bytes)
+    {
+        if (in_bytes > in_cap) {
+            for (int i = 0; i < 2; ++i) {
+                if (in[i]) CB_CUDA(cudaFree(in[i]));
+                in[i] = nullptr;
+                CB_CUDA(cudaMalloc(&in[i], in_bytes));
+            }
+            in_cap = in_bytes;
+        }
+        if (out_bytes > out_cap) {
+            for (int i = 0; i < 2; ++i) {
+                if (out[i]) CB_CUDA(cudaFree(out[i]));
+                out[i] = nullptr;
+                CB_CUDA(cudaMalloc(&out[i], out_bytes));
+            }
+            out_cap = out_bytes;
+        }
+        return CB_OK;
+    }
+    int sync()
+    {
+        CB_CUDA(cudaStreamSynchronize(lane[0]));
+        CB_CUDA(cudaStreamSynchronize(lane[1]));
+        return CB_OK;
+    }
+    void destroy()
+    {
+        for (int i = 0; i < 2; ++i) {
+            if (in[i]) cudaFree(in[i]);
+            if (out[i]) cudaFree(out[i]);
+        }
+        if (lane[1]) cudaStreamDestroy(lane[1]);
+    }
+};
+
+constexpr size_t HOST_CHUNK = (size_t)1 << 22;  // complex samples per pipelined chunk (32 MiB)
+
+}  // namespace cb
+
+using namespace cb;
+
+// ============================================================================ handles
+struct cb_stream {
+    int device;
+    cudaStream_t s;
+};
+
+struct cb_buf {
+    std::atomic<int> refs;
+    void *ptr;
+    size_t bytes;
+    int is_device;
+    int device;
+};
+
+struct cb_fir {
+    int device;
+    cudaStream_t stream;
+    HostPipe pipe;
+    std::vector<float2> taps;  // as given
+    float2 *taps_dev;
+    size_t nstate;     // reference state length (zero-stuffed domain when interp > 1)
+    uint32_t k_eff;    // min(ntaps, nstate)
+    bool taps_real;
+    uint32_t decim, interp;
+    uint32_t hist_len;  // input-domain samples kept
+    float2 *hist[2];
+    int cur;
+};
+
+struct cb_mixer {
+    int device;
+    cudaStream_t stream;
+    HostPipe pipe;
+    double phase, dphase;
+};
+
+struct cb_fft {
+    int device;
+    cudaStream_t stream;
+    HostPipe pipe;
+    FftPlanDev plan;
+    float2 *tw, *tw1, *tw2, *scratch;
+};
+
+struct cb_fm {
+    int device;
+    cudaStream_t stream;
+    HostPipe pipe;
+    float2 *prev[2];
+    int cur;
+};
+
+struct cb_chain {
+    int device;
+    cudaStream_t stream;
+    HostPipe pipe;
+    size_t channels;
+    bool mix, fm, cplx;
+    ChainTaps taps;
+    uint32_t ntaps, decim, hist_len;
+    double *phase[2], *dphase;
+    float2 *hist[2], *prev[2];
+    int cur;
+};
+
+static inline cudaStream_t pick_stream(void *user, cudaStream_t own) { return user ? (cudaStream_t)user : own; }
+
+extern "C" {
+
+// ============================================================================ library
+int cb_version(void) { return 1000 * 0 + 1; }
+const char *cb_last_error(void) { return g_err; }
+
+const char *cb_status_str(int st)
+{
+    switch (st) {
+    case CB_OK: return "ok";
+    case CB_ERR_INVALID_ARG: return "invalid argument";
+    case CB_ERR_SIZE: return "size mismatch";
+    case CB_ERR_CUDA: return "CUDA failure";
+    case CB_ERR_NO_DEVICE: return "no CUDA device";
+    case CB_ERR_OOM: return "out of memory";
+    case CB_ERR_UNSUPPORTED: return "unsupported";
+    default: return "unknown status";
+    }
+}
+
+int cb_device_count(int *count)
+{
+    CB_REQUIRE(count, CB_ERR_INVALID_ARG, "count is NULL");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        c = 0;
+    }
+    *count = c;
+    return CB_OK;
+}
+
+int cb_init(int device)
+{
+    int rc = use_device(device);
+    if (rc) return rc;
+    g_dev = device;
+    CB_CUDA(cudaFree(nullptr));  // force context creation
+    return CB_OK;
+}
+
+int cb_device_synchronize(void)
+{
+    int rc = ensure_device();
+    if (rc) return rc;
+    CB_CUDA(cudaDeviceSynchronize());
+    return CB_OK;
+}
+
+// ============================================================================ streams
+int cb_stream_create(cb_stream **out)
+{
+    CB_REQUIRE(out, CB_ERR_INVALID_ARG, "out is NULL");
+    int rc = ensure_device();
+    if (rc) return rc;
+    cb_stream *s = new (std::nothrow) cb_stream;
+    CB_REQUIRE(s, CB_ERR_OOM, "host allocation failed");
+    s->device = g_dev;
+    cudaError_t e = cudaStreamCreateWithFlags(&s->s, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete s;
+        return cuda_fail(e, "cudaStreamCreateWithFlags", __FILE__, __LINE__);
+    }
+    *out = s;
+    return CB_OK;
+}
+
+int cb_stream_destroy(cb_stream *s)
+{
+    if (!s) return CB_OK;
+    cudaSetDevice(s->device);
+    cudaStreamDestroy(s->s);
+    delete s;
+    return CB_OK;
+}
+
+int cb_stream_sync(cb_stream *s)
+{
+    CB_REQUIRE(s, CB_ERR_INVALID_ARG, "stream is NULL");
+    CB_CUDA(cudaSetDevice(s->device));
+    CB_CUDA(cudaStreamSynchronize(s->s));
+    return CB_OK;
+}
+
+void *cb_stream_handle(cb_stream *s) { return s ? (void *)s->s : nullptr; }
+
+// ============================================================================ buffers
+static int buf_alloc(size_t bytes, int is_device, cb_buf **out)
+{
+    CB_REQUIRE(out, CB_ERR_INVALID_ARG, "out is NULL");
+    int rc = ensure_device();
+    if (rc) return rc;
+    cb_buf *b = new (std::nothrow) cb_buf;
+    CB_REQUIRE(b, CB_ERR_OOM, "host allocation failed");
+    b->refs.store(1);
+    b->bytes = bytes;
+    b->is_device = is_device;
+    b->device = g_dev;
+    b->ptr = nullptr;
+    cudaError_t e = is_device ? cudaMalloc(&b->ptr, bytes ? bytes : 1) : cudaMallocHost(&b->ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        delete b;
+        return cuda_fail(e, is_device ? "cudaMalloc" : "cudaMallocHost", __FILE__, __LINE__);
+    }
+    *out = b;
+    return CB_OK;
+}
+
+int cb_buf_alloc_pinned(size_t bytes, cb_buf **out) { return buf_alloc(bytes, 0, out); }
+int cb_buf_alloc_device(size_t bytes, cb_buf **out) { return buf_alloc(bytes, 1, out); }
+
+int cb_buf_retain(cb_buf *b)
+{
+    CB_REQUIRE(b, CB_ERR_INVALID_ARG, "buffer is NULL");
+    b->refs.fetch_add(1);
+    return CB_OK;
+}
+
+int cb_buf_release(cb_buf *b)
+{
+    if (!b) return CB_OK;
+    if (b->refs.fetch_sub(1) == 1) {
+        cudaSetDevice(b->device);
+        if (b->is_device) cudaFree(b->ptr);
+        else cudaFreeHost(b->ptr);
+        delete b;
+    }
+    return CB_OK;
+}
+
+void *cb_buf_ptr(cb_buf *b) { return b ? b->ptr : nullptr; }
+size_t cb_buf_bytes(cb_buf *b) { return b ? b->bytes : 0; }
+int cb_buf_is_device(cb_buf *b) { return b ? b->is_device : 0; }
+
+int cb_copy_h2d_async(void *dst, const void *src, size_t bytes, void *stream)
+{
+    CB_REQUIRE(dst && src, CB_ERR_INVALID_ARG, "NULL pointer");
+    int rc = ensure_device();
+    if (rc) return rc;
+    CB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return CB_OK;
+}
+
+int cb_copy_d2h_async(void *dst, const void *src, size_t bytes, void *stream)
+{
+    CB_REQUIRE(dst && src, CB_ERR_INVALID_ARG, "NULL pointer");
+    int rc = ensure_device();
+    if (rc) return rc;
+    CB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return CB_OK;
+}
+
+// ============================================================================ FIR
+static size_t fir_out_len(const cb_fir *h, size_t n)
+{
+    const size_t up = n * h->interp;
+    return h->decim > 1 ? ceil_div(up, (size_t)h->decim) : up;
+}
+
+// reference state (newest first, zero-stuffed domain) -> chronological input-domain history
+static int fir_state_to_hist(const cb_fir *h, const float2 *state, size_t nstate, std::vector<float2> &hist)
+{
+    hist.assign(h->hist_len, make_float2(0.f, 0.f));
+    if (!state) return CB_OK;
+    const size_t L = h->interp;
+    for (size_t k = 0; k < nstate; ++k) {
+        const float2 v = state[k];
+        if ((k + 1) % L == 0) {
+            const size_t i = (k + 1) / L;  // i-th most recent input sample
+            if (i <= h->hist_len) hist[h->hist_len - i] = v;
+        } else if (v.x != 0.f || v.y != 0.f) {
+            set_error("fir: with interp=%zu the initial state must be zero off the symbol grid (entry %zu)", L, k);
+            return CB_ERR_UNSUPPORTED;
+        }
+    }
+    return CB_OK;
+}
+
+int cb_fir_create(const float *taps, size_t ntaps, const float *state, size_t nstate, uint32_t decim,
+                  uint32_t interp, cb_fir **out)
+{
+    CB_REQUIRE(out, CB_ERR_INVALID_ARG, "out is NULL");
+    CB_REQUIRE(taps || ntaps == 0, CB_ERR_INVALID_ARG, "taps is NULL");
+    int rc = ensure_device();
+    if (rc) return rc;
+    cb_fir *h = new (std::nothrow) cb_fir();
+    CB_REQUIRE(h, CB_ERR_OOM, "host allocation failed");
+    h->device = g_dev;
+    h->decim = decim == 0 ? 1 : decim;
+    h->interp = interp == 0 ? 1 : interp;
+    h->taps.resize(ntaps);
+    if (ntaps) memcpy(h->taps.data(), taps, ntaps * sizeof(float2));
+    h->nstate = state ? nstate : ntaps;  // None => zeros(len taps)  (fir_node.rs:201-210)
+    h->k_eff = (uint32_t)(ntaps < h->nstate ? ntaps : h->nstate);
+    h->taps_real = true;
+    for (size_t k = 0; k < h->k_eff; ++k)
+        if (h->taps[k].y != 0.f) h->taps_real = false;
+    const size_t need_in = ceil_div(h->nstate > h->k_eff ? h->nstate : (size_t)h->k_eff, (size_t)h->interp);
+    h->hist_len = (uint32_t)round_up(need_in > 128 ? need_in : 128, 2);
+    h->cur = 0;
+    h->taps_dev = nullptr;
+    h->hist[0] = h->hist[1] = nullptr;
+    h->stream = nullptr;
+
+    std::vector<float2> hist;
+    rc = fir_state_to_hist(h, reinterpret_cast<const float2 *>(state), state ? nstate : 0, hist);
+    if (rc) {
+        delete h;
+        return rc;
+    }
+#define FIR_TRY(call)                                                    \
+    do {                                                                 \
+        cudaError_t e__ = (call);                                        \
+        if (e__ != cudaSuccess) {                                        \
+            cb_fir_destroy(h);                                           \
+            return cuda_fail(e__, #call, __FILE__, __LINE__);            \
+        }                                                                \
+    } while (0)
+    FIR_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    if (h->pipe.init(h->stream)) {
+        cb_fir_destroy(h);
+        return CB_ERR_CUDA;
+    }
+    FIR_TRY(cudaMalloc(&h->taps_dev, (ntaps ? ntaps : 1) * sizeof(float2)));
+    if (ntaps) FIR_TRY(cudaMemcpy(h->taps_dev, h->taps.data(), ntaps * sizeof(float2), cudaMemcpyHostToDevice));
+    for (int i = 0; i < 2; ++i) {
+        FIR_TRY(cudaMalloc(&h->hist[i], h->hist_len * sizeof(float2)));
+        FIR_TRY(cudaMemcpy(h->hist[i], hist.data(), h->hist_len * sizeof(float2), cudaMemcpyHostToDevice));
+    }
+#undef FIR_TRY
+    *out = h;
+    return CB_OK;
+}
+
+int cb_fir_destroy(cb_fir *h)
+{
+    if (!h) return CB_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    h->pipe.destroy();
+    if (h->taps_dev) cudaFree(h->taps_dev);
+    for (int i = 0; i < 2; ++i)
+        if (h->hist[i]) cudaFree(h->hist[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return CB_OK;
+}
+
+int cb_fir_out_len(const cb_fir *h, size_t n_in, size_t *n_out)
+{
+    CB_REQUIRE(h && n_out, CB_ERR_INVALID_ARG, "NULL argument");
+    *n_out = fir_out_len(h, n_in);
+    return CB_OK;
+}
+
+void *cb_fir_stream(cb_fir *h) { return h ? (void *)h->stream : nullptr; }
+
+static int fir_launch_segment(cb_fir *h, const float2 *x, size_t n, const float2 *hist_in, float2 *hist_out,
+                              float2 *y, cudaStream_t s)
+{
+    // k_eff == 0 (zip over an empty state, fir.rs:99) runs as an all-zero filter: outputs are 0
+    FirSeg seg{x, hist_in, hist_out, y, n, fir_out_len(h, n), h->hist_len, h->k_eff, h->interp, h->decim};
+    return launch_fir(seg, h->taps_dev, h->taps.data(), h->taps_real, s);
+}
+
+int cb_fir_run_dev(cb_fir *h, const float *d_in, size_t n_in, float *d_out, size_t out_cap, size_t *n_out,
+                   void *stream)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    const size_t no = fir_out_len(h, n_in);
+    if (n_out) *n_out = no;
+    if (n_in == 0) return CB_OK;
+    CB_REQUIRE(d_in && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_REQUIRE(out_cap >= no, CB_ERR_SIZE, "fir: out_cap %zu < %zu outputs", out_cap, no);
+    CB_CUDA(cudaSetDevice(h->device));
+    int rc = fir_launch_segment(h, reinterpret_cast<const float2 *>(d_in), n_in, h->hist[h->cur], h->hist[h->cur ^ 1],
+                                reinterpret_cast<float2 *>(d_out), pick_stream(stream, h->stream));
+    if (rc) return rc;
+    h->cur ^= 1;
+    return CB_OK;
+}
+
+int cb_fir_run(cb_fir *h, const float *in, size_t n_in, float *out, size_t out_cap, size_t *n_out)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    const size_t no = fir_out_len(h, n_in);
+    if (n_out) *n_out = no;
+    if (n_in == 0) return CB_OK;
+    CB_REQUIRE(in && out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_REQUIRE(out_cap >= no, CB_ERR_SIZE, "fir: out_cap %zu < %zu outputs", out_cap, no);
+    CB_CUDA(cudaSetDevice(h->device));
+    const float2 *hin = reinterpret_cast<const float2 *>(in);
+    float2 *hout = reinterpret_cast<float2 *>(out);
+    const size_t H = h->hist_len;
+    // chunk starts must keep the decimation grid: multiples of D input samples
+    size_t chunk = HOST_CHUNK / h->decim * h->decim;
+    if (chunk < 4 * H || n_in <= chunk) chunk = n_in;
+    int rc = h->pipe.reserve((chunk + H) * sizeof(float2), fir_out_len(h, chunk) * sizeof(float2));
+    if (rc) return rc;
+    size_t done = 0, out_done = 0;
+    for (int i = 0; done < n_in; ++i) {
+        const int l = i & 1;
+        const size_t n = n_in - done < chunk ? n_in - done : chunk;
+        const bool last = done + n == n_in;
+        cudaStream_t s = h->pipe.lane[l];
+        float2 *slot = reinterpret_cast<float2 *>(h->pipe.in[l]);
+        const float2 *hist_in;
+        if (done == 0) {
+            hist_in = h->hist[h->cur];
+            CB_CUDA(cudaMemcpyAsync(slot + H, hin, n * sizeof(float2), cudaMemcpyHostToDevice, s));
+        } else {  // the halo is the tail of the previous chunk, re-sent with this one
+            hist_in = slot;
+            CB_CUDA(cudaMemcpyAsync(slot, hin + done - H, (n + H) * sizeof(float2), cudaMemcpyHostToDevice, s));
+        }
+        float2 *y = reinterpret_cast<float2 *>(h->pipe.out[l]);
+        rc = fir_launch_segment(h, slot + H, n, hist_in, last ? h->hist[h->cur ^ 1] : nullptr, y, s);
+        if (rc) return rc;
+        const size_t m = fir_out_len(h, n);
+        CB_CUDA(cudaMemcpyAsync(hout + out_done, y, m * sizeof(float2), cudaMemcpyDeviceToHost, s));
+        done += n;
+        out_done += m;
+    }
+    rc = h->pipe.sync();
+    if (rc) return rc;
+    h->cur ^= 1;
+    return CB_OK;
+}
+
+int cb_fir_state_len(const cb_fir *h, size_t *nstate)
+{
+    CB_REQUIRE(h && nstate, CB_ERR_INVALID_ARG, "NULL argument");
+    *nstate = h->nstate;
+    return CB_OK;
+}
+
+int cb_fir_get_state(cb_fir *h, float *state, size_t nstate)
+{
+    CB_REQUIRE(h && (state || nstate == 0), CB_ERR_INVALID_ARG, "NULL argument");
+    CB_REQUIRE(nstate == h->nstate, CB_ERR_SIZE, "fir: state length %zu != %zu", nstate, h->nstate);
+    CB_CUDA(cudaSetDevice(h->device));
+    CB_CUDA(cudaStreamSynchronize(h->stream));
+    std::vector<float2> hist(h->hist_len);
+    CB_CUDA(cudaMemcpy(hist.data(), h->hist[h->cur], h->hist_len * sizeof(float2), cudaMemcpyDeviceToHost));
+    float2 *st = reinterpret_cast<float2 *>(state);
+    const size_t L = h->interp;
+    for (size_t k = 0; k < nstate; ++k) {
+        float2 v = make_float2(0.f, 0.f);
+        if ((k + 1) % L == 0) {
+            const size_t i = (k + 1) / L;
+            if (i <= h->hist_len) v = hist[h->hist_len - i];
+        }
+        st[k] = v;
+    }
+    return CB_OK;
+}
+
+int cb_fir_set_state(cb_fir *h, const float *state, size_t nstate)
+{
+    CB_REQUIRE(h && state, CB_ERR_INVALID_ARG, "NULL argument");
+    CB_REQUIRE(nstate == h->nstate, CB_ERR_SIZE, "fir: state length %zu != %zu", nstate, h->nstate);
+    CB_CUDA(cudaSetDevice(h->device));
+    std::vector<float2> hist;
+    int rc = fir_state_to_hist(h, reinterpret_cast<const float2 *>(state), nstate, hist);
+    if (rc) return rc;
+    CB_CUDA(cudaStreamSynchronize(h->stream));
+    CB_CUDA(cudaMemcpy(h->hist[h->cur], hist.data(), h->hist_len * sizeof(float2), cudaMemcpyHostToDevice));
+    return CB_OK;
+}
+
+// ============================================================================ resample
+static size_t decim_len(size_t n, size_t rate) { return rate <= 1 ? n : ceil_div(n, rate); }
+static size_t ups_len(size_t n, size_t rate) { return rate <= 1 ? n : n * rate; }
+
+int cb_decimate_dev(const void *d_in, size_t n, size_t elem, size_t rate, void *d_out, size_t out_cap, size_t *n_out,
+                    void *stream)
+{
+    const size_t m = decim_len(n, rate);
+    if (n_out) *n_out = m;
+    if (n == 0) return CB_OK;
+    CB_REQUIRE(d_in && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_REQUIRE(out_cap >= m, CB_ERR_SIZE, "decimate: out_cap %zu < %zu", out_cap, m);
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (rate <= 1) {
+        CB_CUDA(cudaMemcpyAsync(d_out, d_in, n * elem, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        return CB_OK;
+    }
+    return launch_decimate(d_in, d_out, m, elem, rate, (cudaStream_t)stream);
+}
+
+int cb_upsample_dev(const void *d_in, size_t n, size_t elem, size_t rate, void *d_out, size_t out_cap, size_t *n_out,
+                    void *stream)
+{
+    const size_t m = ups_len(n, rate);
+    if (n_out) *n_out = m;
+    if (n == 0) return CB_OK;
+    CB_REQUIRE(d_in && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_REQUIRE(out_cap >= m, CB_ERR_SIZE, "upsample: out_cap %zu < %zu", out_cap, m);
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (rate <= 1) {
+        CB_CUDA(cudaMemcpyAsync(d_out, d_in, n * elem, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        return CB_OK;
+    }
+    return launch_upsample(d_in, d_out, m, elem, rate, (cudaStream_t)stream);
+}
+
+static int resample_host(bool up, const void *in, size_t n, size_t elem, size_t rate, void *out, size_t out_cap,
+                         size_t *n_out)
+{
+    const size_t m = up ? ups_len(n, rate) : decim_len(n, rate);
+    if (n_out) *n_out = m;
+    if (n == 0) return CB_OK;
+    CB_REQUIRE(in && out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_REQUIRE(out_cap >= m, CB_ERR_SIZE, "resample: out_cap %zu < %zu", out_cap, m);
+    int rc = ensure_device();
+    if (rc) return rc;
+    void *din = nullptr, *dout = nullptr;
+    CB_CUDA(cudaMalloc(&din, n * elem));
+    cudaError_t e = cudaMalloc(&dout, m * elem);
+    if (e != cudaSuccess) {
+        cudaFree(din);
+        return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+    }
+    rc = CB_OK;
+    e = cudaMemcpy(din, in, n * elem, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        size_t mm;
+        rc = up ? cb_upsample_dev(din, n, elem, rate, dout, m, &mm, nullptr)
+                : cb_decimate_dev(din, n, elem, rate, dout, m, &mm, nullptr);
+        if (rc == CB_OK) e = cudaMemcpy(out, dout, m * elem, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(din);
+    cudaFree(dout);
+    if (e != cudaSuccess) return cuda_fail(e, "resample copy", __FILE__, __LINE__);
+    return rc;
+}
+
+int cb_decimate(const void *in, size_t n, size_t elem, size_t rate, void *out, size_t out_cap, size_t *n_out)
+{
+    return resample_host(false, in, n, elem, rate, out, out_cap, n_out);
+}
+
+int cb_upsample(const void *in, size_t n, size_t elem, size_t rate, void *out, size_t out_cap, size_t *n_out)
+{
+    return resample_host(true, in, n, elem, rate, out, out_cap, n_out);
+}
+
+// ============================================================================ mixer
+static double wrap_dphase(double d)  // Mixer::new (src/mixer.rs:43-51)
+{
+    const double twopi = 2.0 * M_PI;
+    if (!std::isfinite(d)) return d;
+    while (d >= twopi) d -= twopi;
+    while (d < 0.0) d += twopi;
+    return d;
+}
+
+static double advance_phase(double phase, double dphase, size_t n)
+{
+    const long double twopi = 6.283185307179586476925286766559L;
+    long double p = (long double)phase + (long double)n * (long double)dphase;
+    p = fmodl(p, twopi);
+    if (p < 0) p += twopi;
+    return (double)p;
+}
+
+int cb_mixer_create(double dphase, double phase, cb_mixer **out)
+{
+    CB_REQUIRE(out, CB_ERR_INVALID_ARG, "out is NULL");
+    CB_REQUIRE(std::isfinite(dphase) && std::isfinite(phase), CB_ERR_INVALID_ARG, "mixer: non-finite phase");
+    int rc = ensure_device();
+    if (rc) return rc;
+    cb_mixer *h = new (std::nothrow) cb_mixer();
+    CB_REQUIRE(h, CB_ERR_OOM, "host allocation failed");
+    h->device = g_dev;
+    h->phase = phase;
+    h->dphase = wrap_dphase(dphase);
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete h;
+        return cuda_fail(e, "cudaStreamCreateWithFlags", __FILE__, __LINE__);
+    }
+    if (h->pipe.init(h->stream)) {
+        cudaStreamDestroy(h->stream);
+        delete h;
+        return CB_ERR_CUDA;
+    }
+    *out = h;
+    return CB_OK;
+}
+
+int cb_mixer_destroy(cb_mixer *h)
+{
+    if (!h) return CB_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    h->pipe.destroy();
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return CB_OK;
+}
+
+int cb_mixer_run_dev(cb_mixer *h, const float *d_in, size_t n, float *d_out, void *stream)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    if (n == 0) return CB_OK;
+    CB_REQUIRE(d_in && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_CUDA(cudaSetDevice(h->device));
+    int rc = launch_mixer(reinterpret_cast<const float2 *>(d_in), reinterpret_cast<float2 *>(d_out), n, h->phase,
+                          h->dphase, pick_stream(stream, h->stream));
+    if (rc) return rc;
+    h->phase = advance_phase(h->phase, h->dphase, n);
+    return CB_OK;
+}
+
+int cb_mixer_run(cb_mixer *h, const float *in, size_t n, float *out)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    if (n == 0) return CB_OK;
+    CB_REQUIRE(in && out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_CUDA(cudaSetDevice(h->device));
+    const size_t chunk = n < HOST_CHUNK ? n : HOST_CHUNK;
+    int rc = h->pipe.reserve(chunk * sizeof(float2), chunk * sizeof(float2));
+    if (rc) return rc;
+    const float2 *hin = reinterpret_cast<const float2 *>(in);
+    float2 *hout = reinterpret_cast<float2 *>(out);
+    size_t done = 0;
+    for (int i = 0; done < n; ++i) {
+        const int l = i & 1;
+        const size_t m = n - done < chunk ? n - done : chunk;
+        cudaStream_t s = h->pipe.lane[l];
+        float2 *di = reinterpret_cast<float2 *>(h->pipe.in[l]), *dout = reinterpret_cast<float2 *>(h->pipe.out[l]);
+        CB_CUDA(cudaMemcpyAsync(di, hin + done, m * sizeof(float2), cudaMemcpyHostToDevice, s));
+        rc = launch_mixer(di, dout, m, h->phase, h->dphase, s);
+        if (rc) return rc;
+        h->phase = advance_phase(h->phase, h->dphase, m);
+        CB_CUDA(cudaMemcpyAsync(hout + done, dout, m * sizeof(float2), cudaMemcpyDeviceToHost, s));
+        done += m;
+    }
+    return h->pipe.sync();
+}
+
+int cb_mixer_get_phase(const cb_mixer *h, double *phase, double *dphase)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    if (phase) *phase = h->phase;
+    if (dphase) *dphase = h->dphase;
+    return CB_OK;
+}
+
+int cb_mixer_set_phase(cb_mixer *h, double phase)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    CB_REQUIRE(std::isfinite(phase), CB_ERR_INVALID_ARG, "mixer: non-finite phase");
+    h->phase = phase;
+    return CB_OK;
+}
+
+// ============================================================================ FFT
+static int upload_twiddles(size_t n, int inverse, float2 **dev)
+{
+    std::vector<float2> t(n);
+    const long double sgn = inverse ? 2.0L : -2.0L;
+    for (size_t k = 0; k < n; ++k) {
+        const long double a = sgn * 3.14159265358979323846264338327950288L * (long double)k / (long double)n;
+        t[k] = make_float2((float)cosl(a), (float)sinl(a));
+    }
+    CB_CUDA(cudaMalloc(dev, n * sizeof(float2)));
+    CB_CUDA(cudaMemcpy(*dev, t.data(), n * sizeof(float2), cudaMemcpyHostToDevice));
+    return CB_OK;
+}
+
+int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
+{
+    CB_REQUIRE(out, CB_ERR_INVALID_ARG, "out is NULL");
+    CB_REQUIRE(fft_size >= 1, CB_ERR_INVALID_ARG, "fft: size must be >= 1");
+    int rc = ensure_device();
+    if (rc) return rc;
+    const bool pow2 = (fft_size & (fft_size - 1)) == 0;
+    int log2n = 0;
+    while (((size_t)1 << log2n) < fft_size) ++log2n;
+    int kind;
+    int l1 = 0, l2 = 0;
+    if (pow2 && log2n >= 3 && log2n <= 13) kind = FFT_SINGLE;
+    else if (pow2 && log2n >= 14) {
+        rc = fft_plan_split(fft_size, &l1, &l2);
+        CB_REQUIRE(rc == CB_OK, CB_ERR_UNSUPPORTED, "fft: size %zu > 2^20 is not provided", fft_size);
+        kind = FFT_FOURSTEP;
+    } else {
+        CB_REQUIRE(fft_size <= 4096, CB_ERR_UNSUPPORTED,
+                   "fft: non power-of-two size %zu > 4096 is not provided", fft_size);
+        kind = FFT_DIRECT;
+    }
+    cb_fft *h = new (std::nothrow) cb_fft();
+    CB_REQUIRE(h, CB_ERR_OOM, "host allocation failed");
+    h->device = g_dev;
+    h->tw = h->tw1 = h->tw2 = h->scratch = nullptr;
+    h->stream = nullptr;
+    h->plan = FftPlanDev{};
+    h->plan.kind = kind;
+    h->plan.inverse = inverse ? 1 : 0;
+    h->plan.n = fft_size;
+    h->plan.log2n = log2n;
+    h->plan.log2n1 = l1;
+    h->plan.log2n2 = l2;
+#define FFT_TRY(expr)                 \
+    do {                              \
+        int rc__ = (expr);            \
+        if (rc__) {                   \
+            cb_fft_destroy(h);        \
+            return rc__;              \
+        }                             \
+    } while (0)
+    {
+        cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            h->stream = nullptr;
+            cb_fft_destroy(h);
+            return cuda_fail(e, "cudaStreamCreateWithFlags", __FILE__, __LINE__);
+        }
+    }
+    FFT_TRY(h->pipe.init(h->stream));
+    FFT_TRY(upload_twiddles(fft_size, inverse, &h->tw));
+    if (kind == FFT_FOURSTEP) {
+        FFT_TRY(upload_twiddles((size_t)1 << l1, inverse, &h->tw1));
+        FFT_TRY(upload_twiddles((size_t)1 << l2, inverse, &h->tw2));
+        size_t frames = ((size_t)32 << 20) / (fft_size * sizeof(float2));
+        if (frames < 1) frames = 1;
+        h->plan.scratch_frames = frames;
+        cudaError_t e = cudaMalloc(&h->scratch, frames * fft_size * sizeof(float2));
+        if (e != cudaSuccess) {
+            cb_fft_destroy(h);
+            return cuda_fail(e, "cudaMalloc(scratch)", __FILE__, __LINE__);
+        }
+    }
+#undef FFT_TRY
+    h->plan.tw = h->tw;
+    h->plan.tw1 = h->tw1;
+    h->plan.tw2 = h->tw2;
+    h->plan.scratch = h->scratch;
+    *out = h;
+    return CB_OK;
+}
+
+int cb_fft_destroy(cb_fft *h)
+{
+    if (!h) return CB_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    h->pipe.destroy();
+    if (h->tw) cudaFree(h->tw);
+    if (h->tw1) cudaFree(h->tw1);
+    if (h->tw2) cudaFree(h->tw2);
+    if (h->scratch) cudaFree(h->scratch);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return CB_OK;
+}
+
+int cb_fft_size(const cb_fft *h, size_t *fft_size, int *inverse)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    if (fft_size) *fft_size = h->plan.n;
+    if (inverse) *inverse = h->plan.inverse;
+    return CB_OK;
+}
+
+int cb_fft_run_dev(cb_fft *h, const float *d_in, size_t n_in, float *d_out, void *stream)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    // rustfft asserts input.len() == fft_size (src/fft/mod.rs:86): a wrong length is an error
+    CB_REQUIRE(n_in > 0 && n_in % h->plan.n == 0, CB_ERR_SIZE, "fft: input length %zu is not a multiple of fft_size %zu",
+               n_in, h->plan.n);
+    CB_REQUIRE(d_in && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_REQUIRE(d_in != d_out, CB_ERR_INVALID_ARG, "fft: in-place transform is not provided");
+    CB_CUDA(cudaSetDevice(h->device));
+    return launch_fft(h->plan, reinterpret_cast<const float2 *>(d_in), reinterpret_cast<float2 *>(d_out),
+                      n_in / h->plan.n, pick_stream(stream, h->stream));
+}
+
+int cb_fft_run(cb_fft *h, const float *in, size_t n_in, float *out)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    CB_REQUIRE(n_in > 0 && n_in % h->plan.n == 0, CB_ERR_SIZE, "fft: input length %zu is not a multiple of fft_size %zu",
+               n_in, h->plan.n);
+    CB_REQUIRE(in && out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_CUDA(cudaSetDevice(h->device));
+    const size_t N = h->plan.n;
+    size_t chunk = HOST_CHUNK / N * N;
+    if (chunk == 0) chunk = N;
+    if (n_in < chunk) chunk = n_in;
+    int rc = h->pipe.reserve(chunk * sizeof(float2), chunk * sizeof(float2));
+    if (rc) return rc;
+    const float2 *hin = reinterpret_cast<const float2 *>(in);
+    float2 *hout = reinterpret_cast<float2 *>(out);
+    size_t done = 0;
+    for (int i = 0; done < n_in; ++i) {
+        const int l = i & 1;
+        const size_t m = n_in - done < chunk ? n_in - done : chunk;
+        cudaStream_t s = h->pipe.lane[l];
+        float2 *di = reinterpret_cast<float2 *>(h->pipe.in[l]), *dout = reinterpret_cast<float2 *>(h->pipe.out[l]);
+        CB_CUDA(cudaMemcpyAsync(di, hin + done, m * sizeof(float2), cudaMemcpyHostToDevice, s));
+        if (h->plan.kind == FFT_FOURSTEP && i > 0) {
+            // the four-step scratch is shared by both lanes: serialise the kernels
+            CB_CUDA(cudaStreamSynchronize(h->pipe.lane[l ^ 1]));
+        }
+        rc = launch_fft(h->plan, di, dout, m / N, s);
+        if (rc) return rc;
+        CB_CUDA(cudaMemcpyAsync(hout + done, dout, m * sizeof(float2), cudaMemcpyDeviceToHost, s));
+        done += m;
+    }
+    return h->pipe.sync();
+}
+
+// ============================================================================ FM demod
+int cb_fm_create(cb_fm **out)
+{
+    CB_REQUIRE(out, CB_ERR_INVALID_ARG, "out is NULL");
+    int rc = ensure_device();
+    if (rc) return rc;
+    cb_fm *h = new (std::nothrow) cb_fm();
+    CB_REQUIRE(h, CB_ERR_OOM, "host allocation failed");
+    h->device = g_dev;
+    h->cur = 0;
+    h->prev[0] = h->prev[1] = nullptr;
+    h->stream = nullptr;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&h->prev[0], sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc(&h->prev[1], sizeof(float2));
+    if (e == cudaSuccess) e = cudaMemset(h->prev[0], 0, sizeof(float2));  // FM::default (analog.rs:43-47)
+    if (e == cudaSuccess) e = cudaMemset(h->prev[1], 0, sizeof(float2));
+    if (e != cudaSuccess || h->pipe.init(h->stream)) {
+        cb_fm_destroy(h);
+        return e != cudaSuccess ? cuda_fail(e, "fm create", __FILE__, __LINE__) : CB_ERR_CUDA;
+    }
+    *out = h;
+    return CB_OK;
+}
+
+int cb_fm_destroy(cb_fm *h)
+{
+    if (!h) return CB_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    h->pipe.destroy();
+    for (int i = 0; i < 2; ++i)
+        if (h->prev[i]) cudaFree(h->prev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return CB_OK;
+}
+
+int cb_fm_run_dev(cb_fm *h, const float *d_in, size_t n, float *d_out, void *stream)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    if (n == 0) return CB_OK;
+    CB_REQUIRE(d_in && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_CUDA(cudaSetDevice(h->device));
+    int rc = launch_fm(reinterpret_cast<const float2 *>(d_in), d_out, n, h->prev[h->cur], h->prev[h->cur ^ 1],
+                       pick_stream(stream, h->stream));
+    if (rc) return rc;
+    h->cur ^= 1;
+    return CB_OK;
+}
+
+int cb_fm_run(cb_fm *h, const float *in, size_t n, float *out)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    if (n == 0) return CB_OK;
+    CB_REQUIRE(in && out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_CUDA(cudaSetDevice(h->device));
+    int rc = h->pipe.reserve(n * sizeof(float2), n * sizeof(float));
+    if (rc) return rc;
+    cudaStream_t s = h->pipe.lane[0];
+    CB_CUDA(cudaMemcpyAsync(h->pipe.in[0], in, n * sizeof(float2), cudaMemcpyHostToDevice, s));
+    rc = cb_fm_run_dev(h, reinterpret_cast<const float *>(h->pipe.in[0]), n, reinterpret_cast<float *>(h->pipe.out[0]), s);
+    if (rc) return rc;
+    CB_CUDA(cudaMemcpyAsync(out, h->pipe.out[0], n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaStreamSynchronize(s));
+    return CB_OK;
+}
+
+// ============================================================================ fused bank
+int cb_chain_create(size_t channels, const double *dphase, const double *phase, const float *taps, size_t ntaps,
+                    uint32_t decim, int with_fm, cb_chain **out)
+{
+    CB_REQUIRE(out, CB_ERR_INVALID_ARG, "out is NULL");
+    CB_REQUIRE(channels >= 1 && channels <= 65535, CB_ERR_INVALID_ARG, "chain: channels must be 1..65535");
+    CB_REQUIRE(taps && ntaps >= 1, CB_ERR_INVALID_ARG, "chain: taps required");
+    int rc = ensure_device();
+    if (rc) return rc;
+    const float2 *t = reinterpret_cast<const float2 *>(taps);
+    bool cplx = false;
+    for (size_t k = 0; k < ntaps; ++k)
+        if (t[k].y != 0.f) cplx = true;
+    CB_REQUIRE(ntaps * (cplx ? 2 : 1) <= (size_t)CHAIN_MAX_TAP_SLOTS, CB_ERR_UNSUPPORTED,
+               "chain: at most %d real or %d complex taps", CHAIN_MAX_TAP_SLOTS, CHAIN_MAX_TAP_SLOTS / 2);
+    cb_chain *h = new (std::nothrow) cb_chain();
+    CB_REQUIRE(h, CB_ERR_OOM, "host allocation failed");
+    h->device = g_dev;
+    h->channels = channels;
+    h->mix = dphase != nullptr;
+    h->fm = with_fm != 0;
+    h->cplx = cplx;
+    h->ntaps = (uint32_t)ntaps;
+    h->decim = decim == 0 ? 1 : decim;
+    h->hist_len = (uint32_t)round_up(ntaps, 2);
+    h->cur = 0;
+    memset(&h->taps, 0, sizeof h->taps);
+    for (size_t k = 0; k < ntaps; ++k) {
+        if (cplx) {
+            h->taps.t[2 * k] = make_float2(t[k].x, t[k].x);
+            h->taps.t[2 * k + 1] = make_float2(t[k].y, t[k].y);
+        } else {
+            h->taps.t[k] = make_float2(t[k].x, t[k].x);
+        }
+    }
+    h->phase[0] = h->phase[1] = h->dphase = nullptr;
+    h->hist[0] = h->hist[1] = h->prev[0] = h->prev[1] = nullptr;
+    h->stream = nullptr;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    const size_t hb = channels * h->hist_len * sizeof(float2);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaMalloc(&h->hist[i], hb);
+        if (e == cudaSuccess) e = cudaMemset(h->hist[i], 0, hb);
+        if (e == cudaSuccess) e = cudaMalloc(&h->prev[i], channels * sizeof(float2));
+        if (e == cudaSuccess) e = cudaMemset(h->prev[i], 0, channels * sizeof(float2));
+        if (e == cudaSuccess) e = cudaMalloc(&h->phase[i], channels * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemset(h->phase[i], 0, channels * sizeof(double));
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&h->dphase, channels * sizeof(double));
+    if (e == cudaSuccess && h->mix) {
+        std::vector<double> d(channels), p(channels, 0.0);
+        for (size_t c = 0; c < channels; ++c) {
+            d[c] = wrap_dphase(dphase[c]);
+            if (phase) p[c] = phase[c];
+        }
+        e = cudaMemcpy(h->dphase, d.data(), channels * sizeof(double), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(h->phase[0], p.data(), channels * sizeof(double), cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess || h->pipe.init(h->stream)) {
+        cb_chain_destroy(h);
+        return e != cudaSuccess ? cuda_fail(e, "chain create", __FILE__, __LINE__) : CB_ERR_CUDA;
+    }
+    *out = h;
+    return CB_OK;
+}
+
+int cb_chain_destroy(cb_chain *h)
+{
+    if (!h) return CB_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    h->pipe.destroy();
+    for (int i = 0; i < 2; ++i) {
+        if (h->hist[i]) cudaFree(h->hist[i]);
+        if (h->prev[i]) cudaFree(h->prev[i]);
+        if (h->phase[i]) cudaFree(h->phase[i]);
+    }
+    if (h->dphase) cudaFree(h->dphase);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return CB_OK;
+}
+
+int cb_chain_out_len(const cb_chain *h, size_t n_in, size_t *n_out)
+{
+    CB_REQUIRE(h && n_out, CB_ERR_INVALID_ARG, "NULL argument");
+    *n_out = decim_len(n_in, h->decim);
+    return CB_OK;
+}
+
+int cb_chain_run_dev(cb_chain *h, const float *d_in, size_t n_in, float *d_out, size_t out_cap, size_t *n_out,
+                     void *stream)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    const size_t no = decim_len(n_in, h->decim);
+    if (n_out) *n_out = no;
+    if (n_in == 0) return CB_OK;
+    CB_REQUIRE(d_in && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_REQUIRE(out_cap >= no, CB_ERR_SIZE, "chain: out_cap %zu < %zu outputs per channel", out_cap, no);
+    CB_CUDA(cudaSetDevice(h->device));
+    ChainArgs a;
+    a.x = reinterpret_cast<const float2 *>(d_in);
+    a.out = d_out;
+    a.phase_in = h->phase[h->cur];
+    a.phase_out = h->phase[h->cur ^ 1];
+    a.dphase = h->dphase;
+    a.hist_in = h->hist[h->cur];
+    a.hist_out = h->hist[h->cur ^ 1];
+    a.prev_in = h->prev[h->cur];
+    a.prev_out = h->prev[h->cur ^ 1];
+    a.n_in = n_in;
+    a.n_out = no;
+    a.ntaps = h->ntaps;
+    a.decim = h->decim;
+    a.hist_len = h->hist_len;
+    // outputs per CTA: keep the staged span around 48 KiB, whole multiples of 256 when possible
+    size_t budget = (6144 > h->ntaps + h->decim ? 6144 - h->ntaps - h->decim : 0) / h->decim;
+    size_t to = budget >= 256 ? budget / 256 * 256 : (budget ? budget : 1);
+    if (to > 2048) to = 2048;
+    if (to > no) to = no;
+    a.tile_out = (unsigned)to;
+    a.span_max = (unsigned)round_up((to + 1) * h->decim + h->ntaps, 2);
+    CB_REQUIRE(ceil_div((size_t)a.span_max, (size_t)256) <= 64, CB_ERR_UNSUPPORTED,
+               "chain: decimation %u with %u taps needs a span beyond the staged window", h->decim, h->ntaps);
+    int rc = launch_chain(a, h->taps, h->mix, h->fm, h->cplx, h->channels, pick_stream(stream, h->stream));
+    if (rc) return rc;
+    h->cur ^= 1;
+    return CB_OK;
+}
+
+int cb_chain_run(cb_chain *h, const float *in, size_t n_in, float *out, size_t out_cap, size_t *n_out)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    const size_t no = decim_len(n_in, h->decim);
+    if (n_out) *n_out = no;
+    if (n_in == 0) return CB_OK;
+    CB_REQUIRE(in && out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_REQUIRE(out_cap >= no, CB_ERR_SIZE, "chain: out_cap %zu < %zu outputs per channel", out_cap, no);
+    CB_CUDA(cudaSetDevice(h->device));
+    const size_t in_bytes = h->channels * n_in * sizeof(float2);
+    const size_t out_bytes = h->channels * no * (h->fm ? sizeof(float) : sizeof(float2));
+    int rc = h->pipe.reserve(in_bytes, out_bytes);
+    if (rc) return rc;
+    cudaStream_t s = h->pipe.lane[0];
+    CB_CUDA(cudaMemcpyAsync(h->pipe.in[0], in, in_bytes, cudaMemcpyHostToDevice, s));
+    rc = cb_chain_run_dev(h, reinterpret_cast<const float *>(h->pipe.in[0]), n_in,
+                          reinterpret_cast<float *>(h->pipe.out[0]), no, nullptr, s);
+    if (rc) return rc;
+    if (out_cap == no) {
+        CB_CUDA(cudaMemcpyAsync(out, h->pipe.out[0], out_bytes, cudaMemcpyDeviceToHost, s));
+    } else {  // caller's rows are out_cap apart
+        const size_t esz = h->fm ? sizeof(float) : sizeof(float2);
+        CB_CUDA(cudaMemcpy2DAsync(out, out_cap * esz, h->pipe.out[0], no * esz, no * esz, h->channels,
+                                  cudaMemcpyDeviceToHost, s));
+    }
+    CB_CUDA(cudaStreamSynchronize(s));
+    return CB_OK;
+}
+
+// ============================================================================ bit-exact edges
+int cb_prn_bits(uint64_t poly_mask, uint64_t *state, unsigned width, size_t n, uint8_t *bits)
+{
+    // PrnGen::next_byte (src/prns.rs:64-71); a serial recurrence, evaluated on the host.
+    CB_REQUIRE(state && (bits || n == 0), CB_ERR_INVALID_ARG, "NULL argument");
+    CB_REQUIRE(width == 8 || width == 16 || width == 32 || width == 64, CB_ERR_INVALID_ARG,
+               "prn: register width must be 8, 16, 32 or 64");
+    const uint64_t wm = width >= 64 ? ~0ULL : ((1ULL << width) - 1ULL);
+    uint64_t st = *state & wm;
+    for (size_t i = 0; i < n; ++i) {
+        const uint64_t fb = (uint64_t)(__builtin_popcountll(st & poly_mask & wm) & 1);
+        bits[i] = (uint8_t)(st >> (width - 1));
+        st = ((st << 1) & wm) | fb;
+    }
+    *state = st;
+    return CB_OK;
+}
+
+int cb_bits_to_symbols_dev(const uint8_t *d_bits, size_t nbits, int mode, float *d_sym, size_t *nsym, void *stream)
+{
+    CB_REQUIRE(mode == 0 || mode == 1, CB_ERR_INVALID_ARG, "bits_to_symbols: mode must be 0 (BPSK) or 1 (QPSK)");
+    const size_t ns = mode == 0 ? nbits : nbits / 2;
+    if (nsym) *nsym = ns;
+    if (ns == 0) return CB_OK;
+    CB_REQUIRE(d_bits && d_sym, CB_ERR_INVALID_ARG, "NULL data pointer");
+    int rc = ensure_device();
+    if (rc) return rc;
+    return launch_bits_to_symbols(d_bits, reinterpret_cast<float2 *>(d_sym), ns, mode, (cudaStream_t)stream);
+}
+
+int cb_quantize_i16_dev(const float *d_in, size_t nfloats, float scale, int16_t *d_out, void *stream)
+{
+    if (nfloats == 0) return CB_OK;
+    CB_REQUIRE(d_in && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    int rc = ensure_device();
+    if (rc) return rc;
+    return launch_quantize_i16(d_in, d_out, nfloats, scale, (cudaStream_t)stream);
+}
+
+int cb_synth_uniform_dev(uint64_t seed, uint64_t first, size_t n, float *d_out, void *stream)
+{
+    if (n == 0) return CB_OK;
+    CB_REQUIRE(d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    int rc = ensure_device();
+    if (rc) return rc;
+    return launch_synth(d_out, 2 * n, seed + 2 * first, (cudaStream_t)stream);
+}
+
+}  // extern "C"

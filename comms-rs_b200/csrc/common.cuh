@@ -1,0 +1,124 @@
+// Shared host/device helpers for libcomms_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/comms_b200.h"
+
+namespace cb {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+int current_device();  // device bound by cb_init for this thread
+
+#define CB_CUDA(call)                                                        \
+    do {                                                                     \
+        cudaError_t e__ = (call);                                            \
+        if (e__ != cudaSuccess) return cb::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define CB_REQUIRE(cond, status, ...)                                        \
+    do {                                                                     \
+        if (!(cond)) {                                                       \
+            cb::set_error(__VA_ARGS__);                                      \
+            return (status);                                                 \
+        }                                                                    \
+    } while (0)
+
+int ensure_device();  // CB_OK or CB_ERR_NO_DEVICE; also cudaSetDevice(current)
+
+static inline size_t ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }
+static inline size_t round_up(size_t a, size_t b) { return ceil_div(a, b) * b; }
+
+// ---------------------------------------------------------------- device PTX
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+// make the mbarrier init visible to the async (TMA) proxy
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier.
+// dst/src 16-byte aligned, bytes a multiple of 16.  SASS: UBLKCP.
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// TMA 1-D bulk copy shared -> global (bulk async-group completion).
+__device__ __forceinline__ void tma_store_1d(void *dst_gmem, const void *src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// streaming (read-once / write-once) 128-bit global accesses
+__device__ __forceinline__ float4 ldg_stream(const float4 *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream(float4 *p, float4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void stg_stream2(float2 *p, float2 v)
+{
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+#endif  // __CUDACC__
+
+}  // namespace cb

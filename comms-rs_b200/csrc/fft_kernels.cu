@@ -1,0 +1,363 @@
+// Batched FFT / IFFT kernels (K5) for sm_100a.
+//
+// Reference semantics (src/fft/mod.rs:73-96): X[k] = sum_n x[n] e^{-/+ j 2 pi k n / N},
+// unnormalised in both directions.  The reference computes in f64 and rounds to f32;
+// here the transform runs in f32 with twiddles rounded from f64 (rel-L2 error ~1e-7,
+// tolerance 1e-4 per BASELINE north_star).
+//
+// Structure: Stockham autosort, radix 8 (+ one radix-4/2 pass), 8 points per thread
+// held in registers, exchanges through padded shared memory.  The first pass reads
+// global memory coalesced (x[j + r*N/8]) and the last pass writes it coalesced
+// (X[j + q*N/R]), so a frame crosses HBM exactly once each way: 16 B per sample.
+// Frames longer than 8192 use a four-step split N = N1*N2 with both steps done as
+// 16-column batches (128-byte row segments) of the same butterfly core.
+#include "fft_kernels.cuh"
+#include "misc_kernels.cuh"
+
+namespace cb {
+
+// ---------------------------------------------------------------- butterflies
+template <bool INV>
+__device__ __forceinline__ float2 mul_mi(float2 a)  // a * (-i) forward, a * (+i) inverse
+{
+    return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+template <bool INV>
+__device__ __forceinline__ void fft4(float2 &x0, float2 &x1, float2 &x2, float2 &x3)
+{
+    const float2 b0 = cadd(x0, x2), b2 = csub(x0, x2), b1 = cadd(x1, x3), b3 = mul_mi<INV>(csub(x1, x3));
+    x0 = cadd(b0, b1);
+    x2 = csub(b0, b1);
+    x1 = cadd(b2, b3);
+    x3 = csub(b2, b3);
+}
+
+// in-place size-8 DFT, natural order in and out
+template <bool INV>
+__device__ __forceinline__ void fft8(float2 *v)
+{
+    const float c = 0.70710678118654752440f;
+    float2 a0 = cadd(v[0], v[4]), a4 = csub(v[0], v[4]);
+    float2 a1 = cadd(v[1], v[5]), a5 = csub(v[1], v[5]);
+    float2 a2 = cadd(v[2], v[6]), a6 = csub(v[2], v[6]);
+    float2 a3 = cadd(v[3], v[7]), a7 = csub(v[3], v[7]);
+    // a5 *= w8, a6 *= w8^2, a7 *= w8^3 with w8 = e^{-/+ j pi/4}
+    if (INV) {
+        a5 = make_float2(c * (a5.x - a5.y), c * (a5.x + a5.y));
+        a7 = make_float2(-c * (a7.x + a7.y), c * (a7.x - a7.y));
+    } else {
+        a5 = make_float2(c * (a5.x + a5.y), c * (a5.y - a5.x));
+        a7 = make_float2(c * (a7.y - a7.x), -c * (a7.x + a7.y));
+    }
+    a6 = mul_mi<INV>(a6);
+    fft4<INV>(a0, a1, a2, a3);  // X[0], X[2], X[4], X[6]
+    fft4<INV>(a4, a5, a6, a7);  // X[1], X[3], X[5], X[7]
+    v[0] = a0; v[2] = a1; v[4] = a2; v[6] = a3;
+    v[1] = a4; v[3] = a5; v[5] = a6; v[7] = a7;
+}
+
+// ---------------------------------------------------------------- FFT core
+// One length-N transform by NT = N/8 cooperating threads (index j), 8 points each.
+// SM(i) maps a logical point index to this transform's shared-memory slot.
+// `v` holds x[j + r*NT] on entry; on exit v[q] holds the LAST pass's outputs:
+//   REM == 0: X[j + q*NT]                      (q = 0..7)
+//   REM == 2: X[jj + q*N/4], jj = j + h*NT     (stored at v[h + 2q])
+//   REM == 1: X[jj + q*N/2], jj = j + h*NT     (stored at v[h + 4q])
+// i.e. in every case v[r] = X[j + r*NT]: natural order with the same mapping as the input.
+template <int LOG2N, bool INV, typename SM>
+__device__ __forceinline__ void fft_core(float2 *v, const int j, const float2 *__restrict__ tw, SM sm)
+{
+    constexpr int N = 1 << LOG2N;
+    constexpr int NT = N / 8;
+    constexpr int P8 = LOG2N / 3;
+    constexpr int REM = LOG2N % 3;
+    int Ns = 1;
+#pragma unroll
+    for (int p = 0; p < P8; ++p) {
+        if (p > 0) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) v[r] = sm(j + r * NT);
+            __syncthreads();
+            const int idx = (j & (Ns - 1)) * (N / (Ns * 8));
+#pragma unroll
+            for (int q = 1; q < 8; ++q) v[q] = cmul(v[q], __ldg(tw + q * idx));
+        }
+        fft8<INV>(v);
+        if (p == P8 - 1 && REM == 0) break;
+        const int d = (j / Ns) * Ns * 8 + (j & (Ns - 1));
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sm(d + q * Ns) = v[q];
+        __syncthreads();
+        Ns *= 8;
+    }
+    if (REM == 2) {  // final radix-4 pass: two butterflies per thread
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v[r] = sm(j + r * NT);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int jj = j + h * NT;  // Ns = N/4, idx = jj
+            float2 x0 = v[h], x1 = cmul(v[h + 2], __ldg(tw + jj)), x2 = cmul(v[h + 4], __ldg(tw + 2 * jj)),
+                   x3 = cmul(v[h + 6], __ldg(tw + 3 * jj));
+            fft4<INV>(x0, x1, x2, x3);
+            v[h] = x0; v[h + 2] = x1; v[h + 4] = x2; v[h + 6] = x3;
+        }
+    } else if (REM == 1) {  // final radix-2 pass: four butterflies per thread
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v[r] = sm(j + r * NT);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const int jj = j + h * NT;  // Ns = N/2, idx = jj
+            const float2 b = cmul(v[h + 4], __ldg(tw + jj));
+            const float2 a = v[h];
+            v[h] = cadd(a, b);
+            v[h + 4] = csub(a, b);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- one CTA, whole frames
+struct SmPadded {
+    float2 *base;
+    __device__ __forceinline__ float2 &operator()(int i) const { return base[i + (i >> 4)]; }
+};
+
+template <int LOG2N, bool INV>
+__global__ void __launch_bounds__((1 << LOG2N) / 8 >= 128 ? (1 << LOG2N) / 8 : 128)
+fft_frames_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, const float2 *__restrict__ tw,
+                  size_t nframes)
+{
+    constexpr int N = 1 << LOG2N;
+    constexpr int NT = N / 8;
+    constexpr int FPB = NT >= 128 ? 1 : 128 / NT;  // frames per block
+    constexpr int PADN = N + N / 16 + 1;
+    extern __shared__ __align__(16) float2 fsm[];
+    const int f = threadIdx.x / NT, j = threadIdx.x % NT;
+    const size_t frame = (size_t)blockIdx.x * FPB + f;
+    const bool live = frame < nframes;
+    const float2 *src = in + frame * N;
+    float2 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = live ? src[j + r * NT] : make_float2(0.f, 0.f);
+    fft_core<LOG2N, INV>(v, j, tw, SmPadded{fsm + f * PADN});
+    if (live) {
+        float2 *dst = out + frame * N;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) dst[j + r * NT] = v[r];
+    }
+}
+
+// ---------------------------------------------------------------- four-step column kernels
+// Column batch: COLS adjacent columns of a (ROWS x ld) matrix, FFT along the rows
+// index.  Thread t: column f = t % COLS, butterfly index j = t / COLS.
+template <int COLS>
+struct SmCols {
+    float2 *base;
+    int f;
+    __device__ __forceinline__ float2 &operator()(int i) const { return base[i * (COLS + 1) + f]; }
+};
+
+// step 1 of N = N1*N2: for each n2, FFT over n1 of x[n1*N2 + n2], times
+// twN[n2*k1], written TRANSPOSED: a[n2*N1 + k1]  (rows of k1 contiguous).
+template <int LOG2N1, bool INV, int COLS>
+__global__ void __launch_bounds__(((1 << LOG2N1) / 8) * COLS)
+fft_step1_kernel(const float2 *__restrict__ in, float2 *__restrict__ scratch, const float2 *__restrict__ tw1,
+                 const float2 *__restrict__ twN, int N2)
+{
+    constexpr int N1 = 1 << LOG2N1;
+    constexpr int NT = N1 / 8;
+    extern __shared__ __align__(16) float2 fsm[];
+    const int f = threadIdx.x % COLS, j = threadIdx.x / COLS;
+    const int colblocks = N2 / COLS;
+    const size_t frame = blockIdx.x / colblocks;
+    const int n2 = (blockIdx.x % colblocks) * COLS + f;
+    const float2 *src = in + frame * (size_t)N1 * N2 + n2;
+    float2 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = src[(size_t)(j + r * NT) * N2];
+    SmCols<COLS> sm{fsm, f};
+    fft_core<LOG2N1, INV>(v, j, tw1, sm);
+    // twiddle by e^{-/+ 2 pi i n2 k1 / N}, k1 = j + r*NT, then stage for the transposed write
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int k1 = j + r * NT;
+        sm(k1) = cmul(v[r], __ldg(twN + (size_t)n2 * k1));
+    }
+    __syncthreads();
+    // write: for each column f' a contiguous run of N1 values (lanes along k1)
+    float2 *dst = scratch + frame * (size_t)N1 * N2 + (size_t)((blockIdx.x % colblocks) * COLS) * N1;
+    for (int e = threadIdx.x; e < N1 * COLS; e += NT * COLS) {
+        const int ff = e / N1, k1 = e % N1;
+        dst[(size_t)ff * N1 + k1] = fsm[k1 * (COLS + 1) + ff];
+    }
+}
+
+// step 2: for each k1, FFT over n2 of a[n2*N1 + k1]; X[k2*N1 + k1].
+template <int LOG2N2, bool INV, int COLS>
+__global__ void __launch_bounds__(((1 << LOG2N2) / 8) * COLS)
+fft_step2_kernel(const float2 *__restrict__ scratch, float2 *__restrict__ out, const float2 *__restrict__ tw2, int N1)
+{
+    constexpr int N2 = 1 << LOG2N2;
+    constexpr int NT = N2 / 8;
+    extern __shared__ __align__(16) float2 fsm[];
+    const int f = threadIdx.x % COLS, j = threadIdx.x / COLS;
+    const int colblocks = N1 / COLS;
+    const size_t frame = blockIdx.x / colblocks;
+    const int k1 = (blockIdx.x % colblocks) * COLS + f;
+    const float2 *src = scratch + frame * (size_t)N1 * N2 + k1;
+    float2 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = src[(size_t)(j + r * NT) * N1];
+    fft_core<LOG2N2, INV>(v, j, tw2, SmCols<COLS>{fsm, f});
+    float2 *dst = out + frame * (size_t)N1 * N2 + k1;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) dst[(size_t)(j + r * NT) * N1] = v[r];
+}
+
+// ---------------------------------------------------------------- any-N direct DFT
+// O(N^2) with an exact table: tw[(k*n) mod N].  Used for non power-of-two and tiny N
+// (the reference accepts any size; its own golden test is N = 10).
+__global__ void __launch_bounds__(128)
+dft_direct_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, const float2 *__restrict__ tw, int N,
+                  size_t nframes)
+{
+    extern __shared__ __align__(16) float2 fsm[];  // one frame
+    for (size_t frame = blockIdx.x; frame < nframes; frame += gridDim.x) {
+        const float2 *src = in + frame * N;
+        for (int i = threadIdx.x; i < N; i += blockDim.x) fsm[i] = src[i];
+        __syncthreads();
+        for (int k = threadIdx.x; k < N; k += blockDim.x) {
+            float ar = 0.f, ai = 0.f, cr = 0.f, ci = 0.f;  // Kahan-compensated: long sums in f32
+            int m = 0;
+            for (int n = 0; n < N; ++n) {
+                const float2 w = __ldg(tw + m);
+                const float2 p = cmul(fsm[n], w);
+                float y = p.x - cr, t = ar + y;
+                cr = (t - ar) - y; ar = t;
+                y = p.y - ci; t = ai + y;
+                ci = (t - ai) - y; ai = t;
+                m += k;
+                if (m >= N) m -= N;
+            }
+            out[frame * N + k] = make_float2(ar, ai);
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- launchers
+template <int LOG2N, bool INV>
+static int launch_frames(const float2 *in, float2 *out, const float2 *tw, size_t nframes, cudaStream_t s)
+{
+    constexpr int N = 1 << LOG2N;
+    constexpr int NT = N / 8;
+    constexpr int FPB = NT >= 128 ? 1 : 128 / NT;
+    constexpr int THREADS = NT * FPB;
+    constexpr int SMEM = FPB * (N + N / 16 + 1) * (int)sizeof(float2);
+    auto kern = fft_frames_kernel<LOG2N, INV>;
+        CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    kern<<<(unsigned)ceil_div(nframes, (size_t)FPB), THREADS, SMEM, s>>>(in, out, tw, nframes);
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+
+template <bool INV>
+static int launch_frames_dir(int log2n, const float2 *in, float2 *out, const float2 *tw, size_t nframes, cudaStream_t s)
+{
+    switch (log2n) {
+    case 3: return launch_frames<3, INV>(in, out, tw, nframes, s);
+    case 4: return launch_frames<4, INV>(in, out, tw, nframes, s);
+    case 5: return launch_frames<5, INV>(in, out, tw, nframes, s);
+    case 6: return launch_frames<6, INV>(in, out, tw, nframes, s);
+    case 7: return launch_frames<7, INV>(in, out, tw, nframes, s);
+    case 8: return launch_frames<8, INV>(in, out, tw, nframes, s);
+    case 9: return launch_frames<9, INV>(in, out, tw, nframes, s);
+    case 10: return launch_frames<10, INV>(in, out, tw, nframes, s);
+    case 11: return launch_frames<11, INV>(in, out, tw, nframes, s);
+    case 12: return launch_frames<12, INV>(in, out, tw, nframes, s);
+    case 13: return launch_frames<13, INV>(in, out, tw, nframes, s);
+    default: set_error("fft: no single-CTA kernel for 2^%d", log2n); return CB_ERR_UNSUPPORTED;
+    }
+}
+
+template <int LOG2M, bool INV, int COLS>
+static int launch_step(int which, const float2 *in, float2 *out, const float2 *twM, const float2 *twN, int other,
+                       size_t nframes, cudaStream_t s)
+{
+    constexpr int M = 1 << LOG2M;
+    constexpr int THREADS = (M / 8) * COLS;
+    constexpr int SMEM = M * (COLS + 1) * (int)sizeof(float2);
+    const unsigned grid = (unsigned)(nframes * (size_t)(other / COLS));
+    if (which == 1) {
+        auto kern = fft_step1_kernel<LOG2M, INV, COLS>;
+            CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        kern<<<grid, THREADS, SMEM, s>>>(in, out, twM, twN, other);
+    } else {
+        auto kern = fft_step2_kernel<LOG2M, INV, COLS>;
+            CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        kern<<<grid, THREADS, SMEM, s>>>(in, out, twM, other);
+    }
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+
+template <bool INV>
+static int launch_step_dir(int which, int log2m, const float2 *in, float2 *out, const float2 *twM, const float2 *twN,
+                           int other, size_t nframes, cudaStream_t s)
+{
+    switch (log2m) {
+    case 7: return launch_step<7, INV, 16>(which, in, out, twM, twN, other, nframes, s);
+    case 8: return launch_step<8, INV, 16>(which, in, out, twM, twN, other, nframes, s);
+    case 9: return launch_step<9, INV, 16>(which, in, out, twM, twN, other, nframes, s);
+    case 10: return launch_step<10, INV, 8>(which, in, out, twM, twN, other, nframes, s);
+    default: set_error("fft: no four-step kernel for 2^%d", log2m); return CB_ERR_UNSUPPORTED;
+    }
+}
+
+int fft_plan_split(size_t n, int *log2n1, int *log2n2)
+{
+    int l = 0;
+    while (((size_t)1 << l) < n) ++l;
+    if (((size_t)1 << l) != n || l < 14 || l > 20) return CB_ERR_UNSUPPORTED;
+    *log2n1 = l / 2;
+    *log2n2 = l - l / 2;
+    return CB_OK;
+}
+
+int launch_fft(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s)
+{
+    if (nframes == 0) return CB_OK;
+    if (p.kind == FFT_SINGLE) {
+        return p.inverse ? launch_frames_dir<true>(p.log2n, in, out, p.tw, nframes, s)
+                         : launch_frames_dir<false>(p.log2n, in, out, p.tw, nframes, s);
+    }
+    if (p.kind == FFT_FOURSTEP) {
+        const int N1 = 1 << p.log2n1, N2 = 1 << p.log2n2;
+        // scratch holds as many frames as fit; process in groups
+        size_t done = 0;
+        while (done < nframes) {
+            const size_t g = nframes - done < p.scratch_frames ? nframes - done : p.scratch_frames;
+            const float2 *gi = in + done * p.n;
+            float2 *go = out + done * p.n;
+            int rc = p.inverse ? launch_step_dir<true>(1, p.log2n1, gi, p.scratch, p.tw1, p.tw, N2, g, s)
+                               : launch_step_dir<false>(1, p.log2n1, gi, p.scratch, p.tw1, p.tw, N2, g, s);
+            if (rc) return rc;
+            rc = p.inverse ? launch_step_dir<true>(2, p.log2n2, p.scratch, go, p.tw2, nullptr, N1, g, s)
+                           : launch_step_dir<false>(2, p.log2n2, p.scratch, go, p.tw2, nullptr, N1, g, s);
+            if (rc) return rc;
+            done += g;
+        }
+        return CB_OK;
+    }
+    // direct
+    const int smem = (int)(p.n * sizeof(float2));
+    size_t blocks = nframes < 148 * 8 ? nframes : 148 * 8;
+    dft_direct_kernel<<<(unsigned)blocks, 128, smem, s>>>(in, out, p.tw, (int)p.n, nframes);
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+
+}  // namespace cb

@@ -1,0 +1,26 @@
+#pragma once
+#include "common.cuh"
+
+namespace cb {
+
+enum FftKind { FFT_SINGLE = 0, FFT_FOURSTEP = 1, FFT_DIRECT = 2 };
+
+// Device-side plan: twiddle tables are e^{-/+ 2 pi i k / n} rounded from f64,
+// with the direction baked in.
+struct FftPlanDev {
+    int kind;
+    int inverse;
+    size_t n;
+    int log2n;            // FFT_SINGLE
+    int log2n1, log2n2;   // FFT_FOURSTEP: n = n1*n2
+    const float2 *tw;     // n entries
+    const float2 *tw1;    // n1 entries (four-step)
+    const float2 *tw2;    // n2 entries (four-step)
+    float2 *scratch;      // four-step intermediate, scratch_frames * n
+    size_t scratch_frames;
+};
+
+int fft_plan_split(size_t n, int *log2n1, int *log2n2);
+int launch_fft(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s);
+
+}  // namespace cb

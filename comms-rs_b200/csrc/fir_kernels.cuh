@@ -1,0 +1,32 @@
+// FIR kernels (K1 / K3 of SURVEY.md section 2): device code + launch wrappers.
+//
+// Reference semantics (src/filter/fir.rs:87-102):
+//   y[n] = sum_{k<K} h[k] * x[n-k],   x[-1-k] = state[k]
+// The K-1 samples before a batch (the reference's `state`) are exactly an
+// overlap-save halo, so every tile of outputs is independent given its input
+// range plus a K-sample halo.
+#pragma once
+#include "common.cuh"
+
+namespace cb {
+
+// One launch of a FIR over a contiguous segment.
+struct FirSeg {
+    const float2 *x;        // n_in input samples (device)
+    const float2 *hist_in;  // hist_len samples preceding x[0], chronological (oldest first)
+    float2 *hist_out;       // may be NULL; receives the last hist_len samples of [hist_in ++ x]
+    float2 *y;              // outputs
+    size_t n_in;
+    size_t n_out;
+    uint32_t hist_len;      // >= taps-per-phase halo, even
+    uint32_t ntaps;         // effective taps (min(len taps, len state)), > 0
+    uint32_t interp;        // L >= 1
+    uint32_t decim;         // D >= 1
+};
+
+// taps_dev: ntaps complex taps in device memory (generic path)
+// taps_host: same on the host (fast paths put them in the kernel parameter constant bank)
+int launch_fir(const FirSeg &seg, const float2 *taps_dev, const float2 *taps_host, bool taps_real,
+               cudaStream_t stream);
+
+}  // namespace cb

@@ -1,0 +1,51 @@
+// Element-wise kernels and the device math shared with the fused chain kernel.
+#pragma once
+#include "common.cuh"
+
+namespace cb {
+
+int launch_mixer(const float2 *x, float2 *y, size_t n, double phase0, double dphase, cudaStream_t s);
+int launch_fm(const float2 *x, float *out, size_t n, const float2 *prev_in, float2 *prev_out, cudaStream_t s);
+int launch_decimate(const void *in, void *out, size_t n_out, size_t elem, size_t rate, cudaStream_t s);
+int launch_upsample(const void *in, void *out, size_t n_out, size_t elem, size_t rate, cudaStream_t s);
+int launch_bits_to_symbols(const uint8_t *bits, float2 *sym, size_t nsym, int mode, cudaStream_t s);
+int launch_quantize_i16(const float *in, int16_t *out, size_t n, float scale, cudaStream_t s);
+int launch_synth(float *out, size_t nfloats, unsigned long long base, cudaStream_t s);
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+// (cos, sin) of an f64 phase: Cody-Waite reduction to [-pi, pi] in f64, then a
+// two-term f32 evaluation (sincosf of the high part, first-order correction by
+// the low part) -- absolute error ~1e-7, i.e. at the rounding level of the f32
+// output the reference produces after its f64 multiply (src/mixer.rs:77-83).
+__device__ __forceinline__ float2 phase_rotation(double theta)
+{
+    const double inv2pi = 0.15915494309189534561;
+    const double twopi_hi = 6.283185307179586232;    // fl(2*pi)
+    const double twopi_lo = 2.4492935982947064e-16;  // 2*pi - twopi_hi
+    const double k = rint(theta * inv2pi);
+    double r = fma(-k, twopi_hi, theta);
+    r = fma(-k, twopi_lo, r);
+    const float hi = (float)r;
+    const float lo = (float)(r - (double)hi);
+    float s, c;
+    sincosf(hi, &s, &c);
+    return make_float2(fmaf(-lo, s, c), fmaf(lo, c, s));
+}
+
+// FM discriminator step: theta = s * conj(p); atan2(theta.im, theta.re), with the
+// reference's operation order and no FMA contraction (src/modulation/analog.rs:27-29).
+__device__ __forceinline__ float fm_angle(float2 s, float2 p)
+{
+    const float br = p.x, bi = -p.y;
+    const float tr = __fsub_rn(__fmul_rn(s.x, br), __fmul_rn(s.y, bi));
+    const float ti = __fadd_rn(__fmul_rn(s.x, bi), __fmul_rn(s.y, br));
+    return atan2f(ti, tr);
+}
+#endif
+
+}  // namespace cb

@@ -1,0 +1,223 @@
+/*
+ * comms_b200.h -- C ABI of libcomms_b200.so, the B200 (sm_100a) implementation
+ * of comms-rs's FIR / mixer / FFT hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ * A `Complex<f32>` slice (`#[repr(C)] {re, im}`) crosses as `const float*`
+ * holding 2*n interleaved floats; lengths are in complex samples unless the
+ * name says otherwise.  Each entry point cites the reference item (path:line in
+ * ostrosco/comms-rs) it replaces; INTEGRATION.md shows the Rust binding.
+ *
+ * Conventions
+ *   - every function returns a cb_status (0 = ok) and never throws or aborts;
+ *     cb_last_error() gives the calling thread's last message.
+ *     Suggested mapping in the Rust shim: CB_ERR_INVALID_ARG / CB_ERR_SIZE ->
+ *     NodeError::DataError, everything else -> NodeError::PermanentError
+ *     (src/node/mod.rs:68-73).
+ *   - handles are used by one thread at a time (Node: Send, not Sync;
+ *     src/node/mod.rs:94) but different handles may be used concurrently from
+ *     different threads: the library keeps no unsynchronised global state,
+ *     sets the device per call and gives each handle its own non-blocking
+ *     stream.
+ *   - `*_run` (host pointers) has Vec-in / Vec-out semantics: it returns when
+ *     `out` is filled.  `*_run_dev` takes device pointers (16-byte aligned for
+ *     full speed) and a cudaStream_t (NULL = the handle's stream), is
+ *     asynchronous, and lets nodes chain on the device.
+ *   - there is no CPU fallback: without a CUDA device every compute call
+ *     fails with CB_ERR_NO_DEVICE.
+ */
+#ifndef COMMS_B200_H
+#define COMMS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define CB_API
+#else
+#define CB_API __attribute__((visibility("default")))
+#endif
+
+typedef enum cb_status {
+    CB_OK = 0,
+    CB_ERR_INVALID_ARG = 1, /* null pointer, zero fft size, bad rate ...      */
+    CB_ERR_SIZE = 2,        /* input length does not fit (e.g. len != fft_size,
+                               out_cap too small)                             */
+    CB_ERR_CUDA = 3,        /* a CUDA runtime call failed                     */
+    CB_ERR_NO_DEVICE = 4,   /* no usable CUDA device / cb_init not possible   */
+    CB_ERR_OOM = 5,         /* host or device allocation failed               */
+    CB_ERR_UNSUPPORTED = 6  /* valid in the reference, not provided here      */
+} cb_status;
+
+typedef struct cb_stream cb_stream;   /* a device + cudaStream_t                  */
+typedef struct cb_buf cb_buf;         /* ref-counted pinned-host or device buffer */
+typedef struct cb_fir cb_fir;         /* BatchFirNode / FirNode / PulseNode state */
+typedef struct cb_mixer cb_mixer;     /* Mixer state                              */
+typedef struct cb_fft cb_fft;         /* BatchFFT plan                            */
+typedef struct cb_fm cb_fm;           /* FM demod state                           */
+typedef struct cb_chain cb_chain;     /* bank of fused mixer->FIR->decimate->FM   */
+
+/* ------------------------------------------------------------------ library */
+CB_API int cb_version(void);                       /* 1000*major + minor        */
+CB_API const char *cb_last_error(void);            /* thread-local, never NULL  */
+CB_API const char *cb_status_str(int status);
+CB_API int cb_device_count(int *count);
+/* Binds the calling thread's subsequent creates to `device` (default 0). */
+CB_API int cb_init(int device);
+CB_API int cb_device_synchronize(void);
+
+/* ------------------------------------------------------------------ streams */
+CB_API int cb_stream_create(cb_stream **out);
+CB_API int cb_stream_destroy(cb_stream *s);
+CB_API int cb_stream_sync(cb_stream *s);
+CB_API void *cb_stream_handle(cb_stream *s);       /* the cudaStream_t          */
+
+/* ------------------------------------------------------------------ buffers
+ * What crosses a NodeSender/NodeReceiver channel instead of a Vec when two GPU
+ * nodes are adjacent: the derive macro clones the result once per downstream
+ * edge (node_derive/src/lib.rs:156), so Clone must be cb_buf_retain, Drop
+ * cb_buf_release. */
+CB_API int cb_buf_alloc_pinned(size_t bytes, cb_buf **out);
+CB_API int cb_buf_alloc_device(size_t bytes, cb_buf **out);
+CB_API int cb_buf_retain(cb_buf *b);
+CB_API int cb_buf_release(cb_buf *b);
+CB_API void *cb_buf_ptr(cb_buf *b);
+CB_API size_t cb_buf_bytes(cb_buf *b);
+CB_API int cb_buf_is_device(cb_buf *b);
+/* async copies on `stream` (NULL = default stream of the bound device) */
+CB_API int cb_copy_h2d_async(void *dst_dev, const void *src_host, size_t bytes, void *stream);
+CB_API int cb_copy_d2h_async(void *dst_host, const void *src_dev, size_t bytes, void *stream);
+
+/* ------------------------------------------------------------------ FIR
+ * Replaces batch_fir / fir (src/filter/fir.rs:87-102, :43-54) and the state
+ * handling of BatchFirNode::new / FirNode::new (src/filter/fir_node.rs:193-211):
+ *   y[n] = sum_{k < min(ntaps, nstate)} taps[k] * x[n-k],  x[-1-k] = state[k].
+ * `state` may be NULL (zeros of length ntaps, like `None`); otherwise nstate
+ * complex samples, newest first.  The state is carried across calls, so batch
+ * boundaries are invisible in the output stream.
+ *
+ * decim / interp fuse the neighbouring resample nodes:
+ *   interp = L > 1: input is zero-stuffed by L first (UpsampleNode::upsample,
+ *     src/util/resample_node.rs:120-131, or PulseNode::run, src/pulse.rs:82-92)
+ *     -- computed as a polyphase bank, n inputs -> n*L outputs;
+ *   decim = D > 1: only outputs 0, D, 2D.. OF EACH CALL survive
+ *     (DecimateNode::decimate, src/util/resample_node.rs:53-65; the phase is
+ *     reset per batch, as in the reference) -> ceil(n*L / D) outputs.
+ *   0 and 1 both mean pass-through, as in the reference.
+ * With interp > 1 an explicit initial `state` must be consistent with a
+ * zero-stuffed history (non-zero only every L-th entry, newest = index L-1
+ * ... ) or be NULL; otherwise CB_ERR_UNSUPPORTED.
+ */
+CB_API int cb_fir_create(const float *taps, size_t ntaps, const float *state, size_t nstate,
+                         uint32_t decim, uint32_t interp, cb_fir **out);
+CB_API int cb_fir_destroy(cb_fir *h);
+CB_API int cb_fir_out_len(const cb_fir *h, size_t n_in, size_t *n_out);
+CB_API int cb_fir_run(cb_fir *h, const float *in, size_t n_in, float *out, size_t out_cap, size_t *n_out);
+CB_API int cb_fir_run_dev(cb_fir *h, const float *d_in, size_t n_in, float *d_out, size_t out_cap,
+                          size_t *n_out, void *stream);
+/* state as the reference would hold it after the samples seen so far
+ * (newest first, nstate entries, in the zero-stuffed domain when interp > 1) */
+CB_API int cb_fir_state_len(const cb_fir *h, size_t *nstate);
+CB_API int cb_fir_get_state(cb_fir *h, float *state, size_t nstate);
+CB_API int cb_fir_set_state(cb_fir *h, const float *state, size_t nstate);
+CB_API void *cb_fir_stream(cb_fir *h);
+
+/* ------------------------------------------------------------------ resample
+ * Stand-alone DecimateNode::decimate / UpsampleNode::upsample
+ * (src/util/resample_node.rs:53-65, :120-131) for graphs that keep them as
+ * separate nodes.  elem_bytes = size of T (4, 8 or 16).  Device pointers. */
+CB_API int cb_decimate_dev(const void *d_in, size_t n, size_t elem_bytes, size_t rate, void *d_out,
+                           size_t out_cap, size_t *n_out, void *stream);
+CB_API int cb_upsample_dev(const void *d_in, size_t n, size_t elem_bytes, size_t rate, void *d_out,
+                           size_t out_cap, size_t *n_out, void *stream);
+CB_API int cb_decimate(const void *in, size_t n, size_t elem_bytes, size_t rate, void *out,
+                       size_t out_cap, size_t *n_out);
+CB_API int cb_upsample(const void *in, size_t n, size_t elem_bytes, size_t rate, void *out,
+                       size_t out_cap, size_t *n_out);
+
+/* ------------------------------------------------------------------ mixer
+ * Replaces Mixer::new / Mixer::mix (src/mixer.rs:43-51, :73-84) over a batch:
+ *   y[n] = x[n] * exp(j*(phase + n*dphase)),  dphase wrapped into [0, 2pi)
+ * Phase arithmetic in f64, carried across calls.  Note the argument order of
+ * MixerNode::new(dphase, phase) (src/mixer.rs:128). */
+CB_API int cb_mixer_create(double dphase, double phase, cb_mixer **out);
+CB_API int cb_mixer_destroy(cb_mixer *h);
+CB_API int cb_mixer_run(cb_mixer *h, const float *in, size_t n, float *out);
+CB_API int cb_mixer_run_dev(cb_mixer *h, const float *d_in, size_t n, float *d_out, void *stream);
+CB_API int cb_mixer_get_phase(const cb_mixer *h, double *phase, double *dphase);
+CB_API int cb_mixer_set_phase(cb_mixer *h, double phase);
+
+/* ------------------------------------------------------------------ FFT
+ * Replaces BatchFFT::run_fft (src/fft/mod.rs:73-96) / FFTBatchNode::new
+ * (src/fft/fft_node.rs:65-74): X[k] = sum_n x[n] exp(-/+ j 2 pi k n / N),
+ * "+" when inverse != 0, no 1/N in either direction, any N >= 1.
+ * n_in must be a multiple of fft_size (the reference requires n_in ==
+ * fft_size, one frame per message; several contiguous frames per call is the
+ * batched form) else CB_ERR_SIZE. */
+CB_API int cb_fft_create(size_t fft_size, int inverse, cb_fft **out);
+CB_API int cb_fft_destroy(cb_fft *h);
+CB_API int cb_fft_run(cb_fft *h, const float *in, size_t n_in, float *out);
+CB_API int cb_fft_run_dev(cb_fft *h, const float *d_in, size_t n_in, float *d_out, void *stream);
+CB_API int cb_fft_size(const cb_fft *h, size_t *fft_size, int *inverse);
+
+/* ------------------------------------------------------------------ FM demod
+ * Replaces FM::demod (src/modulation/analog.rs:22-34): out[n] =
+ * arg(x[n] * conj(x[n-1])), previous sample carried across calls, initially 0
+ * (src/modulation/analog.rs:43-47).  n complex in -> n floats out. */
+CB_API int cb_fm_create(cb_fm **out);
+CB_API int cb_fm_destroy(cb_fm *h);
+CB_API int cb_fm_run(cb_fm *h, const float *in, size_t n, float *out);
+CB_API int cb_fm_run_dev(cb_fm *h, const float *d_in, size_t n, float *d_out, void *stream);
+
+/* ------------------------------------------------------------------ fused bank
+ * `channels` independent instances of
+ *   [MixerNode] -> BatchFirNode -> DecimateNode(D) -> [FMDemodNode]
+ * (the fm_radio front end, examples/fm_radio.rs:144-164, generalised per
+ * BASELINE config 4) in ONE kernel that writes only the surviving samples.
+ * Per channel c the semantics are exactly the four reference nodes in series,
+ * each with its own carried state (mixer phase, FIR delay line, FM prev); the
+ * decimation phase restarts at every call, like DecimateNode.
+ * Layout: in  = channels x n_in complex, channel-major (channel c at
+ *               in + 2*c*n_in floats);
+ *         out = channels x ceil(n_in/D) floats (with_fm) or complex (no fm).
+ * dphase/phase: per-channel arrays (NULL => mixer stage absent).
+ * Taps are shared by all channels. */
+CB_API int cb_chain_create(size_t channels, const double *dphase, const double *phase,
+                           const float *taps, size_t ntaps, uint32_t decim, int with_fm,
+                           cb_chain **out);
+CB_API int cb_chain_destroy(cb_chain *h);
+CB_API int cb_chain_out_len(const cb_chain *h, size_t n_in, size_t *n_out_per_channel);
+CB_API int cb_chain_run(cb_chain *h, const float *in, size_t n_in, float *out, size_t out_cap_per_channel,
+                        size_t *n_out_per_channel);
+CB_API int cb_chain_run_dev(cb_chain *h, const float *d_in, size_t n_in, float *d_out,
+                            size_t out_cap_per_channel, size_t *n_out_per_channel, void *stream);
+
+/* ------------------------------------------------------------------ bit-exact edges
+ * Integer / index stages of the example graphs, device side, so whole example
+ * chains can stay on the GPU.
+ * cb_prn_bits: PrnGen::next_byte (src/prns.rs:64-71), `width` = register bits.
+ * cb_bits_to_symbols: the example maps, mode 0 = BPSK b -> (2b-1) + 0j
+ *   (examples/single_thread_bpsk.rs:29-32), mode 1 = QPSK bit pairs
+ *   (examples/single_thread_qpsk.rs:29-36).
+ * cb_quantize_i16: (scale * x) as i16, truncating and saturating
+ *   (examples/single_thread_bpsk.rs:40-48). */
+CB_API int cb_prn_bits(uint64_t poly_mask, uint64_t *state, unsigned width, size_t n, uint8_t *bits_host);
+CB_API int cb_bits_to_symbols_dev(const uint8_t *d_bits, size_t nbits, int mode, float *d_sym,
+                                  size_t *nsym, void *stream);
+CB_API int cb_quantize_i16_dev(const float *d_in, size_t nfloats, float scale, int16_t *d_out, void *stream);
+
+/* ------------------------------------------------------------------ synthetic input
+ * splitmix64 counter generator shared with the oracle (oracle.c
+ * orc_synth_uniform_f32): float i = top 24 bits of splitmix64(seed + i)
+ * scaled to [-1, 1).  Fills n complex samples starting at complex index
+ * `first`.  Used by tests and bench only. */
+CB_API int cb_synth_uniform_dev(uint64_t seed, uint64_t first, size_t n, float *d_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COMMS_B200_H */
