@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the comms-rs FIR / mixer / FFT hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload fir64] [--impl b200|reference]
+
+A "step" is one pass of the hot path over one batch of synthetic input.  The
+default workload is BASELINE.json configs[1]: one 64-tap complex-f32 FIR
+(BatchFirNode, src/filter/fir_node.rs:146-221) over a 2^28-sample stream.
+One JSON line is printed by rank 0:
+  value     device-resident throughput (inputs already in HBM), CUDA events, max over ranks
+  e2e       same metric through the host-pointer C-ABI call (cb_fir_run ...): pinned
+            host buffers, H2D + kernel + D2H inside the timed region
+  roofline  algorithmic bytes per launch / mean launch time vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the oracle port of the reference algorithm on one host core (N=1, rank 0)
+`--impl reference` times the reference's CPU algorithm (oracle port; the Rust
+reference cannot be built in this image) on all host cores instead.
+N > 1: one process per GPU (torchrun); each rank owns one overlap-save segment of
+the stream (its halo is the K samples before it), no data-path collective ->
+weak scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "FIR/FFT Msamples/s"
+UNIT = "Msamples/s"
+SEED = 20260101
+
+WORKLOADS = {
+    # name: (kind, samples per step per GPU, algorithmic bytes per input sample, description)
+    "fir64": ("fir", 1 << 28, 16.0, "64-tap complex-f32 FIR (complex taps) on one 2^28-sample stream per GPU"),
+    "fir64_real": ("fir", 1 << 28, 16.0, "64-tap complex-f32 FIR (real-valued rrc taps) on one 2^28-sample stream per GPU"),
+    "fft1024": ("fft", 1 << 28, 16.0, "batched 1024-point FFT over 2^28 complex-f32 samples per GPU"),
+    "fft4096": ("fft", 1 << 28, 16.0, "batched 4096-point FFT over 2^28 complex-f32 samples per GPU"),
+    "fft65536": ("fft", 1 << 28, 16.0, "batched 65536-point FFT over 2^28 complex-f32 samples per GPU"),
+    "ifft4096": ("fft", 1 << 28, 16.0, "batched 4096-point IFFT over 2^28 complex-f32 samples per GPU"),
+    "chain": ("chain", 1024 * 131072, 8.4, "fm_radio chain x1024 channels per GPU: mixer -> 63-tap FIR -> /10 -> FM demod, "
+              "131072-sample batches"),
+    "pulse4": ("interp", 1 << 26, 40.0, "BPSK pulse shaping: x4 polyphase 32-tap RRC over 2^26 symbols per GPU (unit = symbols)"),
+    "poly8x1024": ("interp", 1 << 24, 72.0, "QPSK x8 polyphase, 1024-tap RRC bank over 2^24 symbols per GPU (unit = symbols)"),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="fir64", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+    a.steps = max(a.steps, 1)
+    return a
+
+
+# ---------------------------------------------------------------------------- workload parameters
+def fm_radio_lowpass(n=63):
+    k = np.arange(n) - (n - 1) / 2
+    return (np.sinc(k / 5) * np.hamming(n) / 5).astype(np.float32).astype(np.complex64)
+
+
+def fir_taps(workload):
+    import oracle  # taps only (rrc_taps restatement, src/util/math.rs:221-280); not on the timed GPU path
+
+    t = oracle.rrc_taps(64, 4.0, 0.25)
+    if workload == "fir64":
+        t = (t * np.exp(0.1j * np.arange(64))).astype(np.complex64)
+    return t
+
+
+# ---------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index):
+        self.samples, self._stop, self.ok = [], threading.Event(), False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in vis.split(",") if v.strip().isdigit()]
+            phys = int(ids[index]) if index < len(ids) else index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                try:
+                    rs = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    rs = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), mhz, rs))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.ok:
+            self.t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self.ok:
+            self.t.join(timeout=2)
+
+    def summary(self, t0, t1):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvml unavailable: " + getattr(self, "err", "")}
+        win = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples
+        mhz = sorted(s[1] for s in win)
+        bits = 0
+        for s in win:
+            bits |= s[2]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(v for k, v in self.REASONS.items() if bits & k), "samples": len(win)}
+
+
+# ---------------------------------------------------------------------------- CPU legs (oracle port)
+def cpu_rate(workload, samples, threads):
+    """Times the oracle's restatement of the reference algorithm on `samples` units split over
+    `threads` independent segments (each seeded with its halo).  Returns (Msamples/s, seconds)."""
+    import oracle
+
+    oracle.build()
+    kind = WORKLOADS[workload][0]
+    per = max(samples // threads, 1)
+    if kind == "fft":
+        n = int(workload.replace("ifft", "").replace("fft", ""))
+        per = max(per // n, 1) * n
+    jobs = []
+    for i in range(threads):
+        x = oracle.synth_uniform_c32(SEED, i * per, per)
+        if kind == "fir":
+            t = fir_taps(workload)
+            # reference form: per-sample rotate + ordered MACs (src/filter/fir.rs:87-102), release flags
+            jobs.append(lambda x=x, t=t: oracle.batch_fir(x, t, np.zeros(64, np.complex64), literal=True, native=True))
+        elif kind == "fft":
+            jobs.append(lambda x=x: oracle.fft(x, n, workload.startswith("ifft")))
+        elif kind == "chain":
+            ch = oracle.FmChain(-0.7, 0.0, fm_radio_lowpass(), 10, native=True)
+            jobs.append(lambda x=x, ch=ch: [ch.run(x[j:j + 131072]) for j in range(0, len(x), 131072)])
+        else:
+            L, nt = (4, 32) if workload == "pulse4" else (8, 1024)
+            t = oracle.rrc_taps(nt, float(L), 0.25)
+            st = np.zeros(nt, np.complex64)
+            jobs.append(lambda x=x, t=t, st=st: oracle.batch_fir(oracle.upsample(x, L), t, st, literal=True, native=True))
+    ths = [threading.Thread(target=j) for j in jobs]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    dt = time.perf_counter() - t0
+    return per * threads / dt / 1e6, dt, per * threads
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    kind, _, _, desc = WORKLOADS[args.workload]
+    rate1 = {"fir": 8e6, "fft": 30e6, "chain": 20e6, "interp": 2e6}[kind]
+    if args.workload == "poly8x1024":
+        rate1 = 1e4
+    per_thread = int(min(max(150.0 * rate1 / (args.steps + args.warmup), 1 << 12), 1 << 23))
+    sample = per_thread * threads
+    for _ in range(args.warmup):
+        cpu_rate(args.workload, sample, threads)
+    tot_t, tot_n = 0.0, 0
+    for _ in range(args.steps):
+        _, dt, n = cpu_rate(args.workload, sample, threads)
+        tot_t += dt
+        tot_n += n
+    v = tot_n / tot_t / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "description": desc,
+                   "note": "reference CPU algorithm (oracle port of the Rust code; no rustc in this image), "
+                           "independent segments with halo state, one per host thread"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} units per step ({per_thread} per thread), {args.steps} steps"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------- GPU leg
+class Job:
+    """One workload bound to one GPU: device buffers, handles, and the per-step launch."""
+
+    def __init__(self, cb, torch, workload, rank):
+        self.cb, self.torch, self.workload = cb, torch, workload
+        self.kind, self.n, self.bytes_per_unit, self.desc = WORKLOADS[workload]
+        self.stream = torch.cuda.current_stream().cuda_stream
+        n = self.n
+        self.first = rank * n  # this rank's segment of the global synthetic stream
+        self.x = torch.empty(n, dtype=torch.complex64, device="cuda")
+        cb.synth_uniform_dev(SEED, self.first, n, self.x.data_ptr(), self.stream)
+        self.kernels_per_step = 1
+        if self.kind == "fir":
+            self.taps = fir_taps(workload)
+            self.halo = self._halo(64)
+            self.node = cb.BatchFirNode(self.taps, self.halo)
+            self.y = torch.empty(n, dtype=torch.complex64, device="cuda")
+            self.out_bytes = 8 * n
+            self.step = lambda: self.node.run_dev(self.x.data_ptr(), n, self.y.data_ptr(), n, self.stream)
+            self.host_call = lambda hin, hout: cb.load().cb_fir_run(self.node._h, hin, n, hout, n, None)
+        elif self.kind == "fft":
+            N = int(workload.replace("ifft", "").replace("fft", ""))
+            self.node = cb.FFTBatchNode(N, workload.startswith("ifft"))
+            self.y = torch.empty(n, dtype=torch.complex64, device="cuda")
+            self.out_bytes = 8 * n
+            self.kernels_per_step = 2 if N > 8192 else 1
+            self.step = lambda: self.node.run_dev(self.x.data_ptr(), n, self.y.data_ptr(), self.stream)
+            self.host_call = lambda hin, hout: cb.load().cb_fft_run(self.node._h, hin, n, hout)
+        elif self.kind == "chain":
+            C, nb = 1024, 131072
+            fc = (np.arange(C) / C - 0.5) * 0.8
+            self.node = cb.ChainBank(C, fm_radio_lowpass(), 10, dphase=-2 * np.pi * fc, with_fm=True)
+            no = self.node.out_len(nb)
+            self.y = torch.empty(C * no, dtype=torch.float32, device="cuda")
+            self.out_bytes = 4 * C * no
+            self.step = lambda: self.node.run_dev(self.x.data_ptr(), nb, self.y.data_ptr(), no, self.stream)
+            self.host_call = lambda hin, hout: cb.load().cb_chain_run(self.node._h, hin, nb, hout, no, None)
+        else:
+            L, nt = (4, 32) if workload == "pulse4" else (8, 1024)
+            import oracle
+            self.taps = oracle.rrc_taps(nt, float(L), 0.25)
+            self.node = cb.BatchFirNode(self.taps, None, interp=L)
+            self.y = torch.empty(n * L, dtype=torch.complex64, device="cuda")
+            self.out_bytes = 8 * n * L
+            self.step = lambda: self.node.run_dev(self.x.data_ptr(), n, self.y.data_ptr(), n * L, self.stream)
+            self.host_call = lambda hin, hout: cb.load().cb_fir_run(self.node._h, hin, n, hout, n * L, None)
+        self.in_bytes = 8 * n
+
+    def _halo(self, k):
+        """The k samples before this rank's segment, newest first: the reference `state`
+        (src/filter/fir_node.rs:193-200) that makes segment + halo partitioning exact."""
+        if self.first == 0:
+            return None
+        t = self.torch.empty(k, dtype=self.torch.complex64, device="cuda")
+        self.cb.synth_uniform_dev(SEED, self.first - k, k, t.data_ptr(), self.stream)
+        self.torch.cuda.synchronize()
+        return t.cpu().numpy()[::-1].copy()
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    import comms_rs_b200 as cb
+
+    cb.init(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    job = Job(cb, torch, args.workload, rank)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- device-resident: W warm-up steps, then exactly K timed steps
+    for _ in range(args.warmup):
+        job.step()
+    barrier()
+    launches0 = cb.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        ev[i].record()
+        job.step()
+    ev[args.steps].record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches_dev = cb.launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[args.steps])
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    clocks = sampler.summary(t_wall0, t_wall1)
+
+    # ---- end to end: host buffers (pinned), H2D + kernels + D2H inside the timed region
+    e2e = None
+    launches_e2e = 0
+    if not args.no_e2e:
+        import ctypes as C
+        lib = cb.load()
+        hin, hout = C.c_void_p(), C.c_void_p()
+        cb._lib.check(lib.cb_buf_alloc_pinned(job.in_bytes, C.byref(hin)))
+        cb._lib.check(lib.cb_buf_alloc_pinned(job.out_bytes, C.byref(hout)))
+        pin, pout = lib.cb_buf_ptr(hin), lib.cb_buf_ptr(hout)
+        cb._lib.check(lib.cb_copy_d2h_async(pin, job.x.data_ptr(), job.in_bytes, job.stream))
+        torch.cuda.synchronize()
+        k_e2e = max(3, min(args.steps, 10))
+        for _ in range(2):
+            cb._lib.check(job.host_call(pin, pout))
+        barrier()
+        l0 = cb.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            cb._lib.check(job.host_call(pin, pout))  # returns when the host output buffer is filled
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        launches_e2e = cb.launch_count() - l0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * job.n * k_e2e / float(tt.item()) / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": job.in_bytes, "d2h_bytes_per_step": job.out_bytes, "steps": k_e2e,
+               "api": "host-pointer C-ABI call, pinned buffers, 2-lane chunked H2D/kernel/D2H pipeline"}
+        lib.cb_buf_release(hin)
+        lib.cb_buf_release(hout)
+    sampler.stop()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        peak = peaks.get("hbm_gbs")
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        if not peak:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        ms_launch = total_ms / args.steps / job.kernels_per_step
+        alg_bytes = job.bytes_per_unit * job.n / job.kernels_per_step
+        achieved = alg_bytes / (ms_launch * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        except Exception:  # noqa: BLE001
+            pass
+        line = {
+            "metric": METRIC, "value": world * job.n * args.steps / (total_ms_max * 1e-3) / 1e6, "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "description": job.desc, "units_per_step_per_gpu": job.n,
+                       "l2": "inputs larger than L2 (%.1f GiB read + %.1f GiB written per step, L2 = 126 MB)"
+                             % (job.in_bytes / 2 ** 30, job.out_bytes / 2 ** 30),
+                       "parallelism": "one overlap-save segment (or channel/frame block) per GPU, no data-path collective",
+                       "seed": SEED},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": int(launches_dev + launches_e2e),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernels_per_step": job.kernels_per_step,
+                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_launch},
+        }
+        if world == 1 and not args.no_cpu:
+            kind = job.kind
+            sample = {"fir": 1 << 26, "fft": 1 << 27, "chain": 1 << 26, "interp": 1 << 23}[kind]
+            if args.workload == "poly8x1024":
+                sample = 1 << 17
+            v, dt, n = cpu_rate(args.workload, sample, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"first {n} units of the same synthetic stream, {dt:.1f} s, one thread "
+                                              "(the reference runs one thread per node)",
+                                    "host_cores": os.cpu_count()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        import subprocess
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29577", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

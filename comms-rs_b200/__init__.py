@@ -1,0 +1,36 @@
+"""comms-rs_b200: B200-native (sm_100a) implementation of comms-rs's FIR / mixer /
+FFT hot path.  The product is libcomms_b200.so (csrc/, C ABI in
+include/comms_b200.h); this package is the thin host-side mirror of the
+reference's node structs used by tests and bench.  No CPU fallback exists.
+"""
+from . import _lib
+from ._lib import CbError, NodeError, load
+from .nodes import (BatchFirNode, ChainBank, DecimateNode, FFTBatchNode, FFTSampleNode, FirNode, FMDemodNode,
+                    MixerNode, PulseNode, UpsampleNode, bits_to_symbols_dev, prn_bits, quantize_i16_dev,
+                    synth_uniform_dev)
+
+
+def init(device: int = 0) -> None:
+    """cb_init: bind this thread to `device`; raises CbError(NO_DEVICE) without a GPU."""
+    _lib.check(load().cb_init(device))
+
+
+def device_count() -> int:
+    import ctypes as C
+    n = C.c_int()
+    _lib.check(load().cb_device_count(C.byref(n)))
+    return n.value
+
+
+def synchronize() -> None:
+    _lib.check(load().cb_device_synchronize())
+
+
+def launch_count() -> int:
+    """Kernels launched by libcomms_b200 in this process so far (cb_launch_count)."""
+    import ctypes as C
+    n = C.c_uint64()
+    _lib.check(load().cb_launch_count(C.byref(n)))
+    return n.value
+
+from . import sharding  # noqa: E402

@@ -36,6 +36,9 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 
 int current_device() { return g_dev; }
 
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 static int use_device(int dev)
 {
     int count = 0;
@@ -206,6 +209,13 @@ int cb_device_count(int *count)
         c = 0;
     }
     *count = c;
+    return CB_OK;
+}
+
+int cb_launch_count(uint64_t *count)
+{
+    CB_REQUIRE(count, CB_ERR_INVALID_ARG, "count is NULL");
+    *count = g_launches.load(std::memory_order_relaxed);
     return CB_OK;
 }
 

@@ -136,6 +136,7 @@ int launch_chain(const ChainArgs &args, const ChainTaps &taps, bool mix, bool fm
     CB_CHAIN_CASE(true, true, false)
     CB_CHAIN_CASE(true, true, true)
 #undef CB_CHAIN_CASE
+    count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;
 }

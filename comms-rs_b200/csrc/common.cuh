@@ -14,6 +14,7 @@ namespace cb {
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 int current_device();  // device bound by cb_init for this thread
+void count_launch();   // bumps the process-wide kernel-launch counter (cb_launch_count)
 
 #define CB_CUDA(call)                                                        \
     do {                                                                     \

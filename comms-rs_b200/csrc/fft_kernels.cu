@@ -260,6 +260,7 @@ static int launch_frames(const float2 *in, float2 *out, const float2 *tw, size_t
     auto kern = fft_frames_kernel<LOG2N, INV>;
         CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     kern<<<(unsigned)ceil_div(nframes, (size_t)FPB), THREADS, SMEM, s>>>(in, out, tw, nframes);
+    count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;
 }
@@ -300,6 +301,7 @@ static int launch_step(int which, const float2 *in, float2 *out, const float2 *t
             CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         kern<<<grid, THREADS, SMEM, s>>>(in, out, twM, other);
     }
+    count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;
 }
@@ -356,6 +358,7 @@ int launch_fft(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframe
     const int smem = (int)(p.n * sizeof(float2));
     size_t blocks = nframes < 148 * 8 ? nframes : 148 * 8;
     dft_direct_kernel<<<(unsigned)blocks, 128, smem, s>>>(in, out, p.tw, (int)p.n, nframes);
+    count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;
 }

@@ -346,6 +346,7 @@ static int launch_stream(const FirSeg &seg, const float2 *taps_host, cudaStream_
         CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const unsigned grid = (unsigned)ceil_div(seg.n_in, (size_t)TILE);
     kern<<<grid, 256, SMEM, stream>>>(a, bank);
+    count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;
 }
@@ -377,6 +378,7 @@ static int launch_interp(const FirSeg &seg, const float2 *taps_host, cudaStream_
         CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const unsigned grid = (unsigned)ceil_div(seg.n_in, (size_t)TILE);
     kern<<<grid, 256, SMEM, stream>>>(a, bank);
+    count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;
 }
@@ -386,6 +388,7 @@ static int launch_generic(const FirSeg &seg, const float2 *taps_dev, cudaStream_
     size_t blocks = ceil_div(seg.n_out ? seg.n_out : 1, (size_t)256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     fir_generic_kernel<<<(unsigned)blocks, 256, 0, stream>>>(seg, taps_dev);
+    count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;
 }

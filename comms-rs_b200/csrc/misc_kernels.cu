@@ -44,6 +44,7 @@ int launch_mixer(const float2 *x, float2 *y, size_t n, double phase0, double dph
 {
     if (n == 0) return CB_OK;
     mixer_kernel<<<grid_for(n / 2 + 1, 256), 256, 0, s>>>(x, y, n, phase0, dphase);
+    count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;
 }
@@ -68,6 +69,7 @@ fm_kernel(const float2 *__restrict__ x, float *__restrict__ out, size_t n, const
 int launch_fm(const float2 *x, float *out, size_t n, const float2 *prev_in, float2 *prev_out, cudaStream_t s)
 {
     fm_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, out, n, prev_in, prev_out);
+    count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;
 }
@@ -104,6 +106,7 @@ int launch_decimate(const void *in, void *out, size_t n_out, size_t elem, size_t
     case 1: decimate_kernel<char><<<g, 256, 0, s>>>((const char *)in, (char *)out, n_out, rate); break;
     default: set_error("decimate: unsupported element size %zu", elem); return CB_ERR_UNSUPPORTED;
     }
+    count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;
 }
@@ -120,6 +123,7 @@ int launch_upsample(const void *in, void *out, size_t n_out, size_t elem, size_t
     case 1: upsample_kernel<char><<<g, 256, 0, s>>>((const char *)in, (char *)out, n_out, rate); break;
     default: set_error("upsample: unsupported element size %zu", elem); return CB_ERR_UNSUPPORTED;
     }
+    count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;
 }
@@ -139,6 +143,7 @@ int launch_bits_to_symbols(const uint8_t *bits, float2 *sym, size_t nsym, int mo
 {
     if (nsym == 0) return CB_OK;
     bits_to_symbols_kernel<<<grid_for(nsym, 256), 256, 0, s>>>(bits, sym, nsym, mode);
+    count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;
 }
@@ -159,6 +164,7 @@ int launch_quantize_i16(const float *in, int16_t *out, size_t n, float scale, cu
 {
     if (n == 0) return CB_OK;
     quantize_i16_kernel<<<grid_for(n, 256), 256, 0, s>>>(in, out, n, scale);
+    count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;
 }
@@ -186,6 +192,7 @@ int launch_synth(float *out, size_t nfloats, unsigned long long base, cudaStream
 {
     if (nfloats == 0) return CB_OK;
     synth_kernel<<<grid_for(nfloats, 256), 256, 0, s>>>(out, nfloats, base);
+    count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;
 }

@@ -1,0 +1,324 @@
+"""Host-side mirror of the comms-rs node structs on the hot path, over the C ABI.
+
+Same names, constructor arguments and `run()` meaning as the reference:
+  BatchFirNode / FirNode   src/filter/fir_node.rs:43-221
+  PulseNode                src/pulse.rs:36-92
+  DecimateNode/UpsampleNode src/util/resample_node.rs:18-131
+  MixerNode                src/mixer.rs:91-148
+  FFTBatchNode/FFTSampleNode src/fft/fft_node.rs:26-168
+  FMDemodNode              src/modulation/analog_node.rs:18-52
+`run(host array) -> host array` is the drop-in Vec-in / Vec-out form;
+`run_dev(ptr, n, out_ptr, ...)` chains device buffers on a stream.  All
+arithmetic happens in libcomms_b200.so; nothing here computes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import CbError, NodeError, check, node_error
+
+_vp, _sz = C.c_void_p, C.c_size_t
+
+
+def _c32(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.complex64))
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(_vp)
+
+
+class _Handle:
+    _destroy = None
+
+    def __init__(self):
+        self._h = _vp()
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h and _lib._LIB is not None:
+            getattr(_lib.load(), self._destroy)(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BatchFirNode(_Handle):
+    """BatchFirNode::new(taps, state) (src/filter/fir_node.rs:193-211) with the
+    neighbouring Upsample/Decimate nodes optionally fused (interp / decim)."""
+
+    _destroy = "cb_fir_destroy"
+
+    def __init__(self, taps, state=None, decim: int = 1, interp: int = 1):
+        super().__init__()
+        t = _c32(taps)
+        s = None if state is None else _c32(state)
+        check(_lib.load().cb_fir_create(_ptr(t), len(t), None if s is None else _ptr(s), 0 if s is None else len(s),
+                                        decim, interp, C.byref(self._h)))
+
+    def out_len(self, n_in: int) -> int:
+        m = _sz()
+        check(_lib.load().cb_fir_out_len(self._h, n_in, C.byref(m)))
+        return m.value
+
+    def run(self, samples) -> np.ndarray:
+        x = _c32(samples)
+        out = np.empty(self.out_len(len(x)), dtype=np.complex64)
+        m = _sz()
+        try:
+            check(_lib.load().cb_fir_run(self._h, _ptr(x), len(x), _ptr(out), len(out), C.byref(m)))
+        except CbError as e:
+            raise node_error(e) from e
+        return out[: m.value]
+
+    def run_dev(self, d_in: int, n_in: int, d_out: int, out_cap: int, stream: int = 0) -> int:
+        m = _sz()
+        check(_lib.load().cb_fir_run_dev(self._h, d_in, n_in, d_out, out_cap, C.byref(m), stream))
+        return m.value
+
+    @property
+    def state(self) -> np.ndarray:
+        n = _sz()
+        check(_lib.load().cb_fir_state_len(self._h, C.byref(n)))
+        st = np.empty(n.value, dtype=np.complex64)
+        check(_lib.load().cb_fir_get_state(self._h, _ptr(st), n.value))
+        return st
+
+    @state.setter
+    def state(self, value):
+        s = _c32(value)
+        check(_lib.load().cb_fir_set_state(self._h, _ptr(s), len(s)))
+
+    @property
+    def stream(self) -> int:
+        return _lib.load().cb_fir_stream(self._h) or 0
+
+
+class FirNode(BatchFirNode):
+    """FirNode (src/filter/fir_node.rs:43-114): one sample per run()."""
+
+    def run(self, sample) -> np.complex64:  # type: ignore[override]
+        return super().run(np.asarray([sample], dtype=np.complex64))[0]
+
+
+class PulseNode(BatchFirNode):
+    """PulseNode::new(taps, sam_per_sym) (src/pulse.rs:71-80): one symbol in,
+    `sam_per_sym` samples out; run() also accepts a batch of symbols."""
+
+    def __init__(self, taps, sam_per_sym: int):
+        if sam_per_sym < 1:
+            raise NodeError(NodeError.DataError, "sam_per_sym must be >= 1")
+        super().__init__(taps, None, decim=1, interp=sam_per_sym)
+        self.sam_per_sym = sam_per_sym
+
+
+class _Resample:
+    _fn = ""
+
+    def __init__(self, rate: int):
+        self.rate = int(rate)
+
+    def _len(self, n: int) -> int:
+        raise NotImplementedError
+
+    def run(self, data) -> np.ndarray:
+        a = np.ascontiguousarray(data)
+        elem = a.dtype.itemsize * int(np.prod(a.shape[1:], dtype=np.int64))
+        out = np.empty((self._len(len(a)),) + a.shape[1:], dtype=a.dtype)
+        m = _sz()
+        try:
+            check(getattr(_lib.load(), self._fn)(_ptr(a), len(a), elem, self.rate, _ptr(out), len(out), C.byref(m)))
+        except CbError as e:
+            raise node_error(e) from e
+        return out[: m.value]
+
+    def run_dev(self, d_in: int, n: int, elem_bytes: int, d_out: int, out_cap: int, stream: int = 0) -> int:
+        m = _sz()
+        check(getattr(_lib.load(), self._fn + "_dev")(d_in, n, elem_bytes, self.rate, d_out, out_cap, C.byref(m), stream))
+        return m.value
+
+
+class DecimateNode(_Resample):
+    """DecimateNode::new(dec_rate) (src/util/resample_node.rs:23-31)."""
+
+    _fn = "cb_decimate"
+
+    def _len(self, n):
+        return n if self.rate <= 1 else -(-n // self.rate)
+
+
+class UpsampleNode(_Resample):
+    """UpsampleNode::new(ups_rate) (src/util/resample_node.rs:87-95)."""
+
+    _fn = "cb_upsample"
+
+    def _len(self, n):
+        return n if self.rate <= 1 else n * self.rate
+
+
+class MixerNode(_Handle):
+    """MixerNode::new(dphase, phase) (src/mixer.rs:128-134) -- note the order."""
+
+    _destroy = "cb_mixer_destroy"
+
+    def __init__(self, dphase: float, phase: float | None = None):
+        super().__init__()
+        check(_lib.load().cb_mixer_create(float(dphase), 0.0 if phase is None else float(phase), C.byref(self._h)))
+
+    def run(self, samples):
+        scalar = np.ndim(samples) == 0
+        x = _c32(np.atleast_1d(samples))
+        out = np.empty_like(x)
+        try:
+            check(_lib.load().cb_mixer_run(self._h, _ptr(x), len(x), _ptr(out)))
+        except CbError as e:
+            raise node_error(e) from e
+        return out[0] if scalar else out
+
+    def run_dev(self, d_in: int, n: int, d_out: int, stream: int = 0) -> None:
+        check(_lib.load().cb_mixer_run_dev(self._h, d_in, n, d_out, stream))
+
+    @property
+    def phase(self) -> float:
+        p = C.c_double()
+        check(_lib.load().cb_mixer_get_phase(self._h, C.byref(p), None))
+        return p.value
+
+    @phase.setter
+    def phase(self, v: float):
+        check(_lib.load().cb_mixer_set_phase(self._h, float(v)))
+
+    @property
+    def dphase(self) -> float:
+        d = C.c_double()
+        check(_lib.load().cb_mixer_get_phase(self._h, None, C.byref(d)))
+        return d.value
+
+
+class FFTBatchNode(_Handle):
+    """FFTBatchNode::new(fft_size, ifft) (src/fft/fft_node.rs:65-74).  run() takes
+    one frame (the reference contract) or several contiguous frames."""
+
+    _destroy = "cb_fft_destroy"
+
+    def __init__(self, fft_size: int, ifft: bool = False):
+        super().__init__()
+        self.fft_size = int(fft_size)
+        check(_lib.load().cb_fft_create(self.fft_size, int(bool(ifft)), C.byref(self._h)))
+
+    def run(self, data) -> np.ndarray:
+        x = _c32(data).reshape(-1)
+        out = np.empty_like(x)
+        try:
+            check(_lib.load().cb_fft_run(self._h, _ptr(x), len(x), _ptr(out)))
+        except CbError as e:
+            raise node_error(e) from e
+        return out
+
+    def run_dev(self, d_in: int, n_in: int, d_out: int, stream: int = 0) -> None:
+        check(_lib.load().cb_fft_run_dev(self._h, d_in, n_in, d_out, stream))
+
+
+class FFTSampleNode(FFTBatchNode):
+    """FFTSampleNode (src/fft/fft_node.rs:101-168, #[aggregate]): collects
+    samples; run() returns None until fft_size samples have arrived."""
+
+    def __init__(self, fft_size: int, ifft: bool = False):
+        super().__init__(fft_size, ifft)
+        self._acc: list = []
+
+    def run(self, sample):  # type: ignore[override]
+        self._acc.append(sample)
+        if len(self._acc) == self.fft_size:
+            frame, self._acc = self._acc, []
+            return super().run(np.asarray(frame, dtype=np.complex64))
+        return None
+
+
+class FMDemodNode(_Handle):
+    """FMDemodNode::new() (src/modulation/analog_node.rs:43-52)."""
+
+    _destroy = "cb_fm_destroy"
+
+    def __init__(self):
+        super().__init__()
+        check(_lib.load().cb_fm_create(C.byref(self._h)))
+
+    def run(self, samples) -> np.ndarray:
+        x = _c32(samples)
+        out = np.empty(len(x), dtype=np.float32)
+        try:
+            check(_lib.load().cb_fm_run(self._h, _ptr(x), len(x), _ptr(out)))
+        except CbError as e:
+            raise node_error(e) from e
+        return out
+
+    def run_dev(self, d_in: int, n: int, d_out: int, stream: int = 0) -> None:
+        check(_lib.load().cb_fm_run_dev(self._h, d_in, n, d_out, stream))
+
+
+class ChainBank(_Handle):
+    """`channels` independent [MixerNode] -> BatchFirNode -> DecimateNode -> [FMDemodNode]
+    chains fused in one kernel (examples/fm_radio.rs:144-164 generalised)."""
+
+    _destroy = "cb_chain_destroy"
+
+    def __init__(self, channels: int, taps, decim: int, dphase=None, phase=None, with_fm: bool = True):
+        super().__init__()
+        t = _c32(taps)
+        d = None if dphase is None else np.ascontiguousarray(np.broadcast_to(np.asarray(dphase, np.float64), (channels,)))
+        p = None if phase is None else np.ascontiguousarray(np.broadcast_to(np.asarray(phase, np.float64), (channels,)))
+        self.channels, self.with_fm, self.decim = int(channels), bool(with_fm), int(decim)
+        check(_lib.load().cb_chain_create(self.channels, None if d is None else _ptr(d), None if p is None else _ptr(p),
+                                          _ptr(t), len(t), self.decim, int(self.with_fm), C.byref(self._h)))
+
+    def out_len(self, n_in: int) -> int:
+        m = _sz()
+        check(_lib.load().cb_chain_out_len(self._h, n_in, C.byref(m)))
+        return m.value
+
+    def run(self, x) -> np.ndarray:
+        x = _c32(x).reshape(self.channels, -1)
+        n_in = x.shape[1]
+        no = self.out_len(n_in)
+        out = np.empty((self.channels, no), dtype=np.float32 if self.with_fm else np.complex64)
+        m = _sz()
+        try:
+            check(_lib.load().cb_chain_run(self._h, _ptr(x), n_in, _ptr(out), no, C.byref(m)))
+        except CbError as e:
+            raise node_error(e) from e
+        return out
+
+    def run_dev(self, d_in: int, n_in: int, d_out: int, out_cap: int, stream: int = 0) -> int:
+        m = _sz()
+        check(_lib.load().cb_chain_run_dev(self._h, d_in, n_in, d_out, out_cap, C.byref(m), stream))
+        return m.value
+
+
+# ------------------------------------------------------------------ edges
+def prn_bits(poly_mask: int, state: int, n: int, width: int = 8):
+    """PrnGen::next_byte n times (src/prns.rs:64-71).  Returns (bits, new_state)."""
+    st = C.c_uint64(state)
+    out = np.empty(n, dtype=np.uint8)
+    check(_lib.load().cb_prn_bits(poly_mask, C.byref(st), width, n, _ptr(out)))
+    return out, st.value
+
+
+def bits_to_symbols_dev(d_bits: int, nbits: int, mode: int, d_sym: int, stream: int = 0) -> int:
+    m = _sz()
+    check(_lib.load().cb_bits_to_symbols_dev(d_bits, nbits, mode, d_sym, C.byref(m), stream))
+    return m.value
+
+
+def quantize_i16_dev(d_in: int, nfloats: int, scale: float, d_out: int, stream: int = 0) -> None:
+    check(_lib.load().cb_quantize_i16_dev(d_in, nfloats, scale, d_out, stream))
+
+
+def synth_uniform_dev(seed: int, first: int, n: int, d_out: int, stream: int = 0) -> None:
+    check(_lib.load().cb_synth_uniform_dev(seed, first, n, d_out, stream))

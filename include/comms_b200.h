@@ -69,6 +69,10 @@ CB_API int cb_device_count(int *count);
 /* Binds the calling thread's subsequent creates to `device` (default 0). */
 CB_API int cb_init(int device);
 CB_API int cb_device_synchronize(void);
+/* Number of CUDA kernels this library has launched in the process so far (a
+ * metrics hook with no reference counterpart; bench.py reports it as
+ * gpu_launches). */
+CB_API int cb_launch_count(uint64_t *count);
 
 /* ------------------------------------------------------------------ streams */
 CB_API int cb_stream_create(cb_stream **out);

@@ -1,0 +1,442 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the
+reference's golden vectors.  Needs a B200: `pytest -m gpu`.
+
+Tolerances (BASELINE.json north_star): FIR / mixer / polyphase complex-f32
+relative L2 <= 1e-5; FFT relative L2 <= 1e-4; integer / index work bit-exact.
+"""
+import numpy as np
+import pytest
+
+from golden import reference_vectors as G
+
+pytestmark = pytest.mark.gpu
+
+FIR_TOL = 1e-5
+FFT_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import comms_rs_b200 as m
+
+    m.init(0)
+    return m
+
+
+def rel_l2(a, b):
+    a = np.asarray(a).astype(np.complex128).ravel()
+    b = np.asarray(b).astype(np.complex128).ravel()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    d = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / d if d > 0 else np.linalg.norm(a - b)
+
+
+def rnd_c32(rng, n):
+    return (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(np.complex64)
+
+
+# ------------------------------------------------------------------ FIR
+def test_fir_golden_vector(cb):
+    # src/filter/fir_node.rs:259-314: small integers are exact in f32 -> exact equality
+    x = np.array([complex(*p) for p in G.FIR_INPUT], np.complex64)
+    t = np.array([complex(*p) for p in G.FIR_TAPS], np.complex64)
+    node = cb.FirNode(t)
+    outs = [node.run(s) for s in x]
+    assert [(int(v.real), int(v.imag)) for v in outs[:9]] == G.FIR_EXPECT
+    node = cb.BatchFirNode(t)
+    out = np.concatenate([node.run(x[i:i + 2]) for i in range(0, len(x), 2)])  # fir_node.rs:368-425
+    assert [(int(v.real), int(v.imag)) for v in out] == G.BATCH_FIR_EXPECT
+
+
+@pytest.mark.parametrize("ntaps", [1, 5, 16, 17, 32, 33, 63, 64, 65, 100, 128, 129, 200, 1024])
+@pytest.mark.parametrize("cplx", [False, True])
+def test_fir_matches_oracle(cb, oracle, ntaps, cplx):
+    rng = np.random.default_rng(ntaps * 2 + cplx)
+    n = 40_000 + ntaps
+    x = rnd_c32(rng, n)
+    t = rnd_c32(rng, ntaps) if cplx else rng.uniform(-1, 1, ntaps).astype(np.complex64)
+    want, st = oracle.batch_fir(x, t, np.zeros(ntaps, np.complex64))
+    node = cb.BatchFirNode(t)
+    got = node.run(x)
+    assert rel_l2(got, want) <= FIR_TOL
+    assert node.state.tobytes() == st.tobytes()  # delay line is bit-exact (copies only)
+
+
+@pytest.mark.parametrize("sizes", [[0], [1], [1, 1, 1], [3, 0, 5], [255, 257, 4096, 1], [100_003, 7, 4097]])
+def test_fir_batch_invariance_and_ragged(cb, oracle, sizes):
+    rng = np.random.default_rng(11)
+    t = rnd_c32(rng, 64)
+    x = rnd_c32(rng, sum(sizes))
+    want, st = oracle.batch_fir(x, t, np.zeros(64, np.complex64))
+    node = cb.BatchFirNode(t)
+    pos, outs = 0, []
+    for s in sizes:
+        outs.append(node.run(x[pos:pos + s]))
+        assert len(outs[-1]) == s
+        pos += s
+    got = np.concatenate(outs) if outs else np.zeros(0, np.complex64)
+    assert rel_l2(got, want) <= FIR_TOL if len(x) else True
+    assert node.state.tobytes() == st.tobytes()
+    # one-shot result equals the batched one bit for bit (batch edges are invisible)
+    one = cb.BatchFirNode(t).run(x)
+    assert one.tobytes() == got.tobytes()
+
+
+@pytest.mark.parametrize("ntaps,nstate", [(64, 64), (33, 40), (40, 17), (5, 5), (8, 0), (64, 200)])
+def test_fir_initial_state_and_zip_truncation(cb, oracle, ntaps, nstate):
+    # BatchFirNode::new(taps, Some(state)); zip(taps, state) truncates (fir.rs:99)
+    rng = np.random.default_rng(ntaps * 100 + nstate)
+    t, s0, x = rnd_c32(rng, ntaps), rnd_c32(rng, nstate), rnd_c32(rng, 3000)
+    want, st = oracle.batch_fir(x, t, s0)
+    node = cb.BatchFirNode(t, s0)
+    got = node.run(x)
+    assert rel_l2(got, want) <= FIR_TOL
+    assert node.state.tobytes() == st.tobytes()
+
+
+def test_fir_state_get_set_resume(cb, oracle):
+    rng = np.random.default_rng(5)
+    t, x = rnd_c32(rng, 64), rnd_c32(rng, 10_000)
+    a = cb.BatchFirNode(t)
+    y1 = a.run(x[:6000])
+    b = cb.BatchFirNode(t)
+    b.state = a.state  # checkpoint / resume on another handle (segment + halo partitioning)
+    y2 = b.run(x[6000:])
+    want, _ = oracle.batch_fir(x, t, np.zeros(64, np.complex64))
+    assert rel_l2(np.concatenate([y1, y2]), want) <= FIR_TOL
+
+
+def test_fir_unaligned_host_pointers(cb, oracle):
+    rng = np.random.default_rng(6)
+    t = rnd_c32(rng, 64)
+    buf = rnd_c32(rng, 5001)
+    x = buf[1:]  # 8-byte aligned only
+    want, _ = oracle.batch_fir(x, t, np.zeros(64, np.complex64))
+    assert rel_l2(cb.BatchFirNode(t).run(x), want) <= FIR_TOL
+
+
+# ------------------------------------------------------------------ resample
+@pytest.mark.parametrize("data,rate,expect", G.DECIMATE_CASES)
+def test_decimate_golden(cb, data, rate, expect):
+    assert cb.DecimateNode(rate).run(np.array(data, np.int32)).tolist() == expect
+
+
+@pytest.mark.parametrize("data,rate,expect", G.UPSAMPLE_CASES)
+def test_upsample_golden(cb, data, rate, expect):
+    assert cb.UpsampleNode(rate).run(np.array(data, np.int32)).tolist() == expect
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.int16, np.float32, np.complex64, np.complex128])
+@pytest.mark.parametrize("rate", [0, 1, 2, 3, 10, 1000])
+def test_resample_bit_exact(cb, oracle, dtype, rate):
+    rng = np.random.default_rng(rate)
+    a = rng.integers(0, 200, 10_001).astype(dtype)
+    assert cb.DecimateNode(rate).run(a).tobytes() == oracle.decimate(a, rate).tobytes()
+    b = a[:1000]
+    assert cb.UpsampleNode(rate).run(b).tobytes() == oracle.upsample(b, rate).tobytes()
+    assert len(cb.DecimateNode(rate).run(a[:0])) == 0
+
+
+# ------------------------------------------------------------------ interp / decim fused
+def test_pulse_golden_vector(cb):
+    # src/pulse.rs:129-183: rect taps x4 -> each symbol repeated 4 times
+    node = cb.PulseNode(np.ones(4, np.complex64), G.PULSE_SPS)
+    out = np.concatenate([node.run(np.array([complex(*s)], np.complex64)) for s in G.PULSE_SYMBOLS])
+    assert [(int(v.real), int(v.imag)) for v in out] == G.PULSE_EXPECT
+
+
+@pytest.mark.parametrize("L,ntaps,cplx", [(4, 32, False), (2, 32, False), (8, 64, False), (8, 1024, False),
+                                          (3, 17, False), (4, 32, True), (5, 100, True), (4, 30, False)])
+def test_polyphase_interp_matches_upsample_then_fir(cb, oracle, L, ntaps, cplx):
+    rng = np.random.default_rng(L * 1000 + ntaps)
+    t = rnd_c32(rng, ntaps) if cplx else rng.uniform(-1, 1, ntaps).astype(np.complex64)
+    sym = rnd_c32(rng, 20_011)
+    st = np.zeros(ntaps, np.complex64)
+    node = cb.BatchFirNode(t, None, decim=1, interp=L)
+    pos, outs, wants = 0, [], []
+    for s in (1, 4095, 10_000, 5915):
+        w, st = oracle.batch_fir(oracle.upsample(sym[pos:pos + s], L), t, st)
+        wants.append(w)
+        outs.append(node.run(sym[pos:pos + s]))
+        assert len(outs[-1]) == s * L  # sample counts are exact
+        pos += s
+    assert rel_l2(np.concatenate(outs), np.concatenate(wants)) <= FIR_TOL
+    assert node.state.tobytes() == st.tobytes()
+
+
+@pytest.mark.parametrize("D,ntaps,cplx", [(5, 63, False), (10, 63, False), (2, 64, True), (7, 33, True), (1000, 16, False)])
+def test_decimating_fir_phase_resets_per_batch(cb, oracle, D, ntaps, cplx):
+    # BatchFirNode -> DecimateNode: indices 0, D, 2D.. of EACH batch (resample_node.rs:53-65)
+    rng = np.random.default_rng(D * 100 + ntaps)
+    t = rnd_c32(rng, ntaps) if cplx else rng.uniform(-1, 1, ntaps).astype(np.complex64)
+    x = rnd_c32(rng, 30_007)
+    st = np.zeros(ntaps, np.complex64)
+    node = cb.BatchFirNode(t, None, decim=D)
+    pos = 0
+    for s in (1, 13, 9999, 10_000, 9994):
+        f, st = oracle.batch_fir(x[pos:pos + s], t, st)
+        want = oracle.decimate(f, D)
+        got = node.run(x[pos:pos + s])
+        assert len(got) == len(want) == -(-s // D)
+        assert rel_l2(got, want) <= FIR_TOL
+        pos += s
+    assert node.state.tobytes() == st.tobytes()
+
+
+def test_interp_then_decim_rational(cb, oracle):
+    rng = np.random.default_rng(77)
+    t = rng.uniform(-1, 1, 48).astype(np.complex64)
+    x = rnd_c32(rng, 5000)
+    f, _ = oracle.batch_fir(oracle.upsample(x, 3), t, np.zeros(48, np.complex64))
+    want = oracle.decimate(f, 2)
+    got = cb.BatchFirNode(t, None, decim=2, interp=3).run(x)
+    assert len(got) == len(want) and rel_l2(got, want) <= FIR_TOL
+
+
+# ------------------------------------------------------------------ mixer
+@pytest.mark.parametrize("phase,expect", [(None, G.MIXER_EXPECT_PHASE0), (0.1, G.MIXER_EXPECT_PHASE01)])
+def test_mixer_golden_vector(cb, phase, expect):
+    # src/mixer.rs:184-223, 274-313; f32 in/out here so the tolerance is f32 rounding of |y| ~ 10
+    node = cb.MixerNode(G.MIXER_DPHASE, phase)
+    got = np.array([node.run(np.complex64(v)) for v in G.MIXER_INPUT])
+    assert np.all(np.abs(got - np.array(expect)) < 2e-6)
+    node = cb.MixerNode(G.MIXER_DPHASE, phase)
+    assert np.all(np.abs(node.run(np.array(G.MIXER_INPUT, np.complex64)) - np.array(expect)) < 2e-6)
+
+
+@pytest.mark.parametrize("dphase", [0.123, -0.7, 6.0, 3 * 2 * np.pi + 0.25, 0.0])
+def test_mixer_matches_oracle_and_carries_phase(cb, oracle, dphase):
+    rng = np.random.default_rng(3)
+    x = rnd_c32(rng, 200_001)
+    ref = oracle.Mixer(0.2, dphase)
+    node = cb.MixerNode(dphase, 0.2)
+    assert node.dphase == ref.dphase
+    pos = 0
+    for s in (1, 2, 99_999, 100_000):
+        want = ref.mix(x[pos:pos + s])
+        got = node.run(x[pos:pos + s])
+        assert rel_l2(got, want) <= FIR_TOL
+        pos += s
+    # phases agree modulo 2 pi (the oracle's single conditional wrap vs fmod)
+    d = (node.phase - ref.phase) % (2 * np.pi)
+    assert min(d, 2 * np.pi - d) < 1e-9
+
+
+# ------------------------------------------------------------------ FFT
+def test_fft10_golden_vector(cb):
+    # src/fft/fft_node.rs:194-244 (batch) and :286-332 (sample node)
+    x = np.array(G.FFT10_INPUT, np.complex64)
+    got = cb.FFTBatchNode(10, False).run(x)
+    assert np.all(np.abs(got - np.array(G.FFT10_EXPECT)) < G.FFT10_TOL)
+    node = cb.FFTSampleNode(10, False)
+    outs = [node.run(v) for v in x]
+    assert all(o is None for o in outs[:-1])
+    assert np.all(np.abs(outs[-1] - np.array(G.FFT10_EXPECT)) < G.FFT10_TOL)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 8, 10, 12, 16, 32, 64, 100, 128, 256, 512, 1000, 1024, 2048, 4096, 8192,
+                               16384, 32768, 65536, 1 << 17, 1 << 20])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_fft_matches_oracle(cb, oracle, n, inverse):
+    rng = np.random.default_rng(n + inverse)
+    frames = 3 if n <= 65536 else 1
+    x = rnd_c32(rng, frames * n)
+    want = oracle.fft(x, n, inverse)
+    got = cb.FFTBatchNode(n, inverse).run(x)
+    assert rel_l2(got, want) <= FFT_TOL
+    for f in range(frames):  # per frame too, so one bad frame cannot hide
+        assert rel_l2(got[f * n:(f + 1) * n], want[f * n:(f + 1) * n]) <= FFT_TOL
+
+
+@pytest.mark.parametrize("n", [1024, 4096, 65536])
+def test_fft_roundtrip_and_linearity(cb, n):
+    rng = np.random.default_rng(n)
+    x, y = rnd_c32(rng, 4 * n), rnd_c32(rng, 4 * n)
+    f, b = cb.FFTBatchNode(n, False), cb.FFTBatchNode(n, True)
+    assert rel_l2(b.run(f.run(x)) / n, x) <= FFT_TOL  # unnormalised both ways
+    assert rel_l2(f.run(x + 2 * y), f.run(x) + 2 * f.run(y)) <= FFT_TOL
+    imp = np.zeros(n, np.complex64)
+    imp[1] = 1
+    k = np.arange(n)
+    assert rel_l2(f.run(imp), np.exp(-2j * np.pi * k / n)) <= FFT_TOL  # sign convention
+    assert rel_l2(b.run(imp), np.exp(+2j * np.pi * k / n)) <= FFT_TOL
+
+
+def test_fft_wrong_length_is_data_error(cb):
+    node = cb.FFTBatchNode(1024, False)
+    with pytest.raises(cb.NodeError) as e:
+        node.run(np.zeros(1000, np.complex64))
+    assert e.value.kind == cb.NodeError.DataError
+    with pytest.raises(cb.CbError):
+        cb.FFTBatchNode(0, False)
+
+
+# ------------------------------------------------------------------ FM demod
+def test_fm_demod_matches_oracle(cb, oracle):
+    rng = np.random.default_rng(9)
+    x = rnd_c32(rng, 100_000)
+    x[0] = -1 - 1j  # first output is atan2(-0, -0) = pi
+    ref, node = oracle.FM(), cb.FMDemodNode()
+    for a, b in ((0, 1), (1, 50_000), (50_000, 100_000)):
+        want, got = ref.demod(x[a:b]), node.run(x[a:b])
+        # the product is formed with the same individually rounded ops; atan2f may differ by an ulp
+        d = np.abs(got.astype(np.float64) - want.astype(np.float64))
+        d = np.minimum(d, 2 * np.pi - d)
+        assert d.max() < 1e-6
+    assert cb.FMDemodNode().run(np.array([-1 - 1j], np.complex64))[0] == np.float32(np.pi)
+    assert cb.FMDemodNode().run(np.array([1 + 1j], np.complex64))[0] == 0.0
+
+
+# ------------------------------------------------------------------ fused bank (BASELINE cfg 4)
+FM_RADIO_TAPS_N = 63
+
+
+def _lowpass(n):
+    k = np.arange(n) - (n - 1) / 2
+    return (np.sinc(k / 5) * np.hamming(n) / 5).astype(np.float32).astype(np.complex64)
+
+
+@pytest.mark.parametrize("mix,fm,cplx,D", [(True, True, False, 10), (True, False, False, 10), (False, True, False, 5),
+                                           (False, False, True, 4), (True, True, True, 3), (True, True, False, 1)])
+def test_chain_bank_matches_node_chain(cb, oracle, mix, fm, cplx, D):
+    rng = np.random.default_rng(D)
+    C, taps = 7, _lowpass(FM_RADIO_TAPS_N)
+    if cplx:
+        taps = (taps * np.exp(1j * 0.1 * np.arange(len(taps)))).astype(np.complex64)
+    dph = -2 * np.pi * rng.uniform(-0.4, 0.4, C)
+    ph0 = rng.uniform(0, 6, C)
+    bank = cb.ChainBank(C, taps, D, dphase=dph if mix else None, phase=ph0 if mix else None, with_fm=fm)
+    refs = [oracle.FmChain(dph[c], ph0[c], taps, D, do_mix=mix, do_fm=fm) for c in range(C)]
+    for n in (1, 131_072 // 8, 9_999, 20_003):
+        x = rnd_c32(rng, C * n).reshape(C, n)
+        got = bank.run(x)
+        assert got.shape == (C, -(-n // D))  # bit-exact sample counts, phase restarts per call
+        for c in range(C):
+            want = refs[c].run(x[c])
+            if fm:
+                d = np.abs(got[c].astype(np.float64) - want.astype(np.float64))
+                d = np.minimum(d, 2 * np.pi - d)
+                # angle error ~ |dy| / |y|: tiny everywhere except where |y| itself is ~0
+                assert np.median(d) < 2e-6 and np.mean(d > 1e-3) < 2e-3, (c, n, np.median(d), d.max())
+            else:
+                assert rel_l2(got[c], want) <= FIR_TOL, (c, n)
+
+
+# ------------------------------------------------------------------ BASELINE cfg 1 (single_thread_bpsk)
+def test_bpsk_chain_config1(cb, oracle):
+    import torch
+
+    nsym, batch, sps = 1 << 16, 4096, 4
+    bits_ref, shaped_ref, iq_ref, st_ref = oracle.bpsk_chain(nsym, batch=batch, sps=sps)
+    bits, _ = cb.prn_bits(0xB8, 0x01, nsym, 8)
+    assert bits.tobytes() == bits_ref.tobytes()  # PRN bits: bit-exact
+    taps = oracle.rrc_taps(32, 4.0, 0.25)
+    fir = cb.BatchFirNode(taps, None, interp=sps)
+    dev = torch.device("cuda:0")
+    s = torch.cuda.current_stream().cuda_stream
+    d_bits = torch.from_numpy(bits).to(dev)
+    d_sym = torch.empty(nsym, dtype=torch.complex64, device=dev)
+    d_shaped = torch.empty(nsym * sps, dtype=torch.complex64, device=dev)
+    d_iq = torch.empty(nsym * sps * 2, dtype=torch.int16, device=dev)
+    assert cb.bits_to_symbols_dev(d_bits.data_ptr(), nsym, 0, d_sym.data_ptr(), s) == nsym
+    for b in range(0, nsym, batch):  # state carried across batches (single_thread_bpsk.rs:19,39)
+        m = fir.run_dev(d_sym.data_ptr() + 8 * b, batch, d_shaped.data_ptr() + 8 * b * sps, batch * sps, s)
+        assert m == batch * sps
+    cb.quantize_i16_dev(d_shaped.data_ptr(), nsym * sps * 2, 8192.0, d_iq.data_ptr(), s)
+    torch.cuda.synchronize()
+    sym = d_sym.cpu().numpy()
+    assert sym.tobytes() == oracle.example_bpsk_map(bits_ref).tobytes()  # symbol map: bit-exact
+    shaped = d_shaped.cpu().numpy()
+    assert rel_l2(shaped, shaped_ref) <= FIR_TOL
+    assert fir.state.tobytes() == st_ref.tobytes()
+    # quantiser itself is bit-exact on identical input
+    assert d_iq.cpu().numpy().tobytes() == oracle.quantize_i16(shaped).tobytes()
+    # and end to end the i16 stream differs from the reference chain by at most 1 LSB, rarely
+    diff = np.abs(d_iq.cpu().numpy().astype(np.int32) - iq_ref.astype(np.int32))
+    assert diff.max() <= 1 and (diff != 0).mean() < 1e-2
+
+
+def test_qpsk_symbol_map_bit_exact(cb, oracle):
+    import torch
+
+    bits, _ = cb.prn_bits(0xB8, 0x01, 20_000, 8)
+    d_bits = torch.from_numpy(bits).cuda()
+    d_sym = torch.empty(10_000, dtype=torch.complex64, device="cuda")
+    assert cb.bits_to_symbols_dev(d_bits.data_ptr(), 20_000, 1, d_sym.data_ptr(), torch.cuda.current_stream().cuda_stream) == 10_000
+    torch.cuda.synchronize()
+    assert d_sym.cpu().numpy().tobytes() == oracle.example_qpsk_map(bits).tobytes()
+    assert cb.prn_bits(0xC0, 0x01, 128, 8)[0].tolist() == G.PRN_C0_01  # src/prns.rs:211-220
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE cfg 2 / 3)
+def test_fir_full_size_windows_and_properties(cb, oracle):
+    """2^28-sample stream resident on the device: random interior windows against the
+    oracle (seeded with the preceding K samples as state), batch invariance, linearity."""
+    import torch
+
+    n, K, seed = 1 << 28, 64, 1234
+    s = torch.cuda.current_stream().cuda_stream
+    x = torch.empty(n, dtype=torch.complex64, device="cuda")
+    y = torch.empty(n, dtype=torch.complex64, device="cuda")
+    cb.synth_uniform_dev(seed, 0, n, x.data_ptr(), s)
+    taps_r = oracle.rrc_taps(64, 4.0, 0.25)
+    taps_c = (taps_r * np.exp(1j * 0.1 * np.arange(64))).astype(np.complex64)
+    for taps in (taps_r, taps_c):
+        node = cb.BatchFirNode(taps)
+        assert node.run_dev(x.data_ptr(), n, y.data_ptr(), n, s) == n
+        torch.cuda.synchronize()
+        rng = np.random.default_rng(1)
+        starts = [0, n - 5000] + [int(v) for v in rng.integers(K, n - 5000, 6)]
+        for st in starts:
+            lo = max(st - K, 0)
+            xin = oracle.synth_uniform_c32(seed, lo, st - lo + 5000)
+            assert xin.tobytes() == x[lo:st + 5000].cpu().numpy().tobytes()  # generator parity, bit-exact
+            state = np.zeros(K, np.complex64)
+            state[: st - lo] = xin[: st - lo][::-1]
+            want, _ = oracle.batch_fir(xin[st - lo:], taps, state)
+            assert rel_l2(y[st:st + 5000].cpu().numpy(), want) <= FIR_TOL
+        # 256 batches of 2^20 with carried state == one shot, bit for bit
+        y2 = torch.empty(n, dtype=torch.complex64, device="cuda")
+        node2 = cb.BatchFirNode(taps)
+        B = 1 << 20
+        for b in range(0, n, B):
+            node2.run_dev(x.data_ptr() + 8 * b, B, y2.data_ptr() + 8 * b, B, s)
+        torch.cuda.synchronize()
+        assert torch.equal(y.view(torch.float32), y2.view(torch.float32))
+        assert node.state.tobytes() == node2.state.tobytes()
+        del y2
+    # impulse response: x = delta at 1000 -> y[1000 + k] = h[k]
+    x.zero_()
+    x[1000] = 1
+    node = cb.BatchFirNode(taps_c)
+    node.run_dev(x.data_ptr(), 1 << 20, y.data_ptr(), 1 << 20, s)
+    torch.cuda.synchronize()
+    assert y[1000:1064].cpu().numpy().tobytes() == taps_c.tobytes()
+    assert float(y[:1000].abs().max()) == 0.0 and float(y[1064:1 << 20].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("n", [1024, 4096, 65536])
+def test_fft_full_size_roundtrip(cb, oracle, n):
+    import torch
+
+    total, seed = 1 << 28, 99
+    s = torch.cuda.current_stream().cuda_stream
+    x = torch.empty(total, dtype=torch.complex64, device="cuda")
+    f = torch.empty(total, dtype=torch.complex64, device="cuda")
+    cb.synth_uniform_dev(seed, 0, total, x.data_ptr(), s)
+    fwd, inv = cb.FFTBatchNode(n, False), cb.FFTBatchNode(n, True)
+    fwd.run_dev(x.data_ptr(), total, f.data_ptr(), s)
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(n)
+    for fr in [0, total // n - 1] + [int(v) for v in rng.integers(0, total // n, 4)]:
+        xin = oracle.synth_uniform_c32(seed, fr * n, n)
+        assert rel_l2(f[fr * n:(fr + 1) * n].cpu().numpy(), oracle.fft(xin, n, False)) <= FFT_TOL
+    # Parseval as a checksum over the whole job: sum|X|^2 = N sum|x|^2
+    ex = float((x.view(torch.float32).double() ** 2).sum())
+    ef = float((f.view(torch.float32).double() ** 2).sum())
+    assert abs(ef / (n * ex) - 1) < 1e-5
+    back = torch.empty(total, dtype=torch.complex64, device="cuda")
+    inv.run_dev(f.data_ptr(), total, back.data_ptr(), s)
+    torch.cuda.synchronize()
+    err = (back.view(torch.float32) / n - x.view(torch.float32)).double().norm() / x.view(torch.float32).double().norm()
+    assert float(err) <= FFT_TOL
