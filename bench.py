@@ -216,7 +216,11 @@ class Job:
     def __init__(self, cb, torch, workload, rank):
         self.cb, self.torch, self.workload = cb, torch, workload
         self.kind, self.n, self.bytes_per_unit, self.desc = WORKLOADS[workload]
-        self.stream = torch.cuda.current_stream().cuda_stream
+        # a real (non-NULL) stream: NULL would mean "the handle's own stream" to *_run_dev,
+        # and the CUDA events below must sit on the stream the kernels are launched on
+        self.tstream = torch.cuda.Stream()
+        self.stream = self.tstream.cuda_stream
+        assert self.stream != 0
         n = self.n
         self.first = rank * n  # this rank's segment of the global synthetic stream
         self.x = torch.empty(n, dtype=torch.complex64, device="cuda")
@@ -300,9 +304,9 @@ def run_b200(args, rank, world, local_rank):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
-        ev[i].record()
+        ev[i].record(job.tstream)
         job.step()
-    ev[args.steps].record()
+    ev[args.steps].record(job.tstream)
     barrier()
     t_wall1 = time.perf_counter()
     launches_dev = cb.launch_count() - launches0

@@ -61,6 +61,9 @@ SIGNATURES = {
     "cb_buf_ptr": (_vp, [_vp]),
     "cb_buf_bytes": (_sz, [_vp]),
     "cb_buf_is_device": (_i, [_vp]),
+    "cb_buf_record_ready": (_i, [_vp, _vp]),
+    "cb_buf_wait_ready": (_i, [_vp, _vp]),
+    "cb_buf_sync": (_i, [_vp]),
     "cb_copy_h2d_async": (_i, [_vp, _vp, _sz, _vp]),
     "cb_copy_d2h_async": (_i, [_vp, _vp, _sz, _vp]),
     "cb_fir_create": (_i, [_vp, _sz, _vp, _sz, _u32, _u32, _pp]),

@@ -124,6 +124,8 @@ struct cb_buf {
     size_t bytes;
     int is_device;
     int device;
+    cudaEvent_t ready;  // recorded by the producing node's stream (cb_buf_record_ready)
+    bool has_ready;
 };
 
 struct cb_fir {
@@ -286,6 +288,8 @@ static int buf_alloc(size_t bytes, int is_device, cb_buf **out)
     b->is_device = is_device;
     b->device = g_dev;
     b->ptr = nullptr;
+    b->ready = nullptr;
+    b->has_ready = false;
     cudaError_t e = is_device ? cudaMalloc(&b->ptr, bytes ? bytes : 1) : cudaMallocHost(&b->ptr, bytes ? bytes : 1);
     if (e != cudaSuccess) {
         delete b;
@@ -310,6 +314,10 @@ int cb_buf_release(cb_buf *b)
     if (!b) return CB_OK;
     if (b->refs.fetch_sub(1) == 1) {
         cudaSetDevice(b->device);
+        if (b->ready) {
+            if (b->has_ready) cudaEventSynchronize(b->ready);  // never free under a pending writer
+            cudaEventDestroy(b->ready);
+        }
         if (b->is_device) cudaFree(b->ptr);
         else cudaFreeHost(b->ptr);
         delete b;
@@ -320,6 +328,32 @@ int cb_buf_release(cb_buf *b)
 void *cb_buf_ptr(cb_buf *b) { return b ? b->ptr : nullptr; }
 size_t cb_buf_bytes(cb_buf *b) { return b ? b->bytes : 0; }
 int cb_buf_is_device(cb_buf *b) { return b ? b->is_device : 0; }
+
+int cb_buf_record_ready(cb_buf *b, void *stream)
+{
+    CB_REQUIRE(b, CB_ERR_INVALID_ARG, "buffer is NULL");
+    CB_CUDA(cudaSetDevice(b->device));
+    if (!b->ready) CB_CUDA(cudaEventCreateWithFlags(&b->ready, cudaEventDisableTiming));
+    CB_CUDA(cudaEventRecord(b->ready, (cudaStream_t)stream));
+    b->has_ready = true;
+    return CB_OK;
+}
+
+int cb_buf_wait_ready(cb_buf *b, void *stream)
+{
+    CB_REQUIRE(b, CB_ERR_INVALID_ARG, "buffer is NULL");
+    if (!b->has_ready) return CB_OK;
+    CB_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, b->ready, 0));
+    return CB_OK;
+}
+
+int cb_buf_sync(cb_buf *b)
+{
+    CB_REQUIRE(b, CB_ERR_INVALID_ARG, "buffer is NULL");
+    if (!b->has_ready) return CB_OK;
+    CB_CUDA(cudaEventSynchronize(b->ready));
+    return CB_OK;
+}
 
 int cb_copy_h2d_async(void *dst, const void *src, size_t bytes, void *stream)
 {

@@ -92,6 +92,12 @@ CB_API int cb_buf_release(cb_buf *b);
 CB_API void *cb_buf_ptr(cb_buf *b);
 CB_API size_t cb_buf_bytes(cb_buf *b);
 CB_API int cb_buf_is_device(cb_buf *b);
+/* Hand-off between nodes on different streams without a host sync: the producer
+ * records "content complete" on its stream, the consumer makes its stream wait
+ * (no-op if nothing was recorded); cb_buf_sync blocks the host until ready. */
+CB_API int cb_buf_record_ready(cb_buf *b, void *stream);
+CB_API int cb_buf_wait_ready(cb_buf *b, void *stream);
+CB_API int cb_buf_sync(cb_buf *b);
 /* async copies on `stream` (NULL = default stream of the bound device) */
 CB_API int cb_copy_h2d_async(void *dst_dev, const void *src_host, size_t bytes, void *stream);
 CB_API int cb_copy_d2h_async(void *dst_host, const void *src_dev, size_t bytes, void *stream);

@@ -440,3 +440,18 @@ def test_fft_full_size_roundtrip(cb, oracle, n):
     torch.cuda.synchronize()
     err = (back.view(torch.float32) / n - x.view(torch.float32)).double().norm() / x.view(torch.float32).double().norm()
     assert float(err) <= FFT_TOL
+
+
+# ------------------------------------------------------------------ C++ host mirror (graph-level conformance)
+def test_cpp_host_graph_conformance():
+    """comms-rs_b200/host/test_graph.cpp: source -> GPU node -> check graphs with one thread per
+    node, expected values = the reference's golden vectors (the reference's own test pattern)."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "comms-rs_b200", "host")
+    subprocess.run(["make", "-C", host, "-s", "all"], check=True)
+    r = subprocess.run([os.path.join(host, "test_graph")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "host graph tests ok" in r.stdout
