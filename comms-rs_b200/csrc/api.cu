@@ -155,7 +155,7 @@ struct cb_fft {
     cudaStream_t stream;
     HostPipe pipe;
     FftPlanDev plan;
-    float2 *tw, *tw1, *tw2, *scratch;
+    float2 *tw, *tw1, *tw2, *tw16, *scratch;
 };
 
 struct cb_fm {
@@ -794,6 +794,15 @@ static int upload_twiddles(size_t n, int inverse, float2 **dev)
     return CB_OK;
 }
 
+static int upload_fft2_table(int log2n, int inverse, float2 **dev)
+{
+    std::vector<float2> t(fft2_table_len(log2n));
+    fft2_fill_table(log2n, inverse, t.data());
+    CB_CUDA(cudaMalloc(dev, t.size() * sizeof(float2)));
+    CB_CUDA(cudaMemcpy(*dev, t.data(), t.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    return CB_OK;
+}
+
 int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
 {
     CB_REQUIRE(out, CB_ERR_INVALID_ARG, "out is NULL");
@@ -818,7 +827,7 @@ int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
     cb_fft *h = new (std::nothrow) cb_fft();
     CB_REQUIRE(h, CB_ERR_OOM, "host allocation failed");
     h->device = g_dev;
-    h->tw = h->tw1 = h->tw2 = h->scratch = nullptr;
+    h->tw = h->tw1 = h->tw2 = h->tw16 = h->scratch = nullptr;
     h->stream = nullptr;
     h->plan = FftPlanDev{};
     h->plan.kind = kind;
@@ -845,6 +854,7 @@ int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
     }
     FFT_TRY(h->pipe.init(h->stream));
     FFT_TRY(upload_twiddles(fft_size, inverse, &h->tw));
+    if (kind == FFT_SINGLE && log2n >= 4) FFT_TRY(upload_fft2_table(log2n, inverse, &h->tw16));
     if (kind == FFT_FOURSTEP) {
         FFT_TRY(upload_twiddles((size_t)1 << l1, inverse, &h->tw1));
         FFT_TRY(upload_twiddles((size_t)1 << l2, inverse, &h->tw2));
@@ -861,6 +871,7 @@ int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
     h->plan.tw = h->tw;
     h->plan.tw1 = h->tw1;
     h->plan.tw2 = h->tw2;
+    h->plan.tw16 = h->tw16;
     h->plan.scratch = h->scratch;
     *out = h;
     return CB_OK;
@@ -875,6 +886,7 @@ int cb_fft_destroy(cb_fft *h)
     if (h->tw) cudaFree(h->tw);
     if (h->tw1) cudaFree(h->tw1);
     if (h->tw2) cudaFree(h->tw2);
+    if (h->tw16) cudaFree(h->tw16);
     if (h->scratch) cudaFree(h->scratch);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;

@@ -110,6 +110,12 @@ __device__ __forceinline__ float4 ldg_stream(const float4 *p)
                  : "l"(p));
     return v;
 }
+__device__ __forceinline__ float2 ldg_stream2(const float2 *p)
+{
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ void stg_stream(float4 *p, float4 v)
 {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),

@@ -12,6 +12,7 @@
 // Frames longer than 8192 use a four-step split N = N1*N2 with both steps done as
 // 16-column batches (128-byte row segments) of the same butterfly core.
 #include "fft_kernels.cuh"
+#include "fft2_core.cuh"
 #include "misc_kernels.cuh"
 
 namespace cb {
@@ -149,6 +150,69 @@ fft_frames_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, const
     }
 }
 
+// ---------------------------------------------------------------- v2: radix-16 frames kernel
+// One frame = T = N/16 threads, 16 points per thread (fft2_core.cuh); FPB frames per CTA.
+// Passes exchange through ping-pong shared-memory buffers (one __syncthreads per exchange) or,
+// when two buffers would not fit, in place with a barrier between a pass's loads and stores.
+// First pass reads HBM and last pass writes HBM with lanes contiguous: 16 B per sample.
+struct DevSm {
+    float2 *base;
+    __device__ __forceinline__ float2 ld(int i) const { return base[fft2::pad16(i)]; }
+    __device__ __forceinline__ void st(int i, float2 v) const { base[fft2::pad16(i)] = v; }
+};
+
+template <int LOG2N>
+struct Fft2Cfg {
+    using PL = fft2::Plan<LOG2N>;
+    static constexpr int THREADS = PL::T >= 256 ? PL::T : 256;
+    static constexpr int FPB = THREADS / PL::T;
+    static constexpr bool PINGPONG = LOG2N <= 12 && PL::PASSES > 2;
+    static constexpr int NBUF = PL::PASSES <= 1 ? 0 : (PINGPONG ? 2 : 1);
+    static constexpr int SMEM = NBUF * FPB * PL::PADN * (int)sizeof(float2);
+    static constexpr int MINB = THREADS >= 512 ? 1 : (LOG2N == 12 ? 3 : 2);
+};
+
+template <int LOG2N, bool INV, int PASS, typename GLD, typename GST>
+__device__ __forceinline__ void fft2_passes(int j, const float2 *tw, GLD gld, GST gst, float2 *b0, float2 *b1)
+{
+    using PL = fft2::Plan<LOG2N>;
+    if constexpr (PASS < PL::PASSES) {
+        if constexpr (PASS > 0) __syncthreads();
+        DevSm sin{((PASS + 1) & 1) ? b1 : b0}, sout{(PASS & 1) ? b1 : b0};
+        auto mid = [] { __syncthreads(); };
+        auto nomid = [] {};
+        if (b0 == b1) fft2::run_pass<LOG2N, INV, PASS>(j, tw, gld, gst, sin, sout, mid);
+        else fft2::run_pass<LOG2N, INV, PASS>(j, tw, gld, gst, sin, sout, nomid);
+        fft2_passes<LOG2N, INV, PASS + 1>(j, tw, gld, gst, b0, b1);
+    }
+}
+
+template <int LOG2N, bool INV>
+__global__ void __launch_bounds__(Fft2Cfg<LOG2N>::THREADS, Fft2Cfg<LOG2N>::MINB)
+fft2_frames_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, const float2 *__restrict__ tw,
+                   size_t nframes)
+{
+    using PL = fft2::Plan<LOG2N>;
+    using CF = Fft2Cfg<LOG2N>;
+    extern __shared__ __align__(16) float2 fsm[];
+    const int f = threadIdx.x / PL::T, j = threadIdx.x % PL::T;
+    const size_t frame = (size_t)blockIdx.x * CF::FPB + f;
+    const bool live = frame < nframes;
+    const float2 *src = in + frame * PL::N;
+    float2 *dst = out + frame * PL::N;
+    float2 *b0 = fsm + f * PL::PADN;
+    float2 *b1 = CF::PINGPONG ? b0 + CF::FPB * PL::PADN : b0;
+    auto gld = [&](int i) { return live ? ldg_stream2(src + i) : make_float2(0.f, 0.f); };
+    auto gst = [&](int i, float2 v) {
+        if (live) stg_stream2(dst + i, v);
+    };
+    if constexpr (CF::PINGPONG) {
+        fft2_passes<LOG2N, INV, 0>(j, tw, gld, gst, b0, b1);
+    } else {
+        fft2_passes<LOG2N, INV, 0>(j, tw, gld, gst, b0, b0);
+    }
+}
+
 // ---------------------------------------------------------------- four-step column kernels
 // Column batch: COLS adjacent columns of a (ROWS x ld) matrix, FFT along the rows
 // index.  Thread t: column f = t % COLS, butterfly index j = t / COLS.
@@ -265,6 +329,69 @@ static int launch_frames(const float2 *in, float2 *out, const float2 *tw, size_t
     return CB_OK;
 }
 
+template <int LOG2N, bool INV>
+static int launch_frames2(const float2 *in, float2 *out, const float2 *tw2, size_t nframes, cudaStream_t s)
+{
+    using CF = Fft2Cfg<LOG2N>;
+    auto kern = fft2_frames_kernel<LOG2N, INV>;
+    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM));
+    kern<<<(unsigned)ceil_div(nframes, (size_t)CF::FPB), CF::THREADS, CF::SMEM, s>>>(in, out, tw2, nframes);
+    count_launch();
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+
+template <bool INV>
+static int launch_frames2_dir(int log2n, const float2 *in, float2 *out, const float2 *tw2, size_t nframes, cudaStream_t s)
+{
+    switch (log2n) {
+    case 4: return launch_frames2<4, INV>(in, out, tw2, nframes, s);
+    case 5: return launch_frames2<5, INV>(in, out, tw2, nframes, s);
+    case 6: return launch_frames2<6, INV>(in, out, tw2, nframes, s);
+    case 7: return launch_frames2<7, INV>(in, out, tw2, nframes, s);
+    case 8: return launch_frames2<8, INV>(in, out, tw2, nframes, s);
+    case 9: return launch_frames2<9, INV>(in, out, tw2, nframes, s);
+    case 10: return launch_frames2<10, INV>(in, out, tw2, nframes, s);
+    case 11: return launch_frames2<11, INV>(in, out, tw2, nframes, s);
+    case 12: return launch_frames2<12, INV>(in, out, tw2, nframes, s);
+    case 13: return launch_frames2<13, INV>(in, out, tw2, nframes, s);
+    default: set_error("fft: no v2 kernel for 2^%d", log2n); return CB_ERR_UNSUPPORTED;
+    }
+}
+
+// host side of fft2::Plan<LOG2N>::tw_off / TW_TOTAL (runtime log2n)
+size_t fft2_table_len(int log2n)
+{
+    const int p16 = log2n / 4, rem = log2n % 4;
+    size_t off = 0;
+    for (int q = 1; q < p16; ++q) off += (size_t)1 << (4 * q);
+    return off + (rem ? ((size_t)1 << log2n) >> rem : 0) + 1;
+}
+
+void fft2_fill_table(int log2n, int inverse, float2 *t)
+{
+    const int p16 = log2n / 4, rem = log2n % 4;
+    const long double sgn = inverse ? 2.0L : -2.0L, pi = 3.14159265358979323846264338327950288L;
+    size_t off = 0;
+    for (int p = 1; p < p16; ++p) {
+        const size_t ns = (size_t)1 << (4 * p);
+        for (size_t s = 0; s < ns; ++s) {
+            const long double a = sgn * pi * (long double)s / (16.0L * (long double)ns);
+            t[off + s] = make_float2((float)cosl(a), (float)sinl(a));
+        }
+        off += ns;
+    }
+    if (rem) {
+        const size_t n = (size_t)1 << log2n, m = n >> rem;
+        for (size_t s = 0; s < m; ++s) {
+            const long double a = sgn * pi * (long double)s / (long double)n;
+            t[off + s] = make_float2((float)cosl(a), (float)sinl(a));
+        }
+        off += m;
+    }
+    t[off] = make_float2(1.f, 0.f);
+}
+
 template <bool INV>
 static int launch_frames_dir(int log2n, const float2 *in, float2 *out, const float2 *tw, size_t nframes, cudaStream_t s)
 {
@@ -332,6 +459,10 @@ int fft_plan_split(size_t n, int *log2n1, int *log2n2)
 int launch_fft(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s)
 {
     if (nframes == 0) return CB_OK;
+    if (p.kind == FFT_SINGLE && p.tw16 != nullptr && p.log2n >= 4) {
+        return p.inverse ? launch_frames2_dir<true>(p.log2n, in, out, p.tw16, nframes, s)
+                         : launch_frames2_dir<false>(p.log2n, in, out, p.tw16, nframes, s);
+    }
     if (p.kind == FFT_SINGLE) {
         return p.inverse ? launch_frames_dir<true>(p.log2n, in, out, p.tw, nframes, s)
                          : launch_frames_dir<false>(p.log2n, in, out, p.tw, nframes, s);

@@ -16,10 +16,13 @@ struct FftPlanDev {
     const float2 *tw;     // n entries
     const float2 *tw1;    // n1 entries (four-step)
     const float2 *tw2;    // n2 entries (four-step)
+    const float2 *tw16;   // per-pass tables of the radix-16 kernel (fft2_core.cuh), or NULL
     float2 *scratch;      // four-step intermediate, scratch_frames * n
     size_t scratch_frames;
 };
 
+size_t fft2_table_len(int log2n);
+void fft2_fill_table(int log2n, int inverse, float2 *host_table);
 int fft_plan_split(size_t n, int *log2n1, int *log2n2);
 int launch_fft(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s);
 
