@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -141,6 +142,8 @@ struct cb_fir {
     uint32_t hist_len;  // input-domain samples kept
     float2 *hist[2];
     int cur;
+    void *tc_img;       // tensor-core path: prepacked tap image (device), or NULL
+    FirTcPlan tc;
 };
 
 struct cb_mixer {
@@ -424,6 +427,8 @@ int cb_fir_create(const float *taps, size_t ntaps, const float *state, size_t ns
     h->taps_dev = nullptr;
     h->hist[0] = h->hist[1] = nullptr;
     h->stream = nullptr;
+    h->tc_img = nullptr;
+    h->tc = FirTcPlan{nullptr, 1.f, 0};
 
     std::vector<float2> hist;
     rc = fir_state_to_hist(h, reinterpret_cast<const float2 *>(state), state ? nstate : 0, hist);
@@ -450,6 +455,22 @@ int cb_fir_create(const float *taps, size_t ntaps, const float *state, size_t ns
         FIR_TRY(cudaMalloc(&h->hist[i], h->hist_len * sizeof(float2)));
         FIR_TRY(cudaMemcpy(h->hist[i], hist.data(), h->hist_len * sizeof(float2), cudaMemcpyHostToDevice));
     }
+    // Tensor-core plan (K1-TC).  COMMS_B200_FIR_PATH = auto (default) | cuda | tc selects the kernel
+    // family for decim = interp = 1 filters of up to 128 taps; "tc" also drops the batch-size floor.
+    {
+        const char *path = getenv("COMMS_B200_FIR_PATH");
+        const bool want_cuda = path && strcmp(path, "cuda") == 0;
+        const bool force_tc = path && strcmp(path, "tc") == 0;
+        if (!want_cuda && h->interp == 1 && h->decim == 1 && h->k_eff >= 1 && h->k_eff <= 128) {
+            const size_t bytes = fir_tc_image_bytes(h->k_eff);
+            std::vector<unsigned char> img(bytes);
+            float inv = 1.f;
+            fir_tc_build_image(h->taps.data(), h->k_eff, img.data(), &inv);
+            FIR_TRY(cudaMalloc(&h->tc_img, bytes));
+            FIR_TRY(cudaMemcpy(h->tc_img, img.data(), bytes, cudaMemcpyHostToDevice));
+            h->tc = FirTcPlan{h->tc_img, inv, force_tc ? (size_t)1 : ((size_t)1 << 16)};
+        }
+    }
 #undef FIR_TRY
     *out = h;
     return CB_OK;
@@ -462,6 +483,7 @@ int cb_fir_destroy(cb_fir *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->pipe.destroy();
     if (h->taps_dev) cudaFree(h->taps_dev);
+    if (h->tc_img) cudaFree(h->tc_img);
     for (int i = 0; i < 2; ++i)
         if (h->hist[i]) cudaFree(h->hist[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -483,7 +505,7 @@ static int fir_launch_segment(cb_fir *h, const float2 *x, size_t n, const float2
 {
     // k_eff == 0 (zip over an empty state, fir.rs:99) runs as an all-zero filter: outputs are 0
     FirSeg seg{x, hist_in, hist_out, y, n, fir_out_len(h, n), h->hist_len, h->k_eff, h->interp, h->decim};
-    return launch_fir(seg, h->taps_dev, h->taps.data(), h->taps_real, s);
+    return launch_fir(seg, h->taps_dev, h->taps.data(), h->taps_real, h->tc_img ? &h->tc : nullptr, s);
 }
 
 int cb_fir_run_dev(cb_fir *h, const float *d_in, size_t n_in, float *d_out, size_t out_cap, size_t *n_out,

@@ -24,9 +24,22 @@ struct FirSeg {
     uint32_t decim;         // D >= 1
 };
 
+// Tensor-core path (fir_tc_kernel.cu): prepacked fp16 hi/lo Toeplitz tap image + its scale.
+struct FirTcPlan {
+    const void *bimg_dev;   // fir_tc_image_bytes(ntaps) bytes, device
+    float tap_inv_scale;
+    size_t min_samples;     // use the tensor-core kernel from this batch size on
+};
+size_t fir_tc_image_bytes(uint32_t ntaps);
+int fir_tc_kblocks(uint32_t ntaps);
+void fir_tc_build_image(const float2 *taps, uint32_t ntaps, unsigned char *img, float *tap_inv_scale);
+bool fir_tc_applicable(const FirSeg &seg);
+int launch_fir_tc(const FirSeg &seg, const void *bimg_dev, float tap_inv_scale, cudaStream_t stream);
+
 // taps_dev: ntaps complex taps in device memory (generic path)
 // taps_host: same on the host (fast paths put them in the kernel parameter constant bank)
+// tcplan: NULL = CUDA-core kernels only
 int launch_fir(const FirSeg &seg, const float2 *taps_dev, const float2 *taps_host, bool taps_real,
-               cudaStream_t stream);
+               const FirTcPlan *tcplan, cudaStream_t stream);
 
 }  // namespace cb

@@ -1,0 +1,423 @@
+// K1-TC: complex FIR (decim = interp = 1, up to 128 taps) as a block-Toeplitz GEMM on the
+// 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), sm_100a only.
+//
+// Reference semantics (src/filter/fir.rs:87-102): y[n] = sum_{k<K} h[k] x[n-k], complex f32.
+// In direct form the 64-tap complex filter costs 256 FP32 FMAs per sample, which caps the CUDA
+// core kernel at ~35 % of the HBM roofline; here the MACs run on the tensor pipe instead.
+//
+// Formulation.  A tile is 128 rows x 32 complex outputs.  With S[p] = x[t0 - HALO + p] (the
+// tile's input stream incl. halo, HALO = 32*(KB-1) >= taps) viewed as interleaved reals,
+//     D[m][n] = sum_k A[m][k] * B[n][k],   A[m][k] = S~[64 m + k],   k in [0, 64 KB)
+// where n = 2 i + c enumerates (output i, re/im) of the row and B is the real-ified Toeplitz tap
+// matrix  B[2i+c][2j+d] = { hr, -hi ; hi, hr }[c][d] of tap t = i + HALO - j  (0 outside 0..K-1).
+// Row m of A starts 64 reals = 128 bytes (fp16) after row m-1: the stream itself, stored once in
+// shared memory in the 128-byte-swizzled K-major UMMA layout, IS the Toeplitz operand -- K-block
+// kb of row m is just row m+kb of the same buffer (descriptor start address + 128*kb bytes).
+//
+// Precision.  fp16 operands alone would give ~1e-3; x and h are each split into two fp16 terms
+// (hi + lo, after an exact power-of-two block scaling of the tile / of the taps into [2^14, 2^15)),
+// and three products are accumulated in fp32:  A_hi*B_hi + A_hi*B_lo + A_lo*B_hi  (the lo*lo
+// term is < 2^-22 relative).  A_hi * [B_hi ; B_lo] is one N=128 MMA (columns 0-63 / 64-127 of
+// the accumulator), A_lo * B_hi one N=64 MMA into columns 0-63; the epilogue adds the halves.
+// Relative L2 error against the f32 sequential form ~3e-7 (tolerance 1e-5).
+//
+// Roles (416 threads, one persistent CTA per SM, tiles round-robin):
+//   warps 0-3 / 4-7  two loader groups, even / odd tiles of the CTA, each feeding its own A stage:
+//              coalesced LDG.128 of the raw f32 tile (17 in flight per thread) -> block max ->
+//              scale, split, st.shared (pre-swizzled) -> fence.proxy.async -> mbarrier a_full
+//   warp  12   one thread issues 4*KB x 2 tcgen05.mma per tile, tcgen05.commit -> a_empty, t_full
+//   warps 8-11 epilogue: tcgen05.ld (32 lanes x 32 columns) -> add halves, unscale -> padded
+//              shared staging -> coalesced 128-bit streaming stores
+// Two A stages and two TMEM accumulator stages keep the roles overlapped; the loads of tile i+1
+// are in flight while tile i is converted.
+// Algorithmic HBM traffic: 8 B read + 8 B written per sample (halo re-read: 64 B/KB... negligible).
+#include <cuda_fp16.h>
+
+#include <vector>
+
+#include "fir_kernels.cuh"
+
+namespace cb {
+
+namespace tc {
+
+constexpr int ROWS = 128;          // MMA M
+constexpr int RS = 32;             // complex outputs per row
+constexpr int TILE = ROWS * RS;    // 4096 outputs per tile
+constexpr int NCONV = 128;         // loader threads
+constexpr int NTHREADS = 416;     // 2 loader groups (2 x 4 warps) + 4 epilogue warps + 1 MMA warp
+constexpr int A_PART = 18432;      // bytes reserved for one fp16 stream part (>= (128+4)*128, 1024-aligned)
+constexpr int A_STAGE = 2 * A_PART;
+constexpr int OUT_PITCH = 272;     // padded row pitch of the output staging (bytes)
+constexpr int OUT_WARP = 32 * OUT_PITCH;
+
+struct Args {
+    const float2 *x;
+    const float2 *halo;     // HALO samples preceding x[0] (16-byte aligned)
+    float2 *y;
+    const float2 *hist_in;
+    float2 *hist_out;
+    const uint4 *bimg;      // prepacked B image, KB * 16384 bytes
+    unsigned long long n;
+    unsigned hist_len;
+    float tap_inv_scale;    // 2^-(14 - e_h)
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 operands, fp32 accumulate.  One thread issues.
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t *r)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor: 8-row groups 1024 bytes apart.
+// The hardware applies the swizzle XOR to absolute shared-memory address bits, so a start address
+// that is shifted by whole 128-byte rows (the Toeplitz trick) or by 32-byte K steps needs no
+// base-offset field (measured: setting it to (addr >> 7) & 7 breaks the result).
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr)
+{
+    uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;             // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;   // stride byte offset
+    d |= (uint64_t)1 << 46;             // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;             // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ uint32_t swz128(uint32_t o) { return o ^ (((o >> 7) & 7) << 4); }
+
+template <int KB>
+__global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_constant__ Args a)
+{
+    constexpr int HALO = RS * (KB - 1);            // complex samples of history per tile
+    constexpr int NPAIR = (TILE + HALO) / 2;       // 16-byte pairs of complex samples per tile
+    constexpr int NLD = (NPAIR + NCONV - 1) / NCONV;
+    constexpr int B_BYTES = KB * 16384;
+    constexpr uint32_t IDESC128 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t IDESC64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms need 1024 B
+    unsigned char *sB = smem;                      // B image
+    unsigned char *sA = smem + B_BYTES;            // 2 stages x (hi, lo)
+    unsigned char *sOut = sA + 2 * A_STAGE;        // 4 warps x 32 rows x 272 B
+    __shared__ __align__(8) uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2], sc_ready[8];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float red_max[2][4];  // [loader group][warp]
+    __shared__ float inv_scale[8];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned long long ntiles = (a.n + TILE - 1) / TILE;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_full[i], NCONV);
+            mbar_init(&a_empty[i], 1);
+            mbar_init(&t_full[i], 1);
+            mbar_init(&t_empty[i], 128);
+        }
+        for (int i = 0; i < 8; ++i) mbar_init(&sc_ready[i], 1);
+        fence_mbar_init();
+    }
+    if (warp == 12) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                     "r"(256)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // B image: plain copy, then publish to the async proxy (tcgen05.mma reads it)
+    for (int i = tid; i < B_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4 *>(sB)[i] = a.bimg[i];
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp < 8) {
+        // ------------------------------------------------------------------ loaders
+        const int grp = warp >> 2, gt = tid & (NCONV - 1), gw = warp & 3;
+        if (a.hist_out != nullptr && blockIdx.x == 0 && grp == 0) {
+            const long long H = a.hist_len;
+            for (long long i = gt; i < H; i += NCONV) {
+                const long long g = (long long)a.n - H + i;
+                a.hist_out[i] = g >= 0 ? a.x[g] : a.hist_in[H + g];
+            }
+        }
+        unsigned long long it = grp;
+        for (unsigned long long tile = blockIdx.x + (unsigned long long)grp * gridDim.x; tile < ntiles;
+             tile += 2ull * gridDim.x, it += 2) {
+            const int s = grp;
+            const uint32_t ph = (uint32_t)((it >> 1) & 1);
+            const long long t0 = (long long)tile * TILE;
+            float4 raw[NLD];
+            float mx = 0.f;
+#pragma unroll
+            for (int i = 0; i < NLD; ++i) {
+                const int q = gt + i * NCONV;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (q < NPAIR) {
+                    const long long g = t0 - HALO + 2 * q;  // even
+                    if (g < 0) {
+                        v = ldg_stream(reinterpret_cast<const float4 *>(a.halo + (HALO + g)));
+                    } else if (g + 1 < (long long)a.n) {
+                        v = ldg_stream(reinterpret_cast<const float4 *>(a.x + g));
+                    } else if (g < (long long)a.n) {
+                        const float2 t = a.x[g];
+                        v = make_float4(t.x, t.y, 0.f, 0.f);
+                    }
+                }
+                raw[i] = v;
+                mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if (lane == 0) red_max[s][gw] = mx;
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+            mx = fmaxf(fmaxf(red_max[s][0], red_max[s][1]), fmaxf(red_max[s][2], red_max[s][3]));
+            // exact power-of-two block scale: max * sc in [2^14, 2^15)
+            uint32_t eb = (__float_as_uint(mx) >> 23) & 0xFF;
+            eb = eb < 16 ? 141 : eb;  // all-zero / denormal tile: scale 1
+            const float sc = __uint_as_float((268u - eb) << 23);
+            if (gt == 0) {  // the epilogue is at most 4 tiles behind: an 8-deep ring cannot wrap
+                inv_scale[it & 7] = __uint_as_float((eb - 14u) << 23);
+                mbar_arrive(&sc_ready[it & 7]);
+            }
+
+            mbar_wait(&a_empty[s], ph ^ 1);  // MMAs that read this stage two tiles ago are done
+            unsigned char *hi = sA + s * A_STAGE, *lo = hi + A_PART;
+#pragma unroll
+            for (int i = 0; i < NLD; ++i) {
+                const int q = gt + i * NCONV;
+                if (q < NPAIR) {
+                    const float4 v = make_float4(raw[i].x * sc, raw[i].y * sc, raw[i].z * sc, raw[i].w * sc);
+                    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+                    const float2 b0 = __half22float2(h0), b1 = __half22float2(h1);
+                    const __half2 l0 = __floats2half2_rn(v.x - b0.x, v.y - b0.y);
+                    const __half2 l1 = __floats2half2_rn(v.z - b1.x, v.w - b1.y);
+                    const uint32_t off = swz128((uint32_t)q * 8u);
+                    uint2 ph2, pl2;
+                    ph2.x = *reinterpret_cast<const uint32_t *>(&h0);
+                    ph2.y = *reinterpret_cast<const uint32_t *>(&h1);
+                    pl2.x = *reinterpret_cast<const uint32_t *>(&l0);
+                    pl2.y = *reinterpret_cast<const uint32_t *>(&l1);
+                    *reinterpret_cast<uint2 *>(hi + off) = ph2;
+                    *reinterpret_cast<uint2 *>(lo + off) = pl2;
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(&a_full[s]);
+        }
+    } else if (warp == 12) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            unsigned long long it = 0;
+            const uint32_t bbase = smem_u32(sB);
+            for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int s = (int)(it & 1);
+                const uint32_t ph = (uint32_t)((it >> 1) & 1);
+                mbar_wait(&t_empty[s], ph ^ 1);
+                mbar_wait(&a_full[s], ph);
+                tc_fence_after();
+                const uint32_t ahi = smem_u32(sA + s * A_STAGE), alo = ahi + A_PART;
+                const uint32_t d = tmem_base + (uint32_t)s * 128u;
+#pragma unroll
+                for (int t = 0; t < KB * 4; ++t) {
+                    const uint32_t aoff = (uint32_t)(t >> 2) * 128u + (uint32_t)(t & 3) * 32u;
+                    const uint32_t boff = (uint32_t)(t >> 2) * 16384u + (uint32_t)(t & 3) * 32u;
+                    const uint64_t bd = tc_desc(bbase + boff);
+                    tc_mma(d, tc_desc(ahi + aoff), bd, IDESC128, t > 0 ? 1u : 0u);
+                    tc_mma(d, tc_desc(alo + aoff), bd, IDESC64, 1u);
+                }
+                tc_commit(&a_empty[s]);
+                tc_commit(&t_full[s]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ epilogue
+        const int e = warp - 8;  // TMEM sub-partition = warp % 4
+        unsigned char *stage = sOut + e * OUT_WARP;
+        unsigned long long it = 0;
+        for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int s = (int)(it & 1);
+            const uint32_t ph = (uint32_t)((it >> 1) & 1);
+            const long long t0 = (long long)tile * TILE;
+            mbar_wait(&sc_ready[it & 7], (uint32_t)((it >> 3) & 1));  // acquire the loaders' block scale
+            const float k0 = inv_scale[it & 7], k1 = a.tap_inv_scale;
+            mbar_wait(&t_full[s], ph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * e) << 16) + (uint32_t)s * 128u;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t p[32], r[32];
+                tc_ld32(taddr + half * 32, p);
+                tc_ld32(taddr + 64 + half * 32, r);
+                tc_wait_ld();
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4 v;
+                    v.x = (__uint_as_float(p[4 * c]) + __uint_as_float(r[4 * c])) * k0 * k1;
+                    v.y = (__uint_as_float(p[4 * c + 1]) + __uint_as_float(r[4 * c + 1])) * k0 * k1;
+                    v.z = (__uint_as_float(p[4 * c + 2]) + __uint_as_float(r[4 * c + 2])) * k0 * k1;
+                    v.w = (__uint_as_float(p[4 * c + 3]) + __uint_as_float(r[4 * c + 3])) * k0 * k1;
+                    *reinterpret_cast<float4 *>(stage + lane * OUT_PITCH + half * 128 + c * 16) = v;
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&t_empty[s]);
+            __syncwarp();
+            // 32 rows x 256 B of this warp = 8 KB contiguous in y
+            const long long row0 = t0 + (long long)(32 * e) * RS;
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const int idx = i * 32 + lane, rr = idx >> 4, c = idx & 15;
+                const float4 v = *reinterpret_cast<const float4 *>(stage + rr * OUT_PITCH + c * 16);
+                const long long sidx = row0 + (long long)rr * RS + 2 * c;
+                if (sidx + 1 < (long long)a.n) stg_stream(reinterpret_cast<float4 *>(a.y + sidx), v);
+                else if (sidx < (long long)a.n) a.y[sidx] = make_float2(v.x, v.y);
+            }
+            __syncwarp();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+    }
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------ host side
+// B image for KB K-blocks: region kb (16 KiB) = 128 rows x 128 bytes, row n < 64: fp16 hi part of
+// B[n][64 kb .. 64 kb + 63], row 64 + n: the lo part; 128-byte swizzled like the device reads it.
+size_t fir_tc_image_bytes(uint32_t ntaps)
+{
+    const int kb = 1 + (int)ceil_div(ntaps ? ntaps : 1, (size_t)tc::RS);
+    return (size_t)kb * 16384;
+}
+
+int fir_tc_kblocks(uint32_t ntaps) { return 1 + (int)ceil_div(ntaps ? ntaps : 1, (size_t)tc::RS); }
+
+void fir_tc_build_image(const float2 *taps, uint32_t ntaps, unsigned char *img, float *tap_inv_scale)
+{
+    const int KB = fir_tc_kblocks(ntaps);
+    const int HALO = tc::RS * (KB - 1);
+    float mx = 0.f;
+    for (uint32_t k = 0; k < ntaps; ++k) mx = fmaxf(mx, fmaxf(fabsf(taps[k].x), fabsf(taps[k].y)));
+    uint32_t bits;
+    memcpy(&bits, &mx, 4);
+    uint32_t eb = (bits >> 23) & 0xFF;
+    if (eb < 16 || eb == 255) eb = 141;
+    const uint32_t sb = (268u - eb) << 23, ib = (eb - 14u) << 23;
+    float sc;
+    memcpy(&sc, &sb, 4);
+    memcpy(tap_inv_scale, &ib, 4);
+    memset(img, 0, (size_t)KB * 16384);
+    for (int n = 0; n < 64; ++n) {
+        const int i = n >> 1, c = n & 1;
+        for (int k = 0; k < 64 * KB; ++k) {
+            const int j = k >> 1, d = k & 1;
+            const int t = i + HALO - j;
+            float v = 0.f;
+            if (t >= 0 && t < (int)ntaps) {
+                const float hr = taps[t].x, hi = taps[t].y;
+                v = c == 0 ? (d == 0 ? hr : -hi) : (d == 0 ? hi : hr);
+            }
+            v *= sc;
+            const __half h = __float2half_rn(v);
+            const __half l = __float2half_rn(v - __half2float(h));
+            const int kb = k >> 6, kk = k & 63;
+            uint32_t o_hi = (uint32_t)n * 128u + (uint32_t)kk * 2u;
+            uint32_t o_lo = (uint32_t)(64 + n) * 128u + (uint32_t)kk * 2u;
+            o_hi ^= ((o_hi >> 7) & 7) << 4;
+            o_lo ^= ((o_lo >> 7) & 7) << 4;
+            memcpy(img + (size_t)kb * 16384 + o_hi, &h, 2);
+            memcpy(img + (size_t)kb * 16384 + o_lo, &l, 2);
+        }
+    }
+}
+
+template <int KB>
+static int launch_tc_kb(const tc::Args &a, cudaStream_t stream)
+{
+    constexpr int SMEM = KB * 16384 + 2 * tc::A_STAGE + 4 * tc::OUT_WARP + 1024;
+    auto kern = tc::fir_tc_kernel<KB>;
+    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    const unsigned long long ntiles = (a.n + tc::TILE - 1) / tc::TILE;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid = (unsigned)(ntiles < (unsigned long long)sms ? ntiles : (unsigned long long)sms);
+    kern<<<grid, tc::NTHREADS, SMEM, stream>>>(a);
+    count_launch();
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+
+bool fir_tc_applicable(const FirSeg &seg)
+{
+    if (seg.interp != 1 || seg.decim != 1 || seg.ntaps == 0 || seg.ntaps > 128) return false;
+    const int KB = fir_tc_kblocks(seg.ntaps);
+    const uint32_t halo = (uint32_t)tc::RS * (KB - 1);
+    if (seg.hist_len < halo) return false;
+    const float2 *h = seg.hist_in + (seg.hist_len - halo);
+    return ((reinterpret_cast<uintptr_t>(seg.x) | reinterpret_cast<uintptr_t>(seg.y) | reinterpret_cast<uintptr_t>(h)) & 15) == 0;
+}
+
+int launch_fir_tc(const FirSeg &seg, const void *bimg_dev, float tap_inv_scale, cudaStream_t stream)
+{
+    if (seg.n_in == 0) return CB_OK;
+    const int KB = fir_tc_kblocks(seg.ntaps);
+    tc::Args a;
+    a.x = seg.x;
+    a.halo = seg.hist_in + (seg.hist_len - (uint32_t)tc::RS * (KB - 1));
+    a.y = seg.y;
+    a.hist_in = seg.hist_in;
+    a.hist_out = seg.hist_out;
+    a.bimg = reinterpret_cast<const uint4 *>(bimg_dev);
+    a.n = seg.n_in;
+    a.hist_len = seg.hist_len;
+    a.tap_inv_scale = tap_inv_scale;
+    switch (KB) {
+    case 2: return launch_tc_kb<2>(a, stream);
+    case 3: return launch_tc_kb<3>(a, stream);
+    case 4: return launch_tc_kb<4>(a, stream);
+    case 5: return launch_tc_kb<5>(a, stream);
+    default: set_error("fir_tc: unsupported tap count %u", seg.ntaps); return CB_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace cb
