@@ -315,7 +315,7 @@ def test_chain_bank_matches_node_chain(cb, oracle, mix, fm, cplx, D):
     ph0 = rng.uniform(0, 6, C)
     bank = cb.ChainBank(C, taps, D, dphase=dph if mix else None, phase=ph0 if mix else None, with_fm=fm)
     refs = [oracle.FmChain(dph[c], ph0[c], taps, D, do_mix=mix, do_fm=fm) for c in range(C)]
-    for n in (1, 131_072 // 8, 9_999, 20_003):
+    for n in (1, 131_072 // 8, 9_999, 20_003, 40_000, 131_072):
         x = rnd_c32(rng, C * n).reshape(C, n)
         got = bank.run(x)
         assert got.shape == (C, -(-n // D))  # bit-exact sample counts, phase restarts per call
