@@ -47,7 +47,8 @@ WORKLOADS = {
     "chain": ("chain", 1024 * 131072, 8.4, "fm_radio chain x1024 channels per GPU: mixer -> 63-tap FIR -> /10 -> FM demod, "
               "131072-sample batches"),
     "pulse4": ("interp", 1 << 26, 40.0, "BPSK pulse shaping: x4 polyphase 32-tap RRC over 2^26 symbols per GPU (unit = symbols)"),
-    "poly8x1024": ("interp", 1 << 24, 72.0, "QPSK x8 polyphase, 1024-tap RRC bank over 2^24 symbols per GPU (unit = symbols)"),
+    "poly8x1024": ("interp", 1 << 27, 72.0, "QPSK x8 polyphase, 1024-tap RRC bank (tcgen05 Toeplitz GEMM) over 2^27 symbols per GPU "
+                   "= one of the 8 segments of the 2^30-symbol stream (unit = symbols)"),
 }
 
 

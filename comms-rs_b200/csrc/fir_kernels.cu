@@ -397,8 +397,12 @@ int launch_fir(const FirSeg &seg, const float2 *taps_dev, const float2 *taps_hos
                const FirTcPlan *tcplan, cudaStream_t stream)
 {
     if (seg.n_in == 0) return CB_OK;
-    if (tcplan != nullptr && tcplan->bimg_dev != nullptr && seg.n_in >= tcplan->min_samples && fir_tc_applicable(seg))
-        return launch_fir_tc(seg, tcplan->bimg_dev, tcplan->tap_inv_scale, stream);
+    if (tcplan != nullptr && tcplan->bimg_dev != nullptr && seg.n_in >= tcplan->min_samples) {
+        if (seg.interp == 1 && fir_tc_applicable(seg))
+            return launch_fir_tc(seg, tcplan->bimg_dev, tcplan->tap_inv_scale, stream);
+        if (seg.interp > 1 && fir_ptc_applicable(seg, taps_real))
+            return launch_fir_ptc(seg, tcplan->bimg_dev, tcplan->tap_inv_scale, stream);
+    }
     if (seg.interp == 1 && seg.decim == 1) {
         const uint32_t K = seg.ntaps;
         if (taps_real) {

@@ -1,0 +1,422 @@
+// K3-TC: polyphase interpolating FIR (zero-stuff xL then FIR, real-valued taps) as a Toeplitz GEMM
+// on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), sm_100a only.
+//
+// Reference semantics (src/pulse.rs:82-92, src/util/resample_node.rs:120-131 + src/filter/fir.rs:87-102):
+//   y[L u + p] = sum_{j < TPP} h[L j + p] * x[u - j]          (the products with stuffed zeros dropped)
+// BASELINE config 5 (L = 8, 1024 taps -> 128 taps per phase) needs 4096 real MACs per symbol per
+// component pair; on the FP32 pipe that caps a B200 near 9 Gsym/s.  Here the MACs run on the
+// tensor pipe and the kernel is bounded by the 64 B/symbol it has to write.
+//
+// Formulation.  RS = 128 / L symbols per stream row.  For one tile the symbol stream incl. HALO
+// symbols of history, de-interleaved into a real and an imaginary fp16 stream S_c[e] (e = 0 ..
+// 128 RS - 1), is stored ONCE, contiguously, in shared memory.  Read as a K-major matrix with a row
+// pitch of RS elements (= the 32/64/128-byte swizzle row), row n of that buffer starts RS symbols
+// after row n-1, so the buffer itself is the Toeplitz operand:
+//     D[m][n] = sum_k H[m][k] * S_c[RS n + k],   k in [0, KT),  KT = 16 KS >= RS + TPP - 1
+//     m = i L + p  (symbol i of the row, phase p)  ->  H[m][k] = h[L (i + HALO - k) + p]
+// i.e. TMEM lane m holds output sample (128 n + m) of the tile: the 128 lanes of one column are 128
+// CONSECUTIVE output samples, so the epilogue stores straight from registers, fully coalesced,
+// with no shared-memory transpose.  The imaginary stream sits 128 rows after the real one, so a
+// single N = 256 MMA (columns 0-127 real, 128-255 imaginary) covers both; the last
+// ceil(KT/RS) - 1 columns of each half would read across the seam and are simply not used
+// (VR valid rows per tile, 120 of 128 for config 5).  K step ks of the stream operand is the same
+// buffer shifted by 32 ks bytes (descriptor start address only).
+//
+// Precision.  As in fir_tc_kernel.cu: stream and taps are block-scaled by exact powers of two into
+// [2^14, 2^15) and split into fp16 hi + lo; three products (hi*hi, lo*hi, hi*lo) accumulate in the
+// same fp32 TMEM accumulator.  Relative L2 error vs the sequential f32 form ~3e-7 (tolerance 1e-5).
+//
+// Roles (288 threads, one persistent CTA per SM, tiles round-robin):
+//   warps 4-7  loader: coalesced LDG.128 of the raw f32 tile -> block max -> scale, split,
+//              de-interleave, st.shared (pre-swizzled) -> fence.proxy.async -> mbarrier a_full
+//   warp  8    one thread issues 3 KS tcgen05.mma (M128 N256 K16) per tile, commits a_empty/t_full
+//   warps 0-3  epilogue: tcgen05.ld 32 lanes x 32 columns (re) + (im) -> unscale -> st.global.v2
+// Two stream stages and two TMEM accumulator stages (2 x 256 columns) overlap the roles.
+// Algorithmic HBM traffic: 8 B read + 8 L B written per symbol.
+#include <cuda_fp16.h>
+
+#include <vector>
+
+#include "fir_kernels.cuh"
+
+namespace cb {
+
+namespace ptc {
+
+constexpr int NTHREADS = 288;
+constexpr int NLOAD = 128;  // loader threads
+
+struct Args {
+    const float2 *x;
+    const float2 *halo;     // HALO symbols preceding x[0] (16-byte aligned)
+    float2 *y;
+    const float2 *hist_in;
+    float2 *hist_out;
+    const uint4 *himg;      // prepacked tap image: [hi, lo][KS][128 rows x 32 B], 32-byte swizzled
+    unsigned long long n;   // input symbols
+    unsigned hist_len;
+    unsigned ks;            // K steps of 16
+    float tap_inv_scale;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t *r)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major swizzled shared-memory matrix descriptor.  ROWB = swizzle row bytes (32 / 64 / 128); the
+// 8-row groups are 8 ROWB apart.  The swizzle XOR acts on absolute shared-memory address bits, so
+// a start address shifted by whole rows or 32-byte K steps needs no base-offset field.
+template <int ROWB>
+__device__ __forceinline__ uint64_t kdesc(uint32_t saddr)
+{
+    constexpr uint64_t LAYOUT = ROWB == 128 ? 2 : (ROWB == 64 ? 4 : 6);
+    uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((8 * ROWB) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= LAYOUT << 61;
+    return d;
+}
+
+template <int ROWB>
+__host__ __device__ __forceinline__ uint32_t swz(uint32_t o)
+{
+    return o ^ (((o >> 7) & (uint32_t)(ROWB / 16 - 1)) << 4);
+}
+
+template <int L>
+struct Geo {
+    static constexpr int RS = 128 / L;                 // symbols per stream row
+    static constexpr int ROWB = 2 * RS;                // swizzle row bytes
+    static constexpr int NEL = 128 * RS;               // stream elements per component per tile
+    static constexpr int COMP = 128 * ROWB;            // bytes per component region
+    static constexpr int PART = 2 * COMP + 1024;       // hi (or lo) part: re, im, zeroed tail pad
+    static constexpr int STAGE = 2 * PART;
+    static constexpr int NLD = NEL / 2 / NLOAD;        // float4 loads per loader thread per tile
+};
+
+template <int L>
+__global__ void __launch_bounds__(NTHREADS, 1) fir_ptc_kernel(const __grid_constant__ Args a)
+{
+    using G = Geo<L>;
+    constexpr int RS = G::RS, ROWB = G::ROWB, NLD = G::NLD;
+    constexpr uint32_t IDESC = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, M128 N256
+
+    const int KS = (int)a.ks;
+    const int KT = 16 * KS;
+    const int HALO = KT - RS;                    // history symbols per tile
+    const int VR = (G::NEL - KT) / RS + 1;       // valid stream rows (columns of D) per tile
+    const int TS = VR * RS;                      // symbols per tile
+
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *sS = smem;                            // 2 stages x (hi, lo)
+    unsigned char *sH = smem + 2 * G::STAGE;             // tap image: hi KS*4096, lo KS*4096
+    __shared__ __align__(8) uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2], sc_ready[8];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float red_max[4];
+    __shared__ float inv_scale[8];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned long long ntiles = (a.n + (unsigned long long)TS - 1) / (unsigned long long)TS;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_full[i], NLOAD);
+            mbar_init(&a_empty[i], 1);
+            mbar_init(&t_full[i], 1);
+            mbar_init(&t_empty[i], 128);
+        }
+        for (int i = 0; i < 8; ++i) mbar_init(&sc_ready[i], 1);
+        fence_mbar_init();
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                     "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // tap image -> shared; zero the tail pads the (unused) seam columns read
+    for (int i = tid; i < KS * 8192 / 16; i += NTHREADS) reinterpret_cast<uint4 *>(sH)[i] = a.himg[i];
+    for (int i = tid; i < 4 * 1024 / 16; i += NTHREADS) {
+        const int part = i >> 6, o = i & 63;
+        reinterpret_cast<uint4 *>(sS + part * G::PART + 2 * G::COMP)[o] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp >= 4 && warp < 8) {
+        // ------------------------------------------------------------------ loader
+        const int gt = tid - 128, gw = warp - 4;
+        if (a.hist_out != nullptr && blockIdx.x == 0) {
+            const long long H = a.hist_len;
+            for (long long i = gt; i < H; i += NLOAD) {
+                const long long g = (long long)a.n - H + i;
+                a.hist_out[i] = g >= 0 ? a.x[g] : a.hist_in[H + g];
+            }
+        }
+        unsigned long long it = 0;
+        for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int s = (int)(it & 1);
+            const uint32_t ph = (uint32_t)((it >> 1) & 1);
+            const long long t0 = (long long)tile * TS;
+            float4 raw[NLD];
+            float mx = 0.f;
+#pragma unroll
+            for (int i = 0; i < NLD; ++i) {
+                const int q = gt + i * NLOAD;               // pair index: elements 2q, 2q+1
+                const long long g = t0 - HALO + 2 * q;      // even
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g < 0) {
+                    v = ldg_stream(reinterpret_cast<const float4 *>(a.halo + (HALO + g)));
+                } else if (g + 1 < (long long)a.n) {
+                    v = ldg_stream(reinterpret_cast<const float4 *>(a.x + g));
+                } else if (g < (long long)a.n) {
+                    const float2 t = a.x[g];
+                    v = make_float4(t.x, t.y, 0.f, 0.f);
+                }
+                raw[i] = v;
+                mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if (lane == 0) red_max[gw] = mx;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mx = fmaxf(fmaxf(red_max[0], red_max[1]), fmaxf(red_max[2], red_max[3]));
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // red_max is reused by the next tile
+            uint32_t eb = (__float_as_uint(mx) >> 23) & 0xFF;
+            eb = (eb < 16 || eb == 255) ? 141 : eb;  // all-zero / denormal / non-finite tile: scale 1
+            const float sc = __uint_as_float((268u - eb) << 23);
+            if (gt == 0) {  // the epilogue is at most 4 tiles behind: an 8-deep ring cannot wrap
+                inv_scale[it & 7] = __uint_as_float((eb - 14u) << 23);
+                mbar_arrive(&sc_ready[it & 7]);
+            }
+            mbar_wait(&a_empty[s], ph ^ 1);  // the MMAs that read this stage two tiles ago are done
+            unsigned char *hi = sS + s * G::STAGE, *lo = hi + G::PART;
+#pragma unroll
+            for (int i = 0; i < NLD; ++i) {
+                const int q = gt + i * NLOAD;
+                const float4 v = make_float4(raw[i].x * sc, raw[i].y * sc, raw[i].z * sc, raw[i].w * sc);
+                const __half2 hr = __floats2half2_rn(v.x, v.z), hm = __floats2half2_rn(v.y, v.w);  // (re0,re1), (im0,im1)
+                const float2 br = __half22float2(hr), bm = __half22float2(hm);
+                const __half2 lr = __floats2half2_rn(v.x - br.x, v.z - br.y);
+                const __half2 lm = __floats2half2_rn(v.y - bm.x, v.w - bm.y);
+                const uint32_t off = swz<ROWB>((uint32_t)q * 4u);
+                *reinterpret_cast<__half2 *>(hi + off) = hr;
+                *reinterpret_cast<__half2 *>(hi + G::COMP + off) = hm;
+                *reinterpret_cast<__half2 *>(lo + off) = lr;
+                *reinterpret_cast<__half2 *>(lo + G::COMP + off) = lm;
+            }
+            fence_proxy_async();
+            mbar_arrive(&a_full[s]);
+        }
+    } else if (warp == 8) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            unsigned long long it = 0;
+            const uint32_t hbase = smem_u32(sH), hlo = hbase + (uint32_t)KS * 4096u;
+            for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int s = (int)(it & 1);
+                const uint32_t ph = (uint32_t)((it >> 1) & 1);
+                mbar_wait(&t_empty[s], ph ^ 1);
+                mbar_wait(&a_full[s], ph);
+                tc_fence_after();
+                const uint32_t shi = smem_u32(sS + s * G::STAGE), slo = shi + G::PART;
+                const uint32_t d = tmem_base + (uint32_t)s * 256u;
+                for (int ks = 0; ks < KS; ++ks) {
+                    const uint64_t ah = kdesc<32>(hbase + (uint32_t)ks * 4096u);
+                    const uint64_t al = kdesc<32>(hlo + (uint32_t)ks * 4096u);
+                    const uint64_t bh = kdesc<ROWB>(shi + (uint32_t)ks * 32u);
+                    const uint64_t bl = kdesc<ROWB>(slo + (uint32_t)ks * 32u);
+                    tc_mma(d, ah, bh, IDESC, ks > 0 ? 1u : 0u);
+                    tc_mma(d, al, bh, IDESC, 1u);
+                    tc_mma(d, ah, bl, IDESC, 1u);
+                }
+                tc_commit(&a_empty[s]);
+                tc_commit(&t_full[s]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 0-3)
+        const int e = warp;  // TMEM sub-partition = warp % 4; lane m = 32 e + lane
+        const int m = 32 * e + lane;
+        const int msym = m / L;
+        unsigned long long it = 0;
+        for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int s = (int)(it & 1);
+            const uint32_t ph = (uint32_t)((it >> 1) & 1);
+            const long long t0 = (long long)tile * TS;
+            mbar_wait(&sc_ready[it & 7], (uint32_t)((it >> 3) & 1));
+            const float k = inv_scale[it & 7] * a.tap_inv_scale;
+            mbar_wait(&t_full[s], ph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * e) << 16) + (uint32_t)s * 256u;
+            float2 *yrow = a.y + (long long)L * t0 + m;   // + 128 n per column
+            const long long srem = (long long)a.n - t0 - msym;  // column n is live iff RS n < srem
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                if (32 * c >= VR) break;
+                uint32_t p[32], r[32];
+                tc_ld32(taddr + 32 * c, p);
+                tc_ld32(taddr + 128 + 32 * c, r);
+                tc_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = 32 * c + j;
+                    if (n < VR && (long long)RS * n < srem)
+                        stg_stream2(yrow + 128 * n, make_float2(__uint_as_float(p[j]) * k, __uint_as_float(r[j]) * k));
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&t_empty[s]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+}  // namespace ptc
+
+// ------------------------------------------------------------------------------------ host side
+static int ptc_rs(uint32_t L) { return 128 / (int)L; }
+
+int fir_ptc_ksteps(uint32_t ntaps, uint32_t L)
+{
+    const int tpp = (int)ceil_div(ntaps ? ntaps : 1, (size_t)L);
+    return (int)ceil_div((size_t)(ptc_rs(L) + tpp - 1), (size_t)16);
+}
+
+bool fir_ptc_supported(uint32_t ntaps, uint32_t L, bool taps_real)
+{
+    if (!taps_real || ntaps == 0 || (L != 8 && L != 4)) return false;
+    const int ks = fir_ptc_ksteps(ntaps, L);
+    return ks >= 1 && ks <= 12;
+}
+
+size_t fir_ptc_image_bytes(uint32_t ntaps, uint32_t L) { return (size_t)fir_ptc_ksteps(ntaps, L) * 8192; }
+
+// Tap image: part (0 = hi, 1 = lo) x K step x [128 rows x 32 bytes], 32-byte swizzled, fp16.
+void fir_ptc_build_image(const float2 *taps, uint32_t ntaps, uint32_t L, unsigned char *img, float *tap_inv_scale)
+{
+    const int KS = fir_ptc_ksteps(ntaps, L);
+    const int RS = ptc_rs(L), KT = 16 * KS, HALO = KT - RS;
+    float mx = 0.f;
+    for (uint32_t k = 0; k < ntaps; ++k) mx = fmaxf(mx, fabsf(taps[k].x));
+    uint32_t bits;
+    memcpy(&bits, &mx, 4);
+    uint32_t eb = (bits >> 23) & 0xFF;
+    if (eb < 16 || eb == 255) eb = 141;
+    const uint32_t sb = (268u - eb) << 23, ib = (eb - 14u) << 23;
+    float sc;
+    memcpy(&sc, &sb, 4);
+    memcpy(tap_inv_scale, &ib, 4);
+    memset(img, 0, (size_t)KS * 8192);
+    for (int m = 0; m < 128; ++m) {
+        const int i = m / (int)L, p = m % (int)L;
+        for (int k = 0; k < KT; ++k) {
+            const long long t = (long long)L * (i + HALO - k) + p;
+            float v = 0.f;
+            if (i + HALO - k >= 0 && t < (long long)ntaps) v = taps[t].x;
+            v *= sc;
+            const __half h = __float2half_rn(v);
+            const __half l = __float2half_rn(v - __half2float(h));
+            const int ks = k >> 4, kk = k & 15;
+            const uint32_t o = ptc::swz<32>((uint32_t)m * 32u + (uint32_t)kk * 2u);
+            memcpy(img + (size_t)ks * 4096 + o, &h, 2);
+            memcpy(img + (size_t)KS * 4096 + (size_t)ks * 4096 + o, &l, 2);
+        }
+    }
+}
+
+template <int L>
+static int launch_ptc_l(const ptc::Args &a, cudaStream_t stream)
+{
+    using G = ptc::Geo<L>;
+    const int SMEM = 2 * G::STAGE + (int)a.ks * 8192 + 1024;
+    auto kern = ptc::fir_ptc_kernel<L>;
+    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    const int KT = 16 * (int)a.ks;
+    const unsigned long long TS = (unsigned long long)(((G::NEL - KT) / G::RS + 1) * G::RS);
+    const unsigned long long ntiles = (a.n + TS - 1) / TS;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid = (unsigned)(ntiles < (unsigned long long)sms ? ntiles : (unsigned long long)sms);
+    kern<<<grid, ptc::NTHREADS, SMEM, stream>>>(a);
+    count_launch();
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+
+bool fir_ptc_applicable(const FirSeg &seg, bool taps_real)
+{
+    if (seg.decim != 1 || !fir_ptc_supported(seg.ntaps, seg.interp, taps_real)) return false;
+    const uint32_t halo = 16u * (uint32_t)fir_ptc_ksteps(seg.ntaps, seg.interp) - (uint32_t)ptc_rs(seg.interp);
+    if (seg.hist_len < halo) return false;
+    const float2 *h = seg.hist_in + (seg.hist_len - halo);
+    return ((reinterpret_cast<uintptr_t>(seg.x) | reinterpret_cast<uintptr_t>(h)) & 15) == 0 &&
+           (reinterpret_cast<uintptr_t>(seg.y) & 7) == 0;
+}
+
+int launch_fir_ptc(const FirSeg &seg, const void *himg_dev, float tap_inv_scale, cudaStream_t stream)
+{
+    if (seg.n_in == 0) return CB_OK;
+    ptc::Args a;
+    a.ks = (unsigned)fir_ptc_ksteps(seg.ntaps, seg.interp);
+    a.x = seg.x;
+    a.halo = seg.hist_in + (seg.hist_len - (16u * a.ks - (uint32_t)ptc_rs(seg.interp)));
+    a.y = seg.y;
+    a.hist_in = seg.hist_in;
+    a.hist_out = seg.hist_out;
+    a.himg = reinterpret_cast<const uint4 *>(himg_dev);
+    a.n = seg.n_in;
+    a.hist_len = seg.hist_len;
+    a.tap_inv_scale = tap_inv_scale;
+    switch (seg.interp) {
+    case 8: return launch_ptc_l<8>(a, stream);
+    case 4: return launch_ptc_l<4>(a, stream);
+    default: set_error("fir_ptc: unsupported interpolation factor %u", seg.interp); return CB_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace cb

@@ -172,6 +172,38 @@ def test_polyphase_interp_matches_upsample_then_fir(cb, oracle, L, ntaps, cplx):
     assert node.state.tobytes() == st.tobytes()
 
 
+@pytest.mark.parametrize("L,ntaps", [(8, 1024), (8, 64), (8, 1000), (8, 1), (8, 1100), (4, 32), (4, 30), (4, 400), (4, 3)])
+def test_polyphase_tensor_core_path(cb, oracle, L, ntaps, monkeypatch):
+    # K3-TC (fir_ptc_kernel.cu): the tcgen05 Toeplitz-GEMM polyphase bank, forced for every batch size,
+    # against upsample -> batch_fir of the oracle (src/util/resample_node.rs:120-131 + src/filter/fir.rs:87-102)
+    monkeypatch.setenv("COMMS_B200_FIR_PATH", "tc")
+    rng = np.random.default_rng(L * 7000 + ntaps)
+    t = rng.uniform(-1, 1, ntaps).astype(np.complex64)
+    sizes = (1, 4095, 10_000, 5915, 2, 30_001)
+    sym = rnd_c32(rng, sum(sizes))
+    # per-tile block scaling: a quiet stretch and a loud stretch must both keep 1e-5
+    sym[12_000:16_000] *= np.float32(1e-4)
+    sym[30_000:34_000] *= np.float32(3e3)
+    st = np.zeros(ntaps, np.complex64)
+    node = cb.BatchFirNode(t, None, decim=1, interp=L)
+    pos, outs, wants = 0, [], []
+    for s in sizes:
+        w, st = oracle.batch_fir(oracle.upsample(sym[pos:pos + s], L), t, st)
+        wants.append(w)
+        outs.append(node.run(sym[pos:pos + s]))
+        assert len(outs[-1]) == s * L
+        pos += s
+    got, want = np.concatenate(outs), np.concatenate(wants)
+    assert rel_l2(got, want) <= FIR_TOL
+    # interior of the quiet stretch (its own tiles, after the filter has forgotten the louder past)
+    lo, hi = (12_000 + 2 * ntaps // L + 4200) * L, 16_000 * L
+    assert rel_l2(got[lo:hi], want[lo:hi]) <= FIR_TOL
+    assert node.state.tobytes() == st.tobytes()
+    monkeypatch.setenv("COMMS_B200_FIR_PATH", "cuda")
+    ref = cb.BatchFirNode(t, None, decim=1, interp=L).run(sym)
+    assert rel_l2(got, ref) <= 2e-6
+
+
 @pytest.mark.parametrize("D,ntaps,cplx", [(5, 63, False), (10, 63, False), (2, 64, True), (7, 33, True), (1000, 16, False)])
 def test_decimating_fir_phase_resets_per_batch(cb, oracle, D, ntaps, cplx):
     # BatchFirNode -> DecimateNode: indices 0, D, 2D.. of EACH batch (resample_node.rs:53-65)
