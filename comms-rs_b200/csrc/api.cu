@@ -905,6 +905,15 @@ int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
     h->plan.tw2 = h->tw2;
     h->plan.tw16 = h->tw16;
     h->plan.scratch = h->scratch;
+    // 65536 points: single-pass cluster kernel (K5-C).  COMMS_B200_FFT_PATH = cluster (default: barrier.cluster
+    // exchange) | cluster1 (mbarrier + st.async) | cluster2 (hybrid) | fourstep
+    if (fft_size == 65536) {
+        const char *path = getenv("COMMS_B200_FFT_PATH");
+        h->plan.cluster_tpt = 3;
+        if (path && strcmp(path, "cluster2") == 0) h->plan.cluster_tpt = 2;
+        if (path && strcmp(path, "fourstep") == 0) h->plan.cluster_tpt = 0;
+        if (path && strcmp(path, "cluster1") == 0) h->plan.cluster_tpt = 1;  // exchange variants, see fft_cluster_kernel.cu
+    }
     *out = h;
     return CB_OK;
 }

@@ -467,6 +467,8 @@ int launch_fft(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframe
         return p.inverse ? launch_frames_dir<true>(p.log2n, in, out, p.tw, nframes, s)
                          : launch_frames_dir<false>(p.log2n, in, out, p.tw, nframes, s);
     }
+    if (p.kind == FFT_FOURSTEP && p.n == 65536 && p.cluster_tpt > 0)
+        return launch_fft65536_cluster(in, out, p.tw, nframes, p.inverse != 0, p.cluster_tpt, s);
     if (p.kind == FFT_FOURSTEP) {
         const int N1 = 1 << p.log2n1, N2 = 1 << p.log2n2;
         // scratch holds as many frames as fit; process in groups

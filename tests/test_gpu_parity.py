@@ -288,6 +288,22 @@ def test_fft_matches_oracle(cb, oracle, n, inverse):
         assert rel_l2(got[f * n:(f + 1) * n], want[f * n:(f + 1) * n]) <= FFT_TOL
 
 
+@pytest.mark.parametrize("path", ["cluster", "cluster1", "cluster2", "fourstep"])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_fft65536_paths(cb, oracle, path, inverse, monkeypatch):
+    # K5-C: one HBM pass on an 8-CTA cluster (distributed shared memory) vs the four-step fallback
+    monkeypatch.setenv("COMMS_B200_FFT_PATH", path)
+    rng = np.random.default_rng(65536 + inverse)
+    n, frames = 65536, 5
+    x = rnd_c32(rng, frames * n)
+    x[2 * n:3 * n] = 0
+    x[2 * n + 12345] = 1  # an impulse frame: every output has modulus 1 and a known phase
+    want = oracle.fft(x, n, inverse)
+    got = cb.FFTBatchNode(n, inverse).run(x)
+    for f in range(frames):
+        assert rel_l2(got[f * n:(f + 1) * n], want[f * n:(f + 1) * n]) <= FFT_TOL
+
+
 @pytest.mark.parametrize("n", [1024, 4096, 65536])
 def test_fft_roundtrip_and_linearity(cb, n):
     rng = np.random.default_rng(n)
