@@ -46,6 +46,8 @@ WORKLOADS = {
     "ifft4096": ("fft", 1 << 28, 16.0, "batched 4096-point IFFT over 2^28 complex-f32 samples per GPU"),
     "chain": ("chain", 1024 * 131072, 8.4, "fm_radio chain x1024 channels per GPU: mixer -> 63-tap FIR -> /10 -> FM demod, "
               "131072-sample batches"),
+    "chain5": ("chain", 1024 * 131072, 8.8, "fm_radio as shipped x1024 channels per GPU: 63-tap FIR -> /5 -> FM demod (no mixer), "
+               "131072-sample batches"),
     "pulse4": ("interp", 1 << 26, 40.0, "BPSK pulse shaping: x4 polyphase 32-tap RRC over 2^26 symbols per GPU (unit = symbols)"),
     "poly8x1024": ("interp", 1 << 27, 72.0, "QPSK x8 polyphase, 1024-tap RRC bank (tcgen05 Toeplitz GEMM) over 2^27 symbols per GPU "
                    "= one of the 8 segments of the 2^30-symbol stream (unit = symbols)"),
@@ -160,7 +162,10 @@ def cpu_rate(workload, samples, threads):
         elif kind == "fft":
             jobs.append(lambda x=x: oracle.fft(x, n, workload.startswith("ifft")))
         elif kind == "chain":
-            ch = oracle.FmChain(-0.7, 0.0, fm_radio_lowpass(), 10, native=True)
+            if workload == "chain5":
+                ch = oracle.FmChain(0.0, 0.0, fm_radio_lowpass(), 5, do_mix=False, native=True)
+            else:
+                ch = oracle.FmChain(-0.7, 0.0, fm_radio_lowpass(), 10, native=True)
             jobs.append(lambda x=x, ch=ch: [ch.run(x[j:j + 131072]) for j in range(0, len(x), 131072)])
         else:
             L, nt = (4, 32) if workload == "pulse4" else (8, 1024)
@@ -246,7 +251,10 @@ class Job:
         elif self.kind == "chain":
             C, nb = 1024, 131072
             fc = (np.arange(C) / C - 0.5) * 0.8
-            self.node = cb.ChainBank(C, fm_radio_lowpass(), 10, dphase=-2 * np.pi * fc, with_fm=True)
+            if workload == "chain5":
+                self.node = cb.ChainBank(C, fm_radio_lowpass(), 5, dphase=None, with_fm=True)
+            else:
+                self.node = cb.ChainBank(C, fm_radio_lowpass(), 10, dphase=-2 * np.pi * fc, with_fm=True)
             no = self.node.out_len(nb)
             self.y = torch.empty(C * no, dtype=torch.float32, device="cuda")
             self.out_bytes = 4 * C * no

@@ -1081,7 +1081,8 @@ int cb_chain_create(size_t channels, const double *dphase, const double *phase, 
     h->cplx = cplx;
     h->ntaps = (uint32_t)ntaps;
     h->decim = decim == 0 ? 1 : decim;
-    h->hist_len = (uint32_t)round_up(ntaps, 2);
+    // >= 128 samples of raw history per channel: the TMA-staged kernel bulk-copies whole halo chunks from it
+    h->hist_len = (uint32_t)round_up(ntaps > 128 ? ntaps : 128, 2);
     h->cur = 0;
     memset(&h->taps, 0, sizeof h->taps);
     for (size_t k = 0; k < ntaps; ++k) {

@@ -13,6 +13,9 @@
 // f64 phases), evaluates only every D-th FIR output with FFMA2 and the taps in the
 // kernel-parameter constant bank, then (FM) takes the angle between consecutive
 // outputs.  Algorithmic HBM traffic per input sample: 8 B read + (4 or 8)/D B written.
+#include <cstdlib>
+#include <cstring>
+
 #include "chain_kernels.cuh"
 #include "misc_kernels.cuh"
 
@@ -131,12 +134,14 @@ __device__ __forceinline__ float2 cmul_p(float2 a, float2 b, float2 brr)
     return __ffma2_rn(make_float2(a.x, a.x), b, __fmul2_rn(make_float2(a.y, a.y), brr));
 }
 
-template <bool MIX, bool FM, int D, int KP, int R>
-__global__ void __launch_bounds__(256, 3)
+// PF = true : persistent CTA, the raw span of item i+1 is prefetched into registers while item i is filtered
+// PF = false: the span is loaded in batches of NB 128-bit loads at the start of each item; latency is covered
+//             by the other CTAs of the SM (small tiles, several CTAs per SM)
+template <bool MIX, bool FM, int D, int KP, int R, int NT, bool PF, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ ChainTaps taps, const unsigned tiles_per_ch,
               const unsigned long long nitems)
 {
-    constexpr int NT = 256;
     constexpr int TO = NT * R;                          // decimated outputs per tile
     constexpr int RD = R * D;                           // input samples per thread chunk
     constexpr int OFF = ((KP + D + RD - 1) / RD) * RD;  // halo samples kept in front of the tile
@@ -145,20 +150,21 @@ chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
     constexpr int NCH = NT + OFF / RD;
     constexpr int NIT = (SPAN / 2 + NT - 1) / NT;
     static_assert(RD % 4 == 0, "chunk pitch must be an odd multiple of 16 bytes");
-    static_assert(NIT <= 31 && KP % 2 == 0 && KP <= 64, "");
+    constexpr int NB = PF ? NIT : 6;                    // loads in flight per thread
+    static_assert(NIT <= 61 && NT >= 64 && KP % 2 == 0 && KP <= 64, "");
 
     extern __shared__ __align__(16) unsigned char c2sm[];
     unsigned char *xs = c2sm;                                               // NCH chunks
-    float2 *ftab = reinterpret_cast<float2 *>(c2sm + NCH * PITCH);          // 2 x 32 phasors
-    float2 *ys = ftab + 64;                                                 // TO + 1 outputs
+    float2 *ftab = reinterpret_cast<float2 *>(c2sm + NCH * PITCH);          // 2 x 64 phasors
+    float2 *ys = ftab + 128;                                                // TO + 1 outputs
 
     const int tid = threadIdx.x;
     const long long H = a.hist_len;
 
     // Persistent CTA over work items (channel, tile).  The raw span of item i+1 is loaded into
     // registers while item i is filtered, so HBM loads are always in flight.
-    float4 raw[NIT];
-    auto issue_loads = [&](unsigned long long item) {
+    float4 raw[NB];
+    auto issue_loads = [&](unsigned long long item, const int b0) {
         const size_t c = (size_t)(item / tiles_per_ch);
         const long long g_base = (long long)(item % tiles_per_ch) * TO * D - OFF;  // even
         const float2 *xc = a.x + c * a.n_in;
@@ -166,13 +172,16 @@ chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
             // interior tile (all but the first and last of a channel): no bounds checks
             const float4 *src = reinterpret_cast<const float4 *>(xc + g_base) + tid;
 #pragma unroll
-            for (int it = 0; it < NIT; ++it) {
-                if ((it + 1) * NT <= SPAN / 2 || tid + it * NT < SPAN / 2) raw[it] = ldg_stream(src + it * NT);
+            for (int ib = 0; ib < NB; ++ib) {
+                const int it = b0 + ib;
+                if (it < NIT && ((it + 1) * NT <= SPAN / 2 || tid + it * NT < SPAN / 2)) raw[ib] = ldg_stream(src + it * NT);
             }
         } else {
             const float2 *hc = a.hist_in + c * H;
 #pragma unroll
-            for (int it = 0; it < NIT; ++it) {
+            for (int ib = 0; ib < NB; ++ib) {
+                const int it = b0 + ib;
+                if (it >= NIT) break;
                 const int p = tid + it * NT;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (2 * p < SPAN) {
@@ -183,19 +192,19 @@ chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
                         v = *reinterpret_cast<const float4 *>(hc + (H + g));
                     }
                 }
-                raw[it] = v;
+                raw[ib] = v;
             }
         }
     };
-    // phasor table of an item: slots 0..NIT-1 = e^{j (512 it) dphi}, slot 31 = e^{j dphi},
-    // slot 30 = e^{j (phi0 + g_base dphi)} (the item's first staged sample)
+    // phasor table of an item: slots 0..NIT-1 = e^{j (2 NT it) dphi}, slot 63 = e^{j dphi},
+    // slot 62 = e^{j (phi0 + g_base dphi)} (the item's first staged sample)
     auto fill_ftab = [&](unsigned long long item, int buf) {
-        if (MIX && (tid < NIT || tid >= 30) && tid < 32) {
+        if (MIX && (tid < NIT || tid >= 62) && tid < 64) {
             const size_t c = (size_t)(item / tiles_per_ch);
             const double dphi = a.dphase[c];
             const long long g_base = (long long)(item % tiles_per_ch) * TO * D - OFF;
-            const double th = tid == 31 ? dphi : (tid == 30 ? fma((double)g_base, dphi, a.phase_in[c]) : (double)(tid * 2 * NT) * dphi);
-            ftab[buf * 32 + tid] = phase_rotation(th);
+            const double th = tid == 63 ? dphi : (tid == 62 ? fma((double)g_base, dphi, a.phase_in[c]) : (double)(tid * 2 * NT) * dphi);
+            ftab[buf * 64 + tid] = phase_rotation(th);
         }
     };
 
@@ -204,7 +213,7 @@ chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
     unsigned long long item = (unsigned long long)blockIdx.x * per;
     const unsigned long long item_end = item + per < nitems ? item + per : nitems;
     if (item >= item_end) return;
-    issue_loads(item);
+    if (PF) issue_loads(item, 0);
     fill_ftab(item, 0);
     __syncthreads();
     size_t t_ch = ~(size_t)0;             // channel for which e_thr is valid
@@ -224,17 +233,18 @@ chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
                     e_thr = phase_rotation((double)(2 * tid) * a.dphase[c]);
                     t_ch = c;
                 }
-                e_t = cmul(ftab[cur * 32 + 30], e_thr);
-                e_step = ftab[cur * 32 + 31];
+                e_t = cmul(ftab[cur * 64 + 62], e_thr);
+                e_step = ftab[cur * 64 + 63];
             }
             const float2 e_t_rr = rot90(e_t), e_step_rr = rot90(e_step);
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
+                if (!PF && it % NB == 0) issue_loads(item, it);
                 const int p = tid + it * NT;
                 if ((it + 1) * NT <= SPAN / 2 || p < SPAN / 2) {
-                    float4 v = raw[it];
+                    float4 v = raw[it % NB];
                     if (MIX) {
-                        const float2 r0 = cmul_p(ftab[cur * 32 + it], e_t, e_t_rr);
+                        const float2 r0 = cmul_p(ftab[cur * 64 + it], e_t, e_t_rr);
                         const float2 r1 = cmul_p(r0, e_step, e_step_rr);
                         const float2 s0 = cmul_p(make_float2(v.x, v.y), r0, rot90(r0));
                         const float2 s1 = cmul_p(make_float2(v.z, v.w), r1, rot90(r1));
@@ -250,7 +260,7 @@ chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
         // ---- B: next item's loads go out now and land while this item is filtered
         const unsigned long long nxt = item + 1;
         if (nxt < item_end) {
-            issue_loads(nxt);
+            if (PF) issue_loads(nxt, 0);
             fill_ftab(nxt, cur ^ 1);
         }
 
@@ -339,35 +349,321 @@ chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
     }
 }
 
-template <bool MIX, bool FM, int D, int KP, int R>
+template <bool MIX, bool FM, int D, int KP, int R, int NT, bool PF, int MINB>
 static int launch_chain2(const ChainArgs &args, const ChainTaps &taps, size_t channels, cudaStream_t s)
 {
-    constexpr int TO = 256 * R, RD = R * D, OFF = ((KP + D + RD - 1) / RD) * RD;
-    constexpr int SMEM = (256 + OFF / RD) * (RD * 8 + 16) + 64 * 8 + (TO + 1) * 8;
-    auto kern = chain2_kernel<MIX, FM, D, KP, R>;
+    constexpr int TO = NT * R, RD = R * D, OFF = ((KP + D + RD - 1) / RD) * RD;
+    constexpr int SMEM = (NT + OFF / RD) * (RD * 8 + 16) + 128 * 8 + (TO + 1) * 8;
+    auto kern = chain2_kernel<MIX, FM, D, KP, R, NT, PF, MINB>;
     CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const unsigned tiles = (unsigned)ceil_div(args.n_out, (size_t)TO);
     const unsigned long long nitems = (unsigned long long)tiles * channels;
     int dev = 0, sms = 148, per_sm = 2;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, SMEM);
     if (per_sm < 1) per_sm = 1;
     const unsigned long long cap = (unsigned long long)sms * per_sm;
     const unsigned grid = (unsigned)(nitems < cap ? nitems : cap);
-    kern<<<grid, 256, SMEM, s>>>(args, taps, tiles, nitems);
+    kern<<<grid, NT, SMEM, s>>>(args, taps, tiles, nitems);
     count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;
 }
 
+// ============================================================================
+// v3 (real taps <= 64, compile-time D): TMA-staged, mixer folded into the taps.
+//
+//   y[m] = sum_k h[k] x[mD-k] e^{j phi(mD-k)} = e^{j phi(mD)} sum_k (h[k] e^{-j k dphi}) x[mD-k]
+//
+// so the RAW input span can go from HBM to shared memory by TMA (a few 2 KiB 1-D bulk copies per
+// tile, stored linearly) with no register staging, no per-sample rotation pass and no barrier
+// between staging and filtering.  (One bulk copy per padded thread-chunk was measured 3x slower:
+// small UBLKCPs are issue-bound.)  R outputs per thread with R*D/2 odd makes the linear layout
+// bank-conflict free for the 128-bit window loads.  The per-channel rotated
+// taps h'[k] live in shared memory (64 complex values, recomputed when the CTA moves to another
+// channel) and every output is rotated once by e^{j phi(mD)} = base(item) * e_thr(thread) * step(r).
+// A ring of NSTAGE span buffers per CTA keeps (NSTAGE - 1) spans of HBM reads in flight per CTA.
+// History chunks (g < 0) are bulk-copied from the channel's history buffer (hist_len >= OFF), so
+// the first tile of a channel needs no special path; chunks past n_in are simply not copied.
+// Numerics: identical algebra, different rounding points (rel-L2 ~2e-7 vs the oracle).
+// ============================================================================
+template <bool MIX, bool FM, int D, int R, int NT, int NSTAGE, int MINB>
+__global__ void __launch_bounds__(NT + 32, MINB)
+chain3_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ ChainTaps taps, const unsigned tiles_per_ch,
+              const unsigned long long nitems)
+{
+    constexpr int KP = 64;
+    constexpr int TO = NT * R;
+    constexpr int RD = R * D;
+    constexpr int OFF = (KP + D + 1) / 2 * 2;           // halo samples in front of the tile (even)
+    constexpr int SPAN = TO * D + OFF;
+    constexpr int STAGE = (SPAN * 8 + 127) / 128 * 128;
+    constexpr int PIECE = 256;                          // samples per bulk copy (2 KiB)
+    // the span is stored LINEARLY; thread t reads 128-bit words at a lane stride of RD*8 bytes, which is
+    // bank-conflict free exactly when RD/2 is odd (stride = odd multiple of 16 bytes)
+    static_assert(RD % 2 == 0 && (RD / 2) % 2 == 1 && NT >= 64 + R + 1, "");
+
+    extern __shared__ __align__(128) unsigned char c3sm[];
+    unsigned char *stages = c3sm;
+    float2 *tsm = reinterpret_cast<float2 *>(c3sm + NSTAGE * STAGE);  // tsm[k + 1] = h'[k], tsm[0] = tsm[65] = 0
+    float2 *cst = tsm + KP + 2;                                       // e^{j r D dphi} (r < R), then e^{-j D dphi}
+    float2 *basep = cst + 8;                                          // per stage: e^{j (phi0 + m0 D dphi)}
+    float2 *ys = basep + 8;                                           // 2 x (TO + 1) outputs
+    __shared__ __align__(8) uint64_t full[NSTAGE];
+
+    // NT consumer threads (warps 0 .. NT/32-1) + one producer warp (TMA issue, per-item base phasor,
+    // and the FM look-back output), so that no filtering warp carries extra work into the barrier
+    const int tid = threadIdx.x, lane = tid & 31;
+    const bool producer = tid >= NT;
+    const long long H = a.hist_len;
+
+    const unsigned long long per = (nitems + gridDim.x - 1) / gridDim.x;
+    const unsigned long long item0 = (unsigned long long)blockIdx.x * per;
+    const unsigned long long item_end = item0 + per < nitems ? item0 + per : nitems;
+    if (item0 >= item_end) return;
+
+    // stage memory starts out finite (chunks past the end of a batch are never copied)
+    for (int i = tid; i < NSTAGE * STAGE / 16; i += NT + 32) reinterpret_cast<uint4 *>(stages)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) {
+        for (int i = 0; i < NSTAGE; ++i) mbar_init(&full[i], 1);
+        fence_mbar_init();
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    // warp 0: bulk-copy the span of `item` into stage `st`
+    auto produce = [&](unsigned long long item, int st) {
+        const size_t c = (size_t)(item / tiles_per_ch);
+        const long long tile = (long long)(item % tiles_per_ch);
+        const long long g_base = tile * TO * D - OFF;
+        long long g_hi = g_base + SPAN;
+        if (g_hi > (long long)a.n_in) g_hi = (long long)a.n_in;
+        if (lane == 0) {
+            if (MIX) basep[st] = phase_rotation(fma((double)(tile * TO * D), a.dphase[c], a.phase_in[c]));
+            mbar_arrive_expect_tx(&full[st], (uint32_t)((g_hi - g_base) * 8));
+        }
+        __syncwarp();
+        const float2 *xc = a.x + c * a.n_in;
+        const float2 *hc = a.hist_in + c * H + H;
+        unsigned char *dst = stages + st * STAGE;
+        const long long g_lo = g_base < 0 ? 0 : g_base;
+        if (g_base < 0 && lane == 31) tma_load_1d(dst, hc + g_base, (uint32_t)(-g_base * 8), &full[st]);  // history
+        for (long long g = g_lo + (long long)lane * PIECE; g < g_hi; g += 32 * PIECE) {
+            const long long n = g_hi - g < PIECE ? g_hi - g : PIECE;
+            tma_load_1d(dst + (g - g_base) * 8, xc + g, (uint32_t)(n * 8), &full[st]);
+        }
+    };
+    if (producer) {
+        for (int i = 0; i < NSTAGE; ++i)
+            if (item0 + i < item_end) produce(item0 + i, i);
+    }
+
+    size_t cur_c = ~(size_t)0;
+    float2 e_thr = make_float2(1.f, 0.f);
+    unsigned long long li = 0;
+    for (unsigned long long item = item0; item < item_end; ++item, ++li) {
+        const int st = (int)(li % NSTAGE);
+        const uint32_t parity = (uint32_t)((li / NSTAGE) & 1);
+        const int yb = (int)(li & 1) * (TO + 1);
+        const size_t c = (size_t)(item / tiles_per_ch);
+        const unsigned tile = (unsigned)(item % tiles_per_ch);
+        const long long m0 = (long long)tile * TO;
+
+        if (MIX && c != cur_c) {  // new channel: rotated taps and the per-channel phasors
+            const double dphi = a.dphase[c];
+            if (tid < KP) {
+                const float2 w = phase_rotation(-(double)tid * dphi);
+                const float h = taps.t[tid].x;
+                tsm[tid + 1] = make_float2(h * w.x, h * w.y);
+            } else if (tid < KP + R) {
+                cst[tid - KP] = phase_rotation((double)((tid - KP) * D) * dphi);
+            } else if (tid == KP + R) {
+                cst[R] = phase_rotation(-(double)D * dphi);
+                tsm[0] = tsm[KP + 1] = make_float2(0.f, 0.f);
+            }
+            if (!producer) e_thr = phase_rotation((double)(RD * tid) * dphi);
+            cur_c = c;
+            __syncthreads();
+        }
+
+        mbar_wait(&full[st], parity);
+        const unsigned char *sbase = stages + st * STAGE;
+
+        // ---- FM only: y[m0 - 1] for the first discriminator step of the tile (warp 0, 2 taps per lane)
+        if (FM && producer) {
+            float2 y = make_float2(0.f, 0.f);
+            if (m0 > 0) {
+                float2 yA = make_float2(0.f, 0.f), yB = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int kk = 0; kk < KP / 32; ++kk) {
+                    const int k = lane + 32 * kk;
+                    const int i = OFF - D - k;  // >= 0 by construction of OFF
+                    const float2 sv = *reinterpret_cast<const float2 *>(sbase + i * 8);
+                    if (MIX) {
+                        const float2 h = tsm[k + 1];
+                        yA = __ffma2_rn(sv, make_float2(h.x, h.x), yA);
+                        yB = __ffma2_rn(sv, make_float2(h.y, h.y), yB);
+                    } else {
+                        yA = __ffma2_rn(sv, taps.t[k], yA);
+                    }
+                }
+                y = MIX ? make_float2(yA.x - yB.y, yA.y + yB.x) : yA;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    y.x += __shfl_xor_sync(0xffffffffu, y.x, o);
+                    y.y += __shfl_xor_sync(0xffffffffu, y.y, o);
+                }
+                if (MIX) y = cmul(y, cmul(basep[st], cst[R]));
+            } else {
+                y = a.prev_in[c];
+            }
+            if (lane == 0) ys[yb] = y;
+        }
+
+        // ---- decimated FIR: thread owns outputs o = R*tid + r; sample at relative index cc = r*D - k
+        if (!producer) {
+            const unsigned char *base = sbase + (tid * RD + OFF) * 8;
+            float2 accA[R][2], accB[R][2];
+#pragma unroll
+            for (int r = 0; r < R; ++r) accA[r][0] = accA[r][1] = accB[r][0] = accB[r][1] = make_float2(0.f, 0.f);
+            constexpr int C_LO = -(KP - 1) - ((KP - 1) & 1);  // even start (<= -(KP-1))
+            constexpr int C_HI = (R - 1) * D;                  // last sample used
+            float2 tq[KP + 2];                                 // tq[k + 1] = h'[k]; registers, loaded at first use
+#pragma unroll
+            for (int cc = C_LO; cc <= C_HI; cc += 2) {
+                const float4 w = *reinterpret_cast<const float4 *>(base + cc * 8);
+                if (MIX && cc <= 0) {  // taps k = -cc-1, -cc are used for the first time (by r = 0) now
+                    const float4 t2 = *reinterpret_cast<const float4 *>(tsm + (-cc));
+                    tq[-cc] = make_float2(t2.x, t2.y);
+                    tq[-cc + 1] = make_float2(t2.z, t2.w);
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int ch = cc + h;
+                    const float2 sv = h ? make_float2(w.z, w.w) : make_float2(w.x, w.y);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int k = r * D - ch;
+                        if (k >= 0 && k < KP) {
+                            if (MIX) {
+                                accA[r][k & 1] = __ffma2_rn(sv, make_float2(tq[k + 1].x, tq[k + 1].x), accA[r][k & 1]);
+                                accB[r][k & 1] = __ffma2_rn(sv, make_float2(tq[k + 1].y, tq[k + 1].y), accB[r][k & 1]);
+                            } else {
+                                accA[r][k & 1] = __ffma2_rn(sv, taps.t[k], accA[r][k & 1]);
+                            }
+                        }
+                    }
+                }
+            }
+            float2 ph = make_float2(1.f, 0.f);
+            if (MIX) ph = cmul(basep[st], e_thr);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float2 y = __fadd2_rn(accA[r][0], accA[r][1]);
+                if (MIX) {
+                    const float2 b = __fadd2_rn(accB[r][0], accB[r][1]);
+                    y = cmul(make_float2(y.x - b.y, y.y + b.x), cmul(ph, cst[r]));
+                }
+                ys[yb + 1 + R * tid + r] = y;
+                if (FM && m0 + R * tid + r == (long long)a.n_out - 1) a.prev_out[c] = y;
+            }
+        }
+        __syncthreads();  // outputs staged; every thread is done with stage st
+
+        if (producer) {
+            if (item + NSTAGE < item_end) produce(item + NSTAGE, st);
+            continue;
+        }
+
+        // ---- carried state for the next call (last tile of the channel)
+        if (tile == tiles_per_ch - 1) {
+            const float2 *xc = a.x + c * a.n_in;
+            const float2 *hc = a.hist_in + c * H;
+            float2 *ho = a.hist_out + c * H;
+            for (long long i = tid; i < H; i += NT) {
+                const long long g = (long long)a.n_in - H + i;
+                ho[i] = g >= 0 ? xc[g] : hc[H + g];
+            }
+            if (MIX && tid == 0) {
+                const double twopi = 6.283185307179586232;
+                double phs = fma((double)a.n_in, a.dphase[c], a.phase_in[c]);
+                phs -= twopi * floor(phs / twopi);
+                a.phase_out[c] = phs;
+            }
+        }
+
+        // ---- coalesced output
+        float *out_f = reinterpret_cast<float *>(a.out) + c * a.n_out;
+        float2 *out_c = reinterpret_cast<float2 *>(a.out) + c * a.n_out;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const int o = tid + j * NT;
+            const long long m = m0 + o;
+            if (m < (long long)a.n_out) {
+                if (FM) out_f[m] = fm_angle(ys[yb + o + 1], ys[yb + o]);
+                else out_c[m] = ys[yb + o + 1];
+            }
+        }
+    }
+}
+
+template <bool MIX, bool FM, int D, int R, int NT, int NSTAGE, int MINB>
+static int launch_chain3(const ChainArgs &args, const ChainTaps &taps, size_t channels, cudaStream_t s)
+{
+    constexpr int TO = NT * R, OFF = (64 + D + 1) / 2 * 2;
+    constexpr int SMEM = NSTAGE * (((TO * D + OFF) * 8 + 127) / 128 * 128) + (66 + 8 + 8) * 8 + 2 * (TO + 1) * 8;
+    auto kern = chain3_kernel<MIX, FM, D, R, NT, NSTAGE, MINB>;
+    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    const unsigned tiles = (unsigned)ceil_div(args.n_out, (size_t)TO);
+    const unsigned long long nitems = (unsigned long long)tiles * channels;
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT + 32, SMEM);
+    if (per_sm < 1) per_sm = 1;
+    const unsigned long long cap = (unsigned long long)sms * per_sm;
+    const unsigned grid = (unsigned)(nitems < cap ? nitems : cap);
+    kern<<<grid, NT + 32, SMEM, s>>>(args, taps, tiles, nitems);
+    count_launch();
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+
+template <int D, int R, int NT, int NSTAGE, int MINB>
+static int launch_chain3_shape(const ChainArgs &args, const ChainTaps &taps, bool mix, bool fm, size_t channels, cudaStream_t s)
+{
+    if (mix && fm) return launch_chain3<true, true, D, R, NT, NSTAGE, MINB>(args, taps, channels, s);
+    if (mix) return launch_chain3<true, false, D, R, NT, NSTAGE, MINB>(args, taps, channels, s);
+    if (fm) return launch_chain3<false, true, D, R, NT, NSTAGE, MINB>(args, taps, channels, s);
+    return launch_chain3<false, false, D, R, NT, NSTAGE, MINB>(args, taps, channels, s);
+}
+
+// tile shape of the v2 kernel: R outputs per thread, NT threads, register prefetch or not
+template <int D, int R, int NT, bool PF, int MINB>
+static int launch_chain2_shape(const ChainArgs &args, const ChainTaps &taps, bool mix, bool fm, size_t channels, cudaStream_t s)
+{
+    if (mix && fm) return launch_chain2<true, true, D, 64, R, NT, PF, MINB>(args, taps, channels, s);
+    if (mix) return launch_chain2<true, false, D, 64, R, NT, PF, MINB>(args, taps, channels, s);
+    if (fm) return launch_chain2<false, true, D, 64, R, NT, PF, MINB>(args, taps, channels, s);
+    return launch_chain2<false, false, D, 64, R, NT, PF, MINB>(args, taps, channels, s);
+}
+
+// Kernel choice for real taps <= 64 and compile-time D.  COMMS_B200_CHAIN_PATH = auto (default) | v2 | v3
+// selects the family; v3 (TMA-staged, mixer folded into the taps) needs R*D/2 odd for its linear
+// conflict-free layout, so it is instantiated for D = 10 (R = 3) and D = 5 (R = 6).
 template <int D, int R>
 static int launch_chain2_d(const ChainArgs &args, const ChainTaps &taps, bool mix, bool fm, size_t channels, cudaStream_t s)
 {
-    if (mix && fm) return launch_chain2<true, true, D, 64, R>(args, taps, channels, s);
-    if (mix) return launch_chain2<true, false, D, 64, R>(args, taps, channels, s);
-    if (fm) return launch_chain2<false, true, D, 64, R>(args, taps, channels, s);
-    return launch_chain2<false, false, D, 64, R>(args, taps, channels, s);
+    static const int path = [] {
+        const char *e = getenv("COMMS_B200_CHAIN_PATH");
+        return (e && strcmp(e, "v2") == 0) ? 2 : ((e && strcmp(e, "v3") == 0) ? 3 : 0);
+    }();
+    if (path != 2 && args.hist_len >= 128) {
+        if constexpr (D == 10) return launch_chain3_shape<D, 3, 128, 2, 3>(args, taps, mix, fm, channels, s);
+        if constexpr (D == 5) return launch_chain3_shape<D, 6, 128, 2, 2>(args, taps, mix, fm, channels, s);
+    }
+    return launch_chain2_shape<D, R, 256, true, 2>(args, taps, mix, fm, channels, s);
 }
 
 int launch_chain(const ChainArgs &args, const ChainTaps &taps, bool mix, bool fm, bool cplx, size_t channels,
