@@ -386,7 +386,7 @@ static int launch_chain2(const ChainArgs &args, const ChainTaps &taps, size_t ch
 // A ring of NSTAGE span buffers per CTA keeps (NSTAGE - 1) spans of HBM reads in flight per CTA.
 // History chunks (g < 0) are bulk-copied from the channel's history buffer (hist_len >= OFF), so
 // the first tile of a channel needs no special path; chunks past n_in are simply not copied.
-// Numerics: identical algebra, different rounding points (rel-L2 ~2e-7 vs the oracle).
+// Numerics: identical algebra, different rounding points (rel-L2 ~2e-7 vs the sequential f32 form).
 // ============================================================================
 template <bool MIX, bool FM, int D, int R, int NT, int NSTAGE, int MINB>
 __global__ void __launch_bounds__(NT + 32, MINB)
