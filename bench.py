@@ -75,10 +75,15 @@ def fm_radio_lowpass(n=63):
     return (np.sinc(k / 5) * np.hamming(n) / 5).astype(np.float32).astype(np.complex64)
 
 
-def fir_taps(workload):
-    import oracle  # taps only (rrc_taps restatement, src/util/math.rs:221-280); not on the timed GPU path
+def rrc_taps(n, sps, beta):
+    """rrc_taps (src/util/math.rs:221-280) from the product's host entry (cb_rrc_taps; needs no GPU)."""
+    import comms_rs_b200 as cb
 
-    t = oracle.rrc_taps(64, 4.0, 0.25)
+    return cb.rrc_taps(n, sps, beta)
+
+
+def fir_taps(workload):
+    t = rrc_taps(64, 4.0, 0.25)
     if workload == "fir64":
         t = (t * np.exp(0.1j * np.arange(64))).astype(np.complex64)
     return t
@@ -169,7 +174,7 @@ def cpu_rate(workload, samples, threads):
             jobs.append(lambda x=x, ch=ch: [ch.run(x[j:j + 131072]) for j in range(0, len(x), 131072)])
         else:
             L, nt = (4, 32) if workload == "pulse4" else (8, 1024)
-            t = oracle.rrc_taps(nt, float(L), 0.25)
+            t = rrc_taps(nt, float(L), 0.25)
             st = np.zeros(nt, np.complex64)
             jobs.append(lambda x=x, t=t, st=st: oracle.batch_fir(oracle.upsample(x, L), t, st, literal=True, native=True))
     ths = [threading.Thread(target=j) for j in jobs]
@@ -262,8 +267,7 @@ class Job:
             self.host_call = lambda hin, hout: cb.load().cb_chain_run(self.node._h, hin, nb, hout, no, None)
         else:
             L, nt = (4, 32) if workload == "pulse4" else (8, 1024)
-            import oracle
-            self.taps = oracle.rrc_taps(nt, float(L), 0.25)
+            self.taps = rrc_taps(nt, float(L), 0.25)
             self.node = cb.BatchFirNode(self.taps, None, interp=L)
             self.y = torch.empty(n * L, dtype=torch.complex64, device="cuda")
             self.out_bytes = 8 * n * L

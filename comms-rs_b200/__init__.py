@@ -7,7 +7,7 @@ from . import _lib
 from ._lib import CbError, NodeError, load
 from .nodes import (BatchFirNode, ChainBank, DecimateNode, FFTBatchNode, FFTSampleNode, FirNode, FMDemodNode,
                     MixerNode, PulseNode, UpsampleNode, bits_to_symbols_dev, prn_bits, quantize_i16_dev,
-                    synth_uniform_dev)
+                    rrc_taps, synth_uniform_dev)
 
 
 def init(device: int = 0) -> None:

@@ -1217,6 +1217,43 @@ int cb_chain_run(cb_chain *h, const float *in, size_t n_in, float *out, size_t o
     return CB_OK;
 }
 
+// ============================================================================ pulse-shaping taps
+// rrc_taps (src/util/math.rs:221-280), host side, f64.
+int cb_rrc_taps_f64(uint32_t n_taps, double sam_per_sym, double beta, double *taps)
+{
+    CB_REQUIRE(taps || n_taps == 0, CB_ERR_INVALID_ARG, "taps is NULL");
+    CB_REQUIRE(beta >= 0.0 && beta <= 1.0, CB_ERR_INVALID_ARG, "rrc_taps: rolloff %g outside [0, 1]", beta);
+    const double pi = 3.14159265358979323846, eps = 2.220446049250313e-16;
+    const double at_zero = 1.0 + beta * (4.0 / pi - 1.0);
+    const double at_sing = (beta / sqrt(2.0)) * ((1.0 + 2.0 / pi) * sin(pi / (4.0 * beta)) + (1.0 - 2.0 / pi) * cos(pi / (4.0 * beta)));
+    const double t_sing = beta != 0.0 ? 1.0 / (4.0 * beta) : 0.0;
+    for (uint32_t i = 0; i < n_taps; ++i) {
+        const double t = ((double)i - (double)(n_taps - 1) / 2.0) / sam_per_sym;
+        double v;
+        if (fabs(t) < eps) {
+            v = at_zero;
+        } else if (fabs(t - t_sing) < eps || fabs(t + t_sing) < eps) {
+            v = at_sing;
+        } else {
+            const double q = 4.0 * beta * t;
+            v = (sin(pi * t * (1.0 - beta)) + 4.0 * beta * t * cos(pi * t * (1.0 + beta))) / (pi * t * (1.0 - q * q));
+        }
+        taps[2 * i] = v;
+        taps[2 * i + 1] = 0.0;
+    }
+    return CB_OK;
+}
+
+int cb_rrc_taps(uint32_t n_taps, double sam_per_sym, double beta, float *taps)
+{
+    CB_REQUIRE(taps || n_taps == 0, CB_ERR_INVALID_ARG, "taps is NULL");
+    std::vector<double> t((size_t)2 * n_taps);
+    const int rc = cb_rrc_taps_f64(n_taps, sam_per_sym, beta, t.data());
+    if (rc) return rc;
+    for (size_t i = 0; i < t.size(); ++i) taps[i] = (float)t[i];
+    return CB_OK;
+}
+
 // ============================================================================ bit-exact edges
 int cb_prn_bits(uint64_t poly_mask, uint64_t *state, unsigned width, size_t n, uint8_t *bits)
 {

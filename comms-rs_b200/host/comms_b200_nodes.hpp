@@ -298,4 +298,11 @@ struct FMDemodNode : Node1<FMDemodNode, std::vector<c32>, std::vector<float>> {
     }
 };
 
+// rrc_taps::<f32> (src/util/math.rs:221-280); empty Result.err == InvalidRolloffError for beta outside [0, 1]
+inline bool rrc_taps(uint32_t n_taps, double sam_per_sym, double beta, std::vector<c32> &taps)
+{
+    taps.assign(n_taps, c32(0.f, 0.f));
+    return cb_rrc_taps(n_taps, sam_per_sym, beta, reinterpret_cast<float *>(taps.data())) == CB_OK;
+}
+
 }  // namespace comms_b200

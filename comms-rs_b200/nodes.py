@@ -302,6 +302,19 @@ class ChainBank(_Handle):
 
 
 # ------------------------------------------------------------------ edges
+def rrc_taps(n_taps: int, sam_per_sym: float, beta: float, dtype=np.complex64) -> np.ndarray:
+    """rrc_taps::<T> (src/util/math.rs:221-280): root-raised-cosine taps, imaginary parts 0.
+    Raises NodeError-style ValueError("InvalidRolloffError") for beta outside [0, 1]."""
+    f64 = np.dtype(dtype) == np.complex128
+    out = np.empty(n_taps, dtype=np.complex128 if f64 else np.complex64)
+    fn = _lib.load().cb_rrc_taps_f64 if f64 else _lib.load().cb_rrc_taps
+    try:
+        check(fn(int(n_taps), float(sam_per_sym), float(beta), _ptr(out)))
+    except CbError as e:
+        raise ValueError("InvalidRolloffError") from e
+    return out
+
+
 def prn_bits(poly_mask: int, state: int, n: int, width: int = 8):
     """PrnGen::next_byte n times (src/prns.rs:64-71).  Returns (bits, new_state)."""
     st = C.c_uint64(state)

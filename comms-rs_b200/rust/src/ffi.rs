@@ -87,6 +87,8 @@ extern "C" {
     pub fn cb_chain_run_dev(h: *mut cb_chain, d_in: *const c_float, n_in: usize, d_out: *mut c_float, out_cap: usize,
                             n_out: *mut usize, stream: *mut c_void) -> c_int;
 
+    pub fn cb_rrc_taps(n_taps: u32, sam_per_sym: f64, beta: f64, taps: *mut f32) -> c_int;
+    pub fn cb_rrc_taps_f64(n_taps: u32, sam_per_sym: f64, beta: f64, taps: *mut f64) -> c_int;
     pub fn cb_prn_bits(poly_mask: u64, state: *mut u64, width: c_uint, n: usize, bits: *mut u8) -> c_int;
     pub fn cb_bits_to_symbols_dev(d_bits: *const u8, nbits: usize, mode: c_int, d_sym: *mut c_float, nsym: *mut usize,
                                   stream: *mut c_void) -> c_int;

@@ -70,6 +70,16 @@ fn fir_run(h: &Fir, input: &[C32]) -> Result<Vec<C32>, NodeError> {
     Ok(out)
 }
 
+/// Drop-in for `util::math::rrc_taps::<f32>` (src/util/math.rs:221-280), evaluated by the library's
+/// host entry so that the taps fed to the GPU filters are the reference's, bit for bit.
+pub fn rrc_taps(n_taps: u32, sam_per_sym: f64, beta: f64) -> Result<Vec<C32>, comms_rs::util::MathError> {
+    let mut taps: Vec<C32> = vec![Complex::new(0.0, 0.0); n_taps as usize];
+    match unsafe { ffi::cb_rrc_taps(n_taps, sam_per_sym, beta, taps.as_mut_ptr() as *mut f32) } {
+        ffi::CB_OK => Ok(taps),
+        _ => Err(comms_rs::util::MathError::InvalidRolloffError),
+    }
+}
+
 /// Drop-in for `BatchFirNode<f32>` (src/filter/fir_node.rs:146-221).
 #[derive(Node)]
 #[pass_by_ref]

@@ -206,6 +206,17 @@ CB_API int cb_chain_run(cb_chain *h, const float *in, size_t n_in, float *out, s
 CB_API int cb_chain_run_dev(cb_chain *h, const float *d_in, size_t n_in, float *d_out,
                             size_t out_cap_per_channel, size_t *n_out_per_channel, void *stream);
 
+/* ------------------------------------------------------------------ pulse-shaping taps (host side)
+ * rrc_taps<T> (src/util/math.rs:221-280): root-raised-cosine impulse response
+ * sampled at t_i = (i - (n_taps-1)/2) / sam_per_sym, T_sym = 1, evaluated in f64
+ * with the reference's special cases (|t| < f64::EPSILON; |t -/+ 1/(4 beta)| <
+ * f64::EPSILON) and no energy normalisation; imaginary parts are 0.
+ * beta outside [0, 1] -> CB_ERR_INVALID_ARG (the reference's InvalidRolloffError).
+ * taps: 2*n_taps floats (cb_rrc_taps: the f64 values cast to f32 like
+ * T::from(f64)) or 2*n_taps doubles (cb_rrc_taps_f64).  Needs no device. */
+CB_API int cb_rrc_taps(uint32_t n_taps, double sam_per_sym, double beta, float *taps);
+CB_API int cb_rrc_taps_f64(uint32_t n_taps, double sam_per_sym, double beta, double *taps);
+
 /* ------------------------------------------------------------------ bit-exact edges
  * Integer / index stages of the example graphs, device side, so whole example
  * chains can stay on the GPU.

@@ -70,6 +70,22 @@ def test_status_strings_and_version(cb):
     assert cb.launch_count() == 0 or cb.launch_count() > 0
 
 
+def test_rrc_taps_host_entry(cb, oracle):
+    # cb_rrc_taps restates rrc_taps (src/util/math.rs:221-280) on the host side of the C ABI; it needs no
+    # device.  Golden vector math.rs:359-401, the config banks, and the oracle bit for bit.
+    from golden import reference_vectors as G
+
+    rrc = cb.rrc_taps(33, 3.18, 0.234, dtype=np.complex128)
+    assert np.all(np.abs(rrc - np.array(G.RRC_33)) < np.finfo(np.float32).eps) and np.all(rrc.imag == 0)
+    for n, sps, beta in [(32, 4.0, 0.25), (64, 4.0, 0.25), (1024, 8.0, 0.25), (33, 3.18, 0.234), (17, 4.0, 0.0),
+                         (9, 4.0, 1.0), (41, 4.0, 0.5), (1, 2.0, 0.3), (0, 2.0, 0.3)]:
+        for dt in (np.complex64, np.complex128):
+            assert cb.rrc_taps(n, sps, beta, dtype=dt).tobytes() == oracle.rrc_taps(n, sps, beta, dtype=dt).tobytes()
+    for bad in (-0.1, 1.5):
+        with pytest.raises(ValueError):
+            cb.rrc_taps(8, 4.0, bad)
+
+
 def test_product_never_touches_the_oracle():
     # only tests/, __graft_entry__.smoke() and bench.py's CPU legs may use oracle/
     pkg = os.path.join(ROOT, "comms-rs_b200")
