@@ -49,6 +49,8 @@ WORKLOADS = {
     "chain5": ("chain", 1024 * 131072, 8.8, "fm_radio as shipped x1024 channels per GPU: 63-tap FIR -> /5 -> FM demod (no mixer), "
                "131072-sample batches"),
     "pulse4": ("interp", 1 << 26, 40.0, "BPSK pulse shaping: x4 polyphase 32-tap RRC over 2^26 symbols per GPU (unit = symbols)"),
+    "poly8x1024c": ("interp", 1 << 26, 72.0, "x8 polyphase with a fully complex 1024-tap bank (tcgen05, 54 MMAs per tile) over 2^26 symbols "
+                    "per GPU (unit = symbols)"),
     "poly8x1024": ("interp", 1 << 27, 72.0, "QPSK x8 polyphase, 1024-tap RRC bank (tcgen05 Toeplitz GEMM) over 2^27 symbols per GPU "
                    "= one of the 8 segments of the 2^30-symbol stream (unit = symbols)"),
 }
@@ -193,7 +195,7 @@ def run_reference(args, rank):
     threads = os.cpu_count() or 1
     kind, _, _, desc = WORKLOADS[args.workload]
     rate1 = {"fir": 8e6, "fft": 30e6, "chain": 20e6, "interp": 2e6}[kind]
-    if args.workload == "poly8x1024":
+    if args.workload.startswith("poly8x1024"):
         rate1 = 1e4
     per_thread = int(min(max(150.0 * rate1 / (args.steps + args.warmup), 1 << 12), 1 << 23))
     sample = per_thread * threads
@@ -268,6 +270,8 @@ class Job:
         else:
             L, nt = (4, 32) if workload == "pulse4" else (8, 1024)
             self.taps = rrc_taps(nt, float(L), 0.25)
+            if workload == "poly8x1024c":
+                self.taps = (self.taps * np.exp(0.01j * np.arange(nt))).astype(np.complex64)
             self.node = cb.BatchFirNode(self.taps, None, interp=L)
             self.y = torch.empty(n * L, dtype=torch.complex64, device="cuda")
             self.out_bytes = 8 * n * L
@@ -401,7 +405,7 @@ def run_b200(args, rank, world, local_rank):
         if world == 1 and not args.no_cpu:
             kind = job.kind
             sample = {"fir": 1 << 26, "fft": 1 << 27, "chain": 1 << 26, "interp": 1 << 23}[kind]
-            if args.workload == "poly8x1024":
+            if args.workload.startswith("poly8x1024"):
                 sample = 1 << 17
             v, dt, n = cpu_rate(args.workload, sample, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",

@@ -472,10 +472,10 @@ int cb_fir_create(const float *taps, size_t ntaps, const float *state, size_t ns
         } else if (!want_cuda && h->decim == 1 && h->interp > 1 && fir_ptc_supported(h->k_eff, h->interp, h->taps_real)) {
             // polyphase interpolator on the tensor cores (K3-TC); short banks stay on the CUDA-core
             // polyphase kernel unless forced, long banks (> 16 taps per phase) always use it
-            const size_t bytes = fir_ptc_image_bytes(h->k_eff, h->interp);
+            const size_t bytes = fir_ptc_image_bytes(h->k_eff, h->interp, h->taps_real);
             std::vector<unsigned char> img(bytes);
             float inv = 1.f;
-            fir_ptc_build_image(h->taps.data(), h->k_eff, h->interp, img.data(), &inv);
+            fir_ptc_build_image(h->taps.data(), h->k_eff, h->interp, h->taps_real, img.data(), &inv);
             FIR_TRY(cudaMalloc(&h->tc_img, bytes));
             FIR_TRY(cudaMemcpy(h->tc_img, img.data(), bytes, cudaMemcpyHostToDevice));
             h->tc = FirTcPlan{h->tc_img, inv, force_tc ? (size_t)1 : ((size_t)1 << 16)};

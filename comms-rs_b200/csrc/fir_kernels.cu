@@ -401,7 +401,7 @@ int launch_fir(const FirSeg &seg, const float2 *taps_dev, const float2 *taps_hos
         if (seg.interp == 1 && fir_tc_applicable(seg))
             return launch_fir_tc(seg, tcplan->bimg_dev, tcplan->tap_inv_scale, stream);
         if (seg.interp > 1 && fir_ptc_applicable(seg, taps_real))
-            return launch_fir_ptc(seg, tcplan->bimg_dev, tcplan->tap_inv_scale, stream);
+            return launch_fir_ptc(seg, tcplan->bimg_dev, tcplan->tap_inv_scale, taps_real, stream);
     }
     if (seg.interp == 1 && seg.decim == 1) {
         const uint32_t K = seg.ntaps;

@@ -36,14 +36,15 @@ void fir_tc_build_image(const float2 *taps, uint32_t ntaps, unsigned char *img, 
 bool fir_tc_applicable(const FirSeg &seg);
 int launch_fir_tc(const FirSeg &seg, const void *bimg_dev, float tap_inv_scale, cudaStream_t stream);
 
-// Polyphase tensor-core path (fir_ptc_kernel.cu): interp in {4, 8}, decim = 1, real-valued taps.
+// Polyphase tensor-core path (fir_ptc_kernel.cu): interp in {4, 8}, decim = 1, real or complex taps.
 // The plan's bimg_dev / tap_inv_scale then hold the polyphase tap image.
 bool fir_ptc_supported(uint32_t ntaps, uint32_t interp, bool taps_real);
 int fir_ptc_ksteps(uint32_t ntaps, uint32_t interp);
-size_t fir_ptc_image_bytes(uint32_t ntaps, uint32_t interp);
-void fir_ptc_build_image(const float2 *taps, uint32_t ntaps, uint32_t interp, unsigned char *img, float *tap_inv_scale);
+size_t fir_ptc_image_bytes(uint32_t ntaps, uint32_t interp, bool taps_real);
+void fir_ptc_build_image(const float2 *taps, uint32_t ntaps, uint32_t interp, bool taps_real, unsigned char *img,
+                         float *tap_inv_scale);
 bool fir_ptc_applicable(const FirSeg &seg, bool taps_real);
-int launch_fir_ptc(const FirSeg &seg, const void *himg_dev, float tap_inv_scale, cudaStream_t stream);
+int launch_fir_ptc(const FirSeg &seg, const void *himg_dev, float tap_inv_scale, bool taps_real, cudaStream_t stream);
 
 // taps_dev: ntaps complex taps in device memory (generic path)
 // taps_host: same on the host (fast paths put them in the kernel parameter constant bank)

@@ -1,4 +1,4 @@
-// K3-TC: polyphase interpolating FIR (zero-stuff xL then FIR, real-valued taps) as a Toeplitz GEMM
+// K3-TC: polyphase interpolating FIR (zero-stuff xL then FIR, real or complex taps) as a Toeplitz GEMM
 // on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), sm_100a only.
 //
 // Reference semantics (src/pulse.rs:82-92, src/util/resample_node.rs:120-131 + src/filter/fir.rs:87-102):
@@ -21,6 +21,11 @@
 // ceil(KT/RS) - 1 columns of each half would read across the seam and are simply not used
 // (VR valid rows per tile, 120 of 128 for config 5).  K step ks of the stream operand is the same
 // buffer shifted by 32 ks bytes (descriptor start address only).
+//
+// Complex taps (CPLX): y = Hr*x + j Hi*x needs  D_re += Hr S_re - Hi S_im,  D_im += Hr S_im + Hi S_re.
+// The stage holds a third region, -S_re, behind S_im, so that the same N = 256 operand shifted by one
+// region is [S_im | -S_re]; with the image of -Hi as the M operand that one MMA adds exactly the two
+// cross terms.  Twice the MMAs (54 per tile for config 5), same HBM traffic.
 //
 // Precision.  As in fir_tc_kernel.cu: stream and taps are block-scaled by exact powers of two into
 // [2^14, 2^15) and split into fp16 hi + lo; three products (hi*hi, lo*hi, hi*lo) accumulate in the
@@ -52,7 +57,7 @@ struct Args {
     float2 *y;
     const float2 *hist_in;
     float2 *hist_out;
-    const uint4 *himg;      // prepacked tap image: [hi, lo][KS][128 rows x 32 B], 32-byte swizzled
+    const uint4 *himg;      // prepacked tap image: [Hr hi, Hr lo (, -Hi hi, -Hi lo)][KS][128 rows x 32 B], 32-byte swizzled
     unsigned long long n;   // input symbols
     unsigned hist_len;
     unsigned ks;            // K steps of 16
@@ -116,21 +121,22 @@ __host__ __device__ __forceinline__ uint32_t swz(uint32_t o)
     return o ^ (((o >> 7) & (uint32_t)(ROWB / 16 - 1)) << 4);
 }
 
-template <int L>
+template <int L, bool CPLX>
 struct Geo {
     static constexpr int RS = 128 / L;                 // symbols per stream row
     static constexpr int ROWB = 2 * RS;                // swizzle row bytes
     static constexpr int NEL = 128 * RS;               // stream elements per component per tile
     static constexpr int COMP = 128 * ROWB;            // bytes per component region
-    static constexpr int PART = 2 * COMP + 1024;       // hi (or lo) part: re, im, zeroed tail pad
+    static constexpr int NREG = CPLX ? 3 : 2;          // regions: re, im (, -re)
+    static constexpr int PART = NREG * COMP + 1024;    // hi (or lo) part: regions + zeroed tail pad
     static constexpr int STAGE = 2 * PART;
     static constexpr int NLD = NEL / 2 / NLOAD;        // float4 loads per loader thread per tile
 };
 
-template <int L>
+template <int L, bool CPLX>
 __global__ void __launch_bounds__(NTHREADS, 1) fir_ptc_kernel(const __grid_constant__ Args a)
 {
-    using G = Geo<L>;
+    using G = Geo<L, CPLX>;
     constexpr int RS = G::RS, ROWB = G::ROWB, NLD = G::NLD;
     constexpr uint32_t IDESC = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, M128 N256
 
@@ -143,7 +149,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_ptc_kernel(const __grid_const
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *sS = smem;                            // 2 stages x (hi, lo)
-    unsigned char *sH = smem + 2 * G::STAGE;             // tap image: hi KS*4096, lo KS*4096
+    unsigned char *sH = smem + 2 * G::STAGE;             // tap image: KS*4096 bytes per part
     __shared__ __align__(8) uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2], sc_ready[8];
     __shared__ uint32_t tmem_slot;
     __shared__ float red_max[4];
@@ -169,10 +175,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_ptc_kernel(const __grid_const
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // tap image -> shared; zero the tail pads the (unused) seam columns read
-    for (int i = tid; i < KS * 8192 / 16; i += NTHREADS) reinterpret_cast<uint4 *>(sH)[i] = a.himg[i];
+    for (int i = tid; i < KS * (CPLX ? 16384 : 8192) / 16; i += NTHREADS) reinterpret_cast<uint4 *>(sH)[i] = a.himg[i];
     for (int i = tid; i < 4 * 1024 / 16; i += NTHREADS) {
         const int part = i >> 6, o = i & 63;
-        reinterpret_cast<uint4 *>(sS + part * G::PART + 2 * G::COMP)[o] = make_uint4(0u, 0u, 0u, 0u);
+        reinterpret_cast<uint4 *>(sS + part * G::PART + G::NREG * G::COMP)[o] = make_uint4(0u, 0u, 0u, 0u);
     }
     fence_proxy_async();
     tc_fence_before();
@@ -241,6 +247,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_ptc_kernel(const __grid_const
                 *reinterpret_cast<__half2 *>(hi + G::COMP + off) = hm;
                 *reinterpret_cast<__half2 *>(lo + off) = lr;
                 *reinterpret_cast<__half2 *>(lo + G::COMP + off) = lm;
+                if (CPLX) {  // third region: -re
+                    *reinterpret_cast<__half2 *>(hi + 2 * G::COMP + off) = __hneg2(hr);
+                    *reinterpret_cast<__half2 *>(lo + 2 * G::COMP + off) = __hneg2(lr);
+                }
             }
             fence_proxy_async();
             mbar_arrive(&a_full[s]);
@@ -266,6 +276,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_ptc_kernel(const __grid_const
                     tc_mma(d, ah, bh, IDESC, ks > 0 ? 1u : 0u);
                     tc_mma(d, al, bh, IDESC, 1u);
                     tc_mma(d, ah, bl, IDESC, 1u);
+                    if (CPLX) {  // (-Hi) x [S_im | -S_re]
+                        const uint64_t ch = kdesc<32>(hbase + (uint32_t)(2 * KS + ks) * 4096u);
+                        const uint64_t cl = kdesc<32>(hbase + (uint32_t)(3 * KS + ks) * 4096u);
+                        const uint64_t dh = kdesc<ROWB>(shi + (uint32_t)G::COMP + (uint32_t)ks * 32u);
+                        const uint64_t dl = kdesc<ROWB>(slo + (uint32_t)G::COMP + (uint32_t)ks * 32u);
+                        tc_mma(d, ch, dh, IDESC, 1u);
+                        tc_mma(d, cl, dh, IDESC, 1u);
+                        tc_mma(d, ch, dl, IDESC, 1u);
+                    }
                 }
                 tc_commit(&a_empty[s]);
                 tc_commit(&t_full[s]);
@@ -328,20 +347,28 @@ int fir_ptc_ksteps(uint32_t ntaps, uint32_t L)
 
 bool fir_ptc_supported(uint32_t ntaps, uint32_t L, bool taps_real)
 {
-    if (!taps_real || ntaps == 0 || (L != 8 && L != 4)) return false;
+    if (ntaps == 0 || (L != 8 && L != 4)) return false;
     const int ks = fir_ptc_ksteps(ntaps, L);
-    return ks >= 1 && ks <= 12;
+    if (ks < 1 || ks > 12) return false;
+    // shared memory: two stream stages + the tap image (+ alignment slack) must fit in 227 KiB
+    const size_t comp = (size_t)128 * 2 * ptc_rs(L);
+    const size_t stage = 2 * ((taps_real ? 2 : 3) * comp + 1024);
+    return 2 * stage + fir_ptc_image_bytes(ntaps, L, taps_real) + 1024 <= 227 * 1024;
 }
 
-size_t fir_ptc_image_bytes(uint32_t ntaps, uint32_t L) { return (size_t)fir_ptc_ksteps(ntaps, L) * 8192; }
+size_t fir_ptc_image_bytes(uint32_t ntaps, uint32_t L, bool taps_real)
+{
+    return (size_t)fir_ptc_ksteps(ntaps, L) * (taps_real ? 8192 : 16384);
+}
 
-// Tap image: part (0 = hi, 1 = lo) x K step x [128 rows x 32 bytes], 32-byte swizzled, fp16.
-void fir_ptc_build_image(const float2 *taps, uint32_t ntaps, uint32_t L, unsigned char *img, float *tap_inv_scale)
+// Tap image: part (Hr hi, Hr lo[, -Hi hi, -Hi lo]) x K step x [128 rows x 32 bytes], 32-byte swizzled, fp16.
+void fir_ptc_build_image(const float2 *taps, uint32_t ntaps, uint32_t L, bool taps_real, unsigned char *img,
+                         float *tap_inv_scale)
 {
     const int KS = fir_ptc_ksteps(ntaps, L);
     const int RS = ptc_rs(L), KT = 16 * KS, HALO = KT - RS;
     float mx = 0.f;
-    for (uint32_t k = 0; k < ntaps; ++k) mx = fmaxf(mx, fabsf(taps[k].x));
+    for (uint32_t k = 0; k < ntaps; ++k) mx = fmaxf(mx, fmaxf(fabsf(taps[k].x), fabsf(taps[k].y)));
     uint32_t bits;
     memcpy(&bits, &mx, 4);
     uint32_t eb = (bits >> 23) & 0xFF;
@@ -350,30 +377,32 @@ void fir_ptc_build_image(const float2 *taps, uint32_t ntaps, uint32_t L, unsigne
     float sc;
     memcpy(&sc, &sb, 4);
     memcpy(tap_inv_scale, &ib, 4);
-    memset(img, 0, (size_t)KS * 8192);
-    for (int m = 0; m < 128; ++m) {
-        const int i = m / (int)L, p = m % (int)L;
-        for (int k = 0; k < KT; ++k) {
-            const long long t = (long long)L * (i + HALO - k) + p;
-            float v = 0.f;
-            if (i + HALO - k >= 0 && t < (long long)ntaps) v = taps[t].x;
-            v *= sc;
-            const __half h = __float2half_rn(v);
-            const __half l = __float2half_rn(v - __half2float(h));
-            const int ks = k >> 4, kk = k & 15;
-            const uint32_t o = ptc::swz<32>((uint32_t)m * 32u + (uint32_t)kk * 2u);
-            memcpy(img + (size_t)ks * 4096 + o, &h, 2);
-            memcpy(img + (size_t)KS * 4096 + (size_t)ks * 4096 + o, &l, 2);
+    memset(img, 0, fir_ptc_image_bytes(ntaps, L, taps_real));
+    for (int c = 0; c < (taps_real ? 1 : 2); ++c) {
+        for (int m = 0; m < 128; ++m) {
+            const int i = m / (int)L, p = m % (int)L;
+            for (int k = 0; k < KT; ++k) {
+                const long long t = (long long)L * (i + HALO - k) + p;
+                float v = 0.f;
+                if (i + HALO - k >= 0 && t < (long long)ntaps) v = c == 0 ? taps[t].x : -taps[t].y;
+                v *= sc;
+                const __half h = __float2half_rn(v);
+                const __half l = __float2half_rn(v - __half2float(h));
+                const int ks = k >> 4, kk = k & 15;
+                const uint32_t o = ptc::swz<32>((uint32_t)m * 32u + (uint32_t)kk * 2u);
+                memcpy(img + (size_t)(2 * c * KS + ks) * 4096 + o, &h, 2);
+                memcpy(img + (size_t)((2 * c + 1) * KS + ks) * 4096 + o, &l, 2);
+            }
         }
     }
 }
 
-template <int L>
+template <int L, bool CPLX>
 static int launch_ptc_l(const ptc::Args &a, cudaStream_t stream)
 {
-    using G = ptc::Geo<L>;
-    const int SMEM = 2 * G::STAGE + (int)a.ks * 8192 + 1024;
-    auto kern = ptc::fir_ptc_kernel<L>;
+    using G = ptc::Geo<L, CPLX>;
+    const int SMEM = 2 * G::STAGE + (int)a.ks * (CPLX ? 16384 : 8192) + 1024;
+    auto kern = ptc::fir_ptc_kernel<L, CPLX>;
     CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const int KT = 16 * (int)a.ks;
     const unsigned long long TS = (unsigned long long)(((G::NEL - KT) / G::RS + 1) * G::RS);
@@ -398,7 +427,7 @@ bool fir_ptc_applicable(const FirSeg &seg, bool taps_real)
            (reinterpret_cast<uintptr_t>(seg.y) & 7) == 0;
 }
 
-int launch_fir_ptc(const FirSeg &seg, const void *himg_dev, float tap_inv_scale, cudaStream_t stream)
+int launch_fir_ptc(const FirSeg &seg, const void *himg_dev, float tap_inv_scale, bool taps_real, cudaStream_t stream)
 {
     if (seg.n_in == 0) return CB_OK;
     ptc::Args a;
@@ -413,8 +442,8 @@ int launch_fir_ptc(const FirSeg &seg, const void *himg_dev, float tap_inv_scale,
     a.hist_len = seg.hist_len;
     a.tap_inv_scale = tap_inv_scale;
     switch (seg.interp) {
-    case 8: return launch_ptc_l<8>(a, stream);
-    case 4: return launch_ptc_l<4>(a, stream);
+    case 8: return taps_real ? launch_ptc_l<8, false>(a, stream) : launch_ptc_l<8, true>(a, stream);
+    case 4: return taps_real ? launch_ptc_l<4, false>(a, stream) : launch_ptc_l<4, true>(a, stream);
     default: set_error("fir_ptc: unsupported interpolation factor %u", seg.interp); return CB_ERR_UNSUPPORTED;
     }
 }

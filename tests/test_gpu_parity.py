@@ -172,13 +172,14 @@ def test_polyphase_interp_matches_upsample_then_fir(cb, oracle, L, ntaps, cplx):
     assert node.state.tobytes() == st.tobytes()
 
 
+@pytest.mark.parametrize("cplx", [False, True])
 @pytest.mark.parametrize("L,ntaps", [(8, 1024), (8, 64), (8, 1000), (8, 1), (8, 1100), (4, 32), (4, 30), (4, 400), (4, 3)])
-def test_polyphase_tensor_core_path(cb, oracle, L, ntaps, monkeypatch):
+def test_polyphase_tensor_core_path(cb, oracle, L, ntaps, cplx, monkeypatch):
     # K3-TC (fir_ptc_kernel.cu): the tcgen05 Toeplitz-GEMM polyphase bank, forced for every batch size,
     # against upsample -> batch_fir of the oracle (src/util/resample_node.rs:120-131 + src/filter/fir.rs:87-102)
     monkeypatch.setenv("COMMS_B200_FIR_PATH", "tc")
     rng = np.random.default_rng(L * 7000 + ntaps)
-    t = rng.uniform(-1, 1, ntaps).astype(np.complex64)
+    t = rnd_c32(rng, ntaps) if cplx else rng.uniform(-1, 1, ntaps).astype(np.complex64)
     sizes = (1, 4095, 10_000, 5915, 2, 30_001)
     sym = rnd_c32(rng, sum(sizes))
     # per-tile block scaling: a quiet stretch and a loud stretch must both keep 1e-5
