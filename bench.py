@@ -49,6 +49,8 @@ WORKLOADS = {
     "chain5": ("chain", 1024 * 131072, 8.8, "fm_radio as shipped x1024 channels per GPU: 63-tap FIR -> /5 -> FM demod (no mixer), "
                "131072-sample batches"),
     "pulse4": ("interp", 1 << 26, 40.0, "BPSK pulse shaping: x4 polyphase 32-tap RRC over 2^26 symbols per GPU (unit = symbols)"),
+    "pulse4_i16": ("interp", 1 << 26, 24.0, "BPSK pulse shaping with the example's i16 quantiser fused: x4 polyphase 32-tap RRC -> (8192 x) as i16 "
+                   "IQ over 2^26 symbols per GPU (unit = symbols)"),
     "poly8x1024c": ("interp", 1 << 26, 72.0, "x8 polyphase with a fully complex 1024-tap bank (tcgen05, 54 MMAs per tile) over 2^26 symbols "
                     "per GPU (unit = symbols)"),
     "poly8x1024": ("interp", 1 << 27, 72.0, "QPSK x8 polyphase, 1024-tap RRC bank (tcgen05 Toeplitz GEMM) over 2^27 symbols per GPU "
@@ -175,7 +177,7 @@ def cpu_rate(workload, samples, threads):
                 ch = oracle.FmChain(-0.7, 0.0, fm_radio_lowpass(), 10, native=True)
             jobs.append(lambda x=x, ch=ch: [ch.run(x[j:j + 131072]) for j in range(0, len(x), 131072)])
         else:
-            L, nt = (4, 32) if workload == "pulse4" else (8, 1024)
+            L, nt = (4, 32) if workload.startswith("pulse4") else (8, 1024)
             t = rrc_taps(nt, float(L), 0.25)
             st = np.zeros(nt, np.complex64)
             jobs.append(lambda x=x, t=t, st=st: oracle.batch_fir(oracle.upsample(x, L), t, st, literal=True, native=True))
@@ -268,15 +270,21 @@ class Job:
             self.step = lambda: self.node.run_dev(self.x.data_ptr(), nb, self.y.data_ptr(), no, self.stream)
             self.host_call = lambda hin, hout: cb.load().cb_chain_run(self.node._h, hin, nb, hout, no, None)
         else:
-            L, nt = (4, 32) if workload == "pulse4" else (8, 1024)
+            L, nt = (4, 32) if workload.startswith("pulse4") else (8, 1024)
             self.taps = rrc_taps(nt, float(L), 0.25)
             if workload == "poly8x1024c":
                 self.taps = (self.taps * np.exp(0.01j * np.arange(nt))).astype(np.complex64)
             self.node = cb.BatchFirNode(self.taps, None, interp=L)
-            self.y = torch.empty(n * L, dtype=torch.complex64, device="cuda")
-            self.out_bytes = 8 * n * L
-            self.step = lambda: self.node.run_dev(self.x.data_ptr(), n, self.y.data_ptr(), n * L, self.stream)
-            self.host_call = lambda hin, hout: cb.load().cb_fir_run(self.node._h, hin, n, hout, n * L, None)
+            if workload == "pulse4_i16":
+                self.y = torch.empty(2 * n * L, dtype=torch.int16, device="cuda")
+                self.out_bytes = 4 * n * L
+                self.step = lambda: self.node.run_dev_i16(self.x.data_ptr(), n, 8192.0, self.y.data_ptr(), n * L, self.stream)
+                self.host_call = lambda hin, hout: cb.load().cb_fir_run_i16(self.node._h, hin, n, 8192.0, hout, n * L, None)
+            else:
+                self.y = torch.empty(n * L, dtype=torch.complex64, device="cuda")
+                self.out_bytes = 8 * n * L
+                self.step = lambda: self.node.run_dev(self.x.data_ptr(), n, self.y.data_ptr(), n * L, self.stream)
+                self.host_call = lambda hin, hout: cb.load().cb_fir_run(self.node._h, hin, n, hout, n * L, None)
         self.in_bytes = 8 * n
 
     def _halo(self, k):

@@ -144,6 +144,8 @@ struct cb_fir {
     int cur;
     void *tc_img;       // tensor-core path: prepacked tap image (device), or NULL
     FirTcPlan tc;
+    float2 *qscratch;   // f32 result of the unfused cb_fir_run_dev_i16 path, grown on demand
+    size_t qscratch_len;
 };
 
 struct cb_mixer {
@@ -429,6 +431,8 @@ int cb_fir_create(const float *taps, size_t ntaps, const float *state, size_t ns
     h->stream = nullptr;
     h->tc_img = nullptr;
     h->tc = FirTcPlan{nullptr, 1.f, 0};
+    h->qscratch = nullptr;
+    h->qscratch_len = 0;
 
     std::vector<float2> hist;
     rc = fir_state_to_hist(h, reinterpret_cast<const float2 *>(state), state ? nstate : 0, hist);
@@ -494,6 +498,7 @@ int cb_fir_destroy(cb_fir *h)
     h->pipe.destroy();
     if (h->taps_dev) cudaFree(h->taps_dev);
     if (h->tc_img) cudaFree(h->tc_img);
+    if (h->qscratch) cudaFree(h->qscratch);
     for (int i = 0; i < 2; ++i)
         if (h->hist[i]) cudaFree(h->hist[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -532,6 +537,64 @@ int cb_fir_run_dev(cb_fir *h, const float *d_in, size_t n_in, float *d_out, size
                                 reinterpret_cast<float2 *>(d_out), pick_stream(stream, h->stream));
     if (rc) return rc;
     h->cur ^= 1;
+    return CB_OK;
+}
+
+int cb_fir_run_dev_i16(cb_fir *h, const float *d_in, size_t n_in, float scale, int16_t *d_out, size_t out_cap,
+                       size_t *n_out, void *stream)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    const size_t no = fir_out_len(h, n_in);
+    if (n_out) *n_out = no;
+    if (n_in == 0) return CB_OK;
+    CB_REQUIRE(d_in && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_REQUIRE(out_cap >= no, CB_ERR_SIZE, "fir: out_cap %zu < %zu outputs", out_cap, no);
+    CB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = pick_stream(stream, h->stream);
+    FirSeg seg{reinterpret_cast<const float2 *>(d_in), h->hist[h->cur], h->hist[h->cur ^ 1], nullptr, n_in, no,
+               h->hist_len, h->k_eff, h->interp, h->decim};
+    seg.y16 = d_out;
+    seg.qscale = scale;
+    seg.y = reinterpret_cast<float2 *>(d_out);  // unused by the fused kernel (alignment checks only)
+    int rc;
+    if (fir_fuses_i16(seg, h->taps_real, h->tc_img ? &h->tc : nullptr)) {
+        rc = launch_fir(seg, h->taps_dev, h->taps.data(), h->taps_real, &h->tc, s);
+    } else {  // filter into an f32 scratch, then the stand-alone quantiser
+        if (h->qscratch_len < no) {
+            if (h->qscratch) CB_CUDA(cudaFree(h->qscratch));
+            h->qscratch = nullptr;
+            h->qscratch_len = 0;
+            CB_CUDA(cudaMalloc(&h->qscratch, no * sizeof(float2)));
+            h->qscratch_len = no;
+        }
+        seg.y16 = nullptr;
+        seg.y = h->qscratch;
+        rc = launch_fir(seg, h->taps_dev, h->taps.data(), h->taps_real, h->tc_img ? &h->tc : nullptr, s);
+        if (rc == CB_OK) rc = launch_quantize_i16(reinterpret_cast<const float *>(h->qscratch), d_out, 2 * no, scale, s);
+    }
+    if (rc) return rc;
+    h->cur ^= 1;
+    return CB_OK;
+}
+
+int cb_fir_run_i16(cb_fir *h, const float *in, size_t n_in, float scale, int16_t *out, size_t out_cap, size_t *n_out)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    const size_t no = fir_out_len(h, n_in);
+    if (n_out) *n_out = no;
+    if (n_in == 0) return CB_OK;
+    CB_REQUIRE(in && out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_REQUIRE(out_cap >= no, CB_ERR_SIZE, "fir: out_cap %zu < %zu outputs", out_cap, no);
+    CB_CUDA(cudaSetDevice(h->device));
+    int rc = h->pipe.reserve(n_in * sizeof(float2), no * 2 * sizeof(int16_t));
+    if (rc) return rc;
+    cudaStream_t s = h->pipe.lane[0];
+    CB_CUDA(cudaMemcpyAsync(h->pipe.in[0], in, n_in * sizeof(float2), cudaMemcpyHostToDevice, s));
+    rc = cb_fir_run_dev_i16(h, reinterpret_cast<const float *>(h->pipe.in[0]), n_in, scale,
+                            reinterpret_cast<int16_t *>(h->pipe.out[0]), no, nullptr, s);
+    if (rc) return rc;
+    CB_CUDA(cudaMemcpyAsync(out, h->pipe.out[0], no * 2 * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaStreamSynchronize(s));
     return CB_OK;
 }
 

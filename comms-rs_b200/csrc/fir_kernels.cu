@@ -393,6 +393,12 @@ static int launch_generic(const FirSeg &seg, const float2 *taps_dev, cudaStream_
     return CB_OK;
 }
 
+bool fir_fuses_i16(const FirSeg &seg, bool taps_real, const FirTcPlan *tcplan)
+{
+    return tcplan != nullptr && tcplan->bimg_dev != nullptr && seg.n_in >= tcplan->min_samples && seg.interp > 1 &&
+           fir_ptc_applicable(seg, taps_real);
+}
+
 int launch_fir(const FirSeg &seg, const float2 *taps_dev, const float2 *taps_host, bool taps_real,
                const FirTcPlan *tcplan, cudaStream_t stream)
 {

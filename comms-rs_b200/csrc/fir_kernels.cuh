@@ -22,6 +22,8 @@ struct FirSeg {
     uint32_t ntaps;         // effective taps (min(len taps, len state)), > 0
     uint32_t interp;        // L >= 1
     uint32_t decim;         // D >= 1
+    int16_t *y16 = nullptr; // fused quantiser: write (qscale * y) as interleaved i16 IQ here instead of y
+    float qscale = 1.f;     //   (only the polyphase tensor-core kernel fuses it; see launch_fir_i16)
 };
 
 // Tensor-core path (fir_tc_kernel.cu): prepacked fp16 hi/lo Toeplitz tap image + its scale.
@@ -51,5 +53,8 @@ int launch_fir_ptc(const FirSeg &seg, const void *himg_dev, float tap_inv_scale,
 // tcplan: NULL = CUDA-core kernels only
 int launch_fir(const FirSeg &seg, const float2 *taps_dev, const float2 *taps_host, bool taps_real,
                const FirTcPlan *tcplan, cudaStream_t stream);
+// true when launch_fir would take a kernel that writes seg.y16 itself (otherwise the caller filters into
+// an f32 scratch and runs the stand-alone quantiser)
+bool fir_fuses_i16(const FirSeg &seg, bool taps_real, const FirTcPlan *tcplan);
 
 }  // namespace cb

@@ -31,11 +31,12 @@
 // [2^14, 2^15) and split into fp16 hi + lo; three products (hi*hi, lo*hi, hi*lo) accumulate in the
 // same fp32 TMEM accumulator.  Relative L2 error vs the sequential f32 form ~3e-7 (tolerance 1e-5).
 //
-// Roles (288 threads, one persistent CTA per SM, tiles round-robin):
-//   warps 4-7  loader: coalesced LDG.128 of the raw f32 tile -> block max -> scale, split,
+// Roles (E epilogue warps first, E = 4, or 8 with the fused i16 quantiser; one persistent CTA per SM):
+//   warps E..E+3 loader: coalesced LDG.128 of the raw f32 tile -> block max -> scale, split,
 //              de-interleave, st.shared (pre-swizzled) -> fence.proxy.async -> mbarrier a_full
-//   warp  8    one thread issues 3 KS tcgen05.mma (M128 N256 K16) per tile, commits a_empty/t_full
-//   warps 0-3  epilogue: tcgen05.ld 32 lanes x 32 columns (re) + (im) -> unscale -> st.global.v2
+//   warp  E+4  one thread issues 3 KS tcgen05.mma (M128 N256 K16) per tile, commits a_empty/t_full
+//   warps 0..E-1 epilogue (E/4 per TMEM sub-partition, alternating 32-column chunks): tcgen05.ld 32 lanes
+//              x 32 columns (re) + (im) -> unscale [-> i16] -> st.global
 // Two stream stages and two TMEM accumulator stages (2 x 256 columns) overlap the roles.
 // Algorithmic HBM traffic: 8 B read + 8 L B written per symbol.
 #include <cuda_fp16.h>
@@ -48,8 +49,11 @@ namespace cb {
 
 namespace ptc {
 
-constexpr int NTHREADS = 288;
-constexpr int NLOAD = 128;  // loader threads
+// epilogue warps: warp w drains TMEM sub-partition w % 4, 32-column chunks w / 4, w / 4 + NEPI / 4, ...
+// 4 are enough for f32 output; the fused i16 quantiser doubles the per-column work and gets 8
+__host__ __device__ constexpr int nepi(bool out16) { return out16 ? 8 : 4; }
+__host__ __device__ constexpr int nthreads(bool out16) { return 32 * (nepi(out16) + 4 + 1); }  // + 4 loader warps + 1 MMA warp
+constexpr int NLOAD = 128;                    // loader threads
 
 struct Args {
     const float2 *x;
@@ -62,6 +66,8 @@ struct Args {
     unsigned hist_len;
     unsigned ks;            // K steps of 16
     float tap_inv_scale;
+    int2 *y16;              // OUT16: interleaved i16 IQ output (src/io/raw_iq.rs layout) instead of y
+    float qscale;           // OUT16: (qscale * v) as i16, truncating, saturating
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
@@ -133,9 +139,25 @@ struct Geo {
     static constexpr int NLD = NEL / 2 / NLOAD;        // float4 loads per loader thread per tile
 };
 
-template <int L, bool CPLX>
-__global__ void __launch_bounds__(NTHREADS, 1) fir_ptc_kernel(const __grid_constant__ Args a)
+// Rust `as i16` of a float: truncate toward zero, saturate, NaN -> 0 (examples/single_thread_bpsk.rs:40-48)
+// Rust `v as i16` (truncate toward zero, saturate, NaN -> 0) without F2I, which is a slow-pipe instruction
+// and was measured to make the 4 epilogue warps the bottleneck: clamp, add 2^23 to |v| rounding toward zero
+// (the mantissa then holds floor(|v|) <= 32768), restore the sign in two's complement.  Full-rate ALU / FMA ops only.
+__device__ __forceinline__ uint32_t trunc_i16(float v)
 {
+    v = v == v ? v : 0.f;
+    v = fminf(fmaxf(v, -32768.f), 32767.f);
+    const uint32_t m = __float_as_uint(__fadd_rz(fabsf(v), 8388608.f));  // 0x4B000000 + floor(|v|)
+    const uint32_t s = (uint32_t)((int)__float_as_uint(v) >> 31);         // 0 or 0xFFFFFFFF
+    return (((m & 0xFFFFu) ^ s) - s) & 0xFFFFu;
+}
+
+// OUT16: the example's quantiser `(8192 x) as i16` fused into the epilogue: 4 bytes written per output
+// sample instead of 8 (and no separate pass over the f32 result)
+template <int L, bool CPLX, bool OUT16>
+__global__ void __launch_bounds__(OUT16 ? 512 : 288, 1) fir_ptc_kernel(const __grid_constant__ Args a)  // 512: 128-register cap (13 warps)
+{
+    constexpr int NEPI = nepi(OUT16), NTHREADS = nthreads(OUT16);
     using G = Geo<L, CPLX>;
     constexpr int RS = G::RS, ROWB = G::ROWB, NLD = G::NLD;
     constexpr uint32_t IDESC = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, M128 N256
@@ -163,12 +185,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_ptc_kernel(const __grid_const
             mbar_init(&a_full[i], NLOAD);
             mbar_init(&a_empty[i], 1);
             mbar_init(&t_full[i], 1);
-            mbar_init(&t_empty[i], 128);
+            mbar_init(&t_empty[i], 32 * NEPI);
         }
         for (int i = 0; i < 8; ++i) mbar_init(&sc_ready[i], 1);
         fence_mbar_init();
     }
-    if (warp == 8) {
+    if (warp == NEPI + 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
                      "r"(512)
                      : "memory");
@@ -186,9 +208,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_ptc_kernel(const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
-    if (warp >= 4 && warp < 8) {
+    if (warp >= NEPI && warp < NEPI + 4) {
         // ------------------------------------------------------------------ loader
-        const int gt = tid - 128, gw = warp - 4;
+        const int gt = tid - 32 * NEPI, gw = warp - NEPI;
         if (a.hist_out != nullptr && blockIdx.x == 0) {
             const long long H = a.hist_len;
             for (long long i = gt; i < H; i += NLOAD) {
@@ -255,7 +277,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_ptc_kernel(const __grid_const
             fence_proxy_async();
             mbar_arrive(&a_full[s]);
         }
-    } else if (warp == 8) {
+    } else if (warp == NEPI + 4) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             unsigned long long it = 0;
@@ -292,8 +314,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_ptc_kernel(const __grid_const
         }
         __syncwarp();
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 0-3)
-        const int e = warp;  // TMEM sub-partition = warp % 4; lane m = 32 e + lane
+        // ------------------------------------------------------------------ epilogue (warps 0 .. NEPI-1)
+        const int e = warp & 3;  // TMEM sub-partition = warp % 4; lane m = 32 e + lane
         const int m = 32 * e + lane;
         const int msym = m / L;
         unsigned long long it = 0;
@@ -302,14 +324,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_ptc_kernel(const __grid_const
             const uint32_t ph = (uint32_t)((it >> 1) & 1);
             const long long t0 = (long long)tile * TS;
             mbar_wait(&sc_ready[it & 7], (uint32_t)((it >> 3) & 1));
-            const float k = inv_scale[it & 7] * a.tap_inv_scale;
+            const float k = inv_scale[it & 7] * a.tap_inv_scale;  // a power of two
+            // OUT16: (qscale * (acc * k)) as i16.  When qscale is a power of two as well (8192 in the examples)
+            // the two roundings collapse into one exact product; otherwise both multiplies are kept so that the
+            // result equals quantising the f32 output.
+            const bool q_pow2 = OUT16 && (__float_as_uint(a.qscale) & 0x007FFFFFu) == 0u && a.qscale > 0.f;
+            const float kq = q_pow2 ? k * a.qscale : k;
             mbar_wait(&t_full[s], ph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * e) << 16) + (uint32_t)s * 256u;
             float2 *yrow = a.y + (long long)L * t0 + m;   // + 128 n per column
+            uint32_t *qrow = reinterpret_cast<uint32_t *>(a.y16) + (long long)L * t0 + m;
             const long long srem = (long long)a.n - t0 - msym;  // column n is live iff RS n < srem
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = warp >> 2; c < 4; c += NEPI / 4) {
                 if (32 * c >= VR) break;
                 uint32_t p[32], r[32];
                 tc_ld32(taddr + 32 * c, p);
@@ -318,8 +346,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_ptc_kernel(const __grid_const
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int n = 32 * c + j;
-                    if (n < VR && (long long)RS * n < srem)
-                        stg_stream2(yrow + 128 * n, make_float2(__uint_as_float(p[j]) * k, __uint_as_float(r[j]) * k));
+                    // values are formed unconditionally (branch-free body: the 32 columns interleave in the
+                    // schedule); only the store is predicated
+                    const bool live = n < VR && (long long)RS * n < srem;
+                    if (OUT16) {
+                        float vx = __uint_as_float(p[j]) * kq, vy = __uint_as_float(r[j]) * kq;
+                        if (!q_pow2) {
+                            vx = __fmul_rn(a.qscale, vx);
+                            vy = __fmul_rn(a.qscale, vy);
+                        }
+                        const uint32_t q = trunc_i16(vx) | (trunc_i16(vy) << 16);
+                        if (live) qrow[128 * n] = q;
+                    } else {
+                        const float2 v = make_float2(__uint_as_float(p[j]) * k, __uint_as_float(r[j]) * k);
+                        if (live) stg_stream2(yrow + 128 * n, v);
+                    }
                 }
             }
             tc_fence_before();
@@ -329,7 +370,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_ptc_kernel(const __grid_const
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == NEPI + 4) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
@@ -397,12 +438,12 @@ void fir_ptc_build_image(const float2 *taps, uint32_t ntaps, uint32_t L, bool ta
     }
 }
 
-template <int L, bool CPLX>
+template <int L, bool CPLX, bool OUT16>
 static int launch_ptc_l(const ptc::Args &a, cudaStream_t stream)
 {
     using G = ptc::Geo<L, CPLX>;
     const int SMEM = 2 * G::STAGE + (int)a.ks * (CPLX ? 16384 : 8192) + 1024;
-    auto kern = ptc::fir_ptc_kernel<L, CPLX>;
+    auto kern = ptc::fir_ptc_kernel<L, CPLX, OUT16>;
     CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const int KT = 16 * (int)a.ks;
     const unsigned long long TS = (unsigned long long)(((G::NEL - KT) / G::RS + 1) * G::RS);
@@ -411,7 +452,7 @@ static int launch_ptc_l(const ptc::Args &a, cudaStream_t stream)
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned grid = (unsigned)(ntiles < (unsigned long long)sms ? ntiles : (unsigned long long)sms);
-    kern<<<grid, ptc::NTHREADS, SMEM, stream>>>(a);
+    kern<<<grid, ptc::nthreads(OUT16), SMEM, stream>>>(a);
     count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;
@@ -424,7 +465,7 @@ bool fir_ptc_applicable(const FirSeg &seg, bool taps_real)
     if (seg.hist_len < halo) return false;
     const float2 *h = seg.hist_in + (seg.hist_len - halo);
     return ((reinterpret_cast<uintptr_t>(seg.x) | reinterpret_cast<uintptr_t>(h)) & 15) == 0 &&
-           (reinterpret_cast<uintptr_t>(seg.y) & 7) == 0;
+           (reinterpret_cast<uintptr_t>(seg.y) & 7) == 0 && (reinterpret_cast<uintptr_t>(seg.y16) & 3) == 0;
 }
 
 int launch_fir_ptc(const FirSeg &seg, const void *himg_dev, float tap_inv_scale, bool taps_real, cudaStream_t stream)
@@ -441,9 +482,18 @@ int launch_fir_ptc(const FirSeg &seg, const void *himg_dev, float tap_inv_scale,
     a.n = seg.n_in;
     a.hist_len = seg.hist_len;
     a.tap_inv_scale = tap_inv_scale;
+    a.y16 = reinterpret_cast<int2 *>(seg.y16);
+    a.qscale = seg.qscale;
+    if (seg.y16 != nullptr) {
+        switch (seg.interp) {
+        case 8: return taps_real ? launch_ptc_l<8, false, true>(a, stream) : launch_ptc_l<8, true, true>(a, stream);
+        case 4: return taps_real ? launch_ptc_l<4, false, true>(a, stream) : launch_ptc_l<4, true, true>(a, stream);
+        default: break;
+        }
+    }
     switch (seg.interp) {
-    case 8: return taps_real ? launch_ptc_l<8, false>(a, stream) : launch_ptc_l<8, true>(a, stream);
-    case 4: return taps_real ? launch_ptc_l<4, false>(a, stream) : launch_ptc_l<4, true>(a, stream);
+    case 8: return taps_real ? launch_ptc_l<8, false, false>(a, stream) : launch_ptc_l<8, true, false>(a, stream);
+    case 4: return taps_real ? launch_ptc_l<4, false, false>(a, stream) : launch_ptc_l<4, true, false>(a, stream);
     default: set_error("fir_ptc: unsupported interpolation factor %u", seg.interp); return CB_ERR_UNSUPPORTED;
     }
 }

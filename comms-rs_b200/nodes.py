@@ -82,6 +82,25 @@ class BatchFirNode(_Handle):
         check(_lib.load().cb_fir_run_dev(self._h, d_in, n_in, d_out, out_cap, C.byref(m), stream))
         return m.value
 
+    def run_i16(self, x, scale: float = 8192.0) -> np.ndarray:
+        """Host Vec in, interleaved i16 IQ out ([n_out, 2] int16): filter + `(scale * x) as i16`."""
+        x = _c32(x)
+        n = _sz()
+        check(_lib.load().cb_fir_out_len(self._h, len(x), C.byref(n)))
+        out = np.empty((n.value, 2), dtype=np.int16)
+        m = _sz()
+        try:
+            check(_lib.load().cb_fir_run_i16(self._h, _ptr(x), len(x), float(scale), _ptr(out), n.value, C.byref(m)))
+        except CbError as e:
+            raise node_error(e) from e
+        return out[: m.value]
+
+    def run_dev_i16(self, d_in: int, n_in: int, scale: float, d_out: int, out_cap: int, stream: int = 0) -> int:
+        """Filter + `(scale * x) as i16` (examples/single_thread_bpsk.rs:40-48); d_out: 2*out_cap int16."""
+        m = _sz()
+        check(_lib.load().cb_fir_run_dev_i16(self._h, d_in, n_in, float(scale), d_out, out_cap, C.byref(m), stream))
+        return m.value
+
     @property
     def state(self) -> np.ndarray:
         n = _sz()

@@ -131,6 +131,17 @@ CB_API int cb_fir_run_dev(cb_fir *h, const float *d_in, size_t n_in, float *d_ou
                           size_t *n_out, void *stream);
 /* state as the reference would hold it after the samples seen so far
  * (newest first, nstate entries, in the zero-stuffed domain when interp > 1) */
+/* Same filter step with the example's output quantiser fused behind it
+ * (examples/single_thread_bpsk.rs:40-48: `(8192.0 * x) as i16`, written as the
+ * interleaved native-endian i16 IQ stream of src/io/raw_iq.rs:185-223):
+ * d_out receives 2*n_out int16 (re, im).  Polyphase interpolators on the
+ * tensor-core path quantise in their epilogue (4 instead of 8 bytes written
+ * per sample); every other shape filters into an internal f32 scratch and
+ * runs the stand-alone quantiser.  Results are identical either way. */
+CB_API int cb_fir_run_dev_i16(cb_fir *h, const float *d_in, size_t n_in, float scale, int16_t *d_out,
+                              size_t out_cap, size_t *n_out, void *stream);
+CB_API int cb_fir_run_i16(cb_fir *h, const float *in, size_t n_in, float scale, int16_t *out, size_t out_cap,
+                          size_t *n_out);
 CB_API int cb_fir_state_len(const cb_fir *h, size_t *nstate);
 CB_API int cb_fir_get_state(cb_fir *h, float *state, size_t nstate);
 CB_API int cb_fir_set_state(cb_fir *h, const float *state, size_t nstate);
@@ -216,6 +227,11 @@ CB_API int cb_chain_run_dev(cb_chain *h, const float *d_in, size_t n_in, float *
  * T::from(f64)) or 2*n_taps doubles (cb_rrc_taps_f64).  Needs no device. */
 CB_API int cb_rrc_taps(uint32_t n_taps, double sam_per_sym, double beta, float *taps);
 CB_API int cb_rrc_taps_f64(uint32_t n_taps, double sam_per_sym, double beta, double *taps);
+
+/* Stream argument of the *_dev entry points: a cudaStream_t, or NULL.  For entries that take a handle
+ * NULL means the handle's own non-blocking stream; for the stateless entries below NULL is the legacy
+ * default stream, which does NOT order against the handles' streams.  Pass one explicit stream when
+ * chaining both kinds (as every device-resident example graph does). */
 
 /* ------------------------------------------------------------------ bit-exact edges
  * Integer / index stages of the example graphs, device side, so whole example

@@ -205,6 +205,34 @@ def test_polyphase_tensor_core_path(cb, oracle, L, ntaps, cplx, monkeypatch):
     assert rel_l2(got, ref) <= 2e-6
 
 
+@pytest.mark.parametrize("path", ["tc", "cuda"])
+@pytest.mark.parametrize("L,ntaps,cplx", [(4, 32, False), (8, 1024, False), (8, 64, True), (1, 64, True), (3, 17, False)])
+def test_fir_with_fused_i16_quantiser(cb, oracle, L, ntaps, cplx, path, monkeypatch):
+    # filter -> `(8192.0 * x) as i16` -> interleaved i16 IQ (examples/single_thread_bpsk.rs:40-48, src/io/raw_iq.rs:185-223)
+    # "tc": polyphase banks quantise inside the tcgen05 kernel's epilogue; "cuda": f32 scratch + quantiser kernel.
+    monkeypatch.setenv("COMMS_B200_FIR_PATH", path)
+    rng = np.random.default_rng(L * 31 + ntaps)
+    t = rnd_c32(rng, ntaps) if cplx else rng.uniform(-1, 1, ntaps).astype(np.complex64)
+    t = (t / np.float32(np.abs(t).sum() / 3)).astype(np.complex64)  # some outputs saturate at +-4
+    x = rnd_c32(rng, 20_003)
+    a, b = cb.BatchFirNode(t, None, interp=L), cb.BatchFirNode(t, None, interp=L)
+    f32 = np.concatenate([b.run(x[:7]), b.run(x[7:])])
+    peak = float(np.abs(f32.view(np.float32)).max())
+    # large enough that some outputs saturate; a power of two (one fused multiply) or not (two roundings kept)
+    scale = float(2.0 ** np.ceil(np.log2(50000.0 / peak))) if L != 8 else float(np.float32(50000.0 / peak))
+    got = np.concatenate([a.run_i16(x[:7], scale), a.run_i16(x[7:], scale)])
+    # identical to quantising the product's own f32 result (bit-exact integer stage) ...
+    want_same = oracle.quantize_i16(f32, scale).reshape(-1, 2)
+    assert got.shape == want_same.shape == (len(x) * L, 2)
+    assert np.array_equal(got, want_same)
+    # ... and within one LSB of the quantised oracle filter output (the f32 results differ by ~1e-7 relative)
+    w, _ = oracle.batch_fir(oracle.upsample(x, L), t, np.zeros(ntaps, np.complex64))
+    d = np.abs(got.astype(np.int32) - oracle.quantize_i16(w, scale).reshape(-1, 2).astype(np.int32))
+    assert d.max() <= 1 and (d != 0).mean() < 2e-2
+    assert (np.abs(got) == 32767).any() or (got == -32768).any()
+    assert a.state.tobytes() == b.state.tobytes()
+
+
 @pytest.mark.parametrize("D,ntaps,cplx", [(5, 63, False), (10, 63, False), (2, 64, True), (7, 33, True), (1000, 16, False)])
 def test_decimating_fir_phase_resets_per_batch(cb, oracle, D, ntaps, cplx):
     # BatchFirNode -> DecimateNode: indices 0, D, 2D.. of EACH batch (resample_node.rs:53-65)
@@ -390,8 +418,12 @@ def test_bpsk_chain_config1(cb, oracle):
     taps = oracle.rrc_taps(32, 4.0, 0.25)
     fir = cb.BatchFirNode(taps, None, interp=sps)
     dev = torch.device("cuda:0")
-    s = torch.cuda.current_stream().cuda_stream
+    # one explicit stream for the whole chain: stream 0 would mean "the handle's own stream" to the FIR node
+    # but the legacy default stream to the stateless stages, and the two do not order against each other
+    ts = torch.cuda.Stream()
+    s = ts.cuda_stream
     d_bits = torch.from_numpy(bits).to(dev)
+    torch.cuda.synchronize()
     d_sym = torch.empty(nsym, dtype=torch.complex64, device=dev)
     d_shaped = torch.empty(nsym * sps, dtype=torch.complex64, device=dev)
     d_iq = torch.empty(nsym * sps * 2, dtype=torch.int16, device=dev)
