@@ -48,6 +48,8 @@ WORKLOADS = {
               "131072-sample batches"),
     "chain5": ("chain", 1024 * 131072, 8.8, "fm_radio as shipped x1024 channels per GPU: 63-tap FIR -> /5 -> FM demod (no mixer), "
                "131072-sample batches"),
+    "chain5_u8": ("chain", 1024 * 131072, 2.8, "fm_radio as shipped from raw RTL-SDR bytes x1024 channels per GPU: u8 IQ -> (x-127.5)/127.5 -> "
+                  "63-tap FIR -> /5 -> FM demod, fused, 131072-sample batches"),
     "pulse4": ("interp", 1 << 26, 40.0, "BPSK pulse shaping: x4 polyphase 32-tap RRC over 2^26 symbols per GPU (unit = symbols)"),
     "pulse4_i16": ("interp", 1 << 26, 24.0, "BPSK pulse shaping with the example's i16 quantiser fused: x4 polyphase 32-tap RRC -> (8192 x) as i16 "
                    "IQ over 2^26 symbols per GPU (unit = symbols)"),
@@ -171,7 +173,7 @@ def cpu_rate(workload, samples, threads):
         elif kind == "fft":
             jobs.append(lambda x=x: oracle.fft(x, n, workload.startswith("ifft")))
         elif kind == "chain":
-            if workload == "chain5":
+            if workload.startswith("chain5"):
                 ch = oracle.FmChain(0.0, 0.0, fm_radio_lowpass(), 5, do_mix=False, native=True)
             else:
                 ch = oracle.FmChain(-0.7, 0.0, fm_radio_lowpass(), 10, native=True)
@@ -260,7 +262,7 @@ class Job:
         elif self.kind == "chain":
             C, nb = 1024, 131072
             fc = (np.arange(C) / C - 0.5) * 0.8
-            if workload == "chain5":
+            if workload in ("chain5", "chain5_u8"):
                 self.node = cb.ChainBank(C, fm_radio_lowpass(), 5, dphase=None, with_fm=True)
             else:
                 self.node = cb.ChainBank(C, fm_radio_lowpass(), 10, dphase=-2 * np.pi * fc, with_fm=True)
@@ -269,6 +271,11 @@ class Job:
             self.out_bytes = 4 * C * no
             self.step = lambda: self.node.run_dev(self.x.data_ptr(), nb, self.y.data_ptr(), no, self.stream)
             self.host_call = lambda hin, hout: cb.load().cb_chain_run(self.node._h, hin, nb, hout, no, None)
+            if workload == "chain5_u8":  # the same synthetic stream, quantised to RTL-SDR bytes once, outside the timed region
+                self.x8 = (torch.view_as_real(self.x) * 127.5 + 127.5).clamp_(0, 255).to(torch.uint8).contiguous()
+                self.in_bytes_override = 2 * n
+                self.step = lambda: self.node.run_dev_u8(self.x8.data_ptr(), nb, self.y.data_ptr(), no, self.stream)
+                self.host_call = lambda hin, hout: cb.load().cb_chain_run_u8(self.node._h, hin, nb, hout, no, None)
         else:
             L, nt = (4, 32) if workload.startswith("pulse4") else (8, 1024)
             self.taps = rrc_taps(nt, float(L), 0.25)
@@ -285,7 +292,7 @@ class Job:
                 self.out_bytes = 8 * n * L
                 self.step = lambda: self.node.run_dev(self.x.data_ptr(), n, self.y.data_ptr(), n * L, self.stream)
                 self.host_call = lambda hin, hout: cb.load().cb_fir_run(self.node._h, hin, n, hout, n * L, None)
-        self.in_bytes = 8 * n
+        self.in_bytes = getattr(self, "in_bytes_override", 8 * n)
 
     def _halo(self, k):
         """The k samples before this rank's segment, newest first: the reference `state`
@@ -353,7 +360,8 @@ def run_b200(args, rank, world, local_rank):
         cb._lib.check(lib.cb_buf_alloc_pinned(job.in_bytes, C.byref(hin)))
         cb._lib.check(lib.cb_buf_alloc_pinned(job.out_bytes, C.byref(hout)))
         pin, pout = lib.cb_buf_ptr(hin), lib.cb_buf_ptr(hout)
-        cb._lib.check(lib.cb_copy_d2h_async(pin, job.x.data_ptr(), job.in_bytes, job.stream))
+        src = job.x8 if hasattr(job, "x8") else job.x
+        cb._lib.check(lib.cb_copy_d2h_async(pin, src.data_ptr(), job.in_bytes, job.stream))
         torch.cuda.synchronize()
         k_e2e = max(3, min(args.steps, 10))
         for _ in range(2):

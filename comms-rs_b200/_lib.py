@@ -101,6 +101,10 @@ SIGNATURES = {
     "cb_chain_out_len": (_i, [_vp, _sz, _psz]),
     "cb_chain_run": (_i, [_vp, _vp, _sz, _vp, _sz, _psz]),
     "cb_chain_run_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _psz, _vp]),
+    "cb_chain_run_u8_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _psz, _vp]),
+    "cb_chain_run_u8": (_i, [_vp, _vp, _sz, _vp, _sz, _psz]),
+    "cb_convert_u8_dev": (_i, [_vp, _sz, _vp, _vp]),
+    "cb_convert_i16_dev": (_i, [_vp, _sz, C.c_float, _vp, _vp]),
     "cb_rrc_taps": (_i, [C.c_uint32, C.c_double, C.c_double, _vp]),
     "cb_rrc_taps_f64": (_i, [C.c_uint32, C.c_double, C.c_double, _vp]),
     "cb_prn_bits": (_i, [C.c_uint64, C.POINTER(C.c_uint64), C.c_uint, _sz, _vp]),

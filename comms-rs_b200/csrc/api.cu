@@ -182,6 +182,8 @@ struct cb_chain {
     double *phase[2], *dphase;
     float2 *hist[2], *prev[2];
     int cur;
+    float2 *cscratch;   // converted input of the unfused cb_chain_run_u8 path, grown on demand
+    size_t cscratch_len;
 };
 
 static inline cudaStream_t pick_stream(void *user, cudaStream_t own) { return user ? (cudaStream_t)user : own; }
@@ -1159,6 +1161,8 @@ int cb_chain_create(size_t channels, const double *dphase, const double *phase, 
     h->phase[0] = h->phase[1] = h->dphase = nullptr;
     h->hist[0] = h->hist[1] = h->prev[0] = h->prev[1] = nullptr;
     h->stream = nullptr;
+    h->cscratch = nullptr;
+    h->cscratch_len = 0;
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     const size_t hb = channels * h->hist_len * sizeof(float2);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
@@ -1199,6 +1203,7 @@ int cb_chain_destroy(cb_chain *h)
         if (h->phase[i]) cudaFree(h->phase[i]);
     }
     if (h->dphase) cudaFree(h->dphase);
+    if (h->cscratch) cudaFree(h->cscratch);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return CB_OK;
@@ -1211,18 +1216,20 @@ int cb_chain_out_len(const cb_chain *h, size_t n_in, size_t *n_out)
     return CB_OK;
 }
 
-int cb_chain_run_dev(cb_chain *h, const float *d_in, size_t n_in, float *d_out, size_t out_cap, size_t *n_out,
-                     void *stream)
+// d_in: complex-f32 input, or d_in8: (u8 I, u8 Q) byte pairs (exactly one of the two)
+static int chain_run_dev_impl(cb_chain *h, const float *d_in, const uint8_t *d_in8, size_t n_in, float *d_out,
+                              size_t out_cap, size_t *n_out, void *stream)
 {
     CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
     const size_t no = decim_len(n_in, h->decim);
     if (n_out) *n_out = no;
     if (n_in == 0) return CB_OK;
-    CB_REQUIRE(d_in && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_REQUIRE((d_in || d_in8) && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
     CB_REQUIRE(out_cap >= no, CB_ERR_SIZE, "chain: out_cap %zu < %zu outputs per channel", out_cap, no);
     CB_CUDA(cudaSetDevice(h->device));
     ChainArgs a;
     a.x = reinterpret_cast<const float2 *>(d_in);
+    a.x8 = d_in8;
     a.out = d_out;
     a.phase_in = h->phase[h->cur];
     a.phase_out = h->phase[h->cur ^ 1];
@@ -1245,9 +1252,62 @@ int cb_chain_run_dev(cb_chain *h, const float *d_in, size_t n_in, float *d_out, 
     a.span_max = (unsigned)round_up((to + 1) * h->decim + h->ntaps, 2);
     CB_REQUIRE(ceil_div((size_t)a.span_max, (size_t)256) <= 64, CB_ERR_UNSUPPORTED,
                "chain: decimation %u with %u taps needs a span beyond the staged window", h->decim, h->ntaps);
-    int rc = launch_chain(a, h->taps, h->mix, h->fm, h->cplx, h->channels, pick_stream(stream, h->stream));
+    cudaStream_t s = pick_stream(stream, h->stream);
+    if (d_in8 != nullptr && !chain_fuses_u8(a, h->cplx)) {  // no fused kernel for this shape: convert, then filter
+        const size_t total = h->channels * n_in;
+        if (h->cscratch_len < total) {
+            if (h->cscratch) CB_CUDA(cudaFree(h->cscratch));
+            h->cscratch = nullptr;
+            h->cscratch_len = 0;
+            CB_CUDA(cudaMalloc(&h->cscratch, total * sizeof(float2)));
+            h->cscratch_len = total;
+        }
+        int rcc = launch_convert_u8(d_in8, reinterpret_cast<float *>(h->cscratch), 2 * total, s);
+        if (rcc) return rcc;
+        a.x = h->cscratch;
+        a.x8 = nullptr;
+    }
+    int rc = launch_chain(a, h->taps, h->mix, h->fm, h->cplx, h->channels, s);
     if (rc) return rc;
     h->cur ^= 1;
+    return CB_OK;
+}
+
+int cb_chain_run_dev(cb_chain *h, const float *d_in, size_t n_in, float *d_out, size_t out_cap, size_t *n_out,
+                     void *stream)
+{
+    CB_REQUIRE(d_in || n_in == 0, CB_ERR_INVALID_ARG, "NULL data pointer");
+    return chain_run_dev_impl(h, d_in, nullptr, n_in, d_out, out_cap, n_out, stream);
+}
+
+int cb_chain_run_u8_dev(cb_chain *h, const uint8_t *d_in, size_t n_in, float *d_out, size_t out_cap, size_t *n_out,
+                        void *stream)
+{
+    CB_REQUIRE(d_in || n_in == 0, CB_ERR_INVALID_ARG, "NULL data pointer");
+    return chain_run_dev_impl(h, nullptr, d_in, n_in, d_out, out_cap, n_out, stream);
+}
+
+int cb_chain_run_u8(cb_chain *h, const uint8_t *in, size_t n_in, float *out, size_t out_cap, size_t *n_out)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    const size_t no = decim_len(n_in, h->decim);
+    if (n_out) *n_out = no;
+    if (n_in == 0) return CB_OK;
+    CB_REQUIRE(in && out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_REQUIRE(out_cap >= no, CB_ERR_SIZE, "chain: out_cap %zu < %zu outputs per channel", out_cap, no);
+    CB_CUDA(cudaSetDevice(h->device));
+    const size_t in_bytes = h->channels * n_in * 2;
+    const size_t out_bytes = h->channels * no * (h->fm ? sizeof(float) : sizeof(float2));
+    int rc = h->pipe.reserve(in_bytes, out_bytes);
+    if (rc) return rc;
+    cudaStream_t s = h->pipe.lane[0];
+    CB_CUDA(cudaMemcpyAsync(h->pipe.in[0], in, in_bytes, cudaMemcpyHostToDevice, s));
+    rc = cb_chain_run_u8_dev(h, reinterpret_cast<const uint8_t *>(h->pipe.in[0]), n_in,
+                             reinterpret_cast<float *>(h->pipe.out[0]), no, nullptr, s);
+    if (rc) return rc;
+    const size_t esz = h->fm ? sizeof(float) : sizeof(float2);
+    CB_CUDA(cudaMemcpy2DAsync(out, out_cap * esz, h->pipe.out[0], no * esz, no * esz, h->channels, cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaStreamSynchronize(s));
     return CB_OK;
 }
 
@@ -1345,6 +1405,24 @@ int cb_bits_to_symbols_dev(const uint8_t *d_bits, size_t nbits, int mode, float 
     int rc = ensure_device();
     if (rc) return rc;
     return launch_bits_to_symbols(d_bits, reinterpret_cast<float2 *>(d_sym), ns, mode, (cudaStream_t)stream);
+}
+
+int cb_convert_u8_dev(const uint8_t *d_in, size_t n_samples, float *d_out, void *stream)
+{
+    if (n_samples == 0) return CB_OK;
+    CB_REQUIRE(d_in && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    int rc = ensure_device();
+    if (rc) return rc;
+    return launch_convert_u8(d_in, d_out, 2 * n_samples, (cudaStream_t)stream);
+}
+
+int cb_convert_i16_dev(const int16_t *d_in, size_t n_samples, float scale, float *d_out, void *stream)
+{
+    if (n_samples == 0) return CB_OK;
+    CB_REQUIRE(d_in && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    int rc = ensure_device();
+    if (rc) return rc;
+    return launch_convert_i16(d_in, d_out, 2 * n_samples, scale, (cudaStream_t)stream);
 }
 
 int cb_quantize_i16_dev(const float *d_in, size_t nfloats, float scale, int16_t *d_out, void *stream)

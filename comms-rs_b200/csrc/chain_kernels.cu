@@ -388,7 +388,11 @@ static int launch_chain2(const ChainArgs &args, const ChainTaps &taps, size_t ch
 // the first tile of a channel needs no special path; chunks past n_in are simply not copied.
 // Numerics: identical algebra, different rounding points (rel-L2 ~2e-7 vs the sequential f32 form).
 // ============================================================================
-template <bool MIX, bool FM, int D, int R, int NT, int NSTAGE, int MINB>
+// U8: the input is the RTL-SDR byte stream of examples/fm_radio.rs (u8 I, u8 Q); ConvertNode's
+// (x - 127.5) / 127.5 (fm_radio.rs:84-87) is applied on the way from the raw TMA stage into the f32 span through
+// a 256-entry table of exactly rounded quotients, so the filter sees the same f32 values as after a separate
+// conversion pass while HBM carries 2 instead of 8 bytes per input sample.
+template <bool MIX, bool FM, bool U8, int D, int R, int NT, int NSTAGE, int MINB>
 __global__ void __launch_bounds__(NT + 32, MINB)
 chain3_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ ChainTaps taps, const unsigned tiles_per_ch,
               const unsigned long long nitems)
@@ -396,17 +400,22 @@ chain3_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
     constexpr int KP = 64;
     constexpr int TO = NT * R;
     constexpr int RD = R * D;
-    constexpr int OFF = (KP + D + 1) / 2 * 2;           // halo samples in front of the tile (even)
+    constexpr int OFF = U8 ? (KP + D + 7) / 8 * 8 : (KP + D + 1) / 2 * 2;  // halo samples in front of the tile
     constexpr int SPAN = TO * D + OFF;
-    constexpr int STAGE = (SPAN * 8 + 127) / 128 * 128;
-    constexpr int PIECE = 256;                          // samples per bulk copy (2 KiB)
+    constexpr int STAGE = (SPAN * 8 + 127) / 128 * 128;  // f32 span
+    constexpr int RAWSTAGE = (SPAN * 2 + 127) / 128 * 128;  // U8: raw byte span
+    constexpr int PIECE = U8 ? 1024 : 256;              // samples per bulk copy (2 KiB)
+    static_assert(!U8 || (TO * D) % 8 == 0, "u8 tiles must start on 16-byte boundaries");
     // the span is stored LINEARLY; thread t reads 128-bit words at a lane stride of RD*8 bytes, which is
     // bank-conflict free exactly when RD/2 is odd (stride = odd multiple of 16 bytes)
     static_assert(RD % 2 == 0 && (RD / 2) % 2 == 1 && NT >= 64 + R + 1, "");
 
     extern __shared__ __align__(128) unsigned char c3sm[];
-    unsigned char *stages = c3sm;
-    float2 *tsm = reinterpret_cast<float2 *>(c3sm + NSTAGE * STAGE);  // tsm[k + 1] = h'[k], tsm[0] = tsm[65] = 0
+    unsigned char *stages = c3sm;                                     // ring of raw spans (f32, or bytes when U8)
+    unsigned char *span8 = c3sm + NSTAGE * RAWSTAGE;                  // U8: the one converted f32 span
+    constexpr int RING = U8 ? NSTAGE * RAWSTAGE + STAGE + 1024 : NSTAGE * STAGE;
+    float *lut = reinterpret_cast<float *>(c3sm + NSTAGE * RAWSTAGE + STAGE);  // U8: (b - 127.5) / 127.5
+    float2 *tsm = reinterpret_cast<float2 *>(c3sm + RING);            // tsm[k + 1] = h'[k], tsm[0] = tsm[65] = 0
     float2 *cst = tsm + KP + 2;                                       // e^{j r D dphi} (r < R), then e^{-j D dphi}
     float2 *basep = cst + 8;                                          // per stage: e^{j (phi0 + m0 D dphi)}
     float2 *ys = basep + 8;                                           // 2 x (TO + 1) outputs
@@ -424,7 +433,10 @@ chain3_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
     if (item0 >= item_end) return;
 
     // stage memory starts out finite (chunks past the end of a batch are never copied)
-    for (int i = tid; i < NSTAGE * STAGE / 16; i += NT + 32) reinterpret_cast<uint4 *>(stages)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < (U8 ? NSTAGE * RAWSTAGE + STAGE : NSTAGE * STAGE) / 16; i += NT + 32)
+        reinterpret_cast<uint4 *>(stages)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (U8)
+        for (int i = tid; i < 256; i += NT + 32) lut[i] = __fdiv_rn(__fsub_rn((float)i, 127.5f), 127.5f);
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; ++i) mbar_init(&full[i], 1);
         fence_mbar_init();
@@ -439,19 +451,28 @@ chain3_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
         const long long g_base = tile * TO * D - OFF;
         long long g_hi = g_base + SPAN;
         if (g_hi > (long long)a.n_in) g_hi = (long long)a.n_in;
+        const long long g_lo = g_base < 0 ? 0 : g_base;
         if (lane == 0) {
             if (MIX) basep[st] = phase_rotation(fma((double)(tile * TO * D), a.dphase[c], a.phase_in[c]));
-            mbar_arrive_expect_tx(&full[st], (uint32_t)((g_hi - g_base) * 8));
+            mbar_arrive_expect_tx(&full[st], (uint32_t)(U8 ? (g_hi - g_lo) * 2 : (g_hi - g_base) * 8));
         }
         __syncwarp();
-        const float2 *xc = a.x + c * a.n_in;
-        const float2 *hc = a.hist_in + c * H + H;
-        unsigned char *dst = stages + st * STAGE;
-        const long long g_lo = g_base < 0 ? 0 : g_base;
-        if (g_base < 0 && lane == 31) tma_load_1d(dst, hc + g_base, (uint32_t)(-g_base * 8), &full[st]);  // history
-        for (long long g = g_lo + (long long)lane * PIECE; g < g_hi; g += 32 * PIECE) {
-            const long long n = g_hi - g < PIECE ? g_hi - g : PIECE;
-            tma_load_1d(dst + (g - g_base) * 8, xc + g, (uint32_t)(n * 8), &full[st]);
+        if (U8) {  // bytes only; the f32 history of the first tile is fetched by the conversion pass
+            const unsigned char *xc = a.x8 + 2 * c * a.n_in;
+            unsigned char *dst = stages + st * RAWSTAGE;
+            for (long long g = g_lo + (long long)lane * PIECE; g < g_hi; g += 32 * PIECE) {
+                const long long n = g_hi - g < PIECE ? g_hi - g : PIECE;
+                tma_load_1d(dst + (g - g_base) * 2, xc + 2 * g, (uint32_t)(n * 2), &full[st]);
+            }
+        } else {
+            const float2 *xc = a.x + c * a.n_in;
+            const float2 *hc = a.hist_in + c * H + H;
+            unsigned char *dst = stages + st * STAGE;
+            if (g_base < 0 && lane == 31) tma_load_1d(dst, hc + g_base, (uint32_t)(-g_base * 8), &full[st]);  // history
+            for (long long g = g_lo + (long long)lane * PIECE; g < g_hi; g += 32 * PIECE) {
+                const long long n = g_hi - g < PIECE ? g_hi - g : PIECE;
+                tma_load_1d(dst + (g - g_base) * 8, xc + g, (uint32_t)(n * 8), &full[st]);
+            }
         }
     };
     if (producer) {
@@ -488,7 +509,27 @@ chain3_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
         }
 
         mbar_wait(&full[st], parity);
-        const unsigned char *sbase = stages + st * STAGE;
+        const unsigned char *sbase = U8 ? span8 : stages + st * STAGE;
+        if (U8) {
+            // raw bytes -> f32 span (pairs of samples: one 32-bit word in, one 128-bit word out)
+            if (!producer) {
+                const long long g_base = (long long)tile * TO * D - OFF;
+                const uint32_t *raw = reinterpret_cast<const uint32_t *>(stages + st * RAWSTAGE);
+                const float2 *hc = a.hist_in + c * H + H;
+                for (int p = tid; p < SPAN / 2; p += NT) {
+                    const long long g = g_base + 2 * p;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (g < 0) {
+                        v = *reinterpret_cast<const float4 *>(hc + g);
+                    } else if (g < (long long)a.n_in) {
+                        const uint32_t w = raw[p];
+                        v = make_float4(lut[w & 255u], lut[(w >> 8) & 255u], lut[(w >> 16) & 255u], lut[w >> 24]);
+                    }
+                    reinterpret_cast<float4 *>(span8)[p] = v;
+                }
+            }
+            asm volatile("bar.sync 2, %0;" ::"r"(NT + 32) : "memory");  // span converted (consumers + producer warp)
+        }
 
         // ---- FM only: y[m0 - 1] for the first discriminator step of the tile (warp 0, 2 taps per lane)
         if (FM && producer) {
@@ -578,12 +619,20 @@ chain3_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
 
         // ---- carried state for the next call (last tile of the channel)
         if (tile == tiles_per_ch - 1) {
-            const float2 *xc = a.x + c * a.n_in;
             const float2 *hc = a.hist_in + c * H;
             float2 *ho = a.hist_out + c * H;
             for (long long i = tid; i < H; i += NT) {
                 const long long g = (long long)a.n_in - H + i;
-                ho[i] = g >= 0 ? xc[g] : hc[H + g];
+                float2 v;
+                if (g < 0) {
+                    v = hc[H + g];
+                } else if (U8) {
+                    const unsigned char *b = a.x8 + 2 * (c * a.n_in + g);
+                    v = make_float2(lut[b[0]], lut[b[1]]);
+                } else {
+                    v = a.x[c * a.n_in + g];
+                }
+                ho[i] = v;
             }
             if (MIX && tid == 0) {
                 const double twopi = 6.283185307179586232;
@@ -608,12 +657,13 @@ chain3_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
     }
 }
 
-template <bool MIX, bool FM, int D, int R, int NT, int NSTAGE, int MINB>
+template <bool MIX, bool FM, bool U8, int D, int R, int NT, int NSTAGE, int MINB>
 static int launch_chain3(const ChainArgs &args, const ChainTaps &taps, size_t channels, cudaStream_t s)
 {
-    constexpr int TO = NT * R, OFF = (64 + D + 1) / 2 * 2;
-    constexpr int SMEM = NSTAGE * (((TO * D + OFF) * 8 + 127) / 128 * 128) + (66 + 8 + 8) * 8 + 2 * (TO + 1) * 8;
-    auto kern = chain3_kernel<MIX, FM, D, R, NT, NSTAGE, MINB>;
+    constexpr int TO = NT * R, OFF = U8 ? (64 + D + 7) / 8 * 8 : (64 + D + 1) / 2 * 2;
+    constexpr int F32SPAN = ((TO * D + OFF) * 8 + 127) / 128 * 128, RAWSPAN = ((TO * D + OFF) * 2 + 127) / 128 * 128;
+    constexpr int SMEM = (U8 ? NSTAGE * RAWSPAN + F32SPAN + 1024 : NSTAGE * F32SPAN) + (66 + 8 + 8) * 8 + 2 * (TO + 1) * 8;
+    auto kern = chain3_kernel<MIX, FM, U8, D, R, NT, NSTAGE, MINB>;
     CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const unsigned tiles = (unsigned)ceil_div(args.n_out, (size_t)TO);
     const unsigned long long nitems = (unsigned long long)tiles * channels;
@@ -633,10 +683,16 @@ static int launch_chain3(const ChainArgs &args, const ChainTaps &taps, size_t ch
 template <int D, int R, int NT, int NSTAGE, int MINB>
 static int launch_chain3_shape(const ChainArgs &args, const ChainTaps &taps, bool mix, bool fm, size_t channels, cudaStream_t s)
 {
-    if (mix && fm) return launch_chain3<true, true, D, R, NT, NSTAGE, MINB>(args, taps, channels, s);
-    if (mix) return launch_chain3<true, false, D, R, NT, NSTAGE, MINB>(args, taps, channels, s);
-    if (fm) return launch_chain3<false, true, D, R, NT, NSTAGE, MINB>(args, taps, channels, s);
-    return launch_chain3<false, false, D, R, NT, NSTAGE, MINB>(args, taps, channels, s);
+    if (args.x8 != nullptr) {
+        if (mix && fm) return launch_chain3<true, true, true, D, R, NT, NSTAGE, MINB>(args, taps, channels, s);
+        if (mix) return launch_chain3<true, false, true, D, R, NT, NSTAGE, MINB>(args, taps, channels, s);
+        if (fm) return launch_chain3<false, true, true, D, R, NT, NSTAGE, MINB>(args, taps, channels, s);
+        return launch_chain3<false, false, true, D, R, NT, NSTAGE, MINB>(args, taps, channels, s);
+    }
+    if (mix && fm) return launch_chain3<true, true, false, D, R, NT, NSTAGE, MINB>(args, taps, channels, s);
+    if (mix) return launch_chain3<true, false, false, D, R, NT, NSTAGE, MINB>(args, taps, channels, s);
+    if (fm) return launch_chain3<false, true, false, D, R, NT, NSTAGE, MINB>(args, taps, channels, s);
+    return launch_chain3<false, false, false, D, R, NT, NSTAGE, MINB>(args, taps, channels, s);
 }
 
 // tile shape of the v2 kernel: R outputs per thread, NT threads, register prefetch or not
@@ -659,17 +715,35 @@ static int launch_chain2_d(const ChainArgs &args, const ChainTaps &taps, bool mi
         const char *e = getenv("COMMS_B200_CHAIN_PATH");
         return (e && strcmp(e, "v2") == 0) ? 2 : ((e && strcmp(e, "v3") == 0) ? 3 : 0);
     }();
-    if (path != 2 && args.hist_len >= 128) {
+    if ((path != 2 || args.x8 != nullptr) && args.hist_len >= 128) {
         if constexpr (D == 10) return launch_chain3_shape<D, 3, 128, 2, 3>(args, taps, mix, fm, channels, s);
         if constexpr (D == 5) return launch_chain3_shape<D, 6, 128, 2, 2>(args, taps, mix, fm, channels, s);
     }
+    if (args.x8 != nullptr) {
+        set_error("chain: no fused u8 kernel for this shape");
+        return CB_ERR_UNSUPPORTED;
+    }
     return launch_chain2_shape<D, R, 256, true, 2>(args, taps, mix, fm, channels, s);
+}
+
+bool chain_fuses_u8(const ChainArgs &args, bool cplx)
+{
+    return !cplx && args.ntaps <= 64 && args.hist_len >= 128 && args.n_in % 8 == 0 && (args.decim == 10 || args.decim == 5) &&
+           (reinterpret_cast<uintptr_t>(args.x8) & 15) == 0;
 }
 
 int launch_chain(const ChainArgs &args, const ChainTaps &taps, bool mix, bool fm, bool cplx, size_t channels,
                  cudaStream_t s)
 {
     if (args.n_in == 0 || channels == 0) return CB_OK;
+    if (args.x8 != nullptr) {
+        if (!chain_fuses_u8(args, cplx)) {
+            set_error("chain: no fused u8 kernel for this shape");
+            return CB_ERR_UNSUPPORTED;
+        }
+        return args.decim == 10 ? launch_chain2_d<10, 2>(args, taps, mix, fm, channels, s)
+                                : launch_chain2_d<5, 4>(args, taps, mix, fm, channels, s);
+    }
     // v2: real taps <= 64, even batch length and 16-byte aligned input (128-bit staging loads)
     if (!cplx && args.ntaps <= 64 && args.hist_len % 2 == 0 && args.n_in % 2 == 0 &&
         (reinterpret_cast<uintptr_t>(args.x) & 15) == 0) {

@@ -12,6 +12,7 @@ struct ChainTaps {
 
 struct ChainArgs {
     const float2 *x;        // channels x n_in
+    const unsigned char *x8; // or: channels x n_in (u8 I, u8 Q) byte pairs, converted by (b - 127.5) / 127.5 (x unused)
     void *out;              // channels x n_out floats (FM) or complex
     const double *phase_in; // per channel (mixer), wrapped to [0, 2pi)
     double *phase_out;
@@ -26,6 +27,8 @@ struct ChainArgs {
     unsigned span_max;      // shared-memory samples reserved for the input span
 };
 
+// true when launch_chain has a kernel that reads args.x8 itself (otherwise convert first)
+bool chain_fuses_u8(const ChainArgs &args, bool cplx);
 int launch_chain(const ChainArgs &args, const ChainTaps &taps, bool mix, bool fm, bool cplx, size_t channels,
                  cudaStream_t s);
 

@@ -169,6 +169,43 @@ int launch_quantize_i16(const float *in, int16_t *out, size_t n, float scale, cu
     return CB_OK;
 }
 
+// ---------------------------------------------------------------- IQ edge formats
+// u8 offset binary (RTL-SDR; examples/fm_radio.rs:84-87): (x as f32 - 127.5) / 127.5, both operations exactly rounded
+__global__ void __launch_bounds__(256)
+convert_u8_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, size_t n)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = __fdiv_rn(__fsub_rn((float)in[i], 127.5f), 127.5f);
+}
+
+// interleaved i16 IQ (src/io/raw_iq.rs:20-140): scale * (x as f32); scale = 1 is the plain cast
+__global__ void __launch_bounds__(256)
+convert_i16_kernel(const int16_t *__restrict__ in, float *__restrict__ out, size_t n, float scale)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = __fmul_rn(scale, (float)in[i]);
+}
+
+int launch_convert_u8(const uint8_t *in, float *out, size_t n, cudaStream_t s)
+{
+    if (n == 0) return CB_OK;
+    convert_u8_kernel<<<grid_for(n, 256), 256, 0, s>>>(in, out, n);
+    count_launch();
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+
+int launch_convert_i16(const int16_t *in, float *out, size_t n, float scale, cudaStream_t s)
+{
+    if (n == 0) return CB_OK;
+    convert_i16_kernel<<<grid_for(n, 256), 256, 0, s>>>(in, out, n, scale);
+    count_launch();
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+
 // ---------------------------------------------------------------- synthetic data
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x)
 {

@@ -314,6 +314,24 @@ class ChainBank(_Handle):
             raise node_error(e) from e
         return out
 
+    def run_u8(self, iq) -> np.ndarray:
+        """Raw RTL-SDR bytes in ([channels, n_in, 2] uint8: I, Q), ConvertNode (examples/fm_radio.rs:84-87) fused."""
+        b = np.ascontiguousarray(np.asarray(iq, dtype=np.uint8)).reshape(self.channels, -1, 2)
+        n_in = b.shape[1]
+        no = self.out_len(n_in)
+        out = np.empty((self.channels, no), dtype=np.float32 if self.with_fm else np.complex64)
+        m = _sz()
+        try:
+            check(_lib.load().cb_chain_run_u8(self._h, _ptr(b), n_in, _ptr(out), no, C.byref(m)))
+        except CbError as e:
+            raise node_error(e) from e
+        return out
+
+    def run_dev_u8(self, d_in: int, n_in: int, d_out: int, out_cap: int, stream: int = 0) -> int:
+        m = _sz()
+        check(_lib.load().cb_chain_run_u8_dev(self._h, d_in, n_in, d_out, out_cap, C.byref(m), stream))
+        return m.value
+
     def run_dev(self, d_in: int, n_in: int, d_out: int, out_cap: int, stream: int = 0) -> int:
         m = _sz()
         check(_lib.load().cb_chain_run_dev(self._h, d_in, n_in, d_out, out_cap, C.byref(m), stream))
@@ -321,6 +339,16 @@ class ChainBank(_Handle):
 
 
 # ------------------------------------------------------------------ edges
+def convert_u8_dev(d_in: int, n_samples: int, d_out: int, stream: int = 0) -> None:
+    """(u8 I, u8 Q) -> complex f32, (x - 127.5) / 127.5 (examples/fm_radio.rs:84-87)."""
+    check(_lib.load().cb_convert_u8_dev(d_in, n_samples, d_out, stream))
+
+
+def convert_i16_dev(d_in: int, n_samples: int, scale: float, d_out: int, stream: int = 0) -> None:
+    """Interleaved i16 IQ (src/io/raw_iq.rs) -> scale * (x as f32)."""
+    check(_lib.load().cb_convert_i16_dev(d_in, n_samples, float(scale), d_out, stream))
+
+
 def rrc_taps(n_taps: int, sam_per_sym: float, beta: float, dtype=np.complex64) -> np.ndarray:
     """rrc_taps::<T> (src/util/math.rs:221-280): root-raised-cosine taps, imaginary parts 0.
     Raises NodeError-style ValueError("InvalidRolloffError") for beta outside [0, 1]."""

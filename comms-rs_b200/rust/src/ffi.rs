@@ -89,6 +89,10 @@ extern "C" {
 
     pub fn cb_fir_run_i16(h: *mut cb_fir, input: *const f32, n_in: usize, scale: f32, out: *mut i16, out_cap: usize, n_out: *mut usize) -> c_int;
     pub fn cb_fir_run_dev_i16(h: *mut cb_fir, d_in: *const f32, n_in: usize, scale: f32, d_out: *mut i16, out_cap: usize, n_out: *mut usize, stream: *mut c_void) -> c_int;
+    pub fn cb_convert_u8_dev(d_in: *const u8, n_samples: usize, d_out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn cb_convert_i16_dev(d_in: *const i16, n_samples: usize, scale: f32, d_out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn cb_chain_run_u8(h: *mut cb_chain, input: *const u8, n_in: usize, out: *mut f32, out_cap: usize, n_out: *mut usize) -> c_int;
+    pub fn cb_chain_run_u8_dev(h: *mut cb_chain, d_in: *const u8, n_in: usize, d_out: *mut f32, out_cap: usize, n_out: *mut usize, stream: *mut c_void) -> c_int;
     pub fn cb_rrc_taps(n_taps: u32, sam_per_sym: f64, beta: f64, taps: *mut f32) -> c_int;
     pub fn cb_rrc_taps_f64(n_taps: u32, sam_per_sym: f64, beta: f64, taps: *mut f64) -> c_int;
     pub fn cb_prn_bits(poly_mask: u64, state: *mut u64, width: c_uint, n: usize, bits: *mut u8) -> c_int;

@@ -214,6 +214,14 @@ CB_API int cb_chain_destroy(cb_chain *h);
 CB_API int cb_chain_out_len(const cb_chain *h, size_t n_in, size_t *n_out_per_channel);
 CB_API int cb_chain_run(cb_chain *h, const float *in, size_t n_in, float *out, size_t out_cap_per_channel,
                         size_t *n_out_per_channel);
+/* Same bank fed with the raw RTL-SDR byte stream (channel-major, n_in byte pairs per channel): ConvertNode
+ * (examples/fm_radio.rs:84-87) fused in front, so HBM carries 2 instead of 8 bytes per input sample.  Fused
+ * inside the TMA-staged kernel for real taps <= 64, decimation 5 or 10, n_in % 8 == 0 and a 16-byte aligned
+ * input; any other shape converts into an internal f32 scratch first.  Same results either way. */
+CB_API int cb_chain_run_u8(cb_chain *h, const uint8_t *in, size_t n_in, float *out, size_t out_cap_per_channel,
+                           size_t *n_out_per_channel);
+CB_API int cb_chain_run_u8_dev(cb_chain *h, const uint8_t *d_in, size_t n_in, float *d_out,
+                               size_t out_cap_per_channel, size_t *n_out_per_channel, void *stream);
 CB_API int cb_chain_run_dev(cb_chain *h, const float *d_in, size_t n_in, float *d_out,
                             size_t out_cap_per_channel, size_t *n_out_per_channel, void *stream);
 
@@ -246,6 +254,13 @@ CB_API int cb_prn_bits(uint64_t poly_mask, uint64_t *state, unsigned width, size
 CB_API int cb_bits_to_symbols_dev(const uint8_t *d_bits, size_t nbits, int mode, float *d_sym,
                                   size_t *nsym, void *stream);
 CB_API int cb_quantize_i16_dev(const float *d_in, size_t nfloats, float scale, int16_t *d_out, void *stream);
+/* IQ edge formats.  cb_convert_u8: RTL-SDR bytes (u8 I, u8 Q) -> complex f32 by
+ * (x as f32 - 127.5) / 127.5 (ConvertNode, examples/fm_radio.rs:84-87), exactly
+ * rounded.  cb_convert_i16: the interleaved native-endian i16 IQ of
+ * src/io/raw_iq.rs:20-140 -> scale * (x as f32) (scale = 1: the plain cast).
+ * n_samples complex samples each; d_out receives 2*n_samples floats. */
+CB_API int cb_convert_u8_dev(const uint8_t *d_in, size_t n_samples, float *d_out, void *stream);
+CB_API int cb_convert_i16_dev(const int16_t *d_in, size_t n_samples, float scale, float *d_out, void *stream);
 
 /* ------------------------------------------------------------------ synthetic input
  * splitmix64 counter generator shared with the oracle (oracle.c

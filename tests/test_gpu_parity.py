@@ -407,6 +407,60 @@ def test_chain_bank_matches_node_chain(cb, oracle, mix, fm, cplx, D):
                 assert rel_l2(got[c], want) <= FIR_TOL, (c, n)
 
 
+@pytest.mark.parametrize("mix,fm,D,n", [(False, True, 5, 131_072), (True, True, 10, 131_072), (True, False, 10, 40_000),
+                                        (False, True, 5, 9_999), (True, True, 4, 16_384)])
+def test_chain_bank_u8_input_fused_convert(cb, oracle, mix, fm, D, n):
+    # fm_radio as shipped: RTL-SDR bytes -> ConvertNode (x - 127.5) / 127.5 -> FIR -> /D -> FM (examples/fm_radio.rs:84-87,144-164)
+    # D in {5, 10} with n % 8 == 0 converts inside the TMA-staged kernel; other shapes convert into a scratch first.
+    import torch
+
+    rng = np.random.default_rng(D * 7 + n)
+    C, taps = 5, _lowpass(FM_RADIO_TAPS_N)
+    dph = -2 * np.pi * rng.uniform(-0.4, 0.4, C)
+    a = cb.ChainBank(C, taps, D, dphase=dph if mix else None, with_fm=fm)
+    b = cb.ChainBank(C, taps, D, dphase=dph if mix else None, with_fm=fm)
+    refs = [oracle.FmChain(dph[c], 0.0, taps, D, do_mix=mix, do_fm=fm) for c in range(C)]
+    for call in range(3):  # state (history, phase, FM prev) carried across calls
+        iq = rng.integers(0, 256, (C, n, 2), dtype=np.uint8)
+        # stand-alone converter: bit-exact against the oracle's ((x as f32) - 127.5) / 127.5
+        d8 = torch.from_numpy(iq.reshape(-1)).cuda()
+        df = torch.empty(C * n, dtype=torch.complex64, device="cuda")
+        ts = torch.cuda.Stream()
+        torch.cuda.synchronize()
+        cb.convert_u8_dev(d8.data_ptr(), C * n, df.data_ptr(), ts.cuda_stream)
+        torch.cuda.synchronize()
+        xf = df.cpu().numpy().reshape(C, n)
+        assert xf.view(np.float32).tobytes() == oracle.u8_to_f32(iq.reshape(-1)).tobytes()
+        got = a.run_u8(iq)
+        same = b.run(xf)
+        assert got.shape == same.shape == (C, -(-n // D))
+        assert got.tobytes() == same.tobytes()  # the fused kernel feeds the filter the very same f32 values
+        for c in range(C):
+            want = refs[c].run(xf[c])
+            if fm:
+                d = np.abs(got[c].astype(np.float64) - want.astype(np.float64))
+                d = np.minimum(d, 2 * np.pi - d)
+                assert np.median(d) < 2e-6 and np.mean(d > 1e-3) < 2e-3, (c, call)
+            else:
+                assert rel_l2(got[c], want) <= FIR_TOL, (c, call)
+
+
+def test_convert_i16_bit_exact(cb):
+    import torch
+
+    v = np.array([0, 1, -1, 32767, -32768, 8192, -12345, 77], dtype=np.int16)
+    d = torch.from_numpy(v).cuda()
+    out = torch.empty(len(v), dtype=torch.float32, device="cuda")
+    ts = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    cb.convert_i16_dev(d.data_ptr(), len(v) // 2, 1.0, out.data_ptr(), ts.cuda_stream)
+    torch.cuda.synchronize()
+    assert out.cpu().numpy().tobytes() == v.astype(np.float32).tobytes()
+    cb.convert_i16_dev(d.data_ptr(), len(v) // 2, 1.0 / 8192.0, out.data_ptr(), ts.cuda_stream)
+    torch.cuda.synchronize()
+    assert out.cpu().numpy().tobytes() == (v.astype(np.float32) * np.float32(1.0 / 8192.0)).tobytes()
+
+
 # ------------------------------------------------------------------ BASELINE cfg 1 (single_thread_bpsk)
 def test_bpsk_chain_config1(cb, oracle):
     import torch
