@@ -976,6 +976,7 @@ int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
         const char *path = getenv("COMMS_B200_FFT_PATH");
         h->plan.cluster_tpt = 3;
         if (path && strcmp(path, "cluster2") == 0) h->plan.cluster_tpt = 2;
+        if (path && strcmp(path, "cluster16") == 0) h->plan.cluster_tpt = 4;  // 16-CTA clusters, 4 CTAs per SM
         if (path && strcmp(path, "fourstep") == 0) h->plan.cluster_tpt = 0;
         if (path && strcmp(path, "cluster1") == 0) h->plan.cluster_tpt = 1;  // exchange variants, see fft_cluster_kernel.cu
     }

@@ -516,16 +516,19 @@ chain3_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
                 const long long g_base = (long long)tile * TO * D - OFF;
                 const uint32_t *raw = reinterpret_cast<const uint32_t *>(stages + st * RAWSTAGE);
                 const float2 *hc = a.hist_in + c * H + H;
-                for (int p = tid; p < SPAN / 2; p += NT) {
+                constexpr int NCV = (SPAN / 2 + NT - 1) / NT;
+#pragma unroll 8
+                for (int it = 0; it < NCV; ++it) {  // compile-time trip count: the loads of several words overlap
+                    const int p = tid + it * NT;
                     const long long g = g_base + 2 * p;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (g < 0) {
                         v = *reinterpret_cast<const float4 *>(hc + g);
-                    } else if (g < (long long)a.n_in) {
+                    } else if (g < (long long)a.n_in && p < SPAN / 2) {
                         const uint32_t w = raw[p];
                         v = make_float4(lut[w & 255u], lut[(w >> 8) & 255u], lut[(w >> 16) & 255u], lut[w >> 24]);
                     }
-                    reinterpret_cast<float4 *>(span8)[p] = v;
+                    if (p < SPAN / 2) reinterpret_cast<float4 *>(span8)[p] = v;
                 }
             }
             asm volatile("bar.sync 2, %0;" ::"r"(NT + 32) : "memory");  // span converted (consumers + producer warp)
@@ -715,7 +718,11 @@ static int launch_chain2_d(const ChainArgs &args, const ChainTaps &taps, bool mi
         const char *e = getenv("COMMS_B200_CHAIN_PATH");
         return (e && strcmp(e, "v2") == 0) ? 2 : ((e && strcmp(e, "v3") == 0) ? 3 : 0);
     }();
-    if ((path != 2 || args.x8 != nullptr) && args.hist_len >= 128) {
+    if (args.x8 != nullptr && args.hist_len >= 128) {  // byte input: one f32 span + a small raw ring -> more CTAs per SM
+        if constexpr (D == 10) return launch_chain3_shape<D, 3, 128, 2, 4>(args, taps, mix, fm, channels, s);
+        if constexpr (D == 5) return launch_chain3_shape<D, 6, 128, 2, 3>(args, taps, mix, fm, channels, s);
+    }
+    if (path != 2 && args.hist_len >= 128) {
         if constexpr (D == 10) return launch_chain3_shape<D, 3, 128, 2, 3>(args, taps, mix, fm, channels, s);
         if constexpr (D == 5) return launch_chain3_shape<D, 6, 128, 2, 2>(args, taps, mix, fm, channels, s);
     }

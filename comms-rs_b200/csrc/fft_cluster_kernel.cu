@@ -40,9 +40,9 @@ namespace cb {
 
 namespace fftc {
 
-constexpr int CL = 8;            // CTAs per cluster
 constexpr int NF = 65536;
-constexpr int SMEM = (32 * 256 + 2 * 16) * (int)sizeof(float2);
+// CL CTAs per cluster (8: portable; 16: non-portable opt-in), COLS = 256 / CL columns (then rows) per CTA
+__host__ __device__ constexpr int smem_bytes(int cl) { return ((256 / cl) * 256 + 2 * (128 / cl)) * (int)sizeof(float2); }
 
 __device__ __forceinline__ uint32_t cluster_rank()
 {
@@ -149,30 +149,32 @@ __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier
 // MODE 0: remote-arrive mbarrier ("ready") + st.async with transaction bytes ("landed")
 // MODE 1: remote-arrive mbarrier ("ready") + plain remote stores and one barrier.cluster ("landed")
 // MODE 2: barrier.cluster for both
-template <bool INV, int MODE>
-__global__ void __launch_bounds__(256, 2)
+template <bool INV, int MODE, int CL>
+__global__ void __launch_bounds__(2048 / CL, CL == 16 ? 4 : 2)
 fft65536_cluster_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, const float2 *__restrict__ twN,
                         size_t nframes, unsigned prefetch_dist FFTC_DBG_PARAM)
 {
     using namespace fft2;
+    constexpr int COLS = 256 / CL, CP = COLS / 2;  // columns per CTA, column pairs = lanes per task index j
+    constexpr int NTH = CP * 16, NWARP = NTH / 32;
     FFTC_STAMP(0);
     extern __shared__ __align__(16) float2 sbuf[];
     // bar_ready: one arrival per warp of every CTA of the cluster once it no longer reads its own buffer
     // bar_full : the 64 KiB that the 8 CTAs push into this CTA's buffer (transaction bytes)
     __shared__ __align__(8) uint64_t bar_ready, bar_full;
     if (threadIdx.x == 0) {
-        mbar_init(&bar_ready, CL * 8);
+        mbar_init(&bar_ready, CL * NWARP);
         mbar_init(&bar_full, 1);
         fence_mbar_init();
-        if (MODE == 0) mbar_arrive_expect_tx(&bar_full, 32 * 256 * (uint32_t)sizeof(float2));
+        if (MODE == 0) mbar_arrive_expect_tx(&bar_full, COLS * 256 * (uint32_t)sizeof(float2));
     }
     cluster_arrive_relaxed();
     const uint32_t rank = cluster_rank();
     const size_t frame = blockIdx.x / CL;
-    const int lane = threadIdx.x & 31, cp = lane & 15, j = 2 * (threadIdx.x >> 5) + (lane >> 4);
-    const float2 *src = in + frame * NF + 32 * rank + 2 * cp;
-    float2 *dst = out + frame * NF + 32 * rank + 2 * cp;
-    const int sw = cp >> 3;                     // XOR bit of rows 2 cp and 2 cp + 1
+    const int lane = threadIdx.x & 31, cp = lane % CP, j = (32 / CP) * (threadIdx.x >> 5) + lane / CP;
+    const float2 *src = in + frame * NF + COLS * rank + 2 * cp;
+    float2 *dst = out + frame * NF + COLS * rank + 2 * cp;
+    const int sw = (cp >> 3) & 1;               // XOR bit of rows 2 cp and 2 cp + 1
     float2 *row0 = sbuf + rowbase(2 * cp), *row1 = sbuf + rowbase(2 * cp + 1);
 
     float2 y0[16], y1[16];
@@ -183,8 +185,11 @@ fft65536_cluster_kernel(const float2 *__restrict__ in, float2 *__restrict__ out,
         y0[m] = make_float2(t.x, t.y);
         y1[m] = make_float2(t.z, t.w);
     }
-    if (frame + prefetch_dist < nframes)  // one 256-byte row segment of the slice this CTA slot sees next
-        prefetch_l2(in + (frame + prefetch_dist) * NF + 256 * threadIdx.x + 32 * rank, 256);
+    if (frame + prefetch_dist < nframes) {  // the row segments of the slice this CTA slot sees next
+#pragma unroll
+        for (int r = 0; r < 256 / NTH; ++r)
+            prefetch_l2(in + (frame + prefetch_dist) * NF + 256 * (threadIdx.x + r * NTH) + COLS * rank, COLS * 8);
+    }
     FFTC_STAMP(1);
     bfly16<INV>(y0);
     FFTC_STAMP(2);
@@ -221,25 +226,26 @@ fft65536_cluster_kernel(const float2 *__restrict__ in, float2 *__restrict__ out,
 
     // ---- exchange: Y[k1][n2], Y[k1][n2 + 1] -> CTA k1 / 32, row k1 % 32, i = n2 (one 128-bit remote store)
     {
-        // k1 = j + 16 q -> rank q >> 1, row rr = j + 16 (q & 1) whose XOR bit is (q & 1)
-        const uint32_t local = smem_u32(sbuf + rowbase(j) + 32 * (int)rank + 2 * cp), lbar = smem_u32(&bar_full);
+        // k1 = j + 16 q -> rank k1 / COLS, row rr = k1 % COLS = j + 16 (q % (COLS/16)), whose XOR bit is (rr >> 4) & 1
+        const uint32_t local = smem_u32(sbuf + rowbase(j) + COLS * (int)rank + 2 * cp), lbar = smem_u32(&bar_full);
 #pragma unroll
         for (int sl = 0; sl < 16; ++sl) {
             const int q = q16(sl);
-            const uint32_t a = map_rank(local, (uint32_t)(q >> 1)) + (uint32_t)((q & 1) * (256 * 16 + 16) * (int)sizeof(float2));
-            const uint32_t rb = map_rank(lbar, (uint32_t)(q >> 1));
+            const int drank = (16 * q) / COLS, dhi = q % (COLS / 16);  // dhi = 1: rows 16..31 (COLS = 32 only)
+            const uint32_t a = map_rank(local, (uint32_t)drank) + (uint32_t)(dhi * (256 * 16 + 16) * (int)sizeof(float2));
+            const uint32_t rb = map_rank(lbar, (uint32_t)drank);
             if (MODE == 0) {
-                if (q & 1) st_async4(a, y1[sl], y0[sl], rb);
+                if (dhi) st_async4(a, y1[sl], y0[sl], rb);
                 else st_async4(a, y0[sl], y1[sl], rb);
             } else {
-                if (q & 1) st_cluster4(a, y1[sl], y0[sl]);
+                if (dhi) st_cluster4(a, y1[sl], y0[sl]);
                 else st_cluster4(a, y0[sl], y1[sl]);
             }
         }
     }
     if (MODE != 0) cluster_arrive_release();
     // ---- pass 3 twiddles while the pushes land: rows k1 = 32 rank + 2 cp (+ 1), W^{k1 (j + 16 m)}
-    const int k1 = 32 * (int)rank + 2 * cp;
+    const int k1 = COLS * (int)rank + 2 * cp;
     const float2 c0 = __ldg(twN + k1 * j), c1 = __ldg(twN + (k1 + 1) * j);
     const float2 w0 = __ldg(twN + 16 * k1), w1 = __ldg(twN + 16 * (k1 + 1));
     FFTC_STAMP(6);
@@ -294,15 +300,17 @@ static unsigned long long *g_fftc_dbg = nullptr;
 static int g_fftc_resident = 0;
 #endif
 
-template <bool INV, int MODE>
+template <bool INV, int MODE, int CL>
 static int launch(const float2 *in, float2 *out, const float2 *twN, size_t nframes, cudaStream_t s)
 {
-    auto kern = fft65536_cluster_kernel<INV, MODE>;
+    auto kern = fft65536_cluster_kernel<INV, MODE, CL>;
     static int resident[2] = {0, 0};  // co-resident clusters on this device (prefetch distance)
+    constexpr int SMEM = smem_bytes(CL);
     CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    if (CL > 8) CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(nframes * CL), 1, 1);
-    cfg.blockDim = dim3(256, 1, 1);
+    cfg.blockDim = dim3(2048 / CL, 1, 1);
     cfg.dynamicSmemBytes = SMEM;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -315,7 +323,7 @@ static int launch(const float2 *in, float2 *out, const float2 *twN, size_t nfram
     if (resident[INV] == 0) {
         int nc = 0;
         cudaLaunchConfig_t q = cfg;
-        q.gridDim = dim3(148 * 2 * CL, 1, 1);
+        q.gridDim = dim3(148 * 4 * CL, 1, 1);
         if (cudaOccupancyMaxActiveClusters(&nc, kern, &q) != cudaSuccess || nc <= 0) {
             cudaGetLastError();
             nc = 32;
@@ -342,15 +350,16 @@ int launch_fft65536_cluster(const float2 *in, float2 *out, const float2 *twN, si
 {
     if (nframes == 0) return CB_OK;
     // grid.x = 8 * frames must stay below 2^31
-    const size_t max_frames = (size_t)1 << 27;
+    const size_t max_frames = (size_t)1 << 26;
     for (size_t done = 0; done < nframes; done += max_frames) {
         const size_t g = nframes - done < max_frames ? nframes - done : max_frames;
         const float2 *gi = in + done * fftc::NF;
         float2 *go = out + done * fftc::NF;
         int rc;
-        if (tpt == 1) rc = inverse ? fftc::launch<true, 0>(gi, go, twN, g, s) : fftc::launch<false, 0>(gi, go, twN, g, s);
-        else if (tpt == 2) rc = inverse ? fftc::launch<true, 1>(gi, go, twN, g, s) : fftc::launch<false, 1>(gi, go, twN, g, s);
-        else rc = inverse ? fftc::launch<true, 2>(gi, go, twN, g, s) : fftc::launch<false, 2>(gi, go, twN, g, s);
+        if (tpt == 1) rc = inverse ? fftc::launch<true, 0, 8>(gi, go, twN, g, s) : fftc::launch<false, 0, 8>(gi, go, twN, g, s);
+        else if (tpt == 2) rc = inverse ? fftc::launch<true, 1, 8>(gi, go, twN, g, s) : fftc::launch<false, 1, 8>(gi, go, twN, g, s);
+        else if (tpt == 4) rc = inverse ? fftc::launch<true, 2, 16>(gi, go, twN, g, s) : fftc::launch<false, 2, 16>(gi, go, twN, g, s);
+        else rc = inverse ? fftc::launch<true, 2, 8>(gi, go, twN, g, s) : fftc::launch<false, 2, 8>(gi, go, twN, g, s);
         if (rc) return rc;
     }
     return CB_OK;

@@ -29,24 +29,24 @@ int main(int argc, char **argv)
     std::vector<float2> htw(N);
     for (size_t k = 0; k < N; ++k) htw[k] = make_float2((float)cos(-2 * M_PI * k / N), (float)sin(-2 * M_PI * k / N));
     cudaMemcpy(tw, htw.data(), N * 8, cudaMemcpyHostToDevice);
-    cudaMalloc(&cb::fftc::g_fftc_dbg, nframes * 8 * 12 * 8);
+    cudaMalloc(&cb::fftc::g_fftc_dbg, nframes * 16 * 12 * 8);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     for (int it = 0; it < 3; ++it) {
         cudaEventRecord(e0);
-        if (cb::launch_fft65536_cluster(in, out, tw, nframes, false, 2, 0)) return 1;
+        if (cb::launch_fft65536_cluster(in, out, tw, nframes, false, argc > 2 ? atoi(argv[2]) : 3, 0)) return 1;
         cudaEventRecord(e1);
         if (cudaDeviceSynchronize() != cudaSuccess) { fprintf(stderr, "kernel failed: %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
         float ms;
         cudaEventElapsedTime(&ms, e0, e1);
         printf("run %d: %.3f ms  %.1f Gsamples/s  resident clusters %d\n", it, ms, nframes * N / ms / 1e6, cb::fftc::g_fftc_resident);
     }
-    std::vector<unsigned long long> d(nframes * 8 * 12);
+    std::vector<unsigned long long> d(nframes * 16 * 12);
     cudaMemcpy(d.data(), cb::fftc::g_fftc_dbg, d.size() * 8, cudaMemcpyDeviceToHost);
     const char *names[9] = {"issue global loads", "loads land + bfly y0", "bfly y1 + STS + syncthreads", "LDS + startup wait + pass2 math",
                             "wait peers ready", "push (st.async issue) + twiddle LDG", "wait pushes landed", "pass3 LDS/sync/math/STS/sync", "pass4 + STG issue"};
-    const size_t ncta = nframes * 8;
+    const size_t cl = (argc > 2 && atoi(argv[2]) == 4) ? 16 : 8, ncta = nframes * cl;
     double sum[9] = {0}, tot = 0;
     std::vector<double> durs;
     for (size_t c = 0; c < ncta; ++c) {
