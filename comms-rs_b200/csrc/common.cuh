@@ -90,6 +90,22 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
         : "memory");
 }
 
+// Same with an L2 evict-first hint: read-once streams should not displace the write-back lines of the output.
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint64_t pol)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+}
+
 // TMA 1-D bulk copy shared -> global (bulk async-group completion).
 __device__ __forceinline__ void tma_store_1d(void *dst_gmem, const void *src_smem, uint32_t bytes)
 {

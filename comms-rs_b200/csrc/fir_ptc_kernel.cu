@@ -32,8 +32,10 @@
 // same fp32 TMEM accumulator.  Relative L2 error vs the sequential f32 form ~3e-7 (tolerance 1e-5).
 //
 // Roles (E epilogue warps first, E = 4, or 8 with the fused i16 quantiser; one persistent CTA per SM):
-//   warps E..E+3 loader: coalesced LDG.128 of the raw f32 tile -> block max -> scale, split,
-//              de-interleave, st.shared (pre-swizzled) -> fence.proxy.async -> mbarrier a_full
+//   warps E..E+3 loaders / converters: raw f32 tile (coalesced LDG.128; or, with the fused quantiser, from a
+//              ring of raw stages that the TMA warp E+5 fills with 4 KiB bulk copies one or two tiles ahead)
+//              -> block max -> scale, split, de-interleave, st.shared (pre-swizzled) -> fence.proxy.async
+//              -> mbarrier a_full
 //   warp  E+4  one thread issues 3 KS tcgen05.mma (M128 N256 K16) per tile, commits a_empty/t_full
 //   warps 0..E-1 epilogue (E/4 per TMEM sub-partition, alternating 32-column chunks): tcgen05.ld 32 lanes
 //              x 32 columns (re) + (im) -> unscale [-> i16] -> st.global
@@ -52,7 +54,8 @@ namespace ptc {
 // epilogue warps: warp w drains TMEM sub-partition w % 4, 32-column chunks w / 4, w / 4 + NEPI / 4, ...
 // 4 are enough for f32 output; the fused i16 quantiser doubles the per-column work and gets 8
 __host__ __device__ constexpr int nepi(bool out16) { return out16 ? 8 : 4; }
-__host__ __device__ constexpr int nthreads(bool out16) { return 32 * (nepi(out16) + 4 + 1); }  // + 4 loader warps + 1 MMA warp
+// + 4 loader / converter warps + MMA warp (+ TMA warp when the raw tile is staged by bulk copies)
+__host__ __device__ constexpr int nthreads(bool out16) { return 32 * (nepi(out16) + 4 + (out16 ? 2 : 1)); }
 constexpr int NLOAD = 128;                    // loader threads
 
 struct Args {
@@ -154,10 +157,16 @@ __device__ __forceinline__ uint32_t trunc_i16(float v)
 
 // OUT16: the example's quantiser `(8192 x) as i16` fused into the epilogue: 4 bytes written per output
 // sample instead of 8 (and no separate pass over the f32 result)
-template <int L, bool CPLX, bool OUT16>
-__global__ void __launch_bounds__(OUT16 ? 512 : 288, 1) fir_ptc_kernel(const __grid_constant__ Args a)  // 512: 128-register cap (13 warps)
+// Raw tile supply, measured both ways on config 1: with f32 output the kernel is HBM-bound (96 % of the roof) and
+// per-thread LDG.128 loads straight into registers are best; with the i16 output the write traffic halves, the
+// exposed load latency of the single loader group becomes the limiter, and a TMA warp that keeps a ring of NRAW
+// raw tiles filled ahead of the converters wins (0.436 -> 0.398 ms).  TMA_LOAD = OUT16.
+template <int L, bool CPLX, bool OUT16, int NRAW>
+__global__ void __launch_bounds__(OUT16 ? 512 : 288, 1) fir_ptc_kernel(const __grid_constant__ Args a)  // 512: 128-register cap (14 warps)
 {
+    constexpr bool TMA_LOAD = OUT16;
     constexpr int NEPI = nepi(OUT16), NTHREADS = nthreads(OUT16);
+    constexpr int RAWB = Geo<L, CPLX>::NEL * 8;  // bytes of one raw tile (incl. halo)
     using G = Geo<L, CPLX>;
     constexpr int RS = G::RS, ROWB = G::ROWB, NLD = G::NLD;
     constexpr uint32_t IDESC = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, M128 N256
@@ -172,7 +181,9 @@ __global__ void __launch_bounds__(OUT16 ? 512 : 288, 1) fir_ptc_kernel(const __g
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *sS = smem;                            // 2 stages x (hi, lo)
     unsigned char *sH = smem + 2 * G::STAGE;             // tap image: KS*4096 bytes per part
+    unsigned char *sRaw = sH + KS * (CPLX ? 16384 : 8192);  // NRAW raw f32 tiles
     __shared__ __align__(8) uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2], sc_ready[8];
+    __shared__ __align__(8) uint64_t raw_full[NRAW], raw_empty[NRAW];
     __shared__ uint32_t tmem_slot;
     __shared__ float red_max[4];
     __shared__ float inv_scale[8];
@@ -188,6 +199,10 @@ __global__ void __launch_bounds__(OUT16 ? 512 : 288, 1) fir_ptc_kernel(const __g
             mbar_init(&t_empty[i], 32 * NEPI);
         }
         for (int i = 0; i < 8; ++i) mbar_init(&sc_ready[i], 1);
+        for (int i = 0; i < NRAW; ++i) {
+            mbar_init(&raw_full[i], 1);
+            mbar_init(&raw_empty[i], NLOAD);
+        }
         fence_mbar_init();
     }
     if (warp == NEPI + 4) {
@@ -202,14 +217,40 @@ __global__ void __launch_bounds__(OUT16 ? 512 : 288, 1) fir_ptc_kernel(const __g
         const int part = i >> 6, o = i & 63;
         reinterpret_cast<uint4 *>(sS + part * G::PART + G::NREG * G::COMP)[o] = make_uint4(0u, 0u, 0u, 0u);
     }
+    if (TMA_LOAD)
+        for (int i = tid; i < NRAW * RAWB / 16; i += NTHREADS) reinterpret_cast<uint4 *>(sRaw)[i] = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
-    if (warp >= NEPI && warp < NEPI + 4) {
-        // ------------------------------------------------------------------ loader
+    if (TMA_LOAD && warp == NEPI + 5) {
+        // ------------------------------------------------------------------ TMA producer: raw f32 tiles, HBM -> shared
+        // tile elements e = 0 .. NEL-1 are symbols g = t0 - HALO + e: the first tile's halo comes from the history
+        // buffer, everything else from x; an odd trailing sample (16-byte granularity) is left to the converters
+        unsigned long long it = 0;
+        const uint64_t pol = l2_evict_first_policy();
+        for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int rs = (int)(it % NRAW);
+            const uint32_t ph = (uint32_t)((it / NRAW) & 1);
+            const long long g0 = (long long)tile * TS - HALO;
+            const long long g_lo = g0 < 0 ? 0 : g0;
+            long long g_hi = g0 + G::NEL;
+            if (g_hi > (long long)a.n) g_hi = (long long)a.n & ~1ll;
+            if (g_hi < g_lo) g_hi = g_lo;
+            mbar_wait(&raw_empty[rs], ph ^ 1);
+            unsigned char *dstb = sRaw + rs * RAWB;
+            if (lane == 0) mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)((g_hi - g_lo) * 8 + (g0 < 0 ? -g0 * 8 : 0)));
+            __syncwarp();
+            if (g0 < 0 && lane == 31) tma_load_1d(dstb, a.halo + (HALO + g0), (uint32_t)(-g0 * 8), &raw_full[rs]);
+            for (long long g = g_lo + (long long)lane * 512; g < g_hi; g += 32 * 512) {  // 4 KiB pieces
+                const long long n = g_hi - g < 512 ? g_hi - g : 512;
+                tma_load_1d_hint(dstb + (g - g0) * 8, a.x + g, (uint32_t)(n * 8), &raw_full[rs], pol);
+            }
+        }
+    } else if (warp >= NEPI && warp < NEPI + 4) {
+        // ------------------------------------------------------------------ converters (block scale, fp16 split)
         const int gt = tid - 32 * NEPI, gw = warp - NEPI;
         if (a.hist_out != nullptr && blockIdx.x == 0) {
             const long long H = a.hist_len;
@@ -223,24 +264,27 @@ __global__ void __launch_bounds__(OUT16 ? 512 : 288, 1) fir_ptc_kernel(const __g
             const int s = (int)(it & 1);
             const uint32_t ph = (uint32_t)((it >> 1) & 1);
             const long long t0 = (long long)tile * TS;
+            const int rs = (int)(it % NRAW);
             float4 raw[NLD];
             float mx = 0.f;
+            if (TMA_LOAD) mbar_wait(&raw_full[rs], (uint32_t)((it / NRAW) & 1));
+            const float4 *rawt = reinterpret_cast<const float4 *>(sRaw + rs * RAWB);
 #pragma unroll
             for (int i = 0; i < NLD; ++i) {
                 const int q = gt + i * NLOAD;               // pair index: elements 2q, 2q+1
                 const long long g = t0 - HALO + 2 * q;      // even
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (g < 0) {
-                    v = ldg_stream(reinterpret_cast<const float4 *>(a.halo + (HALO + g)));
-                } else if (g + 1 < (long long)a.n) {
-                    v = ldg_stream(reinterpret_cast<const float4 *>(a.x + g));
-                } else if (g < (long long)a.n) {
+                if (g < 0 || g + 1 < (long long)a.n) {
+                    if (TMA_LOAD) v = rawt[q];
+                    else v = ldg_stream(reinterpret_cast<const float4 *>(g < 0 ? a.halo + (HALO + g) : a.x + g));
+                } else if (g < (long long)a.n) {            // odd trailing sample (not covered by 16-byte copies)
                     const float2 t = a.x[g];
                     v = make_float4(t.x, t.y, 0.f, 0.f);
                 }
                 raw[i] = v;
                 mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
             }
+            if (TMA_LOAD) mbar_arrive(&raw_empty[rs]);  // the raw tile is in registers: the TMA warp may refill the stage
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             if (lane == 0) red_max[gw] = mx;
@@ -394,7 +438,8 @@ bool fir_ptc_supported(uint32_t ntaps, uint32_t L, bool taps_real)
     // shared memory: two stream stages + the tap image (+ alignment slack) must fit in 227 KiB
     const size_t comp = (size_t)128 * 2 * ptc_rs(L);
     const size_t stage = 2 * ((taps_real ? 2 : 3) * comp + 1024);
-    return 2 * stage + fir_ptc_image_bytes(ntaps, L, taps_real) + 1024 <= 227 * 1024;
+    const size_t raw = (size_t)128 * ptc_rs(L) * 8;  // one raw f32 tile
+    return 2 * stage + fir_ptc_image_bytes(ntaps, L, taps_real) + raw + 1024 <= 227 * 1024;
 }
 
 size_t fir_ptc_image_bytes(uint32_t ntaps, uint32_t L, bool taps_real)
@@ -438,12 +483,12 @@ void fir_ptc_build_image(const float2 *taps, uint32_t ntaps, uint32_t L, bool ta
     }
 }
 
-template <int L, bool CPLX, bool OUT16>
-static int launch_ptc_l(const ptc::Args &a, cudaStream_t stream)
+template <int L, bool CPLX, bool OUT16, int NRAW>
+static int launch_ptc_raw(const ptc::Args &a, cudaStream_t stream)
 {
     using G = ptc::Geo<L, CPLX>;
-    const int SMEM = 2 * G::STAGE + (int)a.ks * (CPLX ? 16384 : 8192) + 1024;
-    auto kern = ptc::fir_ptc_kernel<L, CPLX, OUT16>;
+    const int SMEM = 2 * G::STAGE + (int)a.ks * (CPLX ? 16384 : 8192) + (OUT16 ? NRAW * G::NEL * 8 : 0) + 1024;
+    auto kern = ptc::fir_ptc_kernel<L, CPLX, OUT16, NRAW>;
     CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const int KT = 16 * (int)a.ks;
     const unsigned long long TS = (unsigned long long)(((G::NEL - KT) / G::RS + 1) * G::RS);
@@ -456,6 +501,16 @@ static int launch_ptc_l(const ptc::Args &a, cudaStream_t stream)
     count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;
+}
+
+// two raw stages when they fit in shared memory, else one
+template <int L, bool CPLX, bool OUT16>
+static int launch_ptc_l(const ptc::Args &a, cudaStream_t stream)
+{
+    using G = ptc::Geo<L, CPLX>;
+    const size_t need2 = 2 * (size_t)G::STAGE + (size_t)a.ks * (CPLX ? 16384 : 8192) + 2 * (size_t)G::NEL * 8 + 1024;
+    if (!OUT16 || need2 <= 227 * 1024) return launch_ptc_raw<L, CPLX, OUT16, 2>(a, stream);
+    return launch_ptc_raw<L, CPLX, OUT16, 1>(a, stream);
 }
 
 bool fir_ptc_applicable(const FirSeg &seg, bool taps_real)
