@@ -138,6 +138,13 @@ __device__ __forceinline__ void stg_stream(float4 *p, float4 v)
                  "f"(v.w)
                  : "memory");
 }
+// 256-bit streaming store (sm_100: STG.E.NA.256), p 32-byte aligned
+__device__ __forceinline__ void stg_stream8(float *p, const float *v)
+{
+    asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
 __device__ __forceinline__ void stg_stream2(float2 *p, float2 v)
 {
     asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");

@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
         // ------------------------------------------------------------------ epilogue
         const int e = warp - 8;  // TMEM sub-partition = warp % 4
         unsigned char *stage = sOut + e * OUT_WARP;
+        const bool direct = (reinterpret_cast<uintptr_t>(a.y) & 31) == 0;
         unsigned long long it = 0;
         for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int s = (int)(it & 1);
@@ -278,6 +279,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
             mbar_wait(&t_full[s], ph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * e) << 16) + (uint32_t)s * 128u;
+            // Lane m of this warp owns row 32 e + m of the tile = 32 consecutive output samples (256 bytes).  With the
+            // y pointer 32-byte aligned the row goes out as 8 x 256-bit stores (whole sectors, no shared-memory
+            // transpose: the staging round trip was 16 B/sample of shared-memory traffic on the busiest pipe);
+            // otherwise through the padded per-warp staging buffer and 128-bit coalesced stores.
+            const long long row = t0 + (long long)(32 * e + lane) * RS;
+            if (direct) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t p[32], r[32];
+                    tc_ld32(taddr + half * 32, p);
+                    tc_ld32(taddr + 64 + half * 32, r);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            v[u] = (__uint_as_float(p[8 * c + u]) + __uint_as_float(r[8 * c + u])) * k0 * k1;
+                        const long long sidx = row + 16 * half + 4 * c;  // 4 complex samples = 32 bytes
+                        if (sidx + 3 < (long long)a.n) {
+                            stg_stream8(reinterpret_cast<float *>(a.y + sidx), v);
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (sidx + u < (long long)a.n) a.y[sidx + u] = make_float2(v[2 * u], v[2 * u + 1]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&t_empty[s]);
+                continue;
+            }
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 uint32_t p[32], r[32];
