@@ -45,7 +45,7 @@ constexpr int ROWS = 128;          // MMA M
 constexpr int RS = 32;             // complex outputs per row
 constexpr int TILE = ROWS * RS;    // 4096 outputs per tile
 constexpr int NCONV = 128;         // loader threads
-constexpr int NTHREADS = 416;     // 2 loader groups (2 x 4 warps) + 4 epilogue warps + 1 MMA warp
+constexpr int NTHREADS = 448;     // 2 converter groups (2 x 4 warps) + 4 epilogue warps + MMA warp + TMA warp
 constexpr int A_PART = 18432;      // bytes reserved for one fp16 stream part (>= (128+4)*128, 1024-aligned)
 constexpr int A_STAGE = 2 * A_PART;
 constexpr int OUT_PITCH = 272;     // padded row pitch of the output staging (bytes)
@@ -117,8 +117,9 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr)
 
 __device__ __forceinline__ uint32_t swz128(uint32_t o) { return o ^ (((o >> 7) & 7) << 4); }
 
-template <int KB>
-__global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_constant__ Args a)
+// NRAW raw f32 tiles are kept in flight by the TMA warp (2 when shared memory allows, i.e. up to 64 taps, else 1)
+template <int KB, int NRAW>
+__global__ void __launch_bounds__(512, 1) fir_tc_kernel(const __grid_constant__ Args a)  // 512: 128-register cap (14 warps)
 {
     constexpr int HALO = RS * (KB - 1);            // complex samples of history per tile
     constexpr int NPAIR = (TILE + HALO) / 2;       // 16-byte pairs of complex samples per tile
@@ -132,6 +133,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
     unsigned char *sB = smem;                      // B image
     unsigned char *sA = smem + B_BYTES;            // 2 stages x (hi, lo)
     unsigned char *sOut = sA + 2 * A_STAGE;        // 4 warps x 32 rows x 272 B
+    constexpr int RAWB = (TILE + HALO) * 8;        // one raw f32 tile incl. halo
+    unsigned char *sRaw = sOut + 4 * OUT_WARP;     // NRAW raw tiles (TMA destination)
+    __shared__ __align__(8) uint64_t raw_full[NRAW], raw_empty[NRAW];
     __shared__ __align__(8) uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2], sc_ready[8];
     __shared__ uint32_t tmem_slot;
     __shared__ float red_max[2][4];  // [loader group][warp]
@@ -148,6 +152,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
             mbar_init(&t_empty[i], 128);
         }
         for (int i = 0; i < 8; ++i) mbar_init(&sc_ready[i], 1);
+        for (int i = 0; i < NRAW; ++i) {
+            mbar_init(&raw_full[i], 1);
+            mbar_init(&raw_empty[i], NCONV);
+        }
         fence_mbar_init();
     }
     if (warp == 12) {
@@ -158,14 +166,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
     }
     // B image: plain copy, then publish to the async proxy (tcgen05.mma reads it)
     for (int i = tid; i < B_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4 *>(sB)[i] = a.bimg[i];
+    for (int i = tid; i < NRAW * RAWB / 16; i += NTHREADS) reinterpret_cast<uint4 *>(sRaw)[i] = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
-    if (warp < 8) {
-        // ------------------------------------------------------------------ loaders
+    if (warp == 13) {
+        // ------------------------------------------------------------------ TMA producer: raw f32 tiles, HBM -> shared
+        // raw stage rs = it % NRAW holds samples g = t0 - HALO + e, e = 0 .. TILE + HALO - 1; the first tile's halo comes
+        // from the history buffer; an odd trailing sample (16-byte copy granularity) is left to the converters
+        unsigned long long it = 0;
+        for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int rs = (int)(it % NRAW);
+            const uint32_t ph = (uint32_t)((it / NRAW) & 1);
+            const long long g0 = (long long)tile * TILE - HALO;
+            const long long g_lo = g0 < 0 ? 0 : g0;
+            long long g_hi = g0 + TILE + HALO;
+            if (g_hi > (long long)a.n) g_hi = (long long)a.n & ~1ll;
+            if (g_hi < g_lo) g_hi = g_lo;
+            mbar_wait(&raw_empty[rs], ph ^ 1);
+            unsigned char *dstb = sRaw + rs * RAWB;
+            if (lane == 0) mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)((g_hi - g_lo) * 8 + (g0 < 0 ? -g0 * 8 : 0)));
+            __syncwarp();
+            if (g0 < 0 && lane == 31) tma_load_1d(dstb, a.halo + (HALO + g0), (uint32_t)(-g0 * 8), &raw_full[rs]);
+            for (long long g = g_lo + (long long)lane * 256; g < g_hi; g += 32 * 256) {  // 2 KiB pieces
+                const long long n = g_hi - g < 256 ? g_hi - g : 256;
+                tma_load_1d(dstb + (g - g0) * 8, a.x + g, (uint32_t)(n * 8), &raw_full[rs]);
+            }
+        }
+    } else if (warp < 8) {
+        // ------------------------------------------------------------------ converters (two groups, even / odd tiles)
         const int grp = warp >> 2, gt = tid & (NCONV - 1), gw = warp & 3;
         if (a.hist_out != nullptr && blockIdx.x == 0 && grp == 0) {
             const long long H = a.hist_len;
@@ -182,17 +214,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
             const long long t0 = (long long)tile * TILE;
             float4 raw[NLD];
             float mx = 0.f;
+            const int rs = (int)(it % NRAW);
+            mbar_wait(&raw_full[rs], (uint32_t)((it / NRAW) & 1));
+            const float4 *rawt = reinterpret_cast<const float4 *>(sRaw + rs * RAWB);
 #pragma unroll
             for (int i = 0; i < NLD; ++i) {
                 const int q = gt + i * NCONV;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (q < NPAIR) {
                     const long long g = t0 - HALO + 2 * q;  // even
-                    if (g < 0) {
-                        v = ldg_stream(reinterpret_cast<const float4 *>(a.halo + (HALO + g)));
-                    } else if (g + 1 < (long long)a.n) {
-                        v = ldg_stream(reinterpret_cast<const float4 *>(a.x + g));
-                    } else if (g < (long long)a.n) {
+                    if (g < 0 || g + 1 < (long long)a.n) {
+                        v = rawt[q];
+                    } else if (g < (long long)a.n) {  // odd trailing sample: not covered by the 16-byte bulk copies
                         const float2 t = a.x[g];
                         v = make_float4(t.x, t.y, 0.f, 0.f);
                     }
@@ -200,6 +233,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
                 raw[i] = v;
                 mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
             }
+            mbar_arrive(&raw_empty[rs]);  // tile is in registers: the TMA warp may refill the stage
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             if (lane == 0) red_max[s][gw] = mx;
@@ -406,8 +440,12 @@ void fir_tc_build_image(const float2 *taps, uint32_t ntaps, unsigned char *img, 
 template <int KB>
 static int launch_tc_kb(const tc::Args &a, cudaStream_t stream)
 {
-    constexpr int SMEM = KB * 16384 + 2 * tc::A_STAGE + 4 * tc::OUT_WARP + 1024;
-    auto kern = tc::fir_tc_kernel<KB>;
+    constexpr int RAWB = (tc::TILE + tc::RS * (KB - 1)) * 8;
+    constexpr int BASE = KB * 16384 + 2 * tc::A_STAGE + 4 * tc::OUT_WARP + 1024;
+    constexpr int NRAW = BASE + 2 * RAWB <= 227 * 1024 ? 2 : 1;
+    constexpr int SMEM = BASE + NRAW * RAWB;
+    static_assert(SMEM <= 227 * 1024, "fir_tc: shared memory budget");
+    auto kern = tc::fir_tc_kernel<KB, NRAW>;
     CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const unsigned long long ntiles = (a.n + tc::TILE - 1) / tc::TILE;
     int dev = 0, sms = 148;
