@@ -955,8 +955,11 @@ int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
     if (kind == FFT_FOURSTEP) {
         FFT_TRY(upload_twiddles((size_t)1 << l1, inverse, &h->tw1));
         FFT_TRY(upload_twiddles((size_t)1 << l2, inverse, &h->tw2));
-        size_t frames = ((size_t)32 << 20) / (fft_size * sizeof(float2));
+        size_t scratch_mb = 32;
+        if (const char *e = getenv("COMMS_B200_FFT_SCRATCH_MB")) scratch_mb = (size_t)atol(e) > 0 ? (size_t)atol(e) : 32;
+        size_t frames = (scratch_mb << 20) / (fft_size * sizeof(float2));
         if (frames < 1) frames = 1;
+        if (fft_size == 65536) FFT_TRY(upload_fft2_table(12, inverse, &h->tw16));  // rows of the 16 x 4096 two-pass form
         h->plan.scratch_frames = frames;
         cudaError_t e = cudaMalloc(&h->scratch, frames * fft_size * sizeof(float2));
         if (e != cudaSuccess) {
@@ -977,6 +980,7 @@ int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
         h->plan.cluster_tpt = 3;
         if (path && strcmp(path, "cluster2") == 0) h->plan.cluster_tpt = 2;
         if (path && strcmp(path, "cluster16") == 0) h->plan.cluster_tpt = 4;  // 16-CTA clusters, 4 CTAs per SM
+        if (path && strcmp(path, "twopass") == 0) h->plan.cluster_tpt = 5;    // 16 x 4096, two streaming passes
         if (path && strcmp(path, "fourstep") == 0) h->plan.cluster_tpt = 0;
         if (path && strcmp(path, "cluster1") == 0) h->plan.cluster_tpt = 1;  // exchange variants, see fft_cluster_kernel.cu
     }

@@ -190,7 +190,9 @@ __device__ __forceinline__ void fft2_passes(int j, const float2 *tw, GLD gld, GS
     }
 }
 
-template <int LOG2N, bool INV>
+// ROWS16: frame fr is row k1 = fr % 16 of the 16 x 4096 intermediate of a 65536-point transform
+// (fft65536_stepA_kernel); output element k2 of the row is X[k1 + 16 k2] of big frame fr / 16.
+template <int LOG2N, bool INV, bool ROWS16 = false>
 __global__ void __launch_bounds__(Fft2Cfg<LOG2N>::THREADS, Fft2Cfg<LOG2N>::MINB)
 fft2_frames_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, const float2 *__restrict__ tw,
                    size_t nframes)
@@ -202,12 +204,12 @@ fft2_frames_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, cons
     const size_t frame = (size_t)blockIdx.x * CF::FPB + f;
     const bool live = frame < nframes;
     const float2 *src = in + frame * PL::N;
-    float2 *dst = out + frame * PL::N;
+    float2 *dst = ROWS16 ? out + (frame >> 4) * (PL::N * 16) + (frame & 15) : out + frame * PL::N;
     float2 *b0 = fsm + f * PL::PADN;
     float2 *b1 = CF::PINGPONG ? b0 + CF::FPB * PL::PADN : b0;
     auto gld = [&](int i) { return live ? ldg_stream2(src + i) : make_float2(0.f, 0.f); };
     auto gst = [&](int i, float2 v) {
-        if (live) stg_stream2(dst + i, v);
+        if (live) stg_stream2(dst + (ROWS16 ? 16 * i : i), v);
     };
     if constexpr (CF::PINGPONG) {
         fft2_passes<LOG2N, INV, 0>(j, tw, gld, gst, b0, b1);
@@ -449,6 +451,107 @@ static int launch_step_dir(int which, int log2m, const float2 *in, float2 *out, 
     }
 }
 
+// ---------------------------------------------------------------- 65536 = 16 x 4096, two streaming passes
+// step A: for every n2, the 16-point DFT over n1 of x[4096 n1 + n2], times W_N^{n2 k1}, stored as row k1
+// (no shared memory: 16 coalesced loads, one radix-16 butterfly, 16 coalesced stores per thread);
+// step B: fft2_frames_kernel<12, INV, true> on the 16 rows, scattering X[k1 + 16 k2].
+template <bool INV>
+__global__ void __launch_bounds__(256)
+fft65536_stepA_kernel(const float2 *__restrict__ in, float2 *__restrict__ mid, const float2 *__restrict__ twN, size_t nframes)
+{
+    const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const size_t frame = idx >> 12;
+    const int n2 = (int)(idx & 4095);
+    if (frame >= nframes) return;
+    const float2 *src = in + frame * 65536 + n2;
+    float2 *dst = mid + frame * 65536 + n2;
+    float2 v[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) v[m] = ldg_stream2(src + 4096 * m);
+    fft2::bfly16<INV>(v);  // slot sl holds k1 = fft2::q16(sl)
+    float2 p[16];    // p[k] = W_N^{n2 k}
+    p[0] = make_float2(1.f, 0.f);
+    p[1] = __ldg(twN + n2);
+    p[2] = fft2::csqr(p[1]);
+    p[3] = fft2::cmul(p[2], p[1]);
+    p[4] = fft2::csqr(p[2]);
+    p[5] = fft2::cmul(p[4], p[1]);
+    p[6] = fft2::csqr(p[3]);
+    p[7] = fft2::cmul(p[4], p[3]);
+    p[8] = fft2::csqr(p[4]);
+#pragma unroll
+    for (int k = 9; k < 16; ++k) p[k] = (k & 1) ? fft2::cmul(p[8], p[k - 8]) : fft2::csqr(p[k / 2]);
+#pragma unroll
+    for (int sl = 0; sl < 16; ++sl) {
+        const int k1 = fft2::q16(sl);
+        stg_stream2(dst + 4096 * k1, k1 ? fft2::cmul(v[sl], p[k1]) : v[sl]);
+    }
+}
+
+// step B, four rows per CTA: rows k1 = 4a .. 4a+3 of one big frame are transformed side by side (256 threads
+// each, passes 0 and 1 as in fft2_frames_kernel); for the last pass the 1024 threads are re-partitioned so that
+// four consecutive lanes hold the same output index k2 of the four rows: X[4a + r + 16 k2], r = 0..3, is one
+// full 32-byte sector per quad of lanes instead of four 8-byte pieces 128 bytes apart.
+template <bool INV>
+__global__ void __launch_bounds__(1024, 1)
+fft65536_stepB_kernel(const float2 *__restrict__ mid, float2 *__restrict__ out, const float2 *__restrict__ tw, size_t nquads)
+{
+    using PL = fft2::Plan<12>;
+    constexpr int RPITCH = PL::PADN + 8;  // + 64 bytes: the four rows of a lane quad fall into different banks
+    extern __shared__ __align__(16) float2 fsm[];
+    const size_t quad = blockIdx.x;
+    if (quad >= nquads) return;
+    const size_t F = quad >> 2;
+    const int a4 = (int)(quad & 3) * 4;
+    const int f = threadIdx.x >> 8, j = threadIdx.x & 255;
+    const float2 *src = mid + (F * 16 + a4 + f) * PL::N;
+    DevSm sm{fsm + f * RPITCH};
+    auto gld = [&](int i) { return ldg_stream2(src + i); };
+    auto nogst = [](int, float2) {};
+    auto nomid = [] {};
+    auto mid_bar = [] { __syncthreads(); };
+    fft2::run_pass<12, INV, 0>(j, tw, gld, nogst, sm, sm, nomid);
+    __syncthreads();
+    fft2::run_pass<12, INV, 1>(j, tw, gld, nogst, sm, sm, mid_bar);
+    __syncthreads();
+    const int r = threadIdx.x & 3, jq = threadIdx.x >> 2;
+    DevSm smr{fsm + r * RPITCH};
+    float2 *dst = out + F * 65536 + a4 + r;
+    auto gst = [&](int i, float2 v) { stg_stream2(dst + 16 * i, v); };
+    fft2::run_pass<12, INV, 2>(jq, tw, gld, gst, smr, smr, nomid);
+}
+
+int launch_fft65536_two_pass(const float2 *in, float2 *out, float2 *scratch, size_t scratch_frames, const float2 *twN,
+                             const float2 *tw16_12, size_t nframes, bool inverse, cudaStream_t s)
+{
+    using CF = Fft2Cfg<12>;
+    size_t done = 0;
+    while (done < nframes) {
+        const size_t g = nframes - done < scratch_frames ? nframes - done : scratch_frames;
+        const float2 *gi = in + done * 65536;
+        float2 *go = out + done * 65536;
+        const unsigned gridA = (unsigned)(g * 4096 / 256);
+        constexpr int SMEMB = 4 * (fft2::Plan<12>::PADN + 8) * (int)sizeof(float2);
+        (void)sizeof(CF);
+        if (inverse) {
+            auto kb = fft65536_stepB_kernel<true>;
+            CB_CUDA(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEMB));
+            fft65536_stepA_kernel<true><<<gridA, 256, 0, s>>>(gi, scratch, twN, g);
+            kb<<<(unsigned)(g * 4), 1024, SMEMB, s>>>(scratch, go, tw16_12, g * 4);
+        } else {
+            auto kb = fft65536_stepB_kernel<false>;
+            CB_CUDA(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEMB));
+            fft65536_stepA_kernel<false><<<gridA, 256, 0, s>>>(gi, scratch, twN, g);
+            kb<<<(unsigned)(g * 4), 1024, SMEMB, s>>>(scratch, go, tw16_12, g * 4);
+        }
+        count_launch();
+        count_launch();
+        CB_CUDA(cudaGetLastError());
+        done += g;
+    }
+    return CB_OK;
+}
+
 int fft_plan_split(size_t n, int *log2n1, int *log2n2)
 {
     int l = 0;
@@ -470,6 +573,8 @@ int launch_fft(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframe
         return p.inverse ? launch_frames_dir<true>(p.log2n, in, out, p.tw, nframes, s)
                          : launch_frames_dir<false>(p.log2n, in, out, p.tw, nframes, s);
     }
+    if (p.kind == FFT_FOURSTEP && p.n == 65536 && p.cluster_tpt == 5 && p.tw16 != nullptr)
+        return launch_fft65536_two_pass(in, out, p.scratch, p.scratch_frames, p.tw, p.tw16, nframes, p.inverse != 0, s);
     if (p.kind == FFT_FOURSTEP && p.n == 65536 && p.cluster_tpt > 0)
         return launch_fft65536_cluster(in, out, p.tw, nframes, p.inverse != 0, p.cluster_tpt, s);
     if (p.kind == FFT_FOURSTEP) {
