@@ -79,6 +79,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         : "memory");
 }
 
+// Same wait for roles that expect to sleep for a whole pipeline stage: a suspend-time hint keeps the thread
+// parked in hardware instead of re-issuing try_wait / branch pairs that compete for issue slots.
+__device__ __forceinline__ void mbar_wait_long(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(20000u)
+        : "memory");
+}
+
 // TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier.
 // dst/src 16-byte aligned, bytes a multiple of 16.  SASS: UBLKCP.
 __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)

@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(OUT16 ? 512 : 288, 1) fir_ptc_kernel(const __g
             long long g_hi = g0 + G::NEL;
             if (g_hi > (long long)a.n) g_hi = (long long)a.n & ~1ll;
             if (g_hi < g_lo) g_hi = g_lo;
-            mbar_wait(&raw_empty[rs], ph ^ 1);
+            mbar_wait_long(&raw_empty[rs], ph ^ 1);
             unsigned char *dstb = sRaw + rs * RAWB;
             if (lane == 0) mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)((g_hi - g_lo) * 8 + (g0 < 0 ? -g0 * 8 : 0)));
             __syncwarp();
@@ -329,8 +329,8 @@ __global__ void __launch_bounds__(OUT16 ? 512 : 288, 1) fir_ptc_kernel(const __g
             for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
                 const int s = (int)(it & 1);
                 const uint32_t ph = (uint32_t)((it >> 1) & 1);
-                mbar_wait(&t_empty[s], ph ^ 1);
-                mbar_wait(&a_full[s], ph);
+                mbar_wait_long(&t_empty[s], ph ^ 1);
+                mbar_wait_long(&a_full[s], ph);
                 tc_fence_after();
                 const uint32_t shi = smem_u32(sS + s * G::STAGE), slo = shi + G::PART;
                 const uint32_t d = tmem_base + (uint32_t)s * 256u;
@@ -374,12 +374,14 @@ __global__ void __launch_bounds__(OUT16 ? 512 : 288, 1) fir_ptc_kernel(const __g
             // result equals quantising the f32 output.
             const bool q_pow2 = OUT16 && (__float_as_uint(a.qscale) & 0x007FFFFFu) == 0u && a.qscale > 0.f;
             const float kq = q_pow2 ? k * a.qscale : k;
-            mbar_wait(&t_full[s], ph);
+            mbar_wait_long(&t_full[s], ph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * e) << 16) + (uint32_t)s * 256u;
             float2 *yrow = a.y + (long long)L * t0 + m;   // + 128 n per column
             uint32_t *qrow = reinterpret_cast<uint32_t *>(a.y16) + (long long)L * t0 + m;
-            const long long srem = (long long)a.n - t0 - msym;  // column n is live iff RS n < srem
+            // columns n < nlive are stored: n < VR and symbol t0 + RS n + msym < a.n
+            const long long srem = (long long)a.n - t0 - msym;
+            const int nlive = srem <= 0 ? 0 : (srem >= (long long)RS * VR ? VR : (int)((srem + RS - 1) / RS));
 #pragma unroll 1
             for (int c = warp >> 2; c < 4; c += NEPI / 4) {
                 if (32 * c >= VR) break;
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(OUT16 ? 512 : 288, 1) fir_ptc_kernel(const __g
                     const int n = 32 * c + j;
                     // values are formed unconditionally (branch-free body: the 32 columns interleave in the
                     // schedule); only the store is predicated
-                    const bool live = n < VR && (long long)RS * n < srem;
+                    const bool live = n < nlive;
                     if (OUT16) {
                         float vx = __uint_as_float(p[j]) * kq, vy = __uint_as_float(r[j]) * kq;
                         if (!q_pow2) {
