@@ -973,16 +973,17 @@ int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
     h->plan.tw2 = h->tw2;
     h->plan.tw16 = h->tw16;
     h->plan.scratch = h->scratch;
-    // 65536 points: single-pass cluster kernel (K5-C).  COMMS_B200_FFT_PATH = cluster (default: barrier.cluster
-    // exchange) | cluster1 (mbarrier + st.async) | cluster2 (hybrid) | fourstep
+    // 65536 points.  COMMS_B200_FFT_PATH = rows (default: two streaming kernels over a 256 x 256 split with a
+    // batch-sized scratch, K5-R) | cluster (one HBM pass on 8-CTA clusters, K5-C; also the fallback when the scratch
+    // cannot be allocated) | cluster1 / cluster2 (its other exchange synchronisations) | cluster16 | twopass | fourstep
     if (fft_size == 65536) {
         const char *path = getenv("COMMS_B200_FFT_PATH");
-        h->plan.cluster_tpt = 3;
+        h->plan.cluster_tpt = 6;
+        if (path && strcmp(path, "cluster") == 0) h->plan.cluster_tpt = 3;
         if (path && strcmp(path, "cluster2") == 0) h->plan.cluster_tpt = 2;
         if (path && strcmp(path, "cluster16") == 0) h->plan.cluster_tpt = 4;  // 16-CTA clusters, 4 CTAs per SM
         if (path && strcmp(path, "twopass") == 0) h->plan.cluster_tpt = 5;    // 16 x 4096, two streaming passes
-        if (path && strcmp(path, "fourstep") == 0) h->plan.cluster_tpt = 0;
-        if (path && strcmp(path, "cluster1") == 0) h->plan.cluster_tpt = 1;  // exchange variants, see fft_cluster_kernel.cu
+        if (path && strcmp(path, "rows") == 0) h->plan.cluster_tpt = 6;       // 256 x 256, two streaming passes, L2 scratch
     }
     *out = h;
     return CB_OK;
@@ -999,6 +1000,7 @@ int cb_fft_destroy(cb_fft *h)
     if (h->tw2) cudaFree(h->tw2);
     if (h->tw16) cudaFree(h->tw16);
     if (h->scratch) cudaFree(h->scratch);
+
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return CB_OK;
@@ -1012,6 +1014,26 @@ int cb_fft_size(const cb_fft *h, size_t *fft_size, int *inverse)
     return CB_OK;
 }
 
+// 65536-point "rows" path: the intermediate of a batch lives in a scratch as large as the batch.  Grown on demand
+// (cudaFree waits for work that may still use the old one); when it cannot be allocated the handle switches to the
+// one-pass cluster kernel, which needs none.
+static void fft_prepare_scratch(cb_fft *h, size_t nframes)
+{
+    if (h->plan.n != 65536 || h->plan.cluster_tpt != 6 || h->plan.scratch_frames >= nframes) return;
+    if (h->scratch) cudaFree(h->scratch);
+    h->scratch = nullptr;
+    h->plan.scratch = nullptr;
+    h->plan.scratch_frames = 0;
+    if (cudaMalloc(&h->scratch, nframes * h->plan.n * sizeof(float2)) != cudaSuccess) {
+        cudaGetLastError();
+        h->scratch = nullptr;
+        h->plan.cluster_tpt = 3;
+        return;
+    }
+    h->plan.scratch = h->scratch;
+    h->plan.scratch_frames = nframes;
+}
+
 int cb_fft_run_dev(cb_fft *h, const float *d_in, size_t n_in, float *d_out, void *stream)
 {
     CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
@@ -1021,6 +1043,7 @@ int cb_fft_run_dev(cb_fft *h, const float *d_in, size_t n_in, float *d_out, void
     CB_REQUIRE(d_in && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
     CB_REQUIRE(d_in != d_out, CB_ERR_INVALID_ARG, "fft: in-place transform is not provided");
     CB_CUDA(cudaSetDevice(h->device));
+    fft_prepare_scratch(h, n_in / h->plan.n);
     return launch_fft(h->plan, reinterpret_cast<const float2 *>(d_in), reinterpret_cast<float2 *>(d_out),
                       n_in / h->plan.n, pick_stream(stream, h->stream));
 }
@@ -1051,6 +1074,7 @@ int cb_fft_run(cb_fft *h, const float *in, size_t n_in, float *out)
             // the four-step scratch is shared by both lanes: serialise the kernels
             CB_CUDA(cudaStreamSynchronize(h->pipe.lane[l ^ 1]));
         }
+        fft_prepare_scratch(h, m / N);
         rc = launch_fft(h->plan, di, dout, m / N, s);
         if (rc) return rc;
         CB_CUDA(cudaMemcpyAsync(hout + done, dout, m * sizeof(float2), cudaMemcpyDeviceToHost, s));

@@ -167,6 +167,22 @@ CB_HD void twiddle16(float2 *v, float2 w1)
     v[15] = cmul(v[15], cmul(w8, w7));
 }
 
+// v[m] *= c * w^m, m = 0..15 (power tree of depth <= 4)
+CB_HD void twiddle16c(float2 *v, float2 c, float2 w1)
+{
+    const float2 w2 = csqr(w1), w4 = csqr(w2), w8 = csqr(w4);
+    float2 u[8];
+    u[0] = c;
+    u[1] = cmul(c, w1);
+    u[2] = cmul(c, w2);
+    u[3] = cmul(u[1], w2);
+    for (int i = 0; i < 4; ++i) u[4 + i] = cmul(u[i], w4);
+    for (int i = 0; i < 8; ++i) {
+        v[i] = cmul(v[i], u[i]);
+        v[8 + i] = cmul(v[8 + i], cmul(u[i], w8));
+    }
+}
+
 // ------------------------------------------------------------------ plan constants
 template <int LOG2N>
 struct Plan {

@@ -92,25 +92,6 @@ __device__ __forceinline__ void prefetch_l2(const void *p, uint32_t bytes)
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
-// v[m] *= c * w^m, m = 0..15 (power tree of depth <= 4)
-__device__ __forceinline__ void twiddle16c(float2 *v, float2 c, float2 w1)
-{
-    using namespace fft2;
-    const float2 w2 = csqr(w1), w4 = csqr(w2), w8 = csqr(w4);
-    float2 u[8];
-    u[0] = c;
-    u[1] = cmul(c, w1);
-    u[2] = cmul(c, w2);
-    u[3] = cmul(u[1], w2);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) u[4 + i] = cmul(u[i], w4);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        v[i] = cmul(v[i], u[i]);
-        v[8 + i] = cmul(v[8 + i], cmul(u[i], w8));
-    }
-}
-
 // float2 index of element (row r, i) of the CTA buffer
 __device__ __forceinline__ int rowbase(int r) { return 256 * r + 2 * (r >> 1); }
 

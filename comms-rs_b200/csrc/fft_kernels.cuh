@@ -19,7 +19,8 @@ struct FftPlanDev {
     const float2 *tw16;   // per-pass tables of the radix-16 kernel (fft2_core.cuh), or NULL
     float2 *scratch;      // four-step intermediate, scratch_frames * n
     size_t scratch_frames;
-    int cluster_tpt;      // n = 65536: 0 = four-step, 1 / 2 / 3 = cluster kernel, exchange variant (3 = default)
+    int cluster_tpt;      // n = 65536: 0 = four-step, 1 / 2 / 3 = cluster kernel exchange variants, 4 = 16-CTA clusters,
+                          // 5 = 16 x 4096 two-pass, 6 = 256 x 256 two-pass with a batch-sized scratch (default)
 };
 
 size_t fft2_table_len(int log2n);
@@ -27,6 +28,7 @@ void fft2_fill_table(int log2n, int inverse, float2 *host_table);
 int fft_plan_split(size_t n, int *log2n1, int *log2n2);
 int launch_fft65536_cluster(const float2 *in, float2 *out, const float2 *twN, size_t nframes, bool inverse, int tpt,
                             cudaStream_t s);
+int launch_fft65536_rows(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s);
 int launch_fft(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s);
 
 }  // namespace cb
