@@ -256,7 +256,7 @@ class Job:
             self.node = cb.FFTBatchNode(N, workload.startswith("ifft"))
             self.y = torch.empty(n, dtype=torch.complex64, device="cuda")
             self.out_bytes = 8 * n
-            self.kernels_per_step = 2 if (N > 8192 and not (N == 65536 and os.environ.get("COMMS_B200_FFT_PATH", "").startswith("cluster"))) else 1
+            self.kernels_per_step = 2 if (N > 8192 and not (N == 65536 and os.environ.get("COMMS_B200_FFT_PATH", "rows") in ("rows", "cluster", "cluster1", "cluster2", "cluster16"))) else 1
             self.step = lambda: self.node.run_dev(self.x.data_ptr(), n, self.y.data_ptr(), self.stream)
             self.host_call = lambda hin, hout: cb.load().cb_fft_run(self.node._h, hin, n, hout)
         elif self.kind == "chain":

@@ -955,8 +955,8 @@ int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
     if (kind == FFT_FOURSTEP) {
         FFT_TRY(upload_twiddles((size_t)1 << l1, inverse, &h->tw1));
         FFT_TRY(upload_twiddles((size_t)1 << l2, inverse, &h->tw2));
-        size_t scratch_mb = 32;
-        if (const char *e = getenv("COMMS_B200_FFT_SCRATCH_MB")) scratch_mb = (size_t)atol(e) > 0 ? (size_t)atol(e) : 32;
+        size_t scratch_mb = fft_size == 65536 ? 16 : 32;  // 65536: ring of 32 frames for the fused rows kernel (measured best)
+        if (const char *e = getenv("COMMS_B200_FFT_SCRATCH_MB")) scratch_mb = (size_t)atol(e) > 0 ? (size_t)atol(e) : scratch_mb;
         size_t frames = (scratch_mb << 20) / (fft_size * sizeof(float2));
         if (frames < 1) frames = 1;
         if (fft_size == 65536) FFT_TRY(upload_fft2_table(12, inverse, &h->tw16));  // rows of the 16 x 4096 two-pass form
@@ -973,9 +973,10 @@ int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
     h->plan.tw2 = h->tw2;
     h->plan.tw16 = h->tw16;
     h->plan.scratch = h->scratch;
-    // 65536 points.  COMMS_B200_FFT_PATH = rows (default: two streaming kernels over a 256 x 256 split with a
-    // batch-sized scratch, K5-R) | cluster (one HBM pass on 8-CTA clusters, K5-C; also the fallback when the scratch
-    // cannot be allocated) | cluster1 / cluster2 (its other exchange synchronisations) | cluster16 | twopass | fourstep
+    // 65536 points.  COMMS_B200_FFT_PATH = rows (default: one persistent kernel over a 256 x 256 split, intermediate in
+    // an L2-resident ring, K5-R) | rows2 (same two steps as two launches with a batch-sized scratch) | cluster (one HBM
+    // pass on 8-CTA clusters, K5-C; also the fallback when an allocation fails) | cluster1 / cluster2 (its other
+    // exchange synchronisations) | cluster16 | twopass | fourstep
     if (fft_size == 65536) {
         const char *path = getenv("COMMS_B200_FFT_PATH");
         h->plan.cluster_tpt = 6;
@@ -983,7 +984,8 @@ int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
         if (path && strcmp(path, "cluster2") == 0) h->plan.cluster_tpt = 2;
         if (path && strcmp(path, "cluster16") == 0) h->plan.cluster_tpt = 4;  // 16-CTA clusters, 4 CTAs per SM
         if (path && strcmp(path, "twopass") == 0) h->plan.cluster_tpt = 5;    // 16 x 4096, two streaming passes
-        if (path && strcmp(path, "rows") == 0) h->plan.cluster_tpt = 6;       // 256 x 256, two streaming passes, L2 scratch
+        if (path && strcmp(path, "rows") == 0) h->plan.cluster_tpt = 6;       // 256 x 256, fused persistent kernel, L2 ring
+        if (path && strcmp(path, "rows2") == 0) h->plan.cluster_tpt = 7;      // 256 x 256, two launches, batch-sized scratch
     }
     *out = h;
     return CB_OK;
@@ -1000,6 +1002,7 @@ int cb_fft_destroy(cb_fft *h)
     if (h->tw2) cudaFree(h->tw2);
     if (h->tw16) cudaFree(h->tw16);
     if (h->scratch) cudaFree(h->scratch);
+    if (h->plan.flags) cudaFree(h->plan.flags);
 
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1014,24 +1017,39 @@ int cb_fft_size(const cb_fft *h, size_t *fft_size, int *inverse)
     return CB_OK;
 }
 
-// 65536-point "rows" path: the intermediate of a batch lives in a scratch as large as the batch.  Grown on demand
-// (cudaFree waits for work that may still use the old one); when it cannot be allocated the handle switches to the
-// one-pass cluster kernel, which needs none.
+// 65536-point "rows" paths.  Fused (mode 6): the scratch is a fixed L2-sized ring allocated with the plan; only the
+// per-frame dependency counters grow with the batch.  Two-launch (mode 7): the scratch is as large as the batch.
+// Both grow on demand (cudaFree waits for work that may still use the old buffer); when an allocation fails the
+// handle switches to the one-pass cluster kernel, which needs neither.
 static void fft_prepare_scratch(cb_fft *h, size_t nframes)
 {
-    if (h->plan.n != 65536 || h->plan.cluster_tpt != 6 || h->plan.scratch_frames >= nframes) return;
-    if (h->scratch) cudaFree(h->scratch);
-    h->scratch = nullptr;
-    h->plan.scratch = nullptr;
-    h->plan.scratch_frames = 0;
-    if (cudaMalloc(&h->scratch, nframes * h->plan.n * sizeof(float2)) != cudaSuccess) {
-        cudaGetLastError();
-        h->scratch = nullptr;
-        h->plan.cluster_tpt = 3;
-        return;
+    if (h->plan.n != 65536) return;
+    if (h->plan.cluster_tpt == 6 && h->plan.flags_frames < nframes) {
+        if (h->plan.flags) cudaFree(h->plan.flags);
+        h->plan.flags = nullptr;
+        h->plan.flags_frames = 0;
+        if (cudaMalloc(&h->plan.flags, 2 * nframes * sizeof(unsigned)) != cudaSuccess) {
+            cudaGetLastError();
+            h->plan.flags = nullptr;
+            h->plan.cluster_tpt = 3;
+            return;
+        }
+        h->plan.flags_frames = nframes;
     }
-    h->plan.scratch = h->scratch;
-    h->plan.scratch_frames = nframes;
+    if (h->plan.cluster_tpt == 7 && h->plan.scratch_frames < nframes) {
+        if (h->scratch) cudaFree(h->scratch);
+        h->scratch = nullptr;
+        h->plan.scratch = nullptr;
+        h->plan.scratch_frames = 0;
+        if (cudaMalloc(&h->scratch, nframes * h->plan.n * sizeof(float2)) != cudaSuccess) {
+            cudaGetLastError();
+            h->scratch = nullptr;
+            h->plan.cluster_tpt = 3;
+            return;
+        }
+        h->plan.scratch = h->scratch;
+        h->plan.scratch_frames = nframes;
+    }
 }
 
 int cb_fft_run_dev(cb_fft *h, const float *d_in, size_t n_in, float *d_out, void *stream)

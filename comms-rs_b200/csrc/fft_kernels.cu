@@ -573,7 +573,7 @@ int launch_fft(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframe
         return p.inverse ? launch_frames_dir<true>(p.log2n, in, out, p.tw, nframes, s)
                          : launch_frames_dir<false>(p.log2n, in, out, p.tw, nframes, s);
     }
-    if (p.kind == FFT_FOURSTEP && p.n == 65536 && p.cluster_tpt == 6)
+    if (p.kind == FFT_FOURSTEP && p.n == 65536 && (p.cluster_tpt == 6 || p.cluster_tpt == 7))
         return launch_fft65536_rows(p, in, out, nframes, s);
     if (p.kind == FFT_FOURSTEP && p.n == 65536 && p.cluster_tpt == 5 && p.tw16 != nullptr)
         return launch_fft65536_two_pass(in, out, p.scratch, p.scratch_frames, p.tw, p.tw16, nframes, p.inverse != 0, s);

@@ -1,5 +1,6 @@
-// K5-R: 65536-point FFT / IFFT as two streaming kernels over a 256 x 256 split, with the intermediate kept in
-// an L2-sized scratch (sm_100a).
+// K5-R: 65536-point FFT / IFFT over a 256 x 256 split: two streaming steps, run either as ONE persistent kernel
+// with the intermediate in an L2-resident ring (fft65536_fused_kernel, the default) or as two launches with a
+// batch-sized scratch (sm_100a).
 //
 // Reference semantics (src/fft/mod.rs:73-96): X[k] = sum_n x[n] e^{-/+ j 2 pi k n / N}, unnormalised.
 //
@@ -100,6 +101,122 @@ fft65536_rows_kernel(const float2 *__restrict__ mid, float2 *__restrict__ out, c
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fused form: ONE persistent kernel runs both steps, step A running `lag` frames ahead of step B, with the
+// intermediate in a small ring of scratch frames that stays resident in L2 (written by step A, read by step B a
+// few microseconds later, overwritten `ring` frames later while still dirty in L2), so that it never travels to
+// HBM.  Work items (16 per frame and step) are taken in a fixed order -- A(0..lag-1), then A(lag+u), B(u)
+// alternating -- by a grid that is fully resident, so an item only ever waits for items that are earlier in the
+// order and therefore finished or running: no deadlock.  Per-frame counters in global memory carry the
+// dependencies (release: st + __threadfence + atomicAdd; acquire: ld.acquire.gpu; the scratch is read with
+// ld.global.cg so that no stale L1 line of an earlier use of the slot is seen).
+__device__ __forceinline__ unsigned ld_acquire(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <bool INV>
+__global__ void __launch_bounds__(256, 4)
+fft65536_fused_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, float2 *__restrict__ scratch,
+                      const float2 *__restrict__ twN, unsigned *flags_a, unsigned *flags_b, unsigned long long nframes,
+                      unsigned lag, unsigned ring)
+{
+    using namespace fft2;
+    extern __shared__ __align__(16) float2 rsm[];
+    const int lane = threadIdx.x & 31, lo = lane & 15, hi = 2 * (threadIdx.x >> 5) + (lane >> 4);
+    const unsigned long long nchunks = lag + 2ull * nframes;
+    for (unsigned long long item = blockIdx.x; item < nchunks * 16; item += gridDim.x) {
+        const unsigned long long chunk = item >> 4;
+        const int part16 = (int)(item & 15) * 16;
+        bool is_a;
+        unsigned long long frame;
+        if (chunk < lag) {
+            is_a = true;
+            frame = chunk;
+        } else {
+            const unsigned long long t = chunk - lag;
+            is_a = (t & 1) == 0;
+            frame = is_a ? lag + (t >> 1) : (t >> 1);
+        }
+        if (frame >= nframes) continue;
+        float2 *slot = scratch + (frame % ring) * NF;
+        float2 v[16];
+        __syncthreads();  // the previous item's shared-memory reads are done
+        if (is_a) {
+            if (frame >= ring && threadIdx.x == 0)
+                while (ld_acquire(flags_b + (frame - ring)) < 16u) __nanosleep(64);  // slot consumed by its last reader
+            const float2 *src = in + frame * NF + part16 + lo;
+            float2 *row = rsm + lo * RP;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) v[m] = ld_cs(src + 256 * (hi + 16 * m));
+            bfly16<INV>(v);
+#pragma unroll
+            for (int sl = 0; sl < 16; ++sl) row[pad16(16 * hi + q16(sl))] = v[sl];
+            __syncthreads();  // (also orders thread 0's slot wait before every thread's stores below)
+#pragma unroll
+            for (int m = 0; m < 16; ++m) v[m] = row[pad16(hi + 16 * m)];
+            twiddle16(v, __ldg(twN + 256 * hi));
+            bfly16<INV>(v);
+            float2 *dst = slot + part16 + lo;
+#pragma unroll
+            for (int sl = 0; sl < 16; ++sl) __stcg(dst + 256 * (hi + 16 * q16(sl)), v[sl]);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                atomicAdd(flags_a + frame, 1u);
+            }
+        } else {
+            if (threadIdx.x == 0)
+                while (ld_acquire(flags_a + frame) < 16u) __nanosleep(64);  // all 16 column blocks of the frame are in
+            __syncthreads();
+            const int k1 = part16 + hi;
+            const float2 *src = slot + (size_t)k1 * 256 + lo;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) v[m] = __ldcg(src + 16 * m);
+            twiddle16c(v, __ldg(twN + k1 * lo), __ldg(twN + 16 * k1));
+            bfly16<INV>(v);
+            float2 *rowp = rsm + hi * RP;
+#pragma unroll
+            for (int sl = 0; sl < 16; ++sl) rowp[pad16(16 * lo + q16(sl))] = v[sl];
+            __syncthreads();  // every thread has consumed its scratch reads
+            if (threadIdx.x == 0) atomicAdd(flags_b + frame, 1u);
+            const float2 *row = rsm + lo * RP;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) v[m] = row[pad16(hi + 16 * m)];
+            twiddle16(v, __ldg(twN + 256 * hi));
+            bfly16<INV>(v);
+            float2 *dst = out + frame * NF + part16 + lo;
+#pragma unroll
+            for (int sl = 0; sl < 16; ++sl) st_cs(dst + 256 * (hi + 16 * q16(sl)), v[sl]);
+        }
+    }
+}
+
+template <bool INV>
+static int launch_fused(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s)
+{
+    auto kf = fft65536_fused_kernel<INV>;
+    CB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kf, 256, SMEM);
+    if (per_sm < 1) per_sm = 1;
+    const unsigned ring = (unsigned)p.scratch_frames;
+    unsigned lag = ring / 2;
+    if (lag < 1) lag = 1;
+    const unsigned long long items = (lag + 2ull * nframes) * 16;
+    const unsigned long long cap = (unsigned long long)sms * per_sm;  // the whole grid must be resident
+    const unsigned grid = (unsigned)(items < cap ? items : cap);
+    CB_CUDA(cudaMemsetAsync(p.flags, 0, 2 * nframes * sizeof(unsigned), s));
+    kf<<<grid, 256, SMEM, s>>>(in, out, p.scratch, p.tw, p.flags, p.flags + nframes, nframes, lag, ring);
+    count_launch();
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+
 // Frames are processed in groups of p.scratch_frames (the caller sizes the scratch to the whole batch when it
 // can: one group = two launches measured fastest; L2-sized groups, with or without overlapping step B of one
 // group with step A of the next on a second stream, or a persisting-L2 window on the scratch, all measured
@@ -128,6 +245,8 @@ static int launch(const FftPlanDev &p, const float2 *in, float2 *out, size_t nfr
 int launch_fft65536_rows(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s)
 {
     if (nframes == 0) return CB_OK;
+    if (p.cluster_tpt == 6 && p.flags != nullptr && p.flags_frames >= nframes && p.scratch_frames >= 4)
+        return p.inverse ? fftr::launch_fused<true>(p, in, out, nframes, s) : fftr::launch_fused<false>(p, in, out, nframes, s);
     return p.inverse ? fftr::launch<true>(p, in, out, nframes, s) : fftr::launch<false>(p, in, out, nframes, s);
 }
 
