@@ -508,7 +508,7 @@ chain3_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
             __syncthreads();
         }
 
-        mbar_wait(&full[st], parity);
+        mbar_wait_long(&full[st], parity);
         const unsigned char *sbase = U8 ? span8 : stages + st * STAGE;
         if (U8) {
             // raw bytes -> f32 span (pairs of samples: one 32-bit word in, one 128-bit word out)
@@ -653,7 +653,7 @@ chain3_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
             const int o = tid + j * NT;
             const long long m = m0 + o;
             if (m < (long long)a.n_out) {
-                if (FM) out_f[m] = fm_angle(ys[yb + o + 1], ys[yb + o]);
+                if (FM) out_f[m] = fm_angle_fast(ys[yb + o + 1], ys[yb + o]);
                 else out_c[m] = ys[yb + o + 1];
             }
         }

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(512, 1) fir_tc_kernel(const __grid_constant__ 
             long long g_hi = g0 + TILE + HALO;
             if (g_hi > (long long)a.n) g_hi = (long long)a.n & ~1ll;
             if (g_hi < g_lo) g_hi = g_lo;
-            mbar_wait(&raw_empty[rs], ph ^ 1);
+            mbar_wait_long(&raw_empty[rs], ph ^ 1);
             unsigned char *dstb = sRaw + rs * RAWB;
             if (lane == 0) mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)((g_hi - g_lo) * 8 + (g0 < 0 ? -g0 * 8 : 0)));
             __syncwarp();
@@ -280,8 +280,8 @@ __global__ void __launch_bounds__(512, 1) fir_tc_kernel(const __grid_constant__ 
             for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
                 const int s = (int)(it & 1);
                 const uint32_t ph = (uint32_t)((it >> 1) & 1);
-                mbar_wait(&t_empty[s], ph ^ 1);
-                mbar_wait(&a_full[s], ph);
+                mbar_wait_long(&t_empty[s], ph ^ 1);
+                mbar_wait_long(&a_full[s], ph);
                 tc_fence_after();
                 const uint32_t ahi = smem_u32(sA + s * A_STAGE), alo = ahi + A_PART;
                 const uint32_t d = tmem_base + (uint32_t)s * 128u;
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(512, 1) fir_tc_kernel(const __grid_constant__ 
             const long long t0 = (long long)tile * TILE;
             mbar_wait(&sc_ready[it & 7], (uint32_t)((it >> 3) & 1));  // acquire the loaders' block scale
             const float k0 = inv_scale[it & 7], k1 = a.tap_inv_scale;
-            mbar_wait(&t_full[s], ph);
+            mbar_wait_long(&t_full[s], ph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * e) << 16) + (uint32_t)s * 128u;
             // Lane m of this warp owns row 32 e + m of the tile = 32 consecutive output samples (256 bytes).  With the

@@ -48,6 +48,34 @@ __device__ __forceinline__ float fm_angle(float2 s, float2 p)
     const float ti = __fadd_rn(__fmul_rn(s.x, bi), __fmul_rn(s.y, br));
     return atan2f(ti, tr);
 }
+
+// Same discriminator step with a branch-free atan2: a = min/max in [0, 1], odd polynomial of degree 17 in a
+// (max error 1.1e-7 rad in f32), quadrant from |im| > |re| and the SIGN BITS of re / im, so that signed zeros pick
+// the branch libm's atan2 picks (atan2(+0, -0) = pi, atan2(-0, +0) = -0).  About half the instructions of atan2f and
+// no divergence; used by the fused chain kernel where the FM step shares issue slots with the filter.
+__device__ __forceinline__ float fm_angle_fast(float2 s, float2 p)
+{
+    const float br = p.x, bi = -p.y;
+    const float tr = __fsub_rn(__fmul_rn(s.x, br), __fmul_rn(s.y, bi));
+    const float ti = __fadd_rn(__fmul_rn(s.x, bi), __fmul_rn(s.y, br));
+    const float ax = fabsf(tr), ay = fabsf(ti);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = mx > 0.f ? __fdividef(mn, mx) : 0.f;
+    const float z = a * a;
+    float q = 0.0028340641874819994f;
+    q = fmaf(q, z, -0.016005029901862144f);
+    q = fmaf(q, z, 0.042587608098983765f);
+    q = fmaf(q, z, -0.07495445758104324f);
+    q = fmaf(q, z, 0.10636754333972931f);
+    q = fmaf(q, z, -0.14202570915222168f);
+    q = fmaf(q, z, 0.19992484152317047f);
+    q = fmaf(q, z, -0.3333306610584259f);
+    q = fmaf(q, z, 1.0f);
+    float r = a * q;
+    r = ay > ax ? 1.57079632679489662f - r : r;
+    r = (__float_as_uint(tr) >> 31) ? 3.14159265358979324f - r : r;
+    return __uint_as_float(__float_as_uint(r) | (__float_as_uint(ti) & 0x80000000u));
+}
 #endif
 
 }  // namespace cb
