@@ -44,6 +44,8 @@ WORKLOADS = {
     "fft4096": ("fft", 1 << 28, 16.0, "batched 4096-point FFT over 2^28 complex-f32 samples per GPU"),
     "fft65536": ("fft", 1 << 28, 16.0, "batched 65536-point FFT over 2^28 complex-f32 samples per GPU"),
     "ifft4096": ("fft", 1 << 28, 16.0, "batched 4096-point IFFT over 2^28 complex-f32 samples per GPU"),
+    "mixer": ("mixer", 1 << 28, 16.0, "MixerNode (src/mixer.rs:73-84): y = x e^{j phi}, f64 phase, over 2^28 complex-f32 samples per GPU"),
+    "fm": ("fm", 1 << 28, 12.0, "FMDemodNode (src/modulation/analog.rs:22-34) over 2^28 complex-f32 samples per GPU"),
     "chain": ("chain", 1024 * 131072, 8.4, "fm_radio chain x1024 channels per GPU: mixer -> 63-tap FIR -> /10 -> FM demod, "
               "131072-sample batches"),
     "chain5": ("chain", 1024 * 131072, 8.8, "fm_radio as shipped x1024 channels per GPU: 63-tap FIR -> /5 -> FM demod (no mixer), "
@@ -172,6 +174,10 @@ def cpu_rate(workload, samples, threads):
             jobs.append(lambda x=x, t=t: oracle.batch_fir(x, t, np.zeros(64, np.complex64), literal=True, native=True))
         elif kind == "fft":
             jobs.append(lambda x=x: oracle.fft(x, n, workload.startswith("ifft")))
+        elif kind == "mixer":
+            jobs.append(lambda x=x: oracle.Mixer(0.2, 0.123).mix(x))
+        elif kind == "fm":
+            jobs.append(lambda x=x: oracle.FM().demod(x))
         elif kind == "chain":
             if workload.startswith("chain5"):
                 ch = oracle.FmChain(0.0, 0.0, fm_radio_lowpass(), 5, do_mix=False, native=True)
@@ -198,7 +204,7 @@ def run_reference(args, rank):
         return
     threads = os.cpu_count() or 1
     kind, _, _, desc = WORKLOADS[args.workload]
-    rate1 = {"fir": 8e6, "fft": 30e6, "chain": 20e6, "interp": 2e6}[kind]
+    rate1 = {"fir": 8e6, "fft": 30e6, "chain": 20e6, "interp": 2e6, "mixer": 30e6, "fm": 60e6}[kind]
     if args.workload.startswith("poly8x1024"):
         rate1 = 1e4
     per_thread = int(min(max(150.0 * rate1 / (args.steps + args.warmup), 1 << 12), 1 << 23))
@@ -259,6 +265,18 @@ class Job:
             self.kernels_per_step = 2 if (N > 8192 and not (N == 65536 and os.environ.get("COMMS_B200_FFT_PATH", "rows") in ("rows", "cluster", "cluster1", "cluster2", "cluster16"))) else 1
             self.step = lambda: self.node.run_dev(self.x.data_ptr(), n, self.y.data_ptr(), self.stream)
             self.host_call = lambda hin, hout: cb.load().cb_fft_run(self.node._h, hin, n, hout)
+        elif self.kind == "mixer":
+            self.node = cb.MixerNode(0.123, 0.2)
+            self.y = torch.empty(n, dtype=torch.complex64, device="cuda")
+            self.out_bytes = 8 * n
+            self.step = lambda: cb._lib.check(cb.load().cb_mixer_run_dev(self.node._h, self.x.data_ptr(), n, self.y.data_ptr(), self.stream))
+            self.host_call = lambda hin, hout: cb.load().cb_mixer_run(self.node._h, hin, n, hout)
+        elif self.kind == "fm":
+            self.node = cb.FMDemodNode()
+            self.y = torch.empty(n, dtype=torch.float32, device="cuda")
+            self.out_bytes = 4 * n
+            self.step = lambda: cb._lib.check(cb.load().cb_fm_run_dev(self.node._h, self.x.data_ptr(), n, self.y.data_ptr(), self.stream))
+            self.host_call = lambda hin, hout: cb.load().cb_fm_run(self.node._h, hin, n, hout)
         elif self.kind == "chain":
             C, nb = 1024, 131072
             fc = (np.arange(C) / C - 0.5) * 0.8
@@ -420,7 +438,7 @@ def run_b200(args, rank, world, local_rank):
         }
         if world == 1 and not args.no_cpu:
             kind = job.kind
-            sample = {"fir": 1 << 26, "fft": 1 << 27, "chain": 1 << 26, "interp": 1 << 23}[kind]
+            sample = {"fir": 1 << 26, "fft": 1 << 27, "chain": 1 << 26, "interp": 1 << 23, "mixer": 1 << 26, "fm": 1 << 27}[kind]
             if args.workload.startswith("poly8x1024"):
                 sample = 1 << 17
             v, dt, n = cpu_rate(args.workload, sample, 1)

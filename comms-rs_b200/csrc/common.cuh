@@ -143,6 +143,13 @@ __device__ __forceinline__ float4 ldg_stream(const float4 *p)
                  : "l"(p));
     return v;
 }
+// 256-bit streaming load (sm_100: LDG.E.256), p 32-byte aligned
+__device__ __forceinline__ void ldg_stream8(const float *p, float *v)
+{
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
 __device__ __forceinline__ float2 ldg_stream2(const float2 *p)
 {
     float2 v;

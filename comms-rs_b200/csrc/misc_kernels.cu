@@ -18,32 +18,33 @@ __global__ void __launch_bounds__(256)
 mixer_kernel(const float2 *__restrict__ x, float2 *__restrict__ y, size_t n, double phase0, double dphase)
 {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    const size_t npair = n >> 1;
-    const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 31) == 0;
+    size_t tail = 0;
     if (vec) {
-        const float2 step = phase_rotation(dphase);  // e^{j dphase}: second sample of the pair
-        for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npair; p += stride) {
-            const float4 v = ldg_stream(reinterpret_cast<const float4 *>(x) + p);
-            const float2 r0 = phase_rotation(fma((double)(2 * p), dphase, phase0));
-            const float2 r1 = cmul(r0, step);
-            const float2 a = cmul(make_float2(v.x, v.y), r0);
-            const float2 b = cmul(make_float2(v.z, v.w), r1);
-            stg_stream(reinterpret_cast<float4 *>(y) + p, make_float4(a.x, a.y, b.x, b.y));
+        // four samples per thread: one 256-bit load and store; the f64 phase is evaluated for the first sample of
+        // the quad, the other three follow by e^{j dphase}, e^{2j dphase}, e^{3j dphase} (each one product away)
+        const float2 s1 = phase_rotation(dphase), s2 = phase_rotation(2.0 * dphase), s3 = phase_rotation(3.0 * dphase);
+        const size_t nquad = n >> 2;
+        for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquad; q += stride) {
+            float v[8], o[8];
+            ldg_stream8(reinterpret_cast<const float *>(x + 4 * q), v);
+            const float2 r0 = phase_rotation(fma((double)(4 * q), dphase, phase0));
+            const float2 r1 = cmul(r0, s1), r2 = cmul(r0, s2), r3 = cmul(r0, s3);
+            const float2 a = cmul(make_float2(v[0], v[1]), r0), b = cmul(make_float2(v[2], v[3]), r1);
+            const float2 c = cmul(make_float2(v[4], v[5]), r2), d = cmul(make_float2(v[6], v[7]), r3);
+            o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y; o[6] = d.x; o[7] = d.y;
+            stg_stream8(reinterpret_cast<float *>(y + 4 * q), o);
         }
-        if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-            const size_t i = n - 1;
-            y[i] = cmul(x[i], phase_rotation(fma((double)i, dphase, phase0)));
-        }
-    } else {
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-            y[i] = cmul(x[i], phase_rotation(fma((double)i, dphase, phase0)));
+        tail = nquad << 2;
     }
+    for (size_t i = tail + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        y[i] = cmul(x[i], phase_rotation(fma((double)i, dphase, phase0)));
 }
 
 int launch_mixer(const float2 *x, float2 *y, size_t n, double phase0, double dphase, cudaStream_t s)
 {
     if (n == 0) return CB_OK;
-    mixer_kernel<<<grid_for(n / 2 + 1, 256), 256, 0, s>>>(x, y, n, phase0, dphase);
+    mixer_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, s>>>(x, y, n, phase0, dphase);
     count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;
@@ -54,21 +55,42 @@ int launch_mixer(const float2 *x, float2 *y, size_t n, double phase0, double dph
 // The product is formed with individually rounded operations in the
 // reference's operand order so that signed zeros (first sample: prev = 0)
 // select the same atan2 branch.
+// Four samples per thread (one 256-bit load, one 128-bit store: 64 KiB of reads in flight per SM at full occupancy
+// and 25 registers); the sample before a thread's quad comes from the neighbouring lane by shuffle (lane 0 re-reads
+// it), the angle from the branch-free atan2 of misc_kernels.cuh.
 __global__ void __launch_bounds__(256)
 fm_kernel(const float2 *__restrict__ x, float *__restrict__ out, size_t n, const float2 *prev_in, float2 *prev_out)
 {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float2 s = x[i];
-        const float2 p = i ? x[i - 1] : *prev_in;
-        out[i] = fm_angle(s, p);
+    const bool vec = ((reinterpret_cast<uintptr_t>(x) & 31) | (reinterpret_cast<uintptr_t>(out) & 15)) == 0;
+    size_t tail = 0;  // first sample not covered by the vector loop
+    if (vec) {
+        const size_t nquad = n >> 2;
+        const size_t nquad_pad = (nquad + 31) & ~(size_t)31;  // whole warps iterate together (shuffles)
+        for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquad_pad; q += stride) {
+            const bool live = q < nquad;
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (live) ldg_stream8(reinterpret_cast<const float *>(x + 4 * q), v);
+            float2 pv = make_float2(__shfl_up_sync(0xffffffffu, v[6], 1), __shfl_up_sync(0xffffffffu, v[7], 1));
+            if ((threadIdx.x & 31) == 0 && live) pv = q ? x[4 * q - 1] : *prev_in;
+            if (live) {
+                const float2 s0 = make_float2(v[0], v[1]), s1 = make_float2(v[2], v[3]);
+                const float2 s2 = make_float2(v[4], v[5]), s3 = make_float2(v[6], v[7]);
+                stg_stream(reinterpret_cast<float4 *>(out) + q,
+                           make_float4(fm_angle_fast(s0, pv), fm_angle_fast(s1, s0), fm_angle_fast(s2, s1), fm_angle_fast(s3, s2)));
+            }
+        }
+        tail = nquad << 2;
     }
+    // unaligned buffers, and the up to three samples behind the last quad
+    for (size_t i = tail + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = fm_angle_fast(x[i], i ? x[i - 1] : *prev_in);
     if (blockIdx.x == 0 && threadIdx.x == 0) *prev_out = n ? x[n - 1] : *prev_in;
 }
 
 int launch_fm(const float2 *x, float *out, size_t n, const float2 *prev_in, float2 *prev_out, cudaStream_t s)
 {
-    fm_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, out, n, prev_in, prev_out);
+    fm_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, s>>>(x, out, n, prev_in, prev_out);
     count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;
