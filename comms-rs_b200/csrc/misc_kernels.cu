@@ -170,22 +170,41 @@ int launch_bits_to_symbols(const uint8_t *bits, float2 *sym, size_t nsym, int mo
     return CB_OK;
 }
 
+// Rust `as i16`: truncate toward zero, saturate, NaN -> 0
+__device__ __forceinline__ int quant_i16(float v, float scale)
+{
+    int q = __float2int_rz(__fmul_rn(scale, v));
+    return q > 32767 ? 32767 : (q < -32768 ? -32768 : q);
+}
+
+// eight floats per thread (256-bit load, 128-bit store) when the buffers allow it
 __global__ void __launch_bounds__(256)
 quantize_i16_kernel(const float *__restrict__ in, int16_t *__restrict__ out, size_t n, float scale)
 {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        // Rust `as i16`: truncate toward zero, saturate, NaN -> 0
-        int v = __float2int_rz(__fmul_rn(scale, in[i]));
-        v = v > 32767 ? 32767 : (v < -32768 ? -32768 : v);
-        out[i] = (int16_t)v;
+    size_t tail = 0;
+    if (((reinterpret_cast<uintptr_t>(in) & 31) | (reinterpret_cast<uintptr_t>(out) & 15)) == 0) {
+        const size_t n8 = n >> 3;
+        for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n8; g += stride) {
+            float v[8];
+            ldg_stream8(in + 8 * g, v);
+            uint4 o;
+            o.x = (uint32_t)(quant_i16(v[0], scale) & 0xFFFF) | ((uint32_t)quant_i16(v[1], scale) << 16);
+            o.y = (uint32_t)(quant_i16(v[2], scale) & 0xFFFF) | ((uint32_t)quant_i16(v[3], scale) << 16);
+            o.z = (uint32_t)(quant_i16(v[4], scale) & 0xFFFF) | ((uint32_t)quant_i16(v[5], scale) << 16);
+            o.w = (uint32_t)(quant_i16(v[6], scale) & 0xFFFF) | ((uint32_t)quant_i16(v[7], scale) << 16);
+            reinterpret_cast<uint4 *>(out)[g] = o;
+        }
+        tail = n8 << 3;
     }
+    for (size_t i = tail + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = (int16_t)quant_i16(in[i], scale);
 }
 
 int launch_quantize_i16(const float *in, int16_t *out, size_t n, float scale, cudaStream_t s)
 {
     if (n == 0) return CB_OK;
-    quantize_i16_kernel<<<grid_for(n, 256), 256, 0, s>>>(in, out, n, scale);
+    quantize_i16_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, s>>>(in, out, n, scale);
     count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;
@@ -193,27 +212,61 @@ int launch_quantize_i16(const float *in, int16_t *out, size_t n, float scale, cu
 
 // ---------------------------------------------------------------- IQ edge formats
 // u8 offset binary (RTL-SDR; examples/fm_radio.rs:84-87): (x as f32 - 127.5) / 127.5, both operations exactly rounded
+__device__ __forceinline__ float conv_u8(uint32_t b) { return __fdiv_rn(__fsub_rn((float)b, 127.5f), 127.5f); }
+
+// eight bytes per thread (64-bit load, 256-bit store) when the buffers allow it
 __global__ void __launch_bounds__(256)
 convert_u8_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, size_t n)
 {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        out[i] = __fdiv_rn(__fsub_rn((float)in[i], 127.5f), 127.5f);
+    size_t tail = 0;
+    if (((reinterpret_cast<uintptr_t>(in) & 7) | (reinterpret_cast<uintptr_t>(out) & 31)) == 0) {
+        const size_t n8 = n >> 3;
+        for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n8; g += stride) {
+            const uint2 w = reinterpret_cast<const uint2 *>(in)[g];
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v[k] = conv_u8((w.x >> (8 * k)) & 255u);
+                v[4 + k] = conv_u8((w.y >> (8 * k)) & 255u);
+            }
+            stg_stream8(out + 8 * g, v);
+        }
+        tail = n8 << 3;
+    }
+    for (size_t i = tail + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = conv_u8(in[i]);
 }
 
 // interleaved i16 IQ (src/io/raw_iq.rs:20-140): scale * (x as f32); scale = 1 is the plain cast
+// eight values per thread (128-bit load, 256-bit store) when the buffers allow it
 __global__ void __launch_bounds__(256)
 convert_i16_kernel(const int16_t *__restrict__ in, float *__restrict__ out, size_t n, float scale)
 {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    size_t tail = 0;
+    if (((reinterpret_cast<uintptr_t>(in) & 15) | (reinterpret_cast<uintptr_t>(out) & 31)) == 0) {
+        const size_t n8 = n >> 3;
+        for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n8; g += stride) {
+            const uint4 w = reinterpret_cast<const uint4 *>(in)[g];
+            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v[2 * k] = __fmul_rn(scale, (float)(int16_t)(ws[k] & 0xFFFFu));
+                v[2 * k + 1] = __fmul_rn(scale, (float)(int16_t)(ws[k] >> 16));
+            }
+            stg_stream8(out + 8 * g, v);
+        }
+        tail = n8 << 3;
+    }
+    for (size_t i = tail + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         out[i] = __fmul_rn(scale, (float)in[i]);
 }
 
 int launch_convert_u8(const uint8_t *in, float *out, size_t n, cudaStream_t s)
 {
     if (n == 0) return CB_OK;
-    convert_u8_kernel<<<grid_for(n, 256), 256, 0, s>>>(in, out, n);
+    convert_u8_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, s>>>(in, out, n);
     count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;
@@ -222,7 +275,7 @@ int launch_convert_u8(const uint8_t *in, float *out, size_t n, cudaStream_t s)
 int launch_convert_i16(const int16_t *in, float *out, size_t n, float scale, cudaStream_t s)
 {
     if (n == 0) return CB_OK;
-    convert_i16_kernel<<<grid_for(n, 256), 256, 0, s>>>(in, out, n, scale);
+    convert_i16_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, s>>>(in, out, n, scale);
     count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;
