@@ -107,7 +107,12 @@ struct HostPipe {
     }
 };
 
-constexpr size_t HOST_CHUNK = (size_t)1 << 22;  // complex samples per pipelined chunk (32 MiB)
+// complex samples per pipelined chunk of the host-pointer entries (default 2^22 = 32 MiB; COMMS_B200_HOST_CHUNK_LOG2)
+static const size_t HOST_CHUNK = [] {
+    const char *e = getenv("COMMS_B200_HOST_CHUNK_LOG2");
+    const int l = e ? atoi(e) : 22;
+    return (size_t)1 << (l >= 12 && l <= 30 ? l : 22);
+}();
 
 }  // namespace cb
 
