@@ -1,0 +1,122 @@
+"""Randomised sizes around the tile boundaries of the tensor-core / TMA kernels, against the CPU oracle.
+Needs a B200: `pytest -m gpu`.  Seeds are fixed: the cases are reproducible."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FIR_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import comms_rs_b200 as m
+
+    m.init(0)
+    return m
+
+
+def rel_l2(a, b):
+    a = np.asarray(a).astype(np.complex128).ravel()
+    b = np.asarray(b).astype(np.complex128).ravel()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    d = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / d if d > 0 else np.linalg.norm(a - b)
+
+
+def rnd_c32(rng, n):
+    return (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(np.complex64)
+
+
+def sizes_near(rng, unit, count, lo=1):
+    """Batch sizes at, just below and just above multiples of `unit`, plus a few arbitrary ones."""
+    out = []
+    for _ in range(count):
+        k = int(rng.integers(0, 4))
+        d = int(rng.choice([-3, -2, -1, 0, 1, 2, 3, 17, -64, 65]))
+        out.append(max(lo, k * unit + d))
+    out += [int(v) for v in rng.integers(lo, 3 * unit, 3)]
+    return out
+
+
+@pytest.mark.parametrize("ntaps,seed", [(64, 1), (63, 2), (33, 3), (100, 4), (128, 5), (7, 6)])
+def test_fir_tensor_core_batches_around_tiles(cb, oracle, ntaps, seed, monkeypatch):
+    # K1-TC (TMA raw-tile ring, 4096-sample tiles): odd / tiny / tile-straddling batches with carried state
+    monkeypatch.setenv("COMMS_B200_FIR_PATH", "tc")
+    rng = np.random.default_rng(seed)
+    t = rnd_c32(rng, ntaps)
+    sizes = sizes_near(rng, 4096, 8)
+    x = rnd_c32(rng, sum(sizes))
+    want, st = oracle.batch_fir(x, t, np.zeros(ntaps, np.complex64))
+    node = cb.BatchFirNode(t)
+    pos, outs = 0, []
+    for s in sizes:
+        outs.append(node.run(x[pos:pos + s]))
+        assert len(outs[-1]) == s
+        pos += s
+    assert rel_l2(np.concatenate(outs), want) <= FIR_TOL, sizes
+    assert node.state.tobytes() == st.tobytes()
+
+
+@pytest.mark.parametrize("L,ntaps,cplx,seed", [(8, 1024, False, 1), (8, 512, True, 2), (4, 32, False, 3), (4, 100, True, 4), (8, 9, False, 5)])
+def test_polyphase_tensor_core_batches_around_tiles(cb, oracle, L, ntaps, cplx, seed, monkeypatch):
+    # K3-TC: tiles of 1920 (x8) / 4064 (x4) symbols; f32 and fused-i16 outputs on the same stream
+    monkeypatch.setenv("COMMS_B200_FIR_PATH", "tc")
+    rng = np.random.default_rng(100 + seed)
+    t = rnd_c32(rng, ntaps) if cplx else rng.uniform(-1, 1, ntaps).astype(np.complex64)
+    sizes = sizes_near(rng, 1920 if L == 8 else 4064, 6)
+    sym = rnd_c32(rng, sum(sizes))
+    want, st = oracle.batch_fir(oracle.upsample(sym, L), t, np.zeros(ntaps, np.complex64))
+    a, b = cb.BatchFirNode(t, None, interp=L), cb.BatchFirNode(t, None, interp=L)
+    pos, outs, q = 0, [], []
+    for s in sizes:
+        outs.append(a.run(sym[pos:pos + s]))
+        q.append(b.run_i16(sym[pos:pos + s], 4096.0))
+        assert len(outs[-1]) == s * L and len(q[-1]) == s * L
+        pos += s
+    got = np.concatenate(outs)
+    assert rel_l2(got, want) <= FIR_TOL, sizes
+    assert a.state.tobytes() == st.tobytes() == b.state.tobytes()
+    assert np.array_equal(np.concatenate(q), oracle.quantize_i16(got, 4096.0).reshape(-1, 2))
+
+
+@pytest.mark.parametrize("D,mix,fm,seed", [(10, True, True, 1), (5, False, True, 2), (10, True, False, 3), (5, True, True, 4)])
+def test_chain_batches_around_tiles(cb, oracle, D, mix, fm, seed):
+    # K2c (TMA span ring, 3840-sample tiles): batch lengths around tile multiples, f32 and u8 input alternating
+    rng = np.random.default_rng(200 + seed)
+    C = 3
+    k = np.arange(63) - 31
+    taps = (np.sinc(k / 5) * np.hamming(63) / 5).astype(np.float32).astype(np.complex64)
+    dph = -2 * np.pi * rng.uniform(-0.4, 0.4, C)
+    bank = cb.ChainBank(C, taps, D, dphase=dph if mix else None, with_fm=fm)
+    refs = [oracle.FmChain(dph[c], 0.0, taps, D, do_mix=mix, do_fm=fm) for c in range(C)]
+    for i, n in enumerate(sizes_near(rng, 3840, 7, lo=2)):
+        n += n & 1  # the fused kernels want even batch lengths; odd ones take the generic kernel (covered elsewhere)
+        if i % 2:
+            iq = rng.integers(0, 256, (C, n, 2), dtype=np.uint8)
+            x = oracle.u8_to_f32(iq.reshape(-1)).view(np.complex64).reshape(C, n)
+            got = bank.run_u8(iq)
+        else:
+            x = rnd_c32(rng, C * n).reshape(C, n)
+            got = bank.run(x)
+        assert got.shape == (C, -(-n // D))
+        for c in range(C):
+            want = refs[c].run(x[c])
+            if fm:
+                d = np.abs(got[c].astype(np.float64) - want.astype(np.float64))
+                d = np.minimum(d, 2 * np.pi - d)
+                assert np.median(d) < 2e-6 and np.mean(d > 1e-3) < 5e-3, (c, n)
+            else:
+                assert rel_l2(got[c], want) <= FIR_TOL, (c, n)
+
+
+@pytest.mark.parametrize("frames", [1, 2, 15, 16, 17, 33, 100])
+def test_fft65536_frame_counts(cb, oracle, frames):
+    # fused rows kernel: lag (16 frames) and ring (32 frames) boundaries
+    rng = np.random.default_rng(frames)
+    n = 65536
+    x = rnd_c32(rng, frames * n)
+    got = cb.FFTBatchNode(n, False).run(x)
+    for f in sorted({0, frames - 1, frames // 2}):
+        want = oracle.fft(x[f * n:(f + 1) * n], n, False)
+        assert rel_l2(got[f * n:(f + 1) * n], want) <= 1e-4, f
