@@ -41,6 +41,8 @@ WORKLOADS = {
     "fir64": ("fir", 1 << 28, 16.0, "64-tap complex-f32 FIR (complex taps) on one 2^28-sample stream per GPU"),
     "fir64_real": ("fir", 1 << 28, 16.0, "64-tap complex-f32 FIR (real-valued rrc taps) on one 2^28-sample stream per GPU"),
     "fft1024": ("fft", 1 << 28, 16.0, "batched 1024-point FFT over 2^28 complex-f32 samples per GPU"),
+    "fft2048": ("fft", 1 << 28, 16.0, "batched 2048-point FFT over 2^28 complex-f32 samples per GPU"),
+    "fft8192": ("fft", 1 << 28, 16.0, "batched 8192-point FFT over 2^28 complex-f32 samples per GPU"),
     "fft4096": ("fft", 1 << 28, 16.0, "batched 4096-point FFT over 2^28 complex-f32 samples per GPU"),
     "fft65536": ("fft", 1 << 28, 16.0, "batched 65536-point FFT over 2^28 complex-f32 samples per GPU"),
     "ifft4096": ("fft", 1 << 28, 16.0, "batched 4096-point IFFT over 2^28 complex-f32 samples per GPU"),

@@ -1033,7 +1033,7 @@ static void fft_prepare_scratch(cb_fft *h, size_t nframes)
         if (h->plan.flags) cudaFree(h->plan.flags);
         h->plan.flags = nullptr;
         h->plan.flags_frames = 0;
-        if (cudaMalloc(&h->plan.flags, 2 * nframes * sizeof(unsigned)) != cudaSuccess) {
+        if (cudaMalloc(&h->plan.flags, (4 + 2 * nframes) * sizeof(unsigned)) != cudaSuccess) {
             cudaGetLastError();
             h->plan.flags = nullptr;
             h->plan.cluster_tpt = 3;

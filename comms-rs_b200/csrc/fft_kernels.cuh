@@ -19,7 +19,8 @@ struct FftPlanDev {
     const float2 *tw16;   // per-pass tables of the radix-16 kernel (fft2_core.cuh), or NULL
     float2 *scratch;      // four-step intermediate, scratch_frames * n
     size_t scratch_frames;
-    unsigned *flags;      // n = 65536 fused "rows" form: 2 * flags_frames per-frame dependency counters (or NULL)
+    unsigned *flags;      // n = 65536 fused "rows" form: ticket counter (4 words) + 2 * flags_frames per-frame
+                          // dependency counters (or NULL)
     size_t flags_frames;
     int cluster_tpt;      // n = 65536: 0 = four-step, 1 / 2 / 3 = cluster kernel exchange variants, 4 = 16-CTA clusters,
                           // 5 = 16 x 4096 two-pass, 6 = 256 x 256 two-pass with a batch-sized scratch (default)

@@ -106,9 +106,12 @@ fft65536_rows_kernel(const float2 *__restrict__ mid, float2 *__restrict__ out, c
 // intermediate in a small ring of scratch frames that stays resident in L2 (written by step A, read by step B a
 // few microseconds later, overwritten `ring` frames later while still dirty in L2), so that it never travels to
 // HBM.  Work items (16 per frame and step) are taken in a fixed order -- A(0..lag-1), then A(lag+u), B(u)
-// alternating -- by a grid that is fully resident, so an item only ever waits for items that are earlier in the
-// order and therefore finished or running: no deadlock.  Per-frame counters in global memory carry the
-// dependencies (release: st + __threadfence + atomicAdd; acquire: ld.acquire.gpu; the scratch is read with
+// alternating -- from a global ticket counter, so an item only ever waits for items with smaller tickets, and a
+// ticket is only ever held by a CTA that is running: the earliest unfinished item can always proceed, whatever
+// share of the grid is resident (two such kernels on different streams cannot deadlock each other, as a static
+// item-to-CTA assignment could).  Per-frame counters in global memory carry the
+// dependencies (release: st + __threadfence + atomicAdd; acquire: ld.acquire.gpu polled by warp 0 as a whole, then the
+// block barrier; the scratch is read with
 // ld.global.cg so that no stale L1 line of an earlier use of the slot is seen).
 __device__ __forceinline__ unsigned ld_acquire(const unsigned *p)
 {
@@ -117,17 +120,36 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned *p)
     return v;
 }
 
+// A whole warp waits, converged, until *p >= need (lane 0 reads, the value is broadcast).  A single thread spinning
+// ahead of a block barrier while the other 31 lanes of its warp run on was observed to let the barrier release
+// without it; keeping the warp together avoids depending on that.
+__device__ __forceinline__ void poll_at_least(const unsigned *p, unsigned need, int lane)
+{
+    for (;;) {
+        unsigned f = lane == 0 ? ld_acquire(p) : 0u;
+        f = __shfl_sync(0xffffffffu, f, 0);
+        if (f >= need) break;
+        __nanosleep(64);
+    }
+}
+
 template <bool INV>
 __global__ void __launch_bounds__(256, 4)
 fft65536_fused_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, float2 *__restrict__ scratch,
-                      const float2 *__restrict__ twN, unsigned *flags_a, unsigned *flags_b, unsigned long long nframes,
-                      unsigned lag, unsigned ring)
+                      const float2 *__restrict__ twN, unsigned *ticket, unsigned *flags_a, unsigned *flags_b,
+                      unsigned long long nframes, unsigned lag, unsigned ring)
 {
     using namespace fft2;
     extern __shared__ __align__(16) float2 rsm[];
+    __shared__ unsigned s_item;
     const int lane = threadIdx.x & 31, lo = lane & 15, hi = 2 * (threadIdx.x >> 5) + (lane >> 4);
     const unsigned long long nchunks = lag + 2ull * nframes;
-    for (unsigned long long item = blockIdx.x; item < nchunks * 16; item += gridDim.x) {
+    for (;;) {
+        __syncthreads();  // the previous item's shared-memory reads (and its read of s_item) are done
+        if (threadIdx.x == 0) s_item = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const unsigned long long item = s_item;
+        if (item >= nchunks * 16) break;
         const unsigned long long chunk = item >> 4;
         const int part16 = (int)(item & 15) * 16;
         bool is_a;
@@ -143,14 +165,15 @@ fft65536_fused_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, f
         if (frame >= nframes) continue;
         float2 *slot = scratch + (frame % ring) * NF;
         float2 v[16];
-        __syncthreads();  // the previous item's shared-memory reads are done
         if (is_a) {
-            if (frame >= ring && threadIdx.x == 0)
-                while (ld_acquire(flags_b + (frame - ring)) < 16u) __nanosleep(64);  // slot consumed by its last reader
             const float2 *src = in + frame * NF + part16 + lo;
             float2 *row = rsm + lo * RP;
 #pragma unroll
             for (int m = 0; m < 16; ++m) v[m] = ld_cs(src + 256 * (hi + 16 * m));
+            // the slot must have been consumed by its last reader before anything is stored into it: warp 0 polls
+            // (all 32 lanes together) while the input loads are in flight; the block barrier below orders the
+            // observation before every thread's stores
+            if (frame >= ring && threadIdx.x < 32) poll_at_least(flags_b + (frame - ring), 16u, lane);
             bfly16<INV>(v);
 #pragma unroll
             for (int sl = 0; sl < 16; ++sl) row[pad16(16 * hi + q16(sl))] = v[sl];
@@ -168,8 +191,8 @@ fft65536_fused_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, f
                 atomicAdd(flags_a + frame, 1u);
             }
         } else {
-            if (threadIdx.x == 0)
-                while (ld_acquire(flags_a + frame) < 16u) __nanosleep(64);  // all 16 column blocks of the frame are in
+            // all 16 column blocks of the frame are in
+            if (threadIdx.x < 32) poll_at_least(flags_a + frame, 16u, lane);
             __syncthreads();
             const int k1 = part16 + hi;
             const float2 *src = slot + (size_t)k1 * 256 + lo;
@@ -181,7 +204,10 @@ fft65536_fused_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, f
 #pragma unroll
             for (int sl = 0; sl < 16; ++sl) rowp[pad16(16 * lo + q16(sl))] = v[sl];
             __syncthreads();  // every thread has consumed its scratch reads
-            if (threadIdx.x == 0) atomicAdd(flags_b + frame, 1u);
+            if (threadIdx.x == 0) {
+                __threadfence();
+                atomicAdd(flags_b + frame, 1u);
+            }
             const float2 *row = rsm + lo * RP;
 #pragma unroll
             for (int m = 0; m < 16; ++m) v[m] = row[pad16(hi + 16 * m)];
@@ -208,10 +234,10 @@ static int launch_fused(const FftPlanDev &p, const float2 *in, float2 *out, size
     unsigned lag = ring / 2;
     if (lag < 1) lag = 1;
     const unsigned long long items = (lag + 2ull * nframes) * 16;
-    const unsigned long long cap = (unsigned long long)sms * per_sm;  // the whole grid must be resident
+    const unsigned long long cap = (unsigned long long)sms * per_sm;  // one CTA per resident slot
     const unsigned grid = (unsigned)(items < cap ? items : cap);
-    CB_CUDA(cudaMemsetAsync(p.flags, 0, 2 * nframes * sizeof(unsigned), s));
-    kf<<<grid, 256, SMEM, s>>>(in, out, p.scratch, p.tw, p.flags, p.flags + nframes, nframes, lag, ring);
+    CB_CUDA(cudaMemsetAsync(p.flags, 0, (4 + 2 * nframes) * sizeof(unsigned), s));
+    kf<<<grid, 256, SMEM, s>>>(in, out, p.scratch, p.tw, p.flags, p.flags + 4, p.flags + 4 + nframes, nframes, lag, ring);
     count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;

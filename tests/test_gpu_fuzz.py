@@ -120,3 +120,36 @@ def test_fft65536_frame_counts(cb, oracle, frames):
     for f in sorted({0, frames - 1, frames // 2}):
         want = oracle.fft(x[f * n:(f + 1) * n], n, False)
         assert rel_l2(got[f * n:(f + 1) * n], want) <= 1e-4, f
+
+
+@pytest.mark.timeout(300)
+def test_fft65536_two_handles_concurrently(cb, oracle):
+    # two fused 65536-point kernels in flight on different streams share the SMs; the ticket-ordered work
+    # distribution must let both finish (a static item-to-CTA assignment could deadlock here) with right results
+    import threading
+
+    import torch
+
+    n, frames = 65536, 512
+    xs = [torch.empty(frames * n, dtype=torch.complex64, device="cuda") for _ in range(2)]
+    ys = [torch.empty_like(x) for x in xs]
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    nodes = [cb.FFTBatchNode(n, False), cb.FFTBatchNode(n, True)]
+    for i in range(2):
+        cb.synth_uniform_dev(7 + i, 0, frames * n, xs[i].data_ptr(), streams[i].cuda_stream)
+    torch.cuda.synchronize()
+
+    def work(i):
+        for _ in range(6):
+            nodes[i].run_dev(xs[i].data_ptr(), frames * n, ys[i].data_ptr(), streams[i].cuda_stream)
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    torch.cuda.synchronize()
+    for i in range(2):
+        for f in (0, frames - 1, 257):
+            xin = oracle.synth_uniform_c32(7 + i, f * n, n)
+            assert rel_l2(ys[i][f * n:(f + 1) * n].cpu().numpy(), oracle.fft(xin, n, bool(i))) <= 1e-4, (i, f)
