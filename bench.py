@@ -40,6 +40,7 @@ WORKLOADS = {
     # name: (kind, samples per step per GPU, algorithmic bytes per input sample, description)
     "fir64": ("fir", 1 << 28, 16.0, "64-tap complex-f32 FIR (complex taps) on one 2^28-sample stream per GPU"),
     "fir64_real": ("fir", 1 << 28, 16.0, "64-tap complex-f32 FIR (real-valued rrc taps) on one 2^28-sample stream per GPU"),
+    "fir63d5": ("firdec", 1 << 28, 9.6, "63-tap real-valued FIR + DecimateNode(5) (fm_radio.rs filt1 -> dec1) fused, one 2^28-sample stream per GPU"),
     "fft1024": ("fft", 1 << 28, 16.0, "batched 1024-point FFT over 2^28 complex-f32 samples per GPU"),
     "fft2048": ("fft", 1 << 28, 16.0, "batched 2048-point FFT over 2^28 complex-f32 samples per GPU"),
     "fft8192": ("fft", 1 << 28, 16.0, "batched 8192-point FFT over 2^28 complex-f32 samples per GPU"),
@@ -176,6 +177,9 @@ def cpu_rate(workload, samples, threads):
             jobs.append(lambda x=x, t=t: oracle.batch_fir(x, t, np.zeros(64, np.complex64), literal=True, native=True))
         elif kind == "fft":
             jobs.append(lambda x=x: oracle.fft(x, n, workload.startswith("ifft")))
+        elif kind == "firdec":
+            t = fm_radio_lowpass()
+            jobs.append(lambda x=x, t=t: oracle.decimate(oracle.batch_fir(x, t, np.zeros(63, np.complex64), literal=True, native=True)[0], 5))
         elif kind == "mixer":
             jobs.append(lambda x=x: oracle.Mixer(0.2, 0.123).mix(x))
         elif kind == "fm":
@@ -206,7 +210,7 @@ def run_reference(args, rank):
         return
     threads = os.cpu_count() or 1
     kind, _, _, desc = WORKLOADS[args.workload]
-    rate1 = {"fir": 8e6, "fft": 30e6, "chain": 20e6, "interp": 2e6, "mixer": 30e6, "fm": 60e6}[kind]
+    rate1 = {"fir": 8e6, "fft": 30e6, "chain": 20e6, "interp": 2e6, "mixer": 30e6, "fm": 60e6, "firdec": 8e6}[kind]
     if args.workload.startswith("poly8x1024"):
         rate1 = 1e4
     per_thread = int(min(max(150.0 * rate1 / (args.steps + args.warmup), 1 << 12), 1 << 23))
@@ -259,6 +263,14 @@ class Job:
             self.out_bytes = 8 * n
             self.step = lambda: self.node.run_dev(self.x.data_ptr(), n, self.y.data_ptr(), n, self.stream)
             self.host_call = lambda hin, hout: cb.load().cb_fir_run(self.node._h, hin, n, hout, n, None)
+        elif self.kind == "firdec":
+            self.taps = fm_radio_lowpass()
+            self.node = cb.BatchFirNode(self.taps, None, decim=5)
+            no = -(-n // 5)
+            self.y = torch.empty(no, dtype=torch.complex64, device="cuda")
+            self.out_bytes = 8 * no
+            self.step = lambda: self.node.run_dev(self.x.data_ptr(), n, self.y.data_ptr(), no, self.stream)
+            self.host_call = lambda hin, hout: cb.load().cb_fir_run(self.node._h, hin, n, hout, no, None)
         elif self.kind == "fft":
             N = int(workload.replace("ifft", "").replace("fft", ""))
             self.node = cb.FFTBatchNode(N, workload.startswith("ifft"))
@@ -440,7 +452,7 @@ def run_b200(args, rank, world, local_rank):
         }
         if world == 1 and not args.no_cpu:
             kind = job.kind
-            sample = {"fir": 1 << 26, "fft": 1 << 27, "chain": 1 << 26, "interp": 1 << 23, "mixer": 1 << 26, "fm": 1 << 27}[kind]
+            sample = {"fir": 1 << 26, "fft": 1 << 27, "chain": 1 << 26, "interp": 1 << 23, "mixer": 1 << 26, "fm": 1 << 27, "firdec": 1 << 26}[kind]
             if args.workload.startswith("poly8x1024"):
                 sample = 1 << 17
             v, dt, n = cpu_rate(args.workload, sample, 1)

@@ -62,7 +62,7 @@ chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ ChainT
     __syncthreads();
 
     // ---- carried state for the next call (last tile of the channel)
-    if (blockIdx.x == gridDim.x - 1) {
+    if (blockIdx.x == gridDim.x - 1 && a.hist_out != nullptr) {
         float2 *ho = a.hist_out + c * H;
         for (long long i = tid; i < H; i += 256) {
             const long long g = (long long)a.n_in - H + i;
@@ -265,7 +265,7 @@ chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
         }
 
         // ---- carried state for the next call (last tile of the channel)
-        if (tile == tiles_per_ch - 1) {
+        if (tile == tiles_per_ch - 1 && a.hist_out != nullptr) {
             float2 *ho = a.hist_out + c * H;
             for (long long i = tid; i < H; i += NT) {
                 const long long g = (long long)a.n_in - H + i;
@@ -621,7 +621,7 @@ chain3_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
         }
 
         // ---- carried state for the next call (last tile of the channel)
-        if (tile == tiles_per_ch - 1) {
+        if (tile == tiles_per_ch - 1 && a.hist_out != nullptr) {
             const float2 *hc = a.hist_in + c * H;
             float2 *ho = a.hist_out + c * H;
             for (long long i = tid; i < H; i += NT) {

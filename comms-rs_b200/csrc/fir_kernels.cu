@@ -1,6 +1,7 @@
 // FIR kernels for sm_100a: overlap-save stream kernel (TMA-staged tiles with
 // halo, taps in the kernel-parameter constant bank, packed FFMA2 inner loop)
 // plus a generic any-shape kernel (interp / decim / long filters).
+#include "chain_kernels.cuh"
 #include "fir_kernels.cuh"
 
 namespace cb {
@@ -422,6 +423,27 @@ int launch_fir(const FirSeg &seg, const float2 *taps_dev, const float2 *taps_hos
             if (K <= 64 && seg.hist_len >= 64) return launch_stream<64, true, 8>(seg, taps_host, stream);
             if (K <= 128 && seg.hist_len >= 128) return launch_stream<128, true, 8>(seg, taps_host, stream);
         }
+    }
+    // BatchFirNode -> DecimateNode with real taps: the fused bank kernel with one channel, no mixer and no FM tail
+    // computes exactly this (only the surviving outputs, per-call decimation phase); TMA-staged for D in {5, 10}
+    if (seg.interp == 1 && seg.decim > 1 && taps_real && seg.ntaps <= 64 && seg.n_in % 2 == 0 && seg.hist_len % 2 == 0 &&
+        seg.hist_len >= 128 && (seg.decim == 2 || seg.decim == 4 || seg.decim == 5 || seg.decim == 8 || seg.decim == 10) &&
+        (reinterpret_cast<uintptr_t>(seg.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(seg.y) & 7) == 0) {
+        ChainArgs a = {};
+        a.x = seg.x;
+        a.out = seg.y;
+        a.hist_in = seg.hist_in;
+        a.hist_out = seg.hist_out;  // may be NULL (host chunks before the last)
+        a.n_in = seg.n_in;
+        a.n_out = seg.n_out;
+        a.ntaps = seg.ntaps;
+        a.decim = seg.decim;
+        a.hist_len = seg.hist_len;
+        a.tile_out = 256;
+        a.span_max = 256 * seg.decim + 64 + seg.decim;
+        ChainTaps ct = {};
+        for (uint32_t k = 0; k < seg.ntaps; ++k) ct.t[k] = make_float2(taps_host[k].x, taps_host[k].x);
+        return launch_chain(a, ct, false, false, false, 1, stream);
     }
     if (seg.decim == 1 && taps_real && seg.interp > 1) {
         const uint32_t kpl = (uint32_t)ceil_div(seg.ntaps, seg.interp);
