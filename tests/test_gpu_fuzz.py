@@ -153,3 +153,21 @@ def test_fft65536_two_handles_concurrently(cb, oracle):
         for f in (0, frames - 1, 257):
             xin = oracle.synth_uniform_c32(7 + i, f * n, n)
             assert rel_l2(ys[i][f * n:(f + 1) * n].cpu().numpy(), oracle.fft(xin, n, bool(i))) <= 1e-4, (i, f)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_fir_tensor_core_dynamic_range(cb, oracle, cplx, monkeypatch):
+    # K1-TC scales every 4096-sample tile by its own power of two before the fp16 split: a quiet stretch next to a
+    # loud one must keep the 1e-5 tolerance on its own, not only in the global norm
+    monkeypatch.setenv("COMMS_B200_FIR_PATH", "tc")
+    rng = np.random.default_rng(77 + cplx)
+    t = rnd_c32(rng, 64) if cplx else rng.uniform(-1, 1, 64).astype(np.complex64)
+    x = rnd_c32(rng, 120_000)
+    x[20_000:40_000] *= np.float32(1e-5)
+    x[60_000:80_000] *= np.float32(1e4)
+    x[100_000:100_003] = 0
+    want, _ = oracle.batch_fir(x, t, np.zeros(64, np.complex64))
+    got = cb.BatchFirNode(t).run(x)
+    assert rel_l2(got, want) <= FIR_TOL
+    for lo, hi in ((20_000 + 4096 + 64, 40_000), (60_000, 80_000), (90_000, 120_000)):
+        assert rel_l2(got[lo:hi], want[lo:hi]) <= FIR_TOL, (lo, hi)
