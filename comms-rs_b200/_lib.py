@@ -103,6 +103,10 @@ SIGNATURES = {
     "cb_chain_run_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _psz, _vp]),
     "cb_chain_run_u8_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _psz, _vp]),
     "cb_chain_run_u8": (_i, [_vp, _vp, _sz, _vp, _sz, _psz]),
+    "cb_comm_unique_id": (_i, [_vp]),
+    "cb_comm_init": (_i, [C.c_int, C.c_int, _vp, C.POINTER(_vp)]),
+    "cb_comm_destroy": (_i, [_vp]),
+    "cb_gather_segments_dev": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "cb_convert_u8_dev": (_i, [_vp, _sz, _vp, _vp]),
     "cb_convert_i16_dev": (_i, [_vp, _sz, C.c_float, _vp, _vp]),
     "cb_rrc_taps": (_i, [C.c_uint32, C.c_double, C.c_double, _vp]),

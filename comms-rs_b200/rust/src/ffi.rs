@@ -3,7 +3,7 @@
 use std::os::raw::{c_char, c_double, c_float, c_int, c_uint, c_void};
 
 macro_rules! opaque { ($($n:ident),*) => { $(#[repr(C)] pub struct $n { _p: [u8; 0] })* } }
-opaque!(cb_stream, cb_buf, cb_fir, cb_mixer, cb_fft, cb_fm, cb_chain);
+opaque!(cb_stream, cb_buf, cb_fir, cb_mixer, cb_fft, cb_fm, cb_chain, cb_comm);
 
 pub const CB_OK: c_int = 0;
 pub const CB_ERR_INVALID_ARG: c_int = 1;
@@ -93,6 +93,10 @@ extern "C" {
     pub fn cb_convert_i16_dev(d_in: *const i16, n_samples: usize, scale: f32, d_out: *mut f32, stream: *mut c_void) -> c_int;
     pub fn cb_chain_run_u8(h: *mut cb_chain, input: *const u8, n_in: usize, out: *mut f32, out_cap: usize, n_out: *mut usize) -> c_int;
     pub fn cb_chain_run_u8_dev(h: *mut cb_chain, d_in: *const u8, n_in: usize, d_out: *mut f32, out_cap: usize, n_out: *mut usize, stream: *mut c_void) -> c_int;
+    pub fn cb_comm_unique_id(id128: *mut c_void) -> c_int;
+    pub fn cb_comm_init(nranks: c_int, rank: c_int, id128: *const c_void, out: *mut *mut cb_comm) -> c_int;
+    pub fn cb_comm_destroy(c: *mut cb_comm) -> c_int;
+    pub fn cb_gather_segments_dev(c: *mut cb_comm, d_seg: *const f32, n_samples: usize, d_all: *mut f32, stream: *mut c_void) -> c_int;
     pub fn cb_rrc_taps(n_taps: u32, sam_per_sym: f64, beta: f64, taps: *mut f32) -> c_int;
     pub fn cb_rrc_taps_f64(n_taps: u32, sam_per_sym: f64, beta: f64, taps: *mut f64) -> c_int;
     pub fn cb_prn_bits(poly_mask: u64, state: *mut u64, width: c_uint, n: usize, bits: *mut u8) -> c_int;

@@ -71,3 +71,44 @@ def gather_ordered(local, sizes=None, group=None):
     pad[: local.numel()] = local
     full = gather_ordered(pad, [cap] * world, group)
     return torch.cat([full[r * cap: r * cap + sizes[r]] for r in range(world)])
+
+
+class SegmentGather:
+    """The same ordered gather through the library's own C-ABI entry (cb_comm_* / cb_gather_segments_dev:
+    ncclAllGather over NVLink), for hosts that do not use torch.distributed.  `id_bytes` is the 128-byte id made
+    by rank 0 with `SegmentGather.unique_id()` and handed to the other ranks over any host channel."""
+
+    def __init__(self, nranks: int, rank: int, id_bytes: bytes):
+        import ctypes as C
+
+        from . import _lib
+
+        self._lib, self._h = _lib, C.c_void_p()
+        buf = C.create_string_buffer(bytes(id_bytes), 128)
+        _lib.check(_lib.load().cb_comm_init(int(nranks), int(rank), buf, C.byref(self._h)))
+        self.nranks, self.rank = int(nranks), int(rank)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        import ctypes as C
+
+        from . import _lib
+
+        buf = C.create_string_buffer(128)
+        _lib.check(_lib.load().cb_comm_unique_id(buf))
+        return buf.raw
+
+    def gather_dev(self, d_seg: int, n_samples: int, d_all: int, stream: int = 0) -> None:
+        """d_all (device, nranks * n_samples complex f32) <- every rank's n_samples-sample segment, in rank order."""
+        self._lib.check(self._lib.load().cb_gather_segments_dev(self._h, d_seg, n_samples, d_all, stream))
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.load().cb_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass

@@ -262,6 +262,20 @@ CB_API int cb_quantize_i16_dev(const float *d_in, size_t nfloats, float scale, i
 CB_API int cb_convert_u8_dev(const uint8_t *d_in, size_t n_samples, float *d_out, void *stream);
 CB_API int cb_convert_i16_dev(const int16_t *d_in, size_t n_samples, float scale, float *d_out, void *stream);
 
+/* ------------------------------------------------------------------ multi-GPU: ordered gather of segments
+ * One process (or thread + cb_init) per GPU.  Channels, frames and overlap-save segments are computed without any
+ * exchange (each rank passes the samples before its segment as the FIR's initial state, fir_node.rs:193-200); the
+ * one collective is the optional gather of equal-length output segments back into one rank-ordered stream, an
+ * ncclAllGather over NVLink.  NCCL is dlopen'ed on first use (libnccl.so.2, or COMMS_B200_NCCL_LIB), so the
+ * library does not depend on it otherwise; CB_ERR_UNSUPPORTED when it cannot be loaded.
+ * cb_comm_unique_id: rank 0 creates the 128-byte id and hands it to the other ranks by any host channel.
+ * cb_gather_segments_dev: d_all receives nranks * n_samples complex samples, rank r's segment at r * n_samples. */
+typedef struct cb_comm cb_comm;
+CB_API int cb_comm_unique_id(void *id128);
+CB_API int cb_comm_init(int nranks, int rank, const void *id128, cb_comm **out);
+CB_API int cb_comm_destroy(cb_comm *c);
+CB_API int cb_gather_segments_dev(cb_comm *c, const float *d_seg, size_t n_samples, float *d_all, void *stream);
+
 /* ------------------------------------------------------------------ synthetic input
  * splitmix64 counter generator shared with the oracle (oracle.c
  * orc_synth_uniform_f32): float i = top 24 bits of splitmix64(seed + i)

@@ -586,6 +586,22 @@ def test_fft_full_size_roundtrip(cb, oracle, n):
     assert float(err) <= FFT_TOL
 
 
+def test_comm_gather_single_rank(cb):
+    # cb_comm_* / cb_gather_segments_dev (ncclAllGather bound by dlopen): with one rank the gather is the identity;
+    # the 2-rank form is scripts/mg_gather_check.py (torchrun, one process per GPU)
+    import torch
+
+    g = cb.sharding.SegmentGather(1, 0, cb.sharding.SegmentGather.unique_id())
+    x = torch.randn(2 * 10_000, device="cuda")
+    y = torch.zeros_like(x)
+    ts = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    g.gather_dev(x.data_ptr(), 10_000, y.data_ptr(), ts.cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(x, y)
+    g.close()
+
+
 # ------------------------------------------------------------------ C++ host mirror (graph-level conformance)
 def test_cpp_host_graph_conformance():
     """comms-rs_b200/host/test_graph.cpp: source -> GPU node -> check graphs with one thread per
