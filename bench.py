@@ -40,6 +40,7 @@ WORKLOADS = {
     # name: (kind, samples per step per GPU, algorithmic bytes per input sample, description)
     "fir64": ("fir", 1 << 28, 16.0, "64-tap complex-f32 FIR (complex taps) on one 2^28-sample stream per GPU"),
     "fir64_real": ("fir", 1 << 28, 16.0, "64-tap complex-f32 FIR (real-valued rrc taps) on one 2^28-sample stream per GPU"),
+    "fir1024": ("fir", 1 << 28, 16.0, "1024-tap complex-f32 FIR (overlap-save fast convolution) on one 2^28-sample stream per GPU"),
     "fir63d5": ("firdec", 1 << 28, 9.6, "63-tap real-valued FIR + DecimateNode(5) (fm_radio.rs filt1 -> dec1) fused, one 2^28-sample stream per GPU"),
     "fft1024": ("fft", 1 << 28, 16.0, "batched 1024-point FFT over 2^28 complex-f32 samples per GPU"),
     "fft2048": ("fft", 1 << 28, 16.0, "batched 2048-point FFT over 2^28 complex-f32 samples per GPU"),
@@ -94,9 +95,10 @@ def rrc_taps(n, sps, beta):
 
 
 def fir_taps(workload):
-    t = rrc_taps(64, 4.0, 0.25)
-    if workload == "fir64":
-        t = (t * np.exp(0.1j * np.arange(64))).astype(np.complex64)
+    nt = 1024 if workload == "fir1024" else 64
+    t = rrc_taps(nt, 4.0, 0.25)
+    if workload in ("fir64", "fir1024"):
+        t = (t * np.exp(0.1j * np.arange(nt))).astype(np.complex64)
     return t
 
 
@@ -174,7 +176,7 @@ def cpu_rate(workload, samples, threads):
         if kind == "fir":
             t = fir_taps(workload)
             # reference form: per-sample rotate + ordered MACs (src/filter/fir.rs:87-102), release flags
-            jobs.append(lambda x=x, t=t: oracle.batch_fir(x, t, np.zeros(64, np.complex64), literal=True, native=True))
+            jobs.append(lambda x=x, t=t: oracle.batch_fir(x, t, np.zeros(len(t), np.complex64), literal=True, native=True))
         elif kind == "fft":
             jobs.append(lambda x=x: oracle.fft(x, n, workload.startswith("ifft")))
         elif kind == "firdec":
@@ -257,7 +259,7 @@ class Job:
         self.kernels_per_step = 1
         if self.kind == "fir":
             self.taps = fir_taps(workload)
-            self.halo = self._halo(64)
+            self.halo = self._halo(len(self.taps))
             self.node = cb.BatchFirNode(self.taps, self.halo)
             self.y = torch.empty(n, dtype=torch.complex64, device="cuda")
             self.out_bytes = 8 * n

@@ -151,6 +151,9 @@ struct cb_fir {
     FirTcPlan tc;
     float2 *qscratch;   // f32 result of the unfused cb_fir_run_dev_i16 path, grown on demand
     size_t qscratch_len;
+    // overlap-save path for 129 .. 1025 taps: taps' spectrum, the two 4096-point twiddle tables, frame spectra
+    float2 *ols_hf, *ols_twf, *ols_twi, *ols_spec;
+    size_t ols_spec_frames;
 };
 
 struct cb_mixer {
@@ -440,6 +443,8 @@ int cb_fir_create(const float *taps, size_t ntaps, const float *state, size_t ns
     h->tc = FirTcPlan{nullptr, 1.f, 0};
     h->qscratch = nullptr;
     h->qscratch_len = 0;
+    h->ols_hf = h->ols_twf = h->ols_twi = h->ols_spec = nullptr;
+    h->ols_spec_frames = 0;
 
     std::vector<float2> hist;
     rc = fir_state_to_hist(h, reinterpret_cast<const float2 *>(state), state ? nstate : 0, hist);
@@ -492,6 +497,31 @@ int cb_fir_create(const float *taps, size_t ntaps, const float *state, size_t ns
             h->tc = FirTcPlan{h->tc_img, inv, force_tc ? (size_t)1 : ((size_t)1 << 16)};
         }
     }
+        const char *path2 = getenv("COMMS_B200_FIR_PATH");
+        if (!(path2 && strcmp(path2, "cuda") == 0) && h->interp == 1 && h->decim == 1 && h->k_eff > 128 && h->k_eff <= 1025) {
+            // long filter: fast convolution.  Hf[k] = sum_t h[t] e^{-2 pi i k t / 4096}, in f64
+            std::vector<float2> hf(4096);
+            const double w0 = -2.0 * 3.14159265358979323846 / 4096.0;
+            for (int k = 0; k < 4096; ++k) {
+                double re = 0.0, im = 0.0;
+                for (uint32_t t = 0; t < h->k_eff; ++t) {
+                    const double ang = w0 * (double)(((long long)k * t) & 4095);
+                    const double c = cos(ang), sn = sin(ang);
+                    re += (double)h->taps[t].x * c - (double)h->taps[t].y * sn;
+                    im += (double)h->taps[t].x * sn + (double)h->taps[t].y * c;
+                }
+                hf[k] = make_float2((float)re, (float)im);
+            }
+            FIR_TRY(cudaMalloc(&h->ols_hf, 4096 * sizeof(float2)));
+            FIR_TRY(cudaMemcpy(h->ols_hf, hf.data(), 4096 * sizeof(float2), cudaMemcpyHostToDevice));
+            for (int inv = 0; inv < 2; ++inv) {
+                std::vector<float2> t(fft2_table_len(12));
+                fft2_fill_table(12, inv, t.data());
+                float2 **dst = inv ? &h->ols_twi : &h->ols_twf;
+                FIR_TRY(cudaMalloc(dst, t.size() * sizeof(float2)));
+                FIR_TRY(cudaMemcpy(*dst, t.data(), t.size() * sizeof(float2), cudaMemcpyHostToDevice));
+            }
+        }
 #undef FIR_TRY
     *out = h;
     return CB_OK;
@@ -506,6 +536,10 @@ int cb_fir_destroy(cb_fir *h)
     if (h->taps_dev) cudaFree(h->taps_dev);
     if (h->tc_img) cudaFree(h->tc_img);
     if (h->qscratch) cudaFree(h->qscratch);
+    if (h->ols_hf) cudaFree(h->ols_hf);
+    if (h->ols_twf) cudaFree(h->ols_twf);
+    if (h->ols_twi) cudaFree(h->ols_twi);
+    if (h->ols_spec) cudaFree(h->ols_spec);
     for (int i = 0; i < 2; ++i)
         if (h->hist[i]) cudaFree(h->hist[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -525,6 +559,21 @@ void *cb_fir_stream(cb_fir *h) { return h ? (void *)h->stream : nullptr; }
 static int fir_launch_segment(cb_fir *h, const float2 *x, size_t n, const float2 *hist_in, float2 *hist_out,
                               float2 *y, cudaStream_t s)
 {
+    // long filters and long batches: overlap-save fast convolution (spectra scratch grown on demand; when it
+    // cannot be allocated the direct-form kernel below is used)
+    if (h->ols_hf != nullptr && n >= 8192) {
+        const size_t frames = fir_ols_frames(n, h->k_eff);
+        if (h->ols_spec_frames < frames) {
+            if (h->ols_spec) cudaFree(h->ols_spec);
+            h->ols_spec = nullptr;
+            h->ols_spec_frames = 0;
+            if (cudaMalloc(&h->ols_spec, frames * 4096 * sizeof(float2)) == cudaSuccess) h->ols_spec_frames = frames;
+            else cudaGetLastError();
+        }
+        if (h->ols_spec_frames >= frames)
+            return launch_fir_ols(x, n, hist_in, hist_out, h->hist_len, h->k_eff, h->ols_hf, h->ols_twf, h->ols_twi,
+                                  h->ols_spec, y, s);
+    }
     // k_eff == 0 (zip over an empty state, fir.rs:99) runs as an all-zero filter: outputs are 0
     FirSeg seg{x, hist_in, hist_out, y, n, fir_out_len(h, n), h->hist_len, h->k_eff, h->interp, h->decim};
     return launch_fir(seg, h->taps_dev, h->taps.data(), h->taps_real, h->tc_img ? &h->tc : nullptr, s);

@@ -451,6 +451,101 @@ static int launch_step_dir(int which, int log2m, const float2 *in, float2 *out, 
     }
 }
 
+// ---------------------------------------------------------------- overlap-save FIR for long filters
+// y = h * x for 129 .. 1025 taps by fast convolution (src/filter/fir.rs:87-102 semantics, state carried):
+//   frame f = input samples [f hop - (K-1), f hop - (K-1) + 4096),  hop = 4096 - (K-1)
+//   stage 0: forward 4096-point FFT of every frame (history / zero fill handled in the loads)      -> spec
+//   stage 1: spec * Hf (FFT of the zero-padded taps, evaluated in f64 on the host), inverse FFT, scale by 1/4096,
+//            keep outputs K-1 .. 4095 of the frame                                                  -> y
+// Both stages are fft2_frames_kernel<12>'s passes with other first-pass loads / last-pass stores.  ~40 B of HBM
+// traffic per sample instead of 16, but O(log N) work per sample where the direct form needs K MACs.
+struct OlsArgs {
+    const float2 *x;
+    const float2 *hist;   // hist_len samples preceding x[0], chronological
+    float2 *spec;         // frames x 4096
+    const float2 *hf;     // 4096
+    float2 *y;
+    unsigned long long n;
+    unsigned hist_len, K, hop;
+};
+
+template <int STAGE>
+__global__ void __launch_bounds__(Fft2Cfg<12>::THREADS, Fft2Cfg<12>::MINB)
+fir_ols_kernel(const __grid_constant__ OlsArgs a, const float2 *__restrict__ tw)
+{
+    using PL = fft2::Plan<12>;
+    extern __shared__ __align__(16) float2 fsm[];
+    const int j = threadIdx.x;
+    const long long frame = blockIdx.x;
+    float2 *b0 = fsm;
+    if constexpr (STAGE == 0) {
+        const long long g0 = frame * a.hop - (long long)(a.K - 1);
+        auto gld = [&](int i) {
+            const long long g = g0 + i;
+            if (g >= (long long)a.n) return make_float2(0.f, 0.f);
+            if (g >= 0) return ldg_stream2(a.x + g);
+            const long long hi = (long long)a.hist_len + g;
+            return hi >= 0 ? a.hist[hi] : make_float2(0.f, 0.f);
+        };
+        float2 *dst = a.spec + frame * PL::N;
+        auto gst = [&](int i, float2 v) { dst[i] = v; };
+        fft2_passes<12, false, 0>(j, tw, gld, gst, b0, b0);
+    } else {
+        const float2 *src = a.spec + frame * PL::N;
+        auto gld = [&](int i) { return fft2::cmul(src[i], __ldg(a.hf + i)); };
+        const long long o0 = frame * a.hop - (long long)(a.K - 1);
+        auto gst = [&](int i, float2 v) {
+            const long long o = o0 + i;
+            if (i >= (int)(a.K - 1) && o < (long long)a.n) stg_stream2(a.y + o, make_float2(v.x * (1.f / 4096.f), v.y * (1.f / 4096.f)));
+        };
+        fft2_passes<12, true, 0>(j, tw, gld, gst, b0, b0);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+fir_hist_update_kernel(const float2 *__restrict__ x, unsigned long long n, const float2 *__restrict__ hist_in,
+                       float2 *__restrict__ hist_out, unsigned H)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < H; i += gridDim.x * blockDim.x) {
+        const long long g = (long long)n - H + i;
+        hist_out[i] = g >= 0 ? x[g] : hist_in[H + g];
+    }
+}
+
+size_t fir_ols_frames(size_t n, uint32_t ntaps) { return ceil_div(n, (size_t)(4096 - (ntaps - 1))); }
+
+int launch_fir_ols(const float2 *x, size_t n, const float2 *hist_in, float2 *hist_out, uint32_t hist_len, uint32_t ntaps,
+                   const float2 *hf, const float2 *tw_fwd, const float2 *tw_inv, float2 *spec, float2 *y, cudaStream_t s)
+{
+    using CF = Fft2Cfg<12>;
+    if (n == 0) return CB_OK;
+    OlsArgs a;
+    a.x = x;
+    a.hist = hist_in;
+    a.spec = spec;
+    a.hf = hf;
+    a.y = y;
+    a.n = n;
+    a.hist_len = hist_len;
+    a.K = ntaps;
+    a.hop = 4096 - (ntaps - 1);
+    const unsigned frames = (unsigned)fir_ols_frames(n, ntaps);
+    auto k0 = fir_ols_kernel<0>;
+    auto k1 = fir_ols_kernel<1>;
+    CB_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM));
+    CB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM));
+    k0<<<frames, CF::THREADS, CF::SMEM, s>>>(a, tw_fwd);
+    count_launch();
+    k1<<<frames, CF::THREADS, CF::SMEM, s>>>(a, tw_inv);
+    count_launch();
+    if (hist_out != nullptr) {
+        fir_hist_update_kernel<<<(hist_len + 255) / 256, 256, 0, s>>>(x, n, hist_in, hist_out, hist_len);
+        count_launch();
+    }
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+
 // ---------------------------------------------------------------- 65536 = 16 x 4096, two streaming passes
 // step A: for every n2, the 16-point DFT over n1 of x[4096 n1 + n2], times W_N^{n2 k1}, stored as row k1
 // (no shared memory: 16 coalesced loads, one radix-16 butterfly, 16 coalesced stores per thread);

@@ -48,6 +48,13 @@ void fir_ptc_build_image(const float2 *taps, uint32_t ntaps, uint32_t interp, bo
 bool fir_ptc_applicable(const FirSeg &seg, bool taps_real);
 int launch_fir_ptc(const FirSeg &seg, const void *himg_dev, float tap_inv_scale, bool taps_real, cudaStream_t stream);
 
+// Overlap-save path for long filters (fft_kernels.cu): 129 .. 1025 taps, decim = interp = 1.
+// hf: 4096-point spectrum of the zero-padded taps; tw_fwd / tw_inv: fft2 tables for 4096 points; spec: scratch of
+// fir_ols_frames(n, ntaps) * 4096 complex samples.
+size_t fir_ols_frames(size_t n, uint32_t ntaps);
+int launch_fir_ols(const float2 *x, size_t n, const float2 *hist_in, float2 *hist_out, uint32_t hist_len, uint32_t ntaps,
+                   const float2 *hf, const float2 *tw_fwd, const float2 *tw_inv, float2 *spec, float2 *y, cudaStream_t s);
+
 // taps_dev: ntaps complex taps in device memory (generic path)
 // taps_host: same on the host (fast paths put them in the kernel parameter constant bank)
 // tcplan: NULL = CUDA-core kernels only

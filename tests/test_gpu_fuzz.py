@@ -171,3 +171,28 @@ def test_fir_tensor_core_dynamic_range(cb, oracle, cplx, monkeypatch):
     assert rel_l2(got, want) <= FIR_TOL
     for lo, hi in ((20_000 + 4096 + 64, 40_000), (60_000, 80_000), (90_000, 120_000)):
         assert rel_l2(got[lo:hi], want[lo:hi]) <= FIR_TOL, (lo, hi)
+
+
+@pytest.mark.parametrize("ntaps,seed", [(129, 1), (500, 2), (1024, 3), (1025, 4)])
+def test_long_fir_overlap_save_batches(cb, oracle, ntaps, seed):
+    # 129 .. 1025 taps: fast convolution (4096-point FFT -> x Hf -> IFFT) from 8192 samples per call on, the direct
+    # form below that; state carried across both kinds of call
+    rng = np.random.default_rng(300 + seed)
+    t = rnd_c32(rng, ntaps)
+    hop = 4096 - (ntaps - 1)
+    sizes = [8192, hop * 3, hop * 3 + 1, 100, 8191, 20_011, 8192 + hop - 1, 3]
+    x = rnd_c32(rng, sum(sizes))
+    want, st = oracle.batch_fir(x, t, np.zeros(ntaps, np.complex64))
+    node = cb.BatchFirNode(t)
+    pos, outs = 0, []
+    for s in sizes:
+        outs.append(node.run(x[pos:pos + s]))
+        assert len(outs[-1]) == s
+        pos += s
+    got = np.concatenate(outs)
+    assert rel_l2(got, want) <= FIR_TOL
+    pos = 0
+    for s in sizes:  # every call on its own, so a bad frame edge cannot hide in the global norm
+        assert rel_l2(got[pos:pos + s], want[pos:pos + s]) <= 2 * FIR_TOL, (s, pos)
+        pos += s
+    assert node.state.tobytes() == st.tobytes()
