@@ -44,6 +44,7 @@ WORKLOADS = {
     "fir63d5": ("firdec", 1 << 28, 9.6, "63-tap real-valued FIR + DecimateNode(5) (fm_radio.rs filt1 -> dec1) fused, one 2^28-sample stream per GPU"),
     "fft1024": ("fft", 1 << 28, 16.0, "batched 1024-point FFT over 2^28 complex-f32 samples per GPU"),
     "fft2048": ("fft", 1 << 28, 16.0, "batched 2048-point FFT over 2^28 complex-f32 samples per GPU"),
+    "fft16384": ("fft", 1 << 28, 16.0, "batched 16384-point FFT over 2^28 complex-f32 samples per GPU"),
     "fft8192": ("fft", 1 << 28, 16.0, "batched 8192-point FFT over 2^28 complex-f32 samples per GPU"),
     "fft4096": ("fft", 1 << 28, 16.0, "batched 4096-point FFT over 2^28 complex-f32 samples per GPU"),
     "fft65536": ("fft", 1 << 28, 16.0, "batched 65536-point FFT over 2^28 complex-f32 samples per GPU"),
@@ -278,7 +279,7 @@ class Job:
             self.node = cb.FFTBatchNode(N, workload.startswith("ifft"))
             self.y = torch.empty(n, dtype=torch.complex64, device="cuda")
             self.out_bytes = 8 * n
-            self.kernels_per_step = 2 if (N > 8192 and not (N == 65536 and os.environ.get("COMMS_B200_FFT_PATH", "rows") in ("rows", "cluster", "cluster1", "cluster2", "cluster16"))) else 1
+            self.kernels_per_step = 2 if (N > 16384 and not (N == 65536 and os.environ.get("COMMS_B200_FFT_PATH", "rows") in ("rows", "cluster", "cluster1", "cluster2", "cluster16"))) else 1
             self.step = lambda: self.node.run_dev(self.x.data_ptr(), n, self.y.data_ptr(), self.stream)
             self.host_call = lambda hin, hout: cb.load().cb_fft_run(self.node._h, hin, n, hout)
         elif self.kind == "mixer":

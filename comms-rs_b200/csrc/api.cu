@@ -965,8 +965,8 @@ int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
     while (((size_t)1 << log2n) < fft_size) ++log2n;
     int kind;
     int l1 = 0, l2 = 0;
-    if (pow2 && log2n >= 3 && log2n <= 13) kind = FFT_SINGLE;
-    else if (pow2 && log2n >= 14) {
+    if (pow2 && log2n >= 3 && log2n <= 14) kind = FFT_SINGLE;  // one CTA per frame up to 16384 points (139 KiB of shared memory)
+    else if (pow2 && log2n >= 15) {
         rc = fft_plan_split(fft_size, &l1, &l2);
         CB_REQUIRE(rc == CB_OK, CB_ERR_UNSUPPORTED, "fft: size %zu > 2^20 is not provided", fft_size);
         kind = FFT_FOURSTEP;

@@ -172,7 +172,7 @@ struct Fft2Cfg {
     static constexpr bool PINGPONG = false;
     static constexpr int NBUF = PL::PASSES <= 1 ? 0 : (PINGPONG ? 2 : 1);
     static constexpr int SMEM = NBUF * FPB * PL::PADN * (int)sizeof(float2);
-    static constexpr int MINB = THREADS >= 512 ? 2 : 4;
+    static constexpr int MINB = THREADS >= 1024 ? 1 : (THREADS >= 512 ? 2 : 4);
 };
 
 template <int LOG2N, bool INV, int PASS, typename GLD, typename GST>
@@ -360,6 +360,7 @@ static int launch_frames2_dir(int log2n, const float2 *in, float2 *out, const fl
     case 11: return launch_frames2<11, INV>(in, out, tw2, nframes, s);
     case 12: return launch_frames2<12, INV>(in, out, tw2, nframes, s);
     case 13: return launch_frames2<13, INV>(in, out, tw2, nframes, s);
+    case 14: return launch_frames2<14, INV>(in, out, tw2, nframes, s);
     default: set_error("fft: no v2 kernel for 2^%d", log2n); return CB_ERR_UNSUPPORTED;
     }
 }
