@@ -196,3 +196,79 @@ def test_long_fir_overlap_save_batches(cb, oracle, ntaps, seed):
         assert rel_l2(got[pos:pos + s], want[pos:pos + s]) <= 2 * FIR_TOL, (s, pos)
         pos += s
     assert node.state.tobytes() == st.tobytes()
+
+
+def test_no_writes_outside_the_output_buffers(cb, monkeypatch):
+    # every device entry writes exactly its output range: outputs sit inside guard regions filled with a sentinel
+    # (compute-sanitizer is not available on the GPU pool; stray stores past a ragged tail would show up here)
+    import torch
+
+    monkeypatch.setenv("COMMS_B200_FIR_PATH", "tc")
+    G = 4096  # guard bytes on both sides
+    ts = torch.cuda.Stream()
+    s = ts.cuda_stream
+
+    def guarded(nbytes):
+        buf = torch.full((G + nbytes + G,), 0xA5, dtype=torch.uint8, device="cuda")
+        return buf, buf.data_ptr() + G
+
+    def check(buf, nbytes, what):
+        torch.cuda.synchronize()
+        assert bool((buf[:G] == 0xA5).all()) and bool((buf[G + nbytes:] == 0xA5).all()), what
+
+    rng = np.random.default_rng(5)
+    for n in (4097, 12_345, 65_537):
+        x = torch.empty(n, dtype=torch.complex64, device="cuda")
+        cb.synth_uniform_dev(3, 0, n, x.data_ptr(), s)
+        # plain FIR (tensor-core kernel forced), x4 / x8 polyphase in f32 and i16, long-filter fast convolution
+        for taps, L in ((rnd_c32(rng, 64), 1), (rnd_c32(rng, 300), 1), (rng.uniform(-1, 1, 32).astype(np.complex64), 4),
+                        (rnd_c32(rng, 200), 8)):
+            buf, p = guarded(8 * n * L)
+            fa, fb = cb.BatchFirNode(taps, None, interp=L), cb.BatchFirNode(taps, None, interp=L)
+            fa.run_dev(x.data_ptr(), n, p, n * L, s)
+            check(buf, 8 * n * L, ("fir", len(taps), L, n))
+            buf, p = guarded(4 * n * L)
+            fb.run_dev_i16(x.data_ptr(), n, 8192.0, p, n * L, s)
+            check(buf, 4 * n * L, ("fir i16", len(taps), L, n))
+        # stand-alone mixer / FM
+        buf, p = guarded(8 * n)
+        mixer = cb.MixerNode(0.3, 0.1)
+        cb._lib.check(cb.load().cb_mixer_run_dev(mixer._h, x.data_ptr(), n, p, s))
+        check(buf, 8 * n, ("mixer", n))
+        buf, p = guarded(4 * n)
+        node = cb.FMDemodNode()
+        cb._lib.check(cb.load().cb_fm_run_dev(node._h, x.data_ptr(), n, p, s))
+        check(buf, 4 * n, ("fm", n))
+        # edge formats
+        buf, p = guarded(4 * n)
+        cb.quantize_i16_dev(x.data_ptr(), 2 * n, 8192.0, p, s)
+        check(buf, 4 * n, ("quantize", n))
+        b8 = torch.randint(0, 256, (2 * n,), dtype=torch.uint8, device="cuda")
+        buf, p = guarded(8 * n)
+        cb.convert_u8_dev(b8.data_ptr(), n, p, s)
+        check(buf, 8 * n, ("convert_u8", n))
+    # fused bank: f32 and byte input, ragged last tile
+    k = np.arange(63) - 31
+    taps = (np.sinc(k / 5) * np.hamming(63) / 5).astype(np.float32).astype(np.complex64)
+    for D, fm in ((10, True), (5, False)):
+        C, n = 3, 10_000
+        bank = cb.ChainBank(C, taps, D, dphase=[0.1, -0.2, 0.3], with_fm=fm)
+        no = bank.out_len(n)
+        x = torch.empty(C * n, dtype=torch.complex64, device="cuda")
+        cb.synth_uniform_dev(4, 0, C * n, x.data_ptr(), s)
+        esz = 4 if fm else 8
+        buf, p = guarded(esz * C * no)
+        bank.run_dev(x.data_ptr(), n, p, no, s)
+        check(buf, esz * C * no, ("chain", D, fm))
+        b8 = torch.randint(0, 256, (C * n * 2,), dtype=torch.uint8, device="cuda")
+        buf, p = guarded(esz * C * no)
+        bank.run_dev_u8(b8.data_ptr(), n, p, no, s)
+        check(buf, esz * C * no, ("chain u8", D, fm))
+    # FFTs
+    for N, frames in ((4096, 5), (16384, 3), (65536, 35)):
+        x = torch.empty(N * frames, dtype=torch.complex64, device="cuda")
+        cb.synth_uniform_dev(5, 0, N * frames, x.data_ptr(), s)
+        buf, p = guarded(8 * N * frames)
+        fft = cb.FFTBatchNode(N, False)
+        fft.run_dev(x.data_ptr(), N * frames, p, s)
+        check(buf, 8 * N * frames, ("fft", N))
