@@ -107,6 +107,8 @@ SIGNATURES = {
     "cb_comm_init": (_i, [C.c_int, C.c_int, _vp, C.POINTER(_vp)]),
     "cb_comm_destroy": (_i, [_vp]),
     "cb_gather_segments_dev": (_i, [_vp, _vp, _sz, _vp, _vp]),
+    "cb_real_to_complex_dev": (_i, [_vp, _sz, _vp, _vp]),
+    "cb_complex_real_dev": (_i, [_vp, _sz, _vp, _vp]),
     "cb_convert_u8_dev": (_i, [_vp, _sz, _vp, _vp]),
     "cb_convert_i16_dev": (_i, [_vp, _sz, C.c_float, _vp, _vp]),
     "cb_rrc_taps": (_i, [C.c_uint32, C.c_double, C.c_double, _vp]),

@@ -1508,6 +1508,24 @@ int cb_bits_to_symbols_dev(const uint8_t *d_bits, size_t nbits, int mode, float 
     return launch_bits_to_symbols(d_bits, reinterpret_cast<float2 *>(d_sym), ns, mode, (cudaStream_t)stream);
 }
 
+int cb_real_to_complex_dev(const float *d_in, size_t n, float *d_out, void *stream)
+{
+    if (n == 0) return CB_OK;
+    CB_REQUIRE(d_in && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    int rc = ensure_device();
+    if (rc) return rc;
+    return launch_real_to_complex(d_in, reinterpret_cast<float2 *>(d_out), n, (cudaStream_t)stream);
+}
+
+int cb_complex_real_dev(const float *d_in, size_t n, float *d_out, void *stream)
+{
+    if (n == 0) return CB_OK;
+    CB_REQUIRE(d_in && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    int rc = ensure_device();
+    if (rc) return rc;
+    return launch_complex_real(reinterpret_cast<const float2 *>(d_in), d_out, n, (cudaStream_t)stream);
+}
+
 int cb_convert_u8_dev(const uint8_t *d_in, size_t n_samples, float *d_out, void *stream)
 {
     if (n_samples == 0) return CB_OK;

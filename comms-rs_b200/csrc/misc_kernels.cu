@@ -281,6 +281,38 @@ int launch_convert_i16(const int16_t *in, float *out, size_t n, float scale, cud
     return CB_OK;
 }
 
+// ---------------------------------------------------------------- real <-> complex glue of examples/fm_radio.rs
+// Convert2Node (fm_radio.rs:98-118): x -> Complex(x, 0);  Convert3Node (:122-142): z -> z.re
+__global__ void __launch_bounds__(256) real_to_complex_kernel(const float *__restrict__ in, float2 *__restrict__ out, size_t n)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = make_float2(in[i], 0.f);
+}
+
+__global__ void __launch_bounds__(256) complex_real_kernel(const float2 *__restrict__ in, float *__restrict__ out, size_t n)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = in[i].x;
+}
+
+int launch_real_to_complex(const float *in, float2 *out, size_t n, cudaStream_t s)
+{
+    if (n == 0) return CB_OK;
+    real_to_complex_kernel<<<grid_for(n, 256), 256, 0, s>>>(in, out, n);
+    count_launch();
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+
+int launch_complex_real(const float2 *in, float *out, size_t n, cudaStream_t s)
+{
+    if (n == 0) return CB_OK;
+    complex_real_kernel<<<grid_for(n, 256), 256, 0, s>>>(in, out, n);
+    count_launch();
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+
 // ---------------------------------------------------------------- synthetic data
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x)
 {

@@ -10,6 +10,8 @@ int launch_decimate(const void *in, void *out, size_t n_out, size_t elem, size_t
 int launch_upsample(const void *in, void *out, size_t n_out, size_t elem, size_t rate, cudaStream_t s);
 int launch_bits_to_symbols(const uint8_t *bits, float2 *sym, size_t nsym, int mode, cudaStream_t s);
 int launch_quantize_i16(const float *in, int16_t *out, size_t n, float scale, cudaStream_t s);
+int launch_real_to_complex(const float *in, float2 *out, size_t n, cudaStream_t s);
+int launch_complex_real(const float2 *in, float *out, size_t n, cudaStream_t s);
 int launch_convert_u8(const uint8_t *in, float *out, size_t nfloats, cudaStream_t s);
 int launch_convert_i16(const int16_t *in, float *out, size_t nfloats, float scale, cudaStream_t s);
 int launch_synth(float *out, size_t nfloats, unsigned long long base, cudaStream_t s);

@@ -339,6 +339,16 @@ class ChainBank(_Handle):
 
 
 # ------------------------------------------------------------------ edges
+def real_to_complex_dev(d_in: int, n: int, d_out: int, stream: int = 0) -> None:
+    """Convert2Node of examples/fm_radio.rs:98-118: x -> Complex(x, 0)."""
+    check(_lib.load().cb_real_to_complex_dev(d_in, n, d_out, stream))
+
+
+def complex_real_dev(d_in: int, n: int, d_out: int, stream: int = 0) -> None:
+    """Convert3Node of examples/fm_radio.rs:122-142: z -> z.re."""
+    check(_lib.load().cb_complex_real_dev(d_in, n, d_out, stream))
+
+
 def convert_u8_dev(d_in: int, n_samples: int, d_out: int, stream: int = 0) -> None:
     """(u8 I, u8 Q) -> complex f32, (x - 127.5) / 127.5 (examples/fm_radio.rs:84-87)."""
     check(_lib.load().cb_convert_u8_dev(d_in, n_samples, d_out, stream))

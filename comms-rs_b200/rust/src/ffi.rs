@@ -97,6 +97,8 @@ extern "C" {
     pub fn cb_comm_init(nranks: c_int, rank: c_int, id128: *const c_void, out: *mut *mut cb_comm) -> c_int;
     pub fn cb_comm_destroy(c: *mut cb_comm) -> c_int;
     pub fn cb_gather_segments_dev(c: *mut cb_comm, d_seg: *const f32, n_samples: usize, d_all: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn cb_real_to_complex_dev(d_in: *const f32, n: usize, d_out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn cb_complex_real_dev(d_in: *const f32, n: usize, d_out: *mut f32, stream: *mut c_void) -> c_int;
     pub fn cb_rrc_taps(n_taps: u32, sam_per_sym: f64, beta: f64, taps: *mut f32) -> c_int;
     pub fn cb_rrc_taps_f64(n_taps: u32, sam_per_sym: f64, beta: f64, taps: *mut f64) -> c_int;
     pub fn cb_prn_bits(poly_mask: u64, state: *mut u64, width: c_uint, n: usize, bits: *mut u8) -> c_int;

@@ -259,6 +259,11 @@ CB_API int cb_quantize_i16_dev(const float *d_in, size_t nfloats, float scale, i
  * rounded.  cb_convert_i16: the interleaved native-endian i16 IQ of
  * src/io/raw_iq.rs:20-140 -> scale * (x as f32) (scale = 1: the plain cast).
  * n_samples complex samples each; d_out receives 2*n_samples floats. */
+/* Real <-> complex glue of examples/fm_radio.rs, device side, so the whole shipped graph can stay on the GPU:
+ * cb_real_to_complex: Convert2Node (fm_radio.rs:98-118), x -> Complex(x, 0); cb_complex_real: Convert3Node
+ * (fm_radio.rs:122-142), z -> z.re.  n elements each. */
+CB_API int cb_real_to_complex_dev(const float *d_in, size_t n, float *d_out, void *stream);
+CB_API int cb_complex_real_dev(const float *d_in, size_t n, float *d_out, void *stream);
 CB_API int cb_convert_u8_dev(const uint8_t *d_in, size_t n_samples, float *d_out, void *stream);
 CB_API int cb_convert_i16_dev(const int16_t *d_in, size_t n_samples, float scale, float *d_out, void *stream);
 

@@ -445,6 +445,46 @@ def test_chain_bank_u8_input_fused_convert(cb, oracle, mix, fm, D, n):
                 assert rel_l2(got[c], want) <= FIR_TOL, (c, call)
 
 
+def test_fm_radio_example_graph_on_device(cb, oracle):
+    # examples/fm_radio.rs:144-164, the whole shipped graph with every hop on the GPU:
+    #   bytes -> ConvertNode -> filt1 -> dec1(5) -> FMDemodNode -> Convert2Node -> filt2 -> Convert3Node -> dec2(5)
+    # batches of 131072 IQ samples (262144 bytes, fm_radio.rs:144), state carried by filt1, fm and filt2
+    import torch
+
+    rng = np.random.default_rng(144)
+    taps = _lowpass(FM_RADIO_TAPS_N)
+    nb, n1 = 131_072, -(-131_072 // 5)
+    n2 = -(-n1 // 5)
+    front = cb.ChainBank(1, taps, 5, dphase=None, with_fm=True)   # convert + filt1 + dec1 + fm fused
+    filt2 = cb.BatchFirNode(taps, None, decim=5)                   # filt2 + dec2 fused (decimation commutes with .re)
+    ref_front = oracle.FmChain(0.0, 0.0, taps, 5, do_mix=False, do_fm=True)
+    st2 = np.zeros(len(taps), np.complex64)
+    ts = torch.cuda.Stream()
+    s = ts.cuda_stream
+    d_fm = torch.empty(n1, dtype=torch.float32, device="cuda")
+    d_c = torch.empty(n1, dtype=torch.complex64, device="cuda")
+    d_f2 = torch.empty(n2, dtype=torch.complex64, device="cuda")
+    d_audio = torch.empty(n2, dtype=torch.float32, device="cuda")
+    for batch in range(3):
+        iq = rng.integers(0, 256, (nb, 2), dtype=np.uint8)
+        d_iq = torch.from_numpy(iq.reshape(-1)).cuda()
+        torch.cuda.synchronize()
+        assert front.run_dev_u8(d_iq.data_ptr(), nb, d_fm.data_ptr(), n1, s) == n1
+        cb.real_to_complex_dev(d_fm.data_ptr(), n1, d_c.data_ptr(), s)
+        assert filt2.run_dev(d_c.data_ptr(), n1, d_f2.data_ptr(), n2, s) == n2
+        cb.complex_real_dev(d_f2.data_ptr(), n2, d_audio.data_ptr(), s)
+        torch.cuda.synchronize()
+        x = oracle.u8_to_f32(iq.reshape(-1)).view(np.complex64)
+        fm_ref = ref_front.run(x)
+        f2, st2 = oracle.batch_fir(fm_ref.astype(np.complex64), taps, st2)
+        audio_ref = oracle.decimate(f2.real.astype(np.float32), 5)
+        got = d_audio.cpu().numpy()
+        assert got.shape == audio_ref.shape == (n2,)
+        # angles wrap at +-pi: a 1e-7 difference there becomes 2 pi in the demodulated sample; compare the bulk
+        d = np.abs(got.astype(np.float64) - audio_ref.astype(np.float64))
+        assert np.median(d) < 5e-6 and np.mean(d > 1e-2) < 5e-3, (batch, np.median(d), d.max())
+
+
 def test_convert_i16_bit_exact(cb):
     import torch
 
