@@ -48,6 +48,11 @@ WORKLOADS = {
     "fft8192": ("fft", 1 << 28, 16.0, "batched 8192-point FFT over 2^28 complex-f32 samples per GPU"),
     "fft4096": ("fft", 1 << 28, 16.0, "batched 4096-point FFT over 2^28 complex-f32 samples per GPU"),
     "fft65536": ("fft", 1 << 28, 16.0, "batched 65536-point FFT over 2^28 complex-f32 samples per GPU"),
+    "fft32768": ("fft", 1 << 28, 16.0, "batched 32768-point FFT over 2^28 complex-f32 samples per GPU"),
+    "fft131072": ("fft", 1 << 28, 16.0, "batched 131072-point FFT over 2^28 complex-f32 samples per GPU"),
+    "fft524288": ("fft", 1 << 28, 16.0, "batched 524288-point FFT over 2^28 complex-f32 samples per GPU"),
+    "fft262144": ("fft", 1 << 28, 16.0, "batched 262144-point FFT over 2^28 complex-f32 samples per GPU"),
+    "fft1048576": ("fft", 1 << 28, 16.0, "batched 1048576-point FFT over 2^28 complex-f32 samples per GPU"),
     "ifft4096": ("fft", 1 << 28, 16.0, "batched 4096-point IFFT over 2^28 complex-f32 samples per GPU"),
     "mixer": ("mixer", 1 << 28, 16.0, "MixerNode (src/mixer.rs:73-84): y = x e^{j phi}, f64 phase, over 2^28 complex-f32 samples per GPU"),
     "fm": ("fm", 1 << 28, 12.0, "FMDemodNode (src/modulation/analog.rs:22-34) over 2^28 complex-f32 samples per GPU"),

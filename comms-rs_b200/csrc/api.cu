@@ -168,7 +168,7 @@ struct cb_fft {
     cudaStream_t stream;
     HostPipe pipe;
     FftPlanDev plan;
-    float2 *tw, *tw1, *tw2, *tw16, *scratch;
+    float2 *tw, *tw1, *tw2, *tw16, *tw16a, *tw16b, *scratch;
 };
 
 struct cb_fm {
@@ -978,7 +978,7 @@ int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
     cb_fft *h = new (std::nothrow) cb_fft();
     CB_REQUIRE(h, CB_ERR_OOM, "host allocation failed");
     h->device = g_dev;
-    h->tw = h->tw1 = h->tw2 = h->tw16 = h->scratch = nullptr;
+    h->tw = h->tw1 = h->tw2 = h->tw16 = h->tw16a = h->tw16b = h->scratch = nullptr;
     h->stream = nullptr;
     h->plan = FftPlanDev{};
     h->plan.kind = kind;
@@ -1009,7 +1009,14 @@ int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
     if (kind == FFT_FOURSTEP) {
         FFT_TRY(upload_twiddles((size_t)1 << l1, inverse, &h->tw1));
         FFT_TRY(upload_twiddles((size_t)1 << l2, inverse, &h->tw2));
-        size_t scratch_mb = fft_size == 65536 ? 16 : 32;  // 65536: ring of 32 frames for the fused rows kernel (measured best)
+        // the fused two-step kernels keep the intermediate in a ring of scratch frames that stays in L2
+        // (65536: 32 frames measured best); the four-step fallback uses the same buffer in groups of frames
+        size_t scratch_mb = log2n <= 18 ? 16 : (log2n == 19 ? 32 : 64);
+        FFT_TRY(upload_fft2_table(l1, inverse, &h->tw16a));
+        FFT_TRY(upload_fft2_table(l2, inverse, &h->tw16b));
+        h->plan.big = 1;
+        if (const char *e = getenv("COMMS_B200_FFT_PATH"))
+            if (strcmp(e, "fourstep") == 0) h->plan.big = 0;
         if (const char *e = getenv("COMMS_B200_FFT_SCRATCH_MB")) scratch_mb = (size_t)atol(e) > 0 ? (size_t)atol(e) : scratch_mb;
         size_t frames = (scratch_mb << 20) / (fft_size * sizeof(float2));
         if (frames < 1) frames = 1;
@@ -1026,6 +1033,8 @@ int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
     h->plan.tw1 = h->tw1;
     h->plan.tw2 = h->tw2;
     h->plan.tw16 = h->tw16;
+    h->plan.tw16a = h->tw16a;
+    h->plan.tw16b = h->tw16b;
     h->plan.scratch = h->scratch;
     // 65536 points.  COMMS_B200_FFT_PATH = rows (default: one persistent kernel over a 256 x 256 split, intermediate in
     // an L2-resident ring, K5-R) | rows2 (same two steps as two launches with a batch-sized scratch) | cluster (one HBM
@@ -1040,6 +1049,7 @@ int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
         if (path && strcmp(path, "twopass") == 0) h->plan.cluster_tpt = 5;    // 16 x 4096, two streaming passes
         if (path && strcmp(path, "rows") == 0) h->plan.cluster_tpt = 6;       // 256 x 256, fused persistent kernel, L2 ring
         if (path && strcmp(path, "rows2") == 0) h->plan.cluster_tpt = 7;      // 256 x 256, two launches, batch-sized scratch
+        if (path && strcmp(path, "big") == 0) h->plan.cluster_tpt = 8;        // the generic fused two-step kernel (K5-B)
     }
     *out = h;
     return CB_OK;
@@ -1055,6 +1065,8 @@ int cb_fft_destroy(cb_fft *h)
     if (h->tw1) cudaFree(h->tw1);
     if (h->tw2) cudaFree(h->tw2);
     if (h->tw16) cudaFree(h->tw16);
+    if (h->tw16a) cudaFree(h->tw16a);
+    if (h->tw16b) cudaFree(h->tw16b);
     if (h->scratch) cudaFree(h->scratch);
     if (h->plan.flags) cudaFree(h->plan.flags);
 
@@ -1077,20 +1089,22 @@ int cb_fft_size(const cb_fft *h, size_t *fft_size, int *inverse)
 // handle switches to the one-pass cluster kernel, which needs neither.
 static void fft_prepare_scratch(cb_fft *h, size_t nframes)
 {
-    if (h->plan.n != 65536) return;
-    if (h->plan.cluster_tpt == 6 && h->plan.flags_frames < nframes) {
+    if (h->plan.kind != FFT_FOURSTEP) return;
+    const bool big = h->plan.big && (h->plan.n != 65536 || h->plan.cluster_tpt == 8);
+    if ((big || (h->plan.n == 65536 && h->plan.cluster_tpt == 6)) && h->plan.flags_frames < nframes) {
         if (h->plan.flags) cudaFree(h->plan.flags);
         h->plan.flags = nullptr;
         h->plan.flags_frames = 0;
         if (cudaMalloc(&h->plan.flags, (4 + 2 * nframes) * sizeof(unsigned)) != cudaSuccess) {
             cudaGetLastError();
             h->plan.flags = nullptr;
-            h->plan.cluster_tpt = 3;
+            h->plan.big = 0;  // four-step
+            if (h->plan.n == 65536) h->plan.cluster_tpt = 3;
             return;
         }
         h->plan.flags_frames = nframes;
     }
-    if (h->plan.cluster_tpt == 7 && h->plan.scratch_frames < nframes) {
+    if (h->plan.n == 65536 && h->plan.cluster_tpt == 7 && h->plan.scratch_frames < nframes) {
         if (h->scratch) cudaFree(h->scratch);
         h->scratch = nullptr;
         h->plan.scratch = nullptr;

@@ -669,6 +669,7 @@ int launch_fft(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframe
         return p.inverse ? launch_frames_dir<true>(p.log2n, in, out, p.tw, nframes, s)
                          : launch_frames_dir<false>(p.log2n, in, out, p.tw, nframes, s);
     }
+    if (fft_big_applicable(p, nframes) && (p.n != 65536 || p.cluster_tpt == 8)) return launch_fft_big(p, in, out, nframes, s);
     if (p.kind == FFT_FOURSTEP && p.n == 65536 && (p.cluster_tpt == 6 || p.cluster_tpt == 7))
         return launch_fft65536_rows(p, in, out, nframes, s);
     if (p.kind == FFT_FOURSTEP && p.n == 65536 && p.cluster_tpt == 5 && p.tw16 != nullptr)

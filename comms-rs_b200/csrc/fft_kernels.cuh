@@ -22,6 +22,8 @@ struct FftPlanDev {
     unsigned *flags;      // n = 65536 fused "rows" form: ticket counter (4 words) + 2 * flags_frames per-frame
                           // dependency counters (or NULL)
     size_t flags_frames;
+    const float2 *tw16a, *tw16b;  // radix-16 tables of the n1- and n2-point step transforms (fused two-step form), or NULL
+    int big;              // 1: sizes 2^15, 2^17 .. 2^20 run the fused two-step kernel (fft_big_kernel.cu); 0: four-step
     int cluster_tpt;      // n = 65536: 0 = four-step, 1 / 2 / 3 = cluster kernel exchange variants, 4 = 16-CTA clusters,
                           // 5 = 16 x 4096 two-pass, 6 = 256 x 256 two-pass with a batch-sized scratch (default)
 };
@@ -32,6 +34,8 @@ int fft_plan_split(size_t n, int *log2n1, int *log2n2);
 int launch_fft65536_cluster(const float2 *in, float2 *out, const float2 *twN, size_t nframes, bool inverse, int tpt,
                             cudaStream_t s);
 int launch_fft65536_rows(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s);
+bool fft_big_applicable(const FftPlanDev &p, size_t nframes);
+int launch_fft_big(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s);
 int launch_fft(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s);
 
 }  // namespace cb

@@ -122,6 +122,29 @@ def test_fft65536_frame_counts(cb, oracle, frames):
         assert rel_l2(got[f * n:(f + 1) * n], want) <= 1e-4, f
 
 
+@pytest.mark.parametrize("path", ["default", "fourstep"])
+@pytest.mark.parametrize("log2n,frames", [(15, 1), (15, 70), (17, 3), (17, 40), (18, 11), (19, 9), (20, 2), (20, 10)])
+def test_fft_large_sizes(cb, oracle, log2n, frames, path, monkeypatch):
+    # K5-B (fused two-step kernel over an N1 x N2 split, intermediate in an L2 ring of 64 / 16 / 8 / 8 / 8 frames) and
+    # the four-step fallback: frame counts below, at and beyond lag and ring; forward and inverse
+    if path != "default":
+        monkeypatch.setenv("COMMS_B200_FFT_PATH", path)
+    n = 1 << log2n
+    rng = np.random.default_rng(log2n * 100 + frames)
+    x = rnd_c32(rng, frames * n)
+    x[(frames // 2) * n:(frames // 2 + 1) * n] = 0
+    x[(frames // 2) * n + 54321 % n] = 1  # an impulse frame: every output has modulus 1 and a known phase
+    for inverse in (False, True):
+        got = cb.FFTBatchNode(n, inverse).run(x)
+        for f in sorted({0, 1 % frames, frames // 2, frames - 1}):
+            want = oracle.fft(x[f * n:(f + 1) * n], n, inverse)
+            assert rel_l2(got[f * n:(f + 1) * n], want) <= 1e-4, (f, inverse)
+        # every frame: Parseval (unnormalised transform: sum |X|^2 = n sum |x|^2)
+        e_in = (np.abs(x.reshape(frames, n).astype(np.complex128)) ** 2).sum(axis=1)
+        e_out = (np.abs(got.reshape(frames, n).astype(np.complex128)) ** 2).sum(axis=1)
+        assert np.all(np.abs(e_out / (n * e_in) - 1) < 1e-5)
+
+
 @pytest.mark.timeout(300)
 def test_fft65536_two_handles_concurrently(cb, oracle):
     # two fused 65536-point kernels in flight on different streams share the SMs; the ticket-ordered work

@@ -317,7 +317,7 @@ def test_fft_matches_oracle(cb, oracle, n, inverse):
         assert rel_l2(got[f * n:(f + 1) * n], want[f * n:(f + 1) * n]) <= FFT_TOL
 
 
-@pytest.mark.parametrize("path", ["cluster", "cluster1", "cluster2", "cluster16", "twopass", "rows", "rows2", "fourstep"])
+@pytest.mark.parametrize("path", ["cluster", "cluster1", "cluster2", "cluster16", "twopass", "rows", "rows2", "big", "fourstep"])
 @pytest.mark.parametrize("inverse", [False, True])
 def test_fft65536_paths(cb, oracle, path, inverse, monkeypatch):
     # K5-C: one HBM pass on an 8-CTA cluster (distributed shared memory) vs the four-step fallback
