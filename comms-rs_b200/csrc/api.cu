@@ -169,6 +169,11 @@ struct cb_fft {
     HostPipe pipe;
     FftPlanDev plan;
     float2 *tw, *tw1, *tw2, *tw16, *tw16a, *tw16b, *scratch;
+    // FFT_BLUESTEIN (any other size): chirp w[n] (n entries), transform of the wrapped conj chirp (bl_m entries),
+    // forward / inverse power-of-two plans of bl_m points, two work buffers of bl_frames frames of bl_m points
+    cb_fft *sub_f, *sub_i;
+    float2 *chirp, *bspec, *bufa, *bufb;
+    size_t bl_m, bl_frames;
 };
 
 struct cb_fm {
@@ -954,6 +959,76 @@ static int upload_fft2_table(int log2n, int inverse, float2 **dev)
     return CB_OK;
 }
 
+// in-place radix-2 transform in f64 (forward), for the one-off spectrum of the Bluestein chirp
+static void host_fft_f64(std::vector<double> &re, std::vector<double> &im)
+{
+    const size_t n = re.size();
+    for (size_t i = 1, j = 0; i < n; ++i) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) {
+            std::swap(re[i], re[j]);
+            std::swap(im[i], im[j]);
+        }
+    }
+    for (size_t len = 2; len <= n; len <<= 1) {
+        const size_t half = len >> 1;
+        std::vector<double> wr(half), wi(half);
+        for (size_t k = 0; k < half; ++k) {
+            const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)len;
+            wr[k] = (double)cosl(a);
+            wi[k] = (double)sinl(a);
+        }
+        for (size_t i = 0; i < n; i += len)
+            for (size_t k = 0; k < half; ++k) {
+                const double xr = re[i + k + half] * wr[k] - im[i + k + half] * wi[k];
+                const double xi = re[i + k + half] * wi[k] + im[i + k + half] * wr[k];
+                re[i + k + half] = re[i + k] - xr;
+                im[i + k + half] = im[i + k] - xi;
+                re[i + k] += xr;
+                im[i + k] += xi;
+            }
+    }
+}
+
+static int bluestein_setup(cb_fft *h, size_t n, int inverse)
+{
+    size_t m = 256;
+    while (m < 2 * n - 1) m <<= 1;
+    h->bl_m = m;
+    // w[i] = e^{-/+ j pi i^2 / n}: i^2 reduced mod 2n in integers so that the angle stays exact for large i
+    std::vector<float2> w(n);
+    std::vector<double> br(m, 0.0), bi(m, 0.0);
+    const long double sgn = inverse ? 1.0L : -1.0L;
+    for (size_t i = 0; i < n; ++i) {
+        const unsigned long long q = ((unsigned long long)i * i) % (2ull * n);
+        const long double a = sgn * 3.14159265358979323846264338327950288L * (long double)q / (long double)n;
+        const long double c = cosl(a), sn = sinl(a);
+        w[i] = make_float2((float)c, (float)sn);
+        br[i] = (double)c;
+        bi[i] = (double)-sn;  // conj(w[i]) at +i and -i (wrapped)
+        if (i) {
+            br[m - i] = br[i];
+            bi[m - i] = bi[i];
+        }
+    }
+    host_fft_f64(br, bi);
+    std::vector<float2> bs(m);
+    for (size_t i = 0; i < m; ++i) bs[i] = make_float2((float)br[i], (float)bi[i]);
+    CB_CUDA(cudaMalloc(&h->chirp, n * sizeof(float2)));
+    CB_CUDA(cudaMemcpy(h->chirp, w.data(), n * sizeof(float2), cudaMemcpyHostToDevice));
+    CB_CUDA(cudaMalloc(&h->bspec, m * sizeof(float2)));
+    CB_CUDA(cudaMemcpy(h->bspec, bs.data(), m * sizeof(float2), cudaMemcpyHostToDevice));
+    h->bl_frames = ((size_t)32 << 20) / (m * sizeof(float2));  // work buffers sized to stay in L2 between the steps
+    if (h->bl_frames < 1) h->bl_frames = 1;
+    CB_CUDA(cudaMalloc(&h->bufa, h->bl_frames * m * sizeof(float2)));
+    CB_CUDA(cudaMalloc(&h->bufb, h->bl_frames * m * sizeof(float2)));
+    int rc = cb_fft_create(m, 0, &h->sub_f);
+    if (rc) return rc;
+    return cb_fft_create(m, 1, &h->sub_i);
+}
+
 int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
 {
     CB_REQUIRE(out, CB_ERR_INVALID_ARG, "out is NULL");
@@ -971,14 +1046,20 @@ int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
         CB_REQUIRE(rc == CB_OK, CB_ERR_UNSUPPORTED, "fft: size %zu > 2^20 is not provided", fft_size);
         kind = FFT_FOURSTEP;
     } else {
-        CB_REQUIRE(fft_size <= 4096, CB_ERR_UNSUPPORTED,
-                   "fft: non power-of-two size %zu > 4096 is not provided", fft_size);
-        kind = FFT_DIRECT;
+        // any other size (rustfft plans every length): O(N^2) with an exact table while that is cheap, else chirp-z
+        const char *path = getenv("COMMS_B200_FFT_PATH");
+        const bool force_direct = path && strcmp(path, "direct") == 0 && fft_size <= 4096;
+        CB_REQUIRE(fft_size <= ((size_t)1 << 19), CB_ERR_UNSUPPORTED,
+                   "fft: non power-of-two size %zu > 2^19 is not provided", fft_size);
+        kind = (fft_size <= 128 || force_direct) ? FFT_DIRECT : FFT_BLUESTEIN;
     }
     cb_fft *h = new (std::nothrow) cb_fft();
     CB_REQUIRE(h, CB_ERR_OOM, "host allocation failed");
     h->device = g_dev;
     h->tw = h->tw1 = h->tw2 = h->tw16 = h->tw16a = h->tw16b = h->scratch = nullptr;
+    h->sub_f = h->sub_i = nullptr;
+    h->chirp = h->bspec = h->bufa = h->bufb = nullptr;
+    h->bl_m = h->bl_frames = 0;
     h->stream = nullptr;
     h->plan = FftPlanDev{};
     h->plan.kind = kind;
@@ -1004,6 +1085,11 @@ int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
         }
     }
     FFT_TRY(h->pipe.init(h->stream));
+    if (kind == FFT_BLUESTEIN) {
+        FFT_TRY(bluestein_setup(h, fft_size, inverse));
+        *out = h;
+        return CB_OK;
+    }
     FFT_TRY(upload_twiddles(fft_size, inverse, &h->tw));
     if (kind == FFT_SINGLE && log2n >= 4) FFT_TRY(upload_fft2_table(log2n, inverse, &h->tw16));
     if (kind == FFT_FOURSTEP) {
@@ -1065,6 +1151,12 @@ int cb_fft_destroy(cb_fft *h)
     if (h->tw1) cudaFree(h->tw1);
     if (h->tw2) cudaFree(h->tw2);
     if (h->tw16) cudaFree(h->tw16);
+    if (h->sub_f) cb_fft_destroy(h->sub_f);
+    if (h->sub_i) cb_fft_destroy(h->sub_i);
+    if (h->chirp) cudaFree(h->chirp);
+    if (h->bspec) cudaFree(h->bspec);
+    if (h->bufa) cudaFree(h->bufa);
+    if (h->bufb) cudaFree(h->bufb);
     if (h->tw16a) cudaFree(h->tw16a);
     if (h->tw16b) cudaFree(h->tw16b);
     if (h->scratch) cudaFree(h->scratch);
@@ -1120,6 +1212,27 @@ static void fft_prepare_scratch(cb_fft *h, size_t nframes)
     }
 }
 
+// one batch of frames on stream s, whatever the plan kind
+static int fft_exec(cb_fft *h, const float2 *in, float2 *out, size_t nframes, cudaStream_t s)
+{
+    if (h->plan.kind != FFT_BLUESTEIN) {
+        fft_prepare_scratch(h, nframes);
+        return launch_fft(h->plan, in, out, nframes, s);
+    }
+    const uint32_t N = (uint32_t)h->plan.n, M = (uint32_t)h->bl_m;
+    for (size_t done = 0; done < nframes;) {
+        const size_t g = nframes - done < h->bl_frames ? nframes - done : h->bl_frames;
+        int rc = launch_bluestein_pre(in + done * N, h->chirp, h->bufa, N, M, g, s);
+        if (!rc) rc = fft_exec(h->sub_f, h->bufa, h->bufb, g, s);
+        if (!rc) rc = launch_bluestein_mul(h->bufb, h->bspec, M, g, s);
+        if (!rc) rc = fft_exec(h->sub_i, h->bufb, h->bufa, g, s);
+        if (!rc) rc = launch_bluestein_post(h->bufa, h->chirp, out + done * N, N, M, g, s);
+        if (rc) return rc;
+        done += g;
+    }
+    return CB_OK;
+}
+
 int cb_fft_run_dev(cb_fft *h, const float *d_in, size_t n_in, float *d_out, void *stream)
 {
     CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
@@ -1129,9 +1242,8 @@ int cb_fft_run_dev(cb_fft *h, const float *d_in, size_t n_in, float *d_out, void
     CB_REQUIRE(d_in && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
     CB_REQUIRE(d_in != d_out, CB_ERR_INVALID_ARG, "fft: in-place transform is not provided");
     CB_CUDA(cudaSetDevice(h->device));
-    fft_prepare_scratch(h, n_in / h->plan.n);
-    return launch_fft(h->plan, reinterpret_cast<const float2 *>(d_in), reinterpret_cast<float2 *>(d_out),
-                      n_in / h->plan.n, pick_stream(stream, h->stream));
+    return fft_exec(h, reinterpret_cast<const float2 *>(d_in), reinterpret_cast<float2 *>(d_out), n_in / h->plan.n,
+                    pick_stream(stream, h->stream));
 }
 
 int cb_fft_run(cb_fft *h, const float *in, size_t n_in, float *out)
@@ -1156,12 +1268,11 @@ int cb_fft_run(cb_fft *h, const float *in, size_t n_in, float *out)
         cudaStream_t s = h->pipe.lane[l];
         float2 *di = reinterpret_cast<float2 *>(h->pipe.in[l]), *dout = reinterpret_cast<float2 *>(h->pipe.out[l]);
         CB_CUDA(cudaMemcpyAsync(di, hin + done, m * sizeof(float2), cudaMemcpyHostToDevice, s));
-        if (h->plan.kind == FFT_FOURSTEP && i > 0) {
-            // the four-step scratch is shared by both lanes: serialise the kernels
+        if ((h->plan.kind == FFT_FOURSTEP || h->plan.kind == FFT_BLUESTEIN) && i > 0) {
+            // the scratch / work buffers are shared by both lanes: serialise the kernels
             CB_CUDA(cudaStreamSynchronize(h->pipe.lane[l ^ 1]));
         }
-        fft_prepare_scratch(h, m / N);
-        rc = launch_fft(h->plan, di, dout, m / N, s);
+        rc = fft_exec(h, di, dout, m / N, s);
         if (rc) return rc;
         CB_CUDA(cudaMemcpyAsync(hout + done, dout, m * sizeof(float2), cudaMemcpyDeviceToHost, s));
         done += m;

@@ -317,6 +317,83 @@ dft_direct_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, const
     }
 }
 
+// ---------------------------------------------------------------- any-N chirp-z (Bluestein) glue
+// X[k] = w[k] sum_n (x[n] w[n]) conj(w[k - n]),  w[n] = e^{-/+ j pi n^2 / N}: a length-N transform as a circular
+// convolution of length M = 2^m >= 2N - 1, done with the power-of-two kernels above.  The three element-wise steps:
+//   pre:  a[f][i] = x[f][i] w[i] for i < N, 0 for N <= i < M
+//   mul:  A[f][i] *= B[i]                (B = M-point transform of the wrapped conj chirp, computed on the host in f64)
+//   post: X[f][k] = c[f][k] w[k] / M
+// One CTA = 1024 consecutive elements of one frame (256 threads x 4, lanes contiguous).
+__global__ void __launch_bounds__(256)
+bluestein_pre_kernel(const float2 *__restrict__ x, const float2 *__restrict__ chirp, float2 *__restrict__ a, unsigned N,
+                     unsigned M, unsigned nseg)
+{
+    const size_t frame = blockIdx.x / nseg;
+    const unsigned i0 = (blockIdx.x % nseg) * 1024 + threadIdx.x;
+    const float2 *src = x + frame * N;
+    float2 *dst = a + frame * M;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const unsigned i = i0 + 256 * u;
+        if (i < M) dst[i] = i < N ? cmul(ldg_stream2(src + i), __ldg(chirp + i)) : make_float2(0.f, 0.f);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bluestein_mul_kernel(float2 *__restrict__ spec, const float2 *__restrict__ bspec, unsigned M, size_t total)
+{
+    const size_t stride = (size_t)gridDim.x * 256;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += stride)
+        spec[i] = cmul(spec[i], __ldg(bspec + (i & (M - 1))));
+}
+
+__global__ void __launch_bounds__(256)
+bluestein_post_kernel(const float2 *__restrict__ c, const float2 *__restrict__ chirp, float2 *__restrict__ out, unsigned N,
+                      unsigned M, unsigned nseg, float scale)
+{
+    const size_t frame = blockIdx.x / nseg;
+    const unsigned i0 = (blockIdx.x % nseg) * 1024 + threadIdx.x;
+    const float2 *src = c + frame * M;
+    float2 *dst = out + frame * N;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const unsigned i = i0 + 256 * u;
+        if (i < N) {
+            const float2 v = cmul(src[i], __ldg(chirp + i));
+            stg_stream2(dst + i, make_float2(v.x * scale, v.y * scale));
+        }
+    }
+}
+
+int launch_bluestein_pre(const float2 *x, const float2 *chirp, float2 *a, uint32_t N, uint32_t M, size_t frames, cudaStream_t s)
+{
+    const unsigned nseg = (M + 1023) / 1024;
+    bluestein_pre_kernel<<<(unsigned)(frames * nseg), 256, 0, s>>>(x, chirp, a, N, M, nseg);
+    count_launch();
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+
+int launch_bluestein_mul(float2 *spec, const float2 *bspec, uint32_t M, size_t frames, cudaStream_t s)
+{
+    const size_t total = frames * M;
+    const size_t blocks = ceil_div(total, (size_t)256);
+    bluestein_mul_kernel<<<(unsigned)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, s>>>(spec, bspec, M, total);
+    count_launch();
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+
+int launch_bluestein_post(const float2 *c, const float2 *chirp, float2 *out, uint32_t N, uint32_t M, size_t frames,
+                          cudaStream_t s)
+{
+    const unsigned nseg = (N + 1023) / 1024;
+    bluestein_post_kernel<<<(unsigned)(frames * nseg), 256, 0, s>>>(c, chirp, out, N, M, nseg, 1.0f / (float)M);
+    count_launch();
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+
 // ---------------------------------------------------------------- launchers
 template <int LOG2N, bool INV>
 static int launch_frames(const float2 *in, float2 *out, const float2 *tw, size_t nframes, cudaStream_t s)

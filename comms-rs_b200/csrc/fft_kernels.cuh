@@ -3,7 +3,7 @@
 
 namespace cb {
 
-enum FftKind { FFT_SINGLE = 0, FFT_FOURSTEP = 1, FFT_DIRECT = 2 };
+enum FftKind { FFT_SINGLE = 0, FFT_FOURSTEP = 1, FFT_DIRECT = 2, FFT_BLUESTEIN = 3 };
 
 // Device-side plan: twiddle tables are e^{-/+ 2 pi i k / n} rounded from f64,
 // with the direction baked in.
@@ -36,6 +36,10 @@ int launch_fft65536_cluster(const float2 *in, float2 *out, const float2 *twN, si
 int launch_fft65536_rows(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s);
 bool fft_big_applicable(const FftPlanDev &p, size_t nframes);
 int launch_fft_big(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s);
+int launch_bluestein_pre(const float2 *x, const float2 *chirp, float2 *a, uint32_t N, uint32_t M, size_t frames, cudaStream_t s);
+int launch_bluestein_mul(float2 *spec, const float2 *bspec, uint32_t M, size_t frames, cudaStream_t s);
+int launch_bluestein_post(const float2 *c, const float2 *chirp, float2 *out, uint32_t N, uint32_t M, size_t frames,
+                          cudaStream_t s);
 int launch_fft(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s);
 
 }  // namespace cb

@@ -175,7 +175,9 @@ CB_API int cb_mixer_set_phase(cb_mixer *h, double phase);
 /* ------------------------------------------------------------------ FFT
  * Replaces BatchFFT::run_fft (src/fft/mod.rs:73-96) / FFTBatchNode::new
  * (src/fft/fft_node.rs:65-74): X[k] = sum_n x[n] exp(-/+ j 2 pi k n / N),
- * "+" when inverse != 0, no 1/N in either direction, any N >= 1.
+ * "+" when inverse != 0, no 1/N in either direction, any N >= 1: powers of
+ * two up to 2^20, any other length up to 2^19 (chirp-z above 128 points);
+ * beyond that cb_fft_create returns CB_ERR_UNSUPPORTED.
  * n_in must be a multiple of fft_size (the reference requires n_in ==
  * fft_size, one frame per message; several contiguous frames per call is the
  * batched form) else CB_ERR_SIZE. */

@@ -145,6 +145,41 @@ def test_fft_large_sizes(cb, oracle, log2n, frames, path, monkeypatch):
         assert np.all(np.abs(e_out / (n * e_in) - 1) < 1e-5)
 
 
+@pytest.mark.parametrize("n,frames", [(1000, 5000), (3000, 1500), (12000, 100), (70000, 9)])
+def test_fft_any_length_many_frames(cb, oracle, n, frames):
+    # chirp-z path: more frames than one work-buffer group (32 MiB / M), device entry, direct path as a second opinion
+    import torch
+
+    rng = np.random.default_rng(n)
+    x = rnd_c32(rng, frames * n)
+    node = cb.FFTBatchNode(n, False)
+    d_x = torch.from_numpy(x).cuda()
+    d_y = torch.empty_like(d_x)
+    ts = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    node.run_dev(d_x.data_ptr(), frames * n, d_y.data_ptr(), ts.cuda_stream)
+    torch.cuda.synchronize()
+    got = d_y.cpu().numpy()
+    for f in sorted({0, 1, frames // 2, frames - 2, frames - 1}):
+        want = oracle.fft(x[f * n:(f + 1) * n], n, False)
+        assert rel_l2(got[f * n:(f + 1) * n], want) <= 1e-4, f
+    e_in = (np.abs(x.reshape(frames, n).astype(np.complex128)) ** 2).sum(axis=1)
+    e_out = (np.abs(got.reshape(frames, n).astype(np.complex128)) ** 2).sum(axis=1)
+    assert np.all(np.abs(e_out / (n * e_in) - 1) < 1e-5)
+    back = cb.FFTBatchNode(n, True).run(got[:3 * n]) / n
+    assert rel_l2(back, x[:3 * n]) <= 1e-4
+
+
+def test_fft_direct_and_chirpz_agree(cb, monkeypatch):
+    rng = np.random.default_rng(5)
+    n = 1000
+    x = rnd_c32(rng, 4 * n)
+    a = cb.FFTBatchNode(n, False).run(x)
+    monkeypatch.setenv("COMMS_B200_FFT_PATH", "direct")
+    b = cb.FFTBatchNode(n, False).run(x)
+    assert rel_l2(a, b) <= 2e-6
+
+
 @pytest.mark.timeout(300)
 def test_fft65536_two_handles_concurrently(cb, oracle):
     # two fused 65536-point kernels in flight on different streams share the SMs; the ticket-ordered work

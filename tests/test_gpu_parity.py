@@ -304,11 +304,13 @@ def test_fft10_golden_vector(cb):
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 8, 10, 12, 16, 32, 64, 100, 128, 256, 512, 1000, 1024, 2048, 4096, 8192,
-                               16384, 32768, 65536, 1 << 17, 1 << 20])
+                               16384, 32768, 65536, 1 << 17, 1 << 20,
+                               # any other length (rustfft plans every size): direct up to 128, chirp-z beyond
+                               127, 129, 255, 384, 1023, 4095, 4097, 5000, 10007, 48000, 65535, 100000, 300000])
 @pytest.mark.parametrize("inverse", [False, True])
 def test_fft_matches_oracle(cb, oracle, n, inverse):
     rng = np.random.default_rng(n + inverse)
-    frames = 3 if n <= 65536 else 1
+    frames = 3 if n <= 65536 else (2 if n & (n - 1) else 1)
     x = rnd_c32(rng, frames * n)
     want = oracle.fft(x, n, inverse)
     got = cb.FFTBatchNode(n, inverse).run(x)

@@ -130,6 +130,24 @@ def test_fft_definition_and_inverse(oracle, n):
     assert np.linalg.norm(oracle.fft(z, n, False) - np.fft.fft(z)) <= 1e-13 * max(np.linalg.norm(z) * np.sqrt(n), 1e-30)
 
 
+def test_fft_long_odd_lengths_use_the_same_definition(oracle, monkeypatch):
+    # lengths that are not a power of two and longer than the C direct sum handles in reasonable time go through numpy's
+    # f64 transform; pin that branch to the direct sum on a length both can do (f64 in and out)
+    rng = np.random.default_rng(3001)
+    n = 3001
+    z = rng.standard_normal(2 * n) + 1j * rng.standard_normal(2 * n)
+    for inverse in (False, True):
+        direct = oracle.fft(z, n, inverse)
+        monkeypatch.setattr(oracle, "_DIRECT_MAX", 1000)
+        fast = oracle.fft(z, n, inverse)
+        monkeypatch.undo()
+        assert fast.dtype == direct.dtype == np.complex128
+        assert np.linalg.norm(fast - direct) <= 1e-12 * np.linalg.norm(direct)
+    x = z.astype(np.complex64)
+    monkeypatch.setattr(oracle, "_DIRECT_MAX", 1000)
+    assert oracle.fft(x, n, False).dtype == np.complex64
+
+
 def test_rrc_rc_gaussian_qfilt_golden(oracle):
     rrc = oracle.rrc_taps(33, 3.18, 0.234, dtype=np.complex128)
     assert np.all(np.abs(rrc - np.array(G.RRC_33)) < np.finfo(np.float32).eps)
