@@ -566,6 +566,11 @@ static int fir_launch_segment(cb_fir *h, const float2 *x, size_t n, const float2
 {
     // long filters and long batches: overlap-save fast convolution (spectra scratch grown on demand; when it
     // cannot be allocated the direct-form kernel below is used)
+    // COMMS_B200_FIR_OLS=split: the two-kernel form with the spectra in a scratch (kept for comparison); default: one
+    // fused kernel per frame, no scratch
+    static const bool ols_split = [] { const char *e = getenv("COMMS_B200_FIR_OLS"); return e && strcmp(e, "split") == 0; }();
+    if (h->ols_hf != nullptr && n >= 8192 && !ols_split)
+        return launch_fir_ols(x, n, hist_in, hist_out, h->hist_len, h->k_eff, h->ols_hf, h->ols_twf, h->ols_twi, nullptr, y, s);
     if (h->ols_hf != nullptr && n >= 8192) {
         const size_t frames = fir_ols_frames(n, h->k_eff);
         if (h->ols_spec_frames < frames) {

@@ -549,7 +549,7 @@ struct OlsArgs {
 
 template <int STAGE>
 __global__ void __launch_bounds__(Fft2Cfg<12>::THREADS, Fft2Cfg<12>::MINB)
-fir_ols_kernel(const __grid_constant__ OlsArgs a, const float2 *__restrict__ tw)
+fir_ols_kernel(const __grid_constant__ OlsArgs a, const float2 *__restrict__ tw, const float2 *__restrict__ tw2)
 {
     using PL = fft2::Plan<12>;
     extern __shared__ __align__(16) float2 fsm[];
@@ -568,6 +568,40 @@ fir_ols_kernel(const __grid_constant__ OlsArgs a, const float2 *__restrict__ tw)
         float2 *dst = a.spec + frame * PL::N;
         auto gst = [&](int i, float2 v) { dst[i] = v; };
         fft2_passes<12, false, 0>(j, tw, gld, gst, b0, b0);
+    } else if constexpr (STAGE == 2) {
+        // fused: forward transform, product with Hf and inverse transform without leaving shared memory
+        // (tw = forward tables, tw2 = inverse tables); HBM traffic 8 * 4096 / hop + 8 bytes per sample
+        constexpr int T = PL::T;
+        const long long g0 = frame * a.hop - (long long)(a.K - 1);
+        auto gld = [&](int i) {
+            const long long g = g0 + i;
+            if (g >= (long long)a.n) return make_float2(0.f, 0.f);
+            if (g >= 0) return ldg_stream2(a.x + g);
+            const long long hi = (long long)a.hist_len + g;
+            return hi >= 0 ? a.hist[hi] : make_float2(0.f, 0.f);
+        };
+        auto gst = [&](int i, float2 v) {
+            const long long o = g0 + i;
+            if (i >= (int)(a.K - 1) && o < (long long)a.n) stg_stream2(a.y + o, make_float2(v.x * (1.f / 4096.f), v.y * (1.f / 4096.f)));
+        };
+        DevSm sm{b0};
+        auto nomid = [] {};
+        auto bar = [] { __syncthreads(); };
+        auto nogst = [](int, float2) {};
+        auto st_s = [&](int idx, float2 v) { sm.st(idx, v); };
+        fft2::run_pass<12, false, 0>(j, tw, gld, nogst, sm, sm, nomid);
+        __syncthreads();
+        fft2::run_pass<12, false, 1>(j, tw, gld, nogst, sm, sm, bar);
+        __syncthreads();
+        auto ld_s = [&](int m) { return sm.ld(j + m * T); };
+        // the spectrum stays in place, multiplied by Hf on the way back into shared memory
+        fft2::pass16<12, false, 2>(j, tw, ld_s, bar, [&](int idx, float2 v) { sm.st(idx, fft2::cmul(v, __ldg(a.hf + idx))); });
+        __syncthreads();
+        fft2::pass16<12, true, 0>(j, tw2, ld_s, bar, st_s);
+        __syncthreads();
+        fft2::run_pass<12, true, 1>(j, tw2, gld, nogst, sm, sm, bar);
+        __syncthreads();
+        fft2::run_pass<12, true, 2>(j, tw2, gld, gst, sm, sm, nomid);
     } else {
         const float2 *src = a.spec + frame * PL::N;
         auto gld = [&](int i) { return fft2::cmul(src[i], __ldg(a.hf + i)); };
@@ -608,14 +642,21 @@ int launch_fir_ols(const float2 *x, size_t n, const float2 *hist_in, float2 *his
     a.K = ntaps;
     a.hop = 4096 - (ntaps - 1);
     const unsigned frames = (unsigned)fir_ols_frames(n, ntaps);
-    auto k0 = fir_ols_kernel<0>;
-    auto k1 = fir_ols_kernel<1>;
-    CB_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM));
-    CB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM));
-    k0<<<frames, CF::THREADS, CF::SMEM, s>>>(a, tw_fwd);
-    count_launch();
-    k1<<<frames, CF::THREADS, CF::SMEM, s>>>(a, tw_inv);
-    count_launch();
+    if (spec == nullptr) {
+        auto kf = fir_ols_kernel<2>;
+        CB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM));
+        kf<<<frames, CF::THREADS, CF::SMEM, s>>>(a, tw_fwd, tw_inv);
+        count_launch();
+    } else {
+        auto k0 = fir_ols_kernel<0>;
+        auto k1 = fir_ols_kernel<1>;
+        CB_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM));
+        CB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM));
+        k0<<<frames, CF::THREADS, CF::SMEM, s>>>(a, tw_fwd, tw_inv);
+        count_launch();
+        k1<<<frames, CF::THREADS, CF::SMEM, s>>>(a, tw_inv, tw_fwd);
+        count_launch();
+    }
     if (hist_out != nullptr) {
         fir_hist_update_kernel<<<(hist_len + 255) / 256, 256, 0, s>>>(x, n, hist_in, hist_out, hist_len);
         count_launch();
