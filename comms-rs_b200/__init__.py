@@ -9,7 +9,8 @@ from .nodes import (BatchFirNode, ChainBank, DecimateNode, FFTBatchNode, FFTSamp
                     MixerNode, PulseNode, UpsampleNode, bits_to_symbols_dev, complex_real_dev, convert_i16_dev, convert_u8_dev,
                     prn_bits, real_to_complex_dev,
                     quantize_i16_dev,
-                    rrc_taps, synth_uniform_dev)
+                    rrc_taps, synth_uniform_dev, TimingEstimator, TimingEstimatorNode, frequency_offset_estimate,
+                    frequency_offset_estimate_dev, qfilt_taps)
 
 
 def init(device: int = 0) -> None:

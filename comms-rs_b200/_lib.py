@@ -111,6 +111,13 @@ SIGNATURES = {
     "cb_complex_real_dev": (_i, [_vp, _sz, _vp, _vp]),
     "cb_convert_u8_dev": (_i, [_vp, _sz, _vp, _vp]),
     "cb_convert_i16_dev": (_i, [_vp, _sz, C.c_float, _vp, _vp]),
+    "cb_qfilt_taps_f64": (_i, [_u32, _dbl, _u32, _vp, C.POINTER(_u32)]),
+    "cb_freq_estimate": (_i, [_vp, _sz, C.POINTER(_dbl)]),
+    "cb_freq_estimate_dev": (_i, [_vp, _sz, C.POINTER(_dbl), _vp]),
+    "cb_timing_create": (_i, [_u32, _u32, _dbl, _pp]),
+    "cb_timing_destroy": (_i, [_vp]),
+    "cb_timing_push": (_i, [_vp, _vp, _sz, C.POINTER(_dbl)]),
+    "cb_timing_push_dev": (_i, [_vp, _vp, _sz, C.POINTER(_dbl), _vp]),
     "cb_rrc_taps": (_i, [C.c_uint32, C.c_double, C.c_double, _vp]),
     "cb_rrc_taps_f64": (_i, [C.c_uint32, C.c_double, C.c_double, _vp]),
     "cb_prn_bits": (_i, [C.c_uint64, C.POINTER(C.c_uint64), C.c_uint, _sz, _vp]),

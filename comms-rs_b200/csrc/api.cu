@@ -10,6 +10,7 @@
 
 #include "chain_kernels.cuh"
 #include "common.cuh"
+#include "estimator_kernels.cuh"
 #include "fft_kernels.cuh"
 #include "fir_kernels.cuh"
 #include "misc_kernels.cuh"
@@ -1606,6 +1607,163 @@ int cb_rrc_taps(uint32_t n_taps, double sam_per_sym, double beta, float *taps)
     if (rc) return rc;
     for (size_t i = 0; i < t.size(); ++i) taps[i] = (float)t[i];
     return CB_OK;
+}
+
+// ============================================================================ f64 estimators
+// qfilt_taps (src/util/math.rs:307-342), host side, f64: Mengali's q(t); an even n_taps is incremented by one.
+int cb_qfilt_taps_f64(uint32_t n_taps, double alpha, uint32_t sam_per_sym, double *taps, uint32_t *n_out)
+{
+    CB_REQUIRE(alpha >= 0.0 && alpha <= 1.0, CB_ERR_INVALID_ARG, "qfilt_taps: rolloff %g outside [0, 1]", alpha);
+    const uint32_t real_n = n_taps % 2 == 0 ? n_taps + 1 : n_taps;
+    if (n_out) *n_out = real_n;
+    CB_REQUIRE(taps, CB_ERR_INVALID_ARG, "taps is NULL");
+    const double pi = 3.14159265358979323846;
+    const int d = (int)floor((double)real_n / 2.0);
+    for (uint32_t i = 0; i < real_n; ++i) {
+        const double tt = (double)((int)i - d) / (double)sam_per_sym;
+        const double two_alpha_tt = 2.0 * alpha * tt;
+        if (fabs(two_alpha_tt) == 1.0) {
+            taps[i] = sin(pi * alpha * tt) / (8.0 * tt);
+        } else {
+            taps[i] = (alpha * cos(pi * alpha * tt)) / (pi * (1.0 - two_alpha_tt * two_alpha_tt));
+        }
+    }
+    return CB_OK;
+}
+
+// scratch of one estimator call, stream-ordered: partial sums, the final sum, optionally a staged copy of the samples
+struct EstScratch {
+    double2 *partial = nullptr, *sum = nullptr, *x = nullptr;
+    cudaStream_t s = nullptr;
+    int alloc(cudaStream_t stream, size_t n_stage)
+    {
+        s = stream;
+        CB_CUDA(cudaMallocAsync(&partial, (estimator_max_partials() + 1) * sizeof(double2), s));
+        sum = partial + estimator_max_partials();
+        if (n_stage) CB_CUDA(cudaMallocAsync(&x, n_stage * sizeof(double2), s));
+        return CB_OK;
+    }
+    ~EstScratch()
+    {
+        if (x) cudaFreeAsync(x, s);
+        if (partial) cudaFreeAsync(partial, s);
+    }
+};
+
+static int freq_estimate_impl(const double2 *samples, bool on_host, size_t n, double *estimate, cudaStream_t s)
+{
+    CB_REQUIRE(estimate, CB_ERR_INVALID_ARG, "estimate is NULL");
+    if (n < 2) {  // empty sum: arg(0 + 0j) = 0
+        *estimate = 0.0;
+        return CB_OK;
+    }
+    CB_REQUIRE(samples, CB_ERR_INVALID_ARG, "NULL data pointer");
+    int rc = ensure_device();
+    if (rc) return rc;
+    EstScratch sc;
+    rc = sc.alloc(s, on_host ? n : 0);
+    if (rc) return rc;
+    if (on_host) CB_CUDA(cudaMemcpyAsync(sc.x, samples, n * sizeof(double2), cudaMemcpyHostToDevice, s));
+    rc = launch_freq_sum(on_host ? sc.x : samples, n, sc.partial, sc.sum, s);
+    if (rc) return rc;
+    double2 sum;
+    CB_CUDA(cudaMemcpyAsync(&sum, sc.sum, sizeof(sum), cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaStreamSynchronize(s));
+    *estimate = atan2(sum.y, sum.x);  // Complex::arg
+    return CB_OK;
+}
+
+int cb_freq_estimate(const double *samples, size_t n, double *estimate)
+{
+    return freq_estimate_impl(reinterpret_cast<const double2 *>(samples), true, n, estimate, cudaStreamPerThread);
+}
+
+int cb_freq_estimate_dev(const double *d_samples, size_t n, double *estimate, void *stream)
+{
+    return freq_estimate_impl(reinterpret_cast<const double2 *>(d_samples), false, n, estimate,
+                              stream ? (cudaStream_t)stream : cudaStreamPerThread);
+}
+
+struct cb_timing {
+    int device;
+    cudaStream_t stream;
+    uint32_t n, d, ntaps;
+    double *taps_dev;
+};
+
+int cb_timing_create(uint32_t n, uint32_t d, double alpha, cb_timing **out)
+{
+    CB_REQUIRE(out, CB_ERR_INVALID_ARG, "out is NULL");
+    CB_REQUIRE(n >= 1, CB_ERR_INVALID_ARG, "timing estimator: samples per symbol must be >= 1");
+    CB_REQUIRE((uint64_t)2 * n * d + 1 <= 8193, CB_ERR_UNSUPPORTED,
+               "timing estimator: filter length 2*n*d+1 = %llu > 8193 is not provided", (unsigned long long)2 * n * d + 1);
+    int rc = ensure_device();
+    if (rc) return rc;
+    std::vector<double> taps((size_t)2 * n * d + 2);
+    uint32_t ntaps = 0;
+    rc = cb_qfilt_taps_f64(2 * n * d + 1, alpha, n, taps.data(), &ntaps);  // MathError::InvalidRolloffError
+    if (rc) return rc;
+    cb_timing *h = new (std::nothrow) cb_timing();
+    CB_REQUIRE(h, CB_ERR_OOM, "host allocation failed");
+    h->device = g_dev;
+    h->stream = nullptr;
+    h->n = n;
+    h->d = d;
+    h->ntaps = ntaps;
+    h->taps_dev = nullptr;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&h->taps_dev, ntaps * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(h->taps_dev, taps.data(), ntaps * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cb_timing_destroy(h);
+        return cuda_fail(e, "timing estimator create", __FILE__, __LINE__);
+    }
+    *out = h;
+    return CB_OK;
+}
+
+int cb_timing_destroy(cb_timing *h)
+{
+    if (!h) return CB_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->taps_dev) cudaFree(h->taps_dev);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return CB_OK;
+}
+
+static int timing_push_impl(cb_timing *h, const double2 *samples, bool on_host, size_t n, double *estimate, cudaStream_t s)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    CB_REQUIRE(estimate, CB_ERR_INVALID_ARG, "estimate is NULL");
+    const double pi = 3.14159265358979323846;
+    double2 sum = make_double2(0.0, 0.0);
+    if (n > 0) {
+        CB_REQUIRE(samples, CB_ERR_INVALID_ARG, "NULL data pointer");
+        CB_CUDA(cudaSetDevice(h->device));
+        EstScratch sc;
+        int rc = sc.alloc(s, on_host ? n : 0);
+        if (rc) return rc;
+        if (on_host) CB_CUDA(cudaMemcpyAsync(sc.x, samples, n * sizeof(double2), cudaMemcpyHostToDevice, s));
+        rc = launch_timing_sum(on_host ? sc.x : samples, n, h->taps_dev, h->ntaps, h->n * h->d, h->n, sc.partial, sc.sum, s);
+        if (rc) return rc;
+        CB_CUDA(cudaMemcpyAsync(&sum, sc.sum, sizeof(sum), cudaMemcpyDeviceToHost, s));
+        CB_CUDA(cudaStreamSynchronize(s));
+    }
+    *estimate = -(double)h->n * atan2(sum.y, sum.x) / (2.0 * pi);  // timing_estimator.rs:111
+    return CB_OK;
+}
+
+int cb_timing_push(cb_timing *h, const double *samples, size_t n, double *estimate)
+{
+    return timing_push_impl(h, reinterpret_cast<const double2 *>(samples), true, n, estimate, h ? h->stream : nullptr);
+}
+
+int cb_timing_push_dev(cb_timing *h, const double *d_samples, size_t n, double *estimate, void *stream)
+{
+    return timing_push_impl(h, reinterpret_cast<const double2 *>(d_samples), false, n, estimate,
+                            h ? pick_stream(stream, h->stream) : nullptr);
 }
 
 // ============================================================================ bit-exact edges

@@ -372,6 +372,71 @@ def rrc_taps(n_taps: int, sam_per_sym: float, beta: float, dtype=np.complex64) -
     return out
 
 
+def qfilt_taps(n_taps: int, alpha: float, sam_per_sym: int) -> np.ndarray:
+    """qfilt_taps (src/util/math.rs:307-342): Mengali's q(t), f64; an even n_taps is incremented by one."""
+    out = np.empty(n_taps + 1, dtype=np.float64)
+    m = C.c_uint32(0)
+    try:
+        check(_lib.load().cb_qfilt_taps_f64(int(n_taps), float(alpha), int(sam_per_sym), _ptr(out), C.byref(m)))
+    except CbError as e:
+        raise ValueError("InvalidRolloffError") from e
+    return out[:m.value].copy()
+
+
+def frequency_offset_estimate(samples) -> float:
+    """frequency_offset_estimate (src/demodulation/frequency_estimator.rs:27-42): carrier offset in
+    radians/sample from complex f64 samples (host array)."""
+    x = np.ascontiguousarray(np.asarray(samples, dtype=np.complex128))
+    est = C.c_double(0.0)
+    check(_lib.load().cb_freq_estimate(_ptr(x), len(x), C.byref(est)))
+    return est.value
+
+
+def frequency_offset_estimate_dev(d_samples: int, n: int, stream: int = 0) -> float:
+    """Same on n complex f64 samples already in device memory."""
+    est = C.c_double(0.0)
+    check(_lib.load().cb_freq_estimate_dev(d_samples, n, C.byref(est), stream))
+    return est.value
+
+
+class TimingEstimator:
+    """TimingEstimator (src/demodulation/timing_estimator.rs:13-112): new(n, d, alpha); push(samples) -> estimate
+    in samples.  TimingEstimatorNode (timing_estimator.rs:116-137) is the same object: run = push."""
+
+    def __init__(self, n: int, d: int, alpha: float):
+        self._h = C.c_void_p()
+        try:
+            check(_lib.load().cb_timing_create(int(n), int(d), float(alpha), C.byref(self._h)))
+        except CbError as e:
+            if e.status == _lib.CB_ERR_INVALID_ARG and not 0.0 <= alpha <= 1.0:
+                raise ValueError("InvalidRolloffError") from e
+            raise
+
+    def push(self, samples) -> float:
+        x = np.ascontiguousarray(np.asarray(samples, dtype=np.complex128))
+        est = C.c_double(0.0)
+        check(_lib.load().cb_timing_push(self._h, _ptr(x), len(x), C.byref(est)))
+        return est.value
+
+    run = push
+
+    def push_dev(self, d_samples: int, n: int, stream: int = 0) -> float:
+        est = C.c_double(0.0)
+        check(_lib.load().cb_timing_push_dev(self._h, d_samples, n, C.byref(est), stream))
+        return est.value
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.load().cb_timing_destroy(h)
+            except Exception:
+                pass
+
+
+TimingEstimatorNode = TimingEstimator
+
+
 def prn_bits(poly_mask: int, state: int, n: int, width: int = 8):
     """PrnGen::next_byte n times (src/prns.rs:64-71).  Returns (bits, new_state)."""
     st = C.c_uint64(state)

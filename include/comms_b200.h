@@ -261,6 +261,26 @@ CB_API int cb_quantize_i16_dev(const float *d_in, size_t nfloats, float scale, i
  * rounded.  cb_convert_i16: the interleaved native-endian i16 IQ of
  * src/io/raw_iq.rs:20-140 -> scale * (x as f32) (scale = 1: the plain cast).
  * n_samples complex samples each; d_out receives 2*n_samples floats. */
+/* ------------------------------------------------------------------ f64 estimators
+ * The two feed-forward estimators of src/demodulation that call batch_fir (complex f64 samples = 2n interleaved
+ * doubles).  Each call is one fused pass (filter, product, reduction) and returns its scalar on the host, so it
+ * synchronises the stream it ran on.
+ * cb_freq_estimate: frequency_offset_estimate (src/demodulation/frequency_estimator.rs:27-42), radians/sample:
+ *   arg(sum_{i<n-1} x[i+1] conj(x[i])); n < 2 gives 0.
+ * cb_timing_*: TimingEstimator::new / push (src/demodulation/timing_estimator.rs:43-58, 85-112), result in
+ *   samples; alpha outside [0, 1] -> CB_ERR_INVALID_ARG (MathError::InvalidRolloffError); the internal filter
+ *   length 2*n*d+1 is limited to 8193 (CB_ERR_UNSUPPORTED beyond).
+ * cb_qfilt_taps_f64: qfilt_taps (src/util/math.rs:307-342); taps must hold n_taps + 1 doubles (an even n_taps is
+ *   incremented by one); *n_out receives the count written. */
+typedef struct cb_timing cb_timing;
+CB_API int cb_qfilt_taps_f64(uint32_t n_taps, double alpha, uint32_t sam_per_sym, double *taps, uint32_t *n_out);
+CB_API int cb_freq_estimate(const double *samples, size_t n, double *estimate);
+CB_API int cb_freq_estimate_dev(const double *d_samples, size_t n, double *estimate, void *stream);
+CB_API int cb_timing_create(uint32_t n, uint32_t d, double alpha, cb_timing **out);
+CB_API int cb_timing_destroy(cb_timing *h);
+CB_API int cb_timing_push(cb_timing *h, const double *samples, size_t n, double *estimate);
+CB_API int cb_timing_push_dev(cb_timing *h, const double *d_samples, size_t n, double *estimate, void *stream);
+
 /* Real <-> complex glue of examples/fm_radio.rs, device side, so the whole shipped graph can stay on the GPU:
  * cb_real_to_complex: Convert2Node (fm_radio.rs:98-118), x -> Complex(x, 0); cb_complex_real: Convert3Node
  * (fm_radio.rs:122-142), z -> z.re.  n elements each. */

@@ -241,6 +241,42 @@ def qfilt_taps(n_taps: int, alpha: float, sam_per_sym: int):
     return out[: m.value].copy()
 
 
+def frequency_offset_estimate(samples) -> float:
+    """frequency_offset_estimate (src/demodulation/frequency_estimator.rs:27-42): f64, the sum taken in
+    index order as Iterator::sum does."""
+    x = np.asarray(samples, dtype=np.complex128)
+    if len(x) < 2:
+        return 0.0
+    mult = x[1:] * np.conj(x[:-1])
+    acc = np.cumsum(mult)[-1]  # sequential left fold
+    return float(np.arctan2(acc.imag, acc.real))
+
+
+class TimingEstimator:
+    """TimingEstimator::new / push (src/demodulation/timing_estimator.rs:43-58, 85-112)."""
+
+    def __init__(self, n: int, d: int, alpha: float):
+        self.n, self.d = int(n), int(d)
+        self.qfilt = qfilt_taps(2 * n * d + 1, alpha, n).astype(np.complex128)  # :47-48
+        self.delay = np.zeros(n * d + 1, dtype=np.complex128)                   # :49-50
+        self.delay[-1] = 1.0
+
+    def push(self, samples) -> float:
+        s = np.asarray(samples, dtype=np.complex128)
+        i = np.arange(len(s), dtype=np.float64)
+        ang = -np.pi * i / float(self.n)                      # :90  (-PI * i) / n
+        r = np.cos(ang) + 1j * np.sin(ang)                    # Complex::new(0, ang).exp()
+        qin = np.conj(s) * r                                  # :93
+        din = s * r                                           # :94
+        qout, _ = batch_fir(qin, self.qfilt, np.zeros(2 * self.n * self.d + 1, np.complex128))  # :98-102
+        dout, _ = batch_fir(din, self.delay, np.zeros(self.n * self.d + 1, np.complex128))      # :100-103
+        if len(s) == 0:
+            acc = 0j
+        else:
+            acc = np.cumsum(qout * dout)[-1]                  # :108-109, sequential sum
+        return float(-float(self.n) * np.arctan2(acc.imag, acc.real) / (2.0 * np.pi))  # :111
+
+
 def sinc(x: float) -> float:
     return float(lib().orc_sinc(C.c_double(x)))
 

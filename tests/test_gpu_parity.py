@@ -487,6 +487,69 @@ def test_fm_radio_example_graph_on_device(cb, oracle):
         assert np.median(d) < 5e-6 and np.mean(d > 1e-2) < 5e-3, (batch, np.median(d), d.max())
 
 
+def _shaped_qpsk_f64(oracle, rng, nsym, sps, ntaps, alpha):
+    sym = np.exp(1j * (2 * np.pi * rng.integers(0, 4, nsym) / 4 + np.pi / 4))
+    up = np.zeros(nsym * sps, np.complex128)
+    up[::sps] = sym
+    taps = oracle.rrc_taps(ntaps, float(sps), alpha, dtype=np.complex128)
+    out, _ = oracle.batch_fir(up, taps, np.zeros(ntaps, np.complex128))
+    return out
+
+
+@pytest.mark.parametrize("n,d,alpha,nsym,drop", [(10, 5, 0.5, 1000, 2), (2, 5, 0.25, 3000, 0), (4, 8, 0.35, 5000, 1),
+                                                 (8, 0, 0.5, 100, 0), (3, 2, 1.0, 50, 0)])
+def test_timing_estimator_matches_oracle(cb, oracle, n, d, alpha, nsym, drop):
+    # TimingEstimator::push (src/demodulation/timing_estimator.rs:85-112): f64; the product sums in a tree, the
+    # reference in index order: 1e-9 samples
+    rng = np.random.default_rng(n * 100 + d)
+    x = _shaped_qpsk_f64(oracle, rng, nsym, n, 10 * n + 1, alpha)[drop:]
+    x = x + 0.01 * (rng.standard_normal(len(x)) + 1j * rng.standard_normal(len(x)))
+    want = oracle.TimingEstimator(n, d, alpha).push(x)
+    est = cb.TimingEstimator(n, d, alpha)
+    got = est.push(x)
+    assert abs(got - want) < 1e-9, (got, want)
+    assert est.push(x) == got  # fixed reduction order: same bits every time
+    if (n, d) == (10, 5):
+        assert abs(drop + got) < 0.01  # the reference's own test (timing_estimator.rs:183-196)
+    import torch
+
+    d_x = torch.from_numpy(x).cuda()
+    assert est.push_dev(d_x.data_ptr(), len(x)) == got
+    assert est.push(x[:0]) == 0.0
+    # fewer samples than the delay N*D + 1: every dout is a zero and the sum is exactly zero.  The reference then
+    # returns the argument of a SIGNED zero (0 or -+N/2, decided by the signs of the first samples); the product
+    # returns 0
+    if d == 0:
+        assert abs(est.push(x[:1]) - oracle.TimingEstimator(n, d, alpha).push(x[:1])) < 1e-12
+    else:
+        assert est.push(x[:n * d]) == 0.0
+        k = n * d + 1  # the first length with a non-zero term
+        assert abs(est.push(x[:k]) - oracle.TimingEstimator(n, d, alpha).push(x[:k])) < 1e-9
+    np.testing.assert_array_equal(cb.qfilt_taps(2 * n * d + 1, alpha, n), oracle.qfilt_taps(2 * n * d + 1, alpha, n))
+    with pytest.raises(ValueError):
+        cb.TimingEstimator(n, d, 1.5)
+
+
+def test_frequency_estimator_matches_oracle(cb, oracle):
+    # frequency_offset_estimate (src/demodulation/frequency_estimator.rs:27-42) and its test (:56-100)
+    rng = np.random.default_rng(7)
+    truth = 0.123456789
+    x = _shaped_qpsk_f64(oracle, rng, 4096, 4, 16, 0.75)
+    x = x * np.exp(1j * truth * np.arange(len(x)))
+    want = oracle.frequency_offset_estimate(x)
+    got = cb.frequency_offset_estimate(x)
+    assert abs(got - want) < 1e-12 and abs(truth - got) < 0.01
+    for m in (0, 1, 2, 3, 255, 256, 257, 2049):
+        assert abs(cb.frequency_offset_estimate(x[:m]) - oracle.frequency_offset_estimate(x[:m])) < 1e-12, m
+    import torch
+
+    # a long pure tone on the device: the estimate is the tone's frequency whatever the length
+    nbig = (1 << 24) + 5
+    t = torch.arange(nbig, dtype=torch.float64, device="cuda") * (-0.3)
+    d_x = torch.polar(torch.ones_like(t), t)
+    assert abs(cb.frequency_offset_estimate_dev(d_x.data_ptr(), nbig) + 0.3) < 1e-9
+
+
 def test_convert_i16_bit_exact(cb):
     import torch
 

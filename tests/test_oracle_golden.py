@@ -148,6 +148,40 @@ def test_fft_long_odd_lengths_use_the_same_definition(oracle, monkeypatch):
     assert oracle.fft(x, n, False).dtype == np.complex64
 
 
+def _qpsk_shaped(oracle, rng, nsym, sps, ntaps, alpha):
+    sym = np.exp(1j * (2 * np.pi * rng.integers(0, 4, nsym) / 4 + np.pi / 4))
+    up = np.zeros(nsym * sps, np.complex128)
+    up[::sps] = sym
+    taps = oracle.rrc_taps(ntaps, float(sps), alpha, dtype=np.complex128)
+    out, _ = oracle.batch_fir(up, taps, np.zeros(ntaps, np.complex128))
+    return out
+
+
+def test_timing_estimator_reference_kat(oracle):
+    # src/demodulation/timing_estimator.rs:139-196: QPSK at 10 samples/symbol, rrc(101 taps, alpha 0.5), the first
+    # `truth` = 2 samples dropped; |truth + estimate| < 0.01.  (The reference seeds rand's SmallRng, which cannot be
+    # reproduced here; the statistic does not depend on the symbol draw.)
+    for seed in (0, 1):
+        samples = _qpsk_shaped(oracle, np.random.default_rng(seed), 1000, 10, 101, 0.5)
+        est = oracle.TimingEstimator(10, 5, 0.5).push(samples[2:])
+        assert abs(2 + est) < 0.01
+
+
+def test_frequency_estimator_reference_kat(oracle):
+    # src/demodulation/frequency_estimator.rs:56-100: 4096 4-PSK symbols, x4, rrc(16 taps, beta 0.75), shifted by
+    # 0.123456789 rad/sample; |truth - estimate| < 0.01
+    rng = np.random.default_rng(0)
+    sym = np.exp(1j * 2 * np.pi * rng.integers(0, 4, 4096) / 4)
+    up = np.zeros(4096 * 4, np.complex128)
+    up[::4] = sym
+    taps = oracle.rrc_taps(16, 4.0, 0.75, dtype=np.complex128)
+    data, _ = oracle.batch_fir(up, taps, np.zeros(16, np.complex128))
+    truth = 0.123456789
+    data = data * np.exp(1j * truth * np.arange(len(data)))
+    assert abs(truth - oracle.frequency_offset_estimate(data)) < 0.01
+    assert oracle.frequency_offset_estimate(data[:1]) == 0.0
+
+
 def test_rrc_rc_gaussian_qfilt_golden(oracle):
     rrc = oracle.rrc_taps(33, 3.18, 0.234, dtype=np.complex128)
     assert np.all(np.abs(rrc - np.array(G.RRC_33)) < np.finfo(np.float32).eps)
