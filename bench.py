@@ -42,6 +42,8 @@ WORKLOADS = {
     "fir64_real": ("fir", 1 << 28, 16.0, "64-tap complex-f32 FIR (real-valued rrc taps) on one 2^28-sample stream per GPU"),
     "fir1024": ("fir", 1 << 28, 16.0, "1024-tap complex-f32 FIR (overlap-save fast convolution) on one 2^28-sample stream per GPU"),
     "fir63d5": ("firdec", 1 << 28, 9.6, "63-tap real-valued FIR + DecimateNode(5) (fm_radio.rs filt1 -> dec1) fused, one 2^28-sample stream per GPU"),
+    "fir63d5_real": ("firreal", 1 << 28, 4.8, "fm_radio second stage (fm_radio.rs:98-164): real f32 samples -> Complex(x,0) -> 63-tap FIR -> .re -> "
+                     "DecimateNode(5), fused, one 2^28-sample real stream per GPU"),
     "fft1024": ("fft", 1 << 28, 16.0, "batched 1024-point FFT over 2^28 complex-f32 samples per GPU"),
     "fft2048": ("fft", 1 << 28, 16.0, "batched 2048-point FFT over 2^28 complex-f32 samples per GPU"),
     "fft16384": ("fft", 1 << 28, 16.0, "batched 16384-point FFT over 2^28 complex-f32 samples per GPU"),
@@ -53,6 +55,9 @@ WORKLOADS = {
     "fft524288": ("fft", 1 << 28, 16.0, "batched 524288-point FFT over 2^28 complex-f32 samples per GPU"),
     "fft262144": ("fft", 1 << 28, 16.0, "batched 262144-point FFT over 2^28 complex-f32 samples per GPU"),
     "fft1048576": ("fft", 1 << 28, 16.0, "batched 1048576-point FFT over 2^28 complex-f32 samples per GPU"),
+    "freqest": ("est", 1 << 27, 16.0, "frequency_offset_estimate (frequency_estimator.rs:27-42) over 2^27 complex-f64 samples per GPU"),
+    "timing10x5": ("est", 1 << 27, 16.0, "TimingEstimator(n=10, d=5, alpha=0.5).push (timing_estimator.rs:85-112, 101-tap f64 filter) "
+                   "over 2^27 complex-f64 samples per GPU"),
     "ifft4096": ("fft", 1 << 28, 16.0, "batched 4096-point IFFT over 2^28 complex-f32 samples per GPU"),
     "mixer": ("mixer", 1 << 28, 16.0, "MixerNode (src/mixer.rs:73-84): y = x e^{j phi}, f64 phase, over 2^28 complex-f32 samples per GPU"),
     "fm": ("fm", 1 << 28, 12.0, "FMDemodNode (src/modulation/analog.rs:22-34) over 2^28 complex-f32 samples per GPU"),
@@ -188,6 +193,17 @@ def cpu_rate(workload, samples, threads):
         elif kind == "firdec":
             t = fm_radio_lowpass()
             jobs.append(lambda x=x, t=t: oracle.decimate(oracle.batch_fir(x, t, np.zeros(63, np.complex64), literal=True, native=True)[0], 5))
+        elif kind == "firreal":
+            t = fm_radio_lowpass()
+            xr = x.view(np.float32)[:per].astype(np.complex64)  # Convert2Node
+            jobs.append(lambda xr=xr, t=t: oracle.decimate(
+                oracle.batch_fir(xr, t, np.zeros(63, np.complex64), literal=True, native=True)[0].real.copy(), 5))
+        elif kind == "est":
+            x = x.astype(np.complex128)
+            if workload == "freqest":
+                jobs.append(lambda x=x: oracle.frequency_offset_estimate(x))
+            else:
+                jobs.append(lambda x=x: oracle.TimingEstimator(10, 5, 0.5).push(x))
         elif kind == "mixer":
             jobs.append(lambda x=x: oracle.Mixer(0.2, 0.123).mix(x))
         elif kind == "fm":
@@ -218,7 +234,7 @@ def run_reference(args, rank):
         return
     threads = os.cpu_count() or 1
     kind, _, _, desc = WORKLOADS[args.workload]
-    rate1 = {"fir": 8e6, "fft": 30e6, "chain": 20e6, "interp": 2e6, "mixer": 30e6, "fm": 60e6, "firdec": 8e6}[kind]
+    rate1 = {"fir": 8e6, "fft": 30e6, "chain": 20e6, "interp": 2e6, "mixer": 30e6, "fm": 60e6, "firdec": 8e6, "est": 3e6, "firreal": 8e6}[kind]
     if args.workload.startswith("poly8x1024"):
         rate1 = 1e4
     per_thread = int(min(max(150.0 * rate1 / (args.steps + args.warmup), 1 << 12), 1 << 23))
@@ -234,7 +250,7 @@ def run_reference(args, rank):
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f64" if kind == "est" else "f32", "data": "synthetic",
         "config": {"workload": args.workload, "description": desc,
                    "note": "reference CPU algorithm (oracle port of the Rust code; no rustc in this image), "
                            "independent segments with halo state, one per host thread"},
@@ -287,6 +303,30 @@ class Job:
             self.kernels_per_step = 2 if (N > 16384 and not (N == 65536 and os.environ.get("COMMS_B200_FFT_PATH", "rows") in ("rows", "cluster", "cluster1", "cluster2", "cluster16"))) else 1
             self.step = lambda: self.node.run_dev(self.x.data_ptr(), n, self.y.data_ptr(), self.stream)
             self.host_call = lambda hin, hout: cb.load().cb_fft_run(self.node._h, hin, n, hout)
+        elif self.kind == "firreal":
+            self.taps = fm_radio_lowpass()
+            self.node = cb.BatchFirNode(self.taps, None, decim=5)
+            no = -(-n // 5)
+            self.y = torch.empty(no, dtype=torch.float32, device="cuda")
+            self.in_bytes_override = 4 * n  # the first n floats of the synthetic stream
+            self.out_bytes = 4 * no
+            self.kernels_per_step = 1  # + the 128-sample history update
+            self.step = lambda: self.node.run_dev_real(self.x.data_ptr(), n, self.y.data_ptr(), no, self.stream)
+            self.host_call = lambda hin, hout: cb.load().cb_fir_run_real(self.node._h, hin, n, hout, no, None)
+        elif self.kind == "est":
+            import ctypes as C
+            self.x = self.x.to(torch.complex128)  # the same synthetic stream, widened once outside the timed region
+            self.in_bytes_override = 16 * n
+            self.out_bytes = 8
+            self.kernels_per_step = 1  # + one single-CTA kernel that adds the per-CTA partial sums
+            self.result = C.c_double(0.0)
+            if workload == "freqest":
+                self.step = lambda: cb._lib.check(cb.load().cb_freq_estimate_dev(self.x.data_ptr(), n, C.byref(self.result), self.stream))
+                self.host_call = lambda hin, hout: cb.load().cb_freq_estimate(hin, n, C.cast(hout, C.POINTER(C.c_double)))
+            else:
+                self.node = cb.TimingEstimator(10, 5, 0.5)
+                self.step = lambda: cb._lib.check(cb.load().cb_timing_push_dev(self.node._h, self.x.data_ptr(), n, C.byref(self.result), self.stream))
+                self.host_call = lambda hin, hout: cb.load().cb_timing_push(self.node._h, hin, n, C.cast(hout, C.POINTER(C.c_double)))
         elif self.kind == "mixer":
             self.node = cb.MixerNode(0.123, 0.2)
             self.y = torch.empty(n, dtype=torch.complex64, device="cuda")
@@ -445,7 +485,7 @@ def run_b200(args, rank, world, local_rank):
         line = {
             "metric": METRIC, "value": world * job.n * args.steps / (total_ms_max * 1e-3) / 1e6, "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if job.kind == "est" else "f32", "data": "synthetic",
             "config": {"workload": args.workload, "description": job.desc, "units_per_step_per_gpu": job.n,
                        "l2": "inputs larger than L2 (%.1f GiB read + %.1f GiB written per step, L2 = 126 MB)"
                              % (job.in_bytes / 2 ** 30, job.out_bytes / 2 ** 30),
@@ -460,7 +500,9 @@ def run_b200(args, rank, world, local_rank):
         }
         if world == 1 and not args.no_cpu:
             kind = job.kind
-            sample = {"fir": 1 << 26, "fft": 1 << 27, "chain": 1 << 26, "interp": 1 << 23, "mixer": 1 << 26, "fm": 1 << 27, "firdec": 1 << 26}[kind]
+            sample = {"fir": 1 << 26, "fft": 1 << 27, "chain": 1 << 26, "interp": 1 << 23, "mixer": 1 << 26, "fm": 1 << 27, "firdec": 1 << 26, "est": 1 << 24, "firreal": 1 << 26}[kind]
+            if args.workload == "timing10x5":
+                sample = 1 << 22
             if args.workload.startswith("poly8x1024"):
                 sample = 1 << 17
             v, dt, n = cpu_rate(args.workload, sample, 1)

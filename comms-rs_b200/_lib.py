@@ -71,6 +71,8 @@ SIGNATURES = {
     "cb_fir_out_len": (_i, [_vp, _sz, _psz]),
     "cb_fir_run": (_i, [_vp, _vp, _sz, _vp, _sz, _psz]),
     "cb_fir_run_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _psz, _vp]),
+    "cb_fir_run_real": (_i, [_vp, _vp, _sz, _vp, _sz, _psz]),
+    "cb_fir_run_real_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _psz, _vp]),
     "cb_fir_run_i16": (_i, [_vp, _vp, _sz, C.c_float, _vp, _sz, C.POINTER(_sz)]),
     "cb_fir_run_dev_i16": (_i, [_vp, _vp, _sz, C.c_float, _vp, _sz, C.POINTER(_sz), _vp]),
     "cb_fir_state_len": (_i, [_vp, _psz]),

@@ -152,6 +152,8 @@ struct cb_fir {
     FirTcPlan tc;
     float2 *qscratch;   // f32 result of the unfused cb_fir_run_dev_i16 path, grown on demand
     size_t qscratch_len;
+    float2 *rscratch;   // unfused cb_fir_run_real_dev path: widened input followed by the complex result
+    size_t rscratch_len;
     // overlap-save path for 129 .. 1025 taps: taps' spectrum, the two 4096-point twiddle tables, frame spectra
     float2 *ols_hf, *ols_twf, *ols_twi, *ols_spec;
     size_t ols_spec_frames;
@@ -450,6 +452,8 @@ int cb_fir_create(const float *taps, size_t ntaps, const float *state, size_t ns
     h->qscratch = nullptr;
     h->qscratch_len = 0;
     h->ols_hf = h->ols_twf = h->ols_twi = h->ols_spec = nullptr;
+    h->rscratch = nullptr;
+    h->rscratch_len = 0;
     h->ols_spec_frames = 0;
 
     std::vector<float2> hist;
@@ -542,6 +546,7 @@ int cb_fir_destroy(cb_fir *h)
     if (h->taps_dev) cudaFree(h->taps_dev);
     if (h->tc_img) cudaFree(h->tc_img);
     if (h->qscratch) cudaFree(h->qscratch);
+    if (h->rscratch) cudaFree(h->rscratch);
     if (h->ols_hf) cudaFree(h->ols_hf);
     if (h->ols_twf) cudaFree(h->ols_twf);
     if (h->ols_twi) cudaFree(h->ols_twi);
@@ -641,6 +646,62 @@ int cb_fir_run_dev_i16(cb_fir *h, const float *d_in, size_t n_in, float scale, i
     }
     if (rc) return rc;
     h->cur ^= 1;
+    return CB_OK;
+}
+
+// Real samples in, real parts out: the Convert2Node -> BatchFirNode -> Convert3Node [-> DecimateNode] run of
+// examples/fm_radio.rs:98-164.  One fused kernel for <= 64 taps and D in {2, 4, 5, 8, 10}; any other shape widens into a
+// scratch, runs the complex filter and takes the real parts.  The carried state stays the handle's complex history.
+int cb_fir_run_real_dev(cb_fir *h, const float *d_in, size_t n_in, float *d_out, size_t out_cap, size_t *n_out, void *stream)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    const size_t no = fir_out_len(h, n_in);
+    if (n_out) *n_out = no;
+    if (n_in == 0) return CB_OK;
+    CB_REQUIRE(d_in && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_REQUIRE(out_cap >= no, CB_ERR_SIZE, "fir: out_cap %zu < %zu outputs", out_cap, no);
+    CB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = pick_stream(stream, h->stream);
+    int rc;
+    if (fir_real_applicable(h->k_eff, h->interp, h->decim) && h->hist_len >= h->k_eff) {
+        rc = launch_fir_real(d_in, n_in, h->hist[h->cur], h->hist[h->cur ^ 1], h->hist_len, h->taps.data(), h->k_eff,
+                             h->decim, d_out, s);
+    } else {
+        if (h->rscratch_len < n_in + no) {
+            if (h->rscratch) CB_CUDA(cudaFree(h->rscratch));
+            h->rscratch = nullptr;
+            h->rscratch_len = 0;
+            CB_CUDA(cudaMalloc(&h->rscratch, (n_in + no) * sizeof(float2)));
+            h->rscratch_len = n_in + no;
+        }
+        float2 *wide = h->rscratch, *res = h->rscratch + n_in;
+        rc = launch_real_to_complex(d_in, wide, n_in, s);
+        if (rc == CB_OK) rc = fir_launch_segment(h, wide, n_in, h->hist[h->cur], h->hist[h->cur ^ 1], res, s);
+        if (rc == CB_OK) rc = launch_complex_real(res, d_out, no, s);
+    }
+    if (rc) return rc;
+    h->cur ^= 1;
+    return CB_OK;
+}
+
+int cb_fir_run_real(cb_fir *h, const float *in, size_t n_in, float *out, size_t out_cap, size_t *n_out)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    const size_t no = fir_out_len(h, n_in);
+    if (n_out) *n_out = no;
+    if (n_in == 0) return CB_OK;
+    CB_REQUIRE(in && out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_REQUIRE(out_cap >= no, CB_ERR_SIZE, "fir: out_cap %zu < %zu outputs", out_cap, no);
+    CB_CUDA(cudaSetDevice(h->device));
+    int rc = h->pipe.reserve(n_in * sizeof(float), no * sizeof(float));
+    if (rc) return rc;
+    cudaStream_t s = h->pipe.lane[0];
+    CB_CUDA(cudaMemcpyAsync(h->pipe.in[0], in, n_in * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = cb_fir_run_real_dev(h, reinterpret_cast<const float *>(h->pipe.in[0]), n_in, reinterpret_cast<float *>(h->pipe.out[0]),
+                             no, nullptr, s);
+    if (rc) return rc;
+    CB_CUDA(cudaMemcpyAsync(out, h->pipe.out[0], no * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaStreamSynchronize(s));
     return CB_OK;
 }
 

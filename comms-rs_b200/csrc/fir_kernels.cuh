@@ -55,6 +55,12 @@ size_t fir_ols_frames(size_t n, uint32_t ntaps);
 int launch_fir_ols(const float2 *x, size_t n, const float2 *hist_in, float2 *hist_out, uint32_t hist_len, uint32_t ntaps,
                    const float2 *hf, const float2 *tw_fwd, const float2 *tw_inv, float2 *spec, float2 *y, cudaStream_t s);
 
+// Real-input / real-output decimating FIR (fir_real_kernel.cu): x -> Complex(x, 0) -> FIR -> .re -> every D-th, fused.
+// interp = 1, <= 64 taps, D in {2, 4, 5, 8, 10}; hist_in / hist_out are the handle's complex history buffers.
+bool fir_real_applicable(uint32_t ntaps, uint32_t interp, uint32_t decim);
+int launch_fir_real(const float *x, size_t n_in, const float2 *hist_in, float2 *hist_out, uint32_t hist_len,
+                    const float2 *taps_host, uint32_t ntaps, uint32_t decim, float *y, cudaStream_t s);
+
 // taps_dev: ntaps complex taps in device memory (generic path)
 // taps_host: same on the host (fast paths put them in the kernel parameter constant bank)
 // tcplan: NULL = CUDA-core kernels only

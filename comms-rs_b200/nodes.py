@@ -82,6 +82,26 @@ class BatchFirNode(_Handle):
         check(_lib.load().cb_fir_run_dev(self._h, d_in, n_in, d_out, out_cap, C.byref(m), stream))
         return m.value
 
+    def run_real(self, x) -> np.ndarray:
+        """Real samples in, real parts out: Convert2Node -> this filter -> Convert3Node [-> DecimateNode]
+        (examples/fm_radio.rs:98-164) in one call."""
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+        n = _sz()
+        check(_lib.load().cb_fir_out_len(self._h, len(x), C.byref(n)))
+        out = np.empty(n.value, dtype=np.float32)
+        m = _sz()
+        try:
+            check(_lib.load().cb_fir_run_real(self._h, _ptr(x), len(x), _ptr(out), n.value, C.byref(m)))
+        except CbError as e:
+            raise node_error(e) from e
+        return out[: m.value]
+
+    def run_dev_real(self, d_in: int, n_in: int, d_out: int, out_cap: int, stream: int = 0) -> int:
+        """Same on device buffers: n_in floats in, out_cap floats of room; returns the number of outputs."""
+        m = _sz()
+        check(_lib.load().cb_fir_run_real_dev(self._h, d_in, n_in, d_out, out_cap, C.byref(m), stream))
+        return m.value
+
     def run_i16(self, x, scale: float = 8192.0) -> np.ndarray:
         """Host Vec in, interleaved i16 IQ out ([n_out, 2] int16): filter + `(scale * x) as i16`."""
         x = _c32(x)

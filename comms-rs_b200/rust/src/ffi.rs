@@ -3,7 +3,7 @@
 use std::os::raw::{c_char, c_double, c_float, c_int, c_uint, c_void};
 
 macro_rules! opaque { ($($n:ident),*) => { $(#[repr(C)] pub struct $n { _p: [u8; 0] })* } }
-opaque!(cb_stream, cb_buf, cb_fir, cb_mixer, cb_fft, cb_fm, cb_chain, cb_comm);
+opaque!(cb_stream, cb_buf, cb_fir, cb_mixer, cb_fft, cb_fm, cb_chain, cb_comm, cb_timing);
 
 pub const CB_OK: c_int = 0;
 pub const CB_ERR_INVALID_ARG: c_int = 1;
@@ -97,6 +97,15 @@ extern "C" {
     pub fn cb_comm_init(nranks: c_int, rank: c_int, id128: *const c_void, out: *mut *mut cb_comm) -> c_int;
     pub fn cb_comm_destroy(c: *mut cb_comm) -> c_int;
     pub fn cb_gather_segments_dev(c: *mut cb_comm, d_seg: *const f32, n_samples: usize, d_all: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn cb_fir_run_real(h: *mut cb_fir, input: *const f32, n_in: usize, out: *mut f32, out_cap: usize, n_out: *mut usize) -> c_int;
+    pub fn cb_fir_run_real_dev(h: *mut cb_fir, d_in: *const f32, n_in: usize, d_out: *mut f32, out_cap: usize, n_out: *mut usize, stream: *mut c_void) -> c_int;
+    pub fn cb_qfilt_taps_f64(n_taps: u32, alpha: f64, sam_per_sym: u32, taps: *mut f64, n_out: *mut u32) -> c_int;
+    pub fn cb_freq_estimate(samples: *const f64, n: usize, estimate: *mut f64) -> c_int;
+    pub fn cb_freq_estimate_dev(d_samples: *const f64, n: usize, estimate: *mut f64, stream: *mut c_void) -> c_int;
+    pub fn cb_timing_create(n: u32, d: u32, alpha: f64, out: *mut *mut cb_timing) -> c_int;
+    pub fn cb_timing_destroy(h: *mut cb_timing) -> c_int;
+    pub fn cb_timing_push(h: *mut cb_timing, samples: *const f64, n: usize, estimate: *mut f64) -> c_int;
+    pub fn cb_timing_push_dev(h: *mut cb_timing, d_samples: *const f64, n: usize, estimate: *mut f64, stream: *mut c_void) -> c_int;
     pub fn cb_real_to_complex_dev(d_in: *const f32, n: usize, d_out: *mut f32, stream: *mut c_void) -> c_int;
     pub fn cb_complex_real_dev(d_in: *const f32, n: usize, d_out: *mut f32, stream: *mut c_void) -> c_int;
     pub fn cb_rrc_taps(n_taps: u32, sam_per_sym: f64, beta: f64, taps: *mut f32) -> c_int;

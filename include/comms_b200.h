@@ -142,6 +142,12 @@ CB_API int cb_fir_run_dev_i16(cb_fir *h, const float *d_in, size_t n_in, float s
                               size_t out_cap, size_t *n_out, void *stream);
 CB_API int cb_fir_run_i16(cb_fir *h, const float *in, size_t n_in, float scale, int16_t *out, size_t out_cap,
                           size_t *n_out);
+/* Real samples in, real parts out: x -> Complex(x, 0) -> this filter -> .re, i.e. Convert2Node -> BatchFirNode ->
+ * Convert3Node [-> DecimateNode] of examples/fm_radio.rs:98-164 in one call (n_in floats in, *n_out floats out; same
+ * state, sizes and errors as cb_fir_run).  Fused into one kernel for <= 64 taps and decim in {2, 4, 5, 8, 10}. */
+CB_API int cb_fir_run_real(cb_fir *h, const float *in, size_t n_in, float *out, size_t out_cap, size_t *n_out);
+CB_API int cb_fir_run_real_dev(cb_fir *h, const float *d_in, size_t n_in, float *d_out, size_t out_cap, size_t *n_out,
+                               void *stream);
 CB_API int cb_fir_state_len(const cb_fir *h, size_t *nstate);
 CB_API int cb_fir_get_state(cb_fir *h, float *state, size_t nstate);
 CB_API int cb_fir_set_state(cb_fir *h, const float *state, size_t nstate);

@@ -447,6 +447,42 @@ def test_chain_bank_u8_input_fused_convert(cb, oracle, mix, fm, D, n):
                 assert rel_l2(got[c], want) <= FIR_TOL, (c, call)
 
 
+@pytest.mark.parametrize("decim,ntaps", [(5, 63), (10, 63), (2, 64), (4, 17), (8, 33), (5, 1), (3, 63), (1, 40), (5, 100)])
+def test_real_input_fir_matches_oracle(cb, oracle, decim, ntaps):
+    # Convert2Node -> filt2 -> Convert3Node -> dec2 (examples/fm_radio.rs:98-164) as one call: real samples in, real
+    # parts out.  Fused kernel for <= 64 taps and D in {2,4,5,8,10}; the other shapes run widen + complex filter + .re
+    rng = np.random.default_rng(decim * 1000 + ntaps)
+    taps = _lowpass(ntaps) if ntaps > 1 else np.array([0.75], np.complex64)
+    node = cb.BatchFirNode(taps, None, decim=decim)
+    st = np.zeros(len(taps), np.complex64)
+    # batch lengths around the 1024-output tile, odd lengths, a batch shorter than the filter
+    for n in (1024 * decim, 1024 * decim + 1, 7, 26_215, 3 * 1024 * decim - 1, 1, 50_001):
+        x = rng.uniform(-1, 1, n).astype(np.float32)
+        got = node.run_real(x)
+        full, st = oracle.batch_fir(x.astype(np.complex64), taps, st)
+        want = oracle.decimate(full.real.astype(np.float32), decim)
+        assert got.shape == want.shape
+        assert rel_l2(got, want) <= FIR_TOL, (n, rel_l2(got, want))
+    # the carried state is the reference's (Complex(x, 0), newest first)
+    assert node.state.tobytes() == st.tobytes()
+    # device entry with input and output that are only 4-byte aligned (scalar load / store paths)
+    import torch
+
+    n = 3 * 1024 * decim + 5
+    x = rng.uniform(-1, 1, n).astype(np.float32)
+    d_x = torch.zeros(n + 1, dtype=torch.float32, device="cuda")
+    d_x[1:] = torch.from_numpy(x).cuda()
+    no = -(-n // decim)
+    d_y = torch.zeros(no + 1, dtype=torch.float32, device="cuda")
+    ts = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    assert node.run_dev_real(d_x.data_ptr() + 4, n, d_y.data_ptr() + 4, no, ts.cuda_stream) == no
+    torch.cuda.synchronize()
+    full, st = oracle.batch_fir(x.astype(np.complex64), taps, st)
+    assert rel_l2(d_y[1:].cpu().numpy(), oracle.decimate(full.real.astype(np.float32), decim)) <= FIR_TOL
+    assert float(d_y[0]) == 0.0
+
+
 def test_fm_radio_example_graph_on_device(cb, oracle):
     # examples/fm_radio.rs:144-164, the whole shipped graph with every hop on the GPU:
     #   bytes -> ConvertNode -> filt1 -> dec1(5) -> FMDemodNode -> Convert2Node -> filt2 -> Convert3Node -> dec2(5)
@@ -472,9 +508,12 @@ def test_fm_radio_example_graph_on_device(cb, oracle):
         d_iq = torch.from_numpy(iq.reshape(-1)).cuda()
         torch.cuda.synchronize()
         assert front.run_dev_u8(d_iq.data_ptr(), nb, d_fm.data_ptr(), n1, s) == n1
-        cb.real_to_complex_dev(d_fm.data_ptr(), n1, d_c.data_ptr(), s)
-        assert filt2.run_dev(d_c.data_ptr(), n1, d_f2.data_ptr(), n2, s) == n2
-        cb.complex_real_dev(d_f2.data_ptr(), n2, d_audio.data_ptr(), s)
+        if batch == 1:  # the same hops as separate device entries (Convert2Node / Convert3Node glue)
+            cb.real_to_complex_dev(d_fm.data_ptr(), n1, d_c.data_ptr(), s)
+            assert filt2.run_dev(d_c.data_ptr(), n1, d_f2.data_ptr(), n2, s) == n2
+            cb.complex_real_dev(d_f2.data_ptr(), n2, d_audio.data_ptr(), s)
+        else:           # Convert2Node -> filt2 -> Convert3Node -> dec2 as one kernel
+            assert filt2.run_dev_real(d_fm.data_ptr(), n1, d_audio.data_ptr(), n2, s) == n2
         torch.cuda.synchronize()
         x = oracle.u8_to_f32(iq.reshape(-1)).view(np.complex64)
         fm_ref = ref_front.run(x)
