@@ -305,4 +305,28 @@ inline bool rrc_taps(uint32_t n_taps, double sam_per_sym, double beta, std::vect
     return cb_rrc_taps(n_taps, sam_per_sym, beta, reinterpret_cast<float *>(taps.data())) == CB_OK;
 }
 
+// TimingEstimatorNode (src/demodulation/timing_estimator.rs:116-137): Vec<Complex<f64>> in, f64 out
+struct TimingEstimatorNode : Node1<TimingEstimatorNode, std::vector<std::complex<double>>, double> {
+    cb_timing *h = nullptr;
+    bool ok = false;  // false: MathError::InvalidRolloffError (or no device)
+    TimingEstimatorNode(uint32_t n, uint32_t d, double alpha) { ok = cb_timing_create(n, d, alpha, &h) == CB_OK; }
+    ~TimingEstimatorNode() { cb_timing_destroy(h); }
+    TimingEstimatorNode(const TimingEstimatorNode &) = delete;
+    TimingEstimatorNode &operator=(const TimingEstimatorNode &) = delete;
+    Result<double> run(const std::vector<std::complex<double>> &in)
+    {
+        double est = 0.0;
+        int st = cb_timing_push(h, reinterpret_cast<const double *>(in.data()), in.size(), &est);
+        return st ? Result<double>::Err(map_status(st)) : Result<double>::Ok(est);
+    }
+};
+
+// frequency_offset_estimate (src/demodulation/frequency_estimator.rs:27-42)
+inline Result<double> frequency_offset_estimate(const std::vector<std::complex<double>> &samples)
+{
+    double est = 0.0;
+    int st = cb_freq_estimate(reinterpret_cast<const double *>(samples.data()), samples.size(), &est);
+    return st ? Result<double>::Err(map_status(st)) : Result<double>::Ok(est);
+}
+
 }  // namespace comms_b200

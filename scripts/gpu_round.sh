@@ -16,7 +16,7 @@ tail -5 $OUT/${TAG}_tests.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke exit $?" >> $OUT/${TAG}_smoke.log
 tail -2 $OUT/${TAG}_smoke.log
 : > $OUT/${TAG}_bench.jsonl
-for wl in fir64 fir64_real fir1024 fir63d5 fft1024 fft4096 ifft4096 fft16384 fft65536 mixer fm chain chain5 chain5_u8 pulse4 pulse4_i16 poly8x1024 poly8x1024c; do
+for wl in fir64 fir64_real fir1024 fir63d5 fir63d5_real fft1024 fft4096 ifft4096 fft8192 fft16384 fft32768 fft65536 fft262144 fft1048576 freqest timing10x5 mixer fm chain chain5 chain5_u8 pulse4 pulse4_i16 poly8x1024 poly8x1024c; do
   extra="--no-cpu"
   [ "$wl" = "fir64" ] && extra=""
   timeout 600 python bench.py --steps 20 --warmup 3 --workload $wl $extra >> $OUT/${TAG}_bench.jsonl 2>> $OUT/${TAG}_bench.err
