@@ -58,6 +58,8 @@ WORKLOADS = {
     "freqest": ("est", 1 << 27, 16.0, "frequency_offset_estimate (frequency_estimator.rs:27-42) over 2^27 complex-f64 samples per GPU"),
     "timing10x5": ("est", 1 << 27, 16.0, "TimingEstimator(n=10, d=5, alpha=0.5).push (timing_estimator.rs:85-112, 101-tap f64 filter) "
                    "over 2^27 complex-f64 samples per GPU"),
+    "fft1000": ("fft", (1 << 28) // 1000 * 1000, 16.0, "batched 1000-point FFT (chirp-z) over ~2^28 complex-f32 samples per GPU"),
+    "fft48000": ("fft", (1 << 28) // 48000 * 48000, 16.0, "batched 48000-point FFT (chirp-z) over ~2^28 complex-f32 samples per GPU"),
     "ifft4096": ("fft", 1 << 28, 16.0, "batched 4096-point IFFT over 2^28 complex-f32 samples per GPU"),
     "mixer": ("mixer", 1 << 28, 16.0, "MixerNode (src/mixer.rs:73-84): y = x e^{j phi}, f64 phase, over 2^28 complex-f32 samples per GPU"),
     "fm": ("fm", 1 << 28, 12.0, "FMDemodNode (src/modulation/analog.rs:22-34) over 2^28 complex-f32 samples per GPU"),
@@ -300,7 +302,7 @@ class Job:
             self.node = cb.FFTBatchNode(N, workload.startswith("ifft"))
             self.y = torch.empty(n, dtype=torch.complex64, device="cuda")
             self.out_bytes = 8 * n
-            self.kernels_per_step = 2 if (N > 16384 and not (N == 65536 and os.environ.get("COMMS_B200_FFT_PATH", "rows") in ("rows", "cluster", "cluster1", "cluster2", "cluster16"))) else 1
+            self.kernels_per_step = 2 if os.environ.get("COMMS_B200_FFT_PATH") in ("fourstep", "rows2", "twopass") and N > 16384 else 1
             self.step = lambda: self.node.run_dev(self.x.data_ptr(), n, self.y.data_ptr(), self.stream)
             self.host_call = lambda hin, hout: cb.load().cb_fft_run(self.node._h, hin, n, hout)
         elif self.kind == "firreal":

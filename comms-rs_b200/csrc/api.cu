@@ -1087,7 +1087,9 @@ static int bluestein_setup(cb_fft *h, size_t n, int inverse)
     CB_CUDA(cudaMemcpy(h->chirp, w.data(), n * sizeof(float2), cudaMemcpyHostToDevice));
     CB_CUDA(cudaMalloc(&h->bspec, m * sizeof(float2)));
     CB_CUDA(cudaMemcpy(h->bspec, bs.data(), m * sizeof(float2), cudaMemcpyHostToDevice));
-    h->bl_frames = ((size_t)32 << 20) / (m * sizeof(float2));  // work buffers sized to stay in L2 between the steps
+    // work buffers: up to 16384 points one L2-sized buffer of spectra (the fused two-kernel form); beyond, the five-launch
+    // form around the two-step transforms wants long batches (their persistent kernels ramp up and down per launch)
+    h->bl_frames = ((size_t)(m <= 16384 ? 32 : 256) << 20) / (m * sizeof(float2));
     if (h->bl_frames < 1) h->bl_frames = 1;
     CB_CUDA(cudaMalloc(&h->bufa, h->bl_frames * m * sizeof(float2)));
     CB_CUDA(cudaMalloc(&h->bufb, h->bl_frames * m * sizeof(float2)));
@@ -1287,8 +1289,17 @@ static int fft_exec(cb_fft *h, const float2 *in, float2 *out, size_t nframes, cu
         return launch_fft(h->plan, in, out, nframes, s);
     }
     const uint32_t N = (uint32_t)h->plan.n, M = (uint32_t)h->bl_m;
+    // COMMS_B200_FFT_CHIRPZ=split: the five-launch form (element-wise kernels around the sub-plans) for every size
+    static const bool bl_split = [] { const char *e = getenv("COMMS_B200_FFT_CHIRPZ"); return e && strcmp(e, "split") == 0; }();
     for (size_t done = 0; done < nframes;) {
         const size_t g = nframes - done < h->bl_frames ? nframes - done : h->bl_frames;
+        if (M <= 16384 && h->sub_f->tw16 && h->sub_i->tw16 && !bl_split) {  // two kernels per group, spectra in bufa
+            int rc = launch_bluestein_fused(in + done * N, h->chirp, h->bspec, h->bufa, out + done * N, N, h->sub_f->plan.log2n,
+                                            h->sub_f->tw16, h->sub_i->tw16, g, s);
+            if (rc) return rc;
+            done += g;
+            continue;
+        }
         int rc = launch_bluestein_pre(in + done * N, h->chirp, h->bufa, N, M, g, s);
         if (!rc) rc = fft_exec(h->sub_f, h->bufa, h->bufb, g, s);
         if (!rc) rc = launch_bluestein_mul(h->bufb, h->bspec, M, g, s);

@@ -365,6 +365,86 @@ bluestein_post_kernel(const float2 *__restrict__ c, const float2 *__restrict__ c
     }
 }
 
+// Chirp-z with M <= 16384: the element-wise steps folded into the first-pass loads and last-pass stores of the two
+// M-point transforms (fft2_frames_kernel's passes): stage 0 = chirp, zero fill, forward transform, product with B;
+// stage 1 = inverse transform, chirp, 1/M, first N outputs.  The spectra make one round trip through a scratch that the
+// caller keeps L2-sized, so HBM carries 8 N bytes in and 8 N bytes out per frame.
+struct BlArgs {
+    const float2 *x, *chirp, *bspec;
+    float2 *spec, *out;
+    unsigned N;
+    size_t nframes;
+    float scale;
+};
+
+template <int LOG2M, int STAGE>
+__global__ void __launch_bounds__(Fft2Cfg<LOG2M>::THREADS, Fft2Cfg<LOG2M>::MINB)
+bluestein_frames_kernel(const __grid_constant__ BlArgs a, const float2 *__restrict__ tw)
+{
+    using PL = fft2::Plan<LOG2M>;
+    using CF = Fft2Cfg<LOG2M>;
+    extern __shared__ __align__(16) float2 fsm[];
+    const int f = threadIdx.x / PL::T, j = threadIdx.x % PL::T;
+    const size_t frame = (size_t)blockIdx.x * CF::FPB + f;
+    const bool live = frame < a.nframes;
+    float2 *b0 = fsm + f * PL::PADN;
+    if constexpr (STAGE == 0) {
+        const float2 *src = a.x + frame * a.N;
+        float2 *dst = a.spec + frame * PL::N;
+        auto gld = [&](int i) {
+            return (live && i < (int)a.N) ? cmul(ldg_stream2(src + i), __ldg(a.chirp + i)) : make_float2(0.f, 0.f);
+        };
+        auto gst = [&](int i, float2 v) {
+            if (live) dst[i] = cmul(v, __ldg(a.bspec + i));
+        };
+        fft2_passes<LOG2M, false, 0>(j, tw, gld, gst, b0, b0);
+    } else {
+        const float2 *src = a.spec + frame * PL::N;
+        float2 *dst = a.out + frame * a.N;
+        auto gld = [&](int i) { return live ? src[i] : make_float2(0.f, 0.f); };
+        auto gst = [&](int i, float2 v) {
+            if (live && i < (int)a.N) {
+                const float2 r = cmul(v, __ldg(a.chirp + i));
+                stg_stream2(dst + i, make_float2(r.x * a.scale, r.y * a.scale));
+            }
+        };
+        fft2_passes<LOG2M, true, 0>(j, tw, gld, gst, b0, b0);
+    }
+}
+
+template <int LOG2M>
+static int launch_bluestein_fused_m(const BlArgs &a, const float2 *tw_fwd, const float2 *tw_inv, cudaStream_t s)
+{
+    using CF = Fft2Cfg<LOG2M>;
+    auto k0 = bluestein_frames_kernel<LOG2M, 0>;
+    auto k1 = bluestein_frames_kernel<LOG2M, 1>;
+    CB_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM));
+    CB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM));
+    const unsigned grid = (unsigned)ceil_div(a.nframes, (size_t)CF::FPB);
+    k0<<<grid, CF::THREADS, CF::SMEM, s>>>(a, tw_fwd);
+    count_launch();
+    k1<<<grid, CF::THREADS, CF::SMEM, s>>>(a, tw_inv);
+    count_launch();
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+
+int launch_bluestein_fused(const float2 *x, const float2 *chirp, const float2 *bspec, float2 *spec, float2 *out, uint32_t N,
+                           int log2m, const float2 *tw_fwd, const float2 *tw_inv, size_t frames, cudaStream_t s)
+{
+    BlArgs a{x, chirp, bspec, spec, out, N, frames, 1.0f / (float)(1u << log2m)};
+    switch (log2m) {
+    case 8: return launch_bluestein_fused_m<8>(a, tw_fwd, tw_inv, s);
+    case 9: return launch_bluestein_fused_m<9>(a, tw_fwd, tw_inv, s);
+    case 10: return launch_bluestein_fused_m<10>(a, tw_fwd, tw_inv, s);
+    case 11: return launch_bluestein_fused_m<11>(a, tw_fwd, tw_inv, s);
+    case 12: return launch_bluestein_fused_m<12>(a, tw_fwd, tw_inv, s);
+    case 13: return launch_bluestein_fused_m<13>(a, tw_fwd, tw_inv, s);
+    case 14: return launch_bluestein_fused_m<14>(a, tw_fwd, tw_inv, s);
+    default: set_error("fft: no fused chirp-z kernel for 2^%d", log2m); return CB_ERR_UNSUPPORTED;
+    }
+}
+
 int launch_bluestein_pre(const float2 *x, const float2 *chirp, float2 *a, uint32_t N, uint32_t M, size_t frames, cudaStream_t s)
 {
     const unsigned nseg = (M + 1023) / 1024;

@@ -36,6 +36,8 @@ int launch_fft65536_cluster(const float2 *in, float2 *out, const float2 *twN, si
 int launch_fft65536_rows(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s);
 bool fft_big_applicable(const FftPlanDev &p, size_t nframes);
 int launch_fft_big(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s);
+int launch_bluestein_fused(const float2 *x, const float2 *chirp, const float2 *bspec, float2 *spec, float2 *out, uint32_t N,
+                           int log2m, const float2 *tw_fwd, const float2 *tw_inv, size_t frames, cudaStream_t s);
 int launch_bluestein_pre(const float2 *x, const float2 *chirp, float2 *a, uint32_t N, uint32_t M, size_t frames, cudaStream_t s);
 int launch_bluestein_mul(float2 *spec, const float2 *bspec, uint32_t M, size_t frames, cudaStream_t s);
 int launch_bluestein_post(const float2 *c, const float2 *chirp, float2 *out, uint32_t N, uint32_t M, size_t frames,

@@ -180,6 +180,31 @@ def test_fft_direct_and_chirpz_agree(cb, monkeypatch):
     assert rel_l2(a, b) <= 2e-6
 
 
+@pytest.mark.parametrize("n", [129, 1000, 4097, 8191])
+def test_fft_chirpz_fused_and_split_forms_agree(cb, oracle, n):
+    # M <= 16384: chirp / product / scaling folded into the two transforms; the five-launch form is the same algebra.
+    # (The choice is read once per process, so the split form runs in a child interpreter.)
+    import os
+    import subprocess
+    import sys
+    import tempfile
+
+    rng = np.random.default_rng(n)
+    x = rnd_c32(rng, 7 * n)
+    a = cb.FFTBatchNode(n, True).run(x)
+    assert rel_l2(a, oracle.fft(x, n, True)) <= 1e-4
+    with tempfile.TemporaryDirectory() as td:
+        np.save(os.path.join(td, "x.npy"), x)
+        code = ("import sys, numpy as np; sys.path.insert(0, %r); import comms_rs_b200 as cb;"
+                "x = np.load(%r); np.save(%r, cb.FFTBatchNode(%d, True).run(x))"
+                % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(td, "x.npy"),
+                   os.path.join(td, "y.npy"), n))
+        env = dict(os.environ, COMMS_B200_FFT_CHIRPZ="split")
+        subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=240)
+        b = np.load(os.path.join(td, "y.npy"))
+    assert rel_l2(a, b) <= 2e-6
+
+
 @pytest.mark.timeout(300)
 def test_fft65536_two_handles_concurrently(cb, oracle):
     # two fused 65536-point kernels in flight on different streams share the SMs; the ticket-ordered work
