@@ -376,3 +376,63 @@ impl GpuBatchFirDevNode {
         Ok(out)
     }
 }
+
+/// The second stage of `examples/fm_radio.rs` (`Convert2Node -> filt2 -> Convert3Node -> dec2`, :98-164) as one node:
+/// real samples in, the real parts of the filtered and decimated stream out.  In the example it replaces the four
+/// nodes between `fm` and `audio`; the ports keep the types of the outer two (`Vec<f32>` in, `Vec<f32>` out).
+#[derive(Node)]
+#[pass_by_ref]
+pub struct GpuRealFirDecimNode {
+    pub input: NodeReceiver<Vec<f32>>,
+    fir: Fir,
+    pub output: NodeSender<Vec<f32>>,
+}
+
+impl GpuRealFirDecimNode {
+    pub fn new(taps: Vec<C32>, state: Option<Vec<C32>>, dec_rate: u32) -> Self {
+        GpuRealFirDecimNode { fir: fir_new(&taps, state.as_deref(), dec_rate.max(1), 1), input: Default::default(), output: Default::default() }
+    }
+    pub fn run(&mut self, input: &[f32]) -> Result<Vec<f32>, NodeError> {
+        let mut n_out = 0usize;
+        check(unsafe { ffi::cb_fir_out_len(self.fir.0, input.len(), &mut n_out) })?;
+        let mut out: Vec<f32> = Vec::with_capacity(n_out);
+        check(unsafe { ffi::cb_fir_run_real(self.fir.0, input.as_ptr(), input.len(), out.as_mut_ptr(), n_out, &mut n_out) })?;
+        unsafe { out.set_len(n_out) };
+        Ok(out)
+    }
+}
+
+handle!(Timing, ffi::cb_timing, ffi::cb_timing_destroy);
+
+/// Drop-in for `TimingEstimatorNode` (src/demodulation/timing_estimator.rs:116-137).
+#[derive(Node)]
+#[pass_by_ref]
+pub struct GpuTimingEstimatorNode {
+    pub input: NodeReceiver<Vec<num::Complex<f64>>>,
+    est: Timing,
+    pub output: NodeSender<f64>,
+}
+
+impl GpuTimingEstimatorNode {
+    pub fn new(n: u32, d: u32, alpha: f64) -> Result<Self, comms_rs::util::MathError> {
+        let mut h = ptr::null_mut();
+        let st = unsafe { ffi::cb_timing_create(n, d, alpha, &mut h) };
+        if st == ffi::CB_ERR_INVALID_ARG && !(0.0..=1.0).contains(&alpha) {
+            return Err(comms_rs::util::MathError::InvalidRolloffError);
+        }
+        assert_eq!(st, ffi::CB_OK, "cb_timing_create failed");
+        Ok(GpuTimingEstimatorNode { est: Timing(h), input: Default::default(), output: Default::default() })
+    }
+    pub fn run(&mut self, input: &[num::Complex<f64>]) -> Result<f64, NodeError> {
+        let mut est = 0.0f64;
+        check(unsafe { ffi::cb_timing_push(self.est.0, input.as_ptr() as *const f64, input.len(), &mut est) })?;
+        Ok(est)
+    }
+}
+
+/// Drop-in for `frequency_offset_estimate` (src/demodulation/frequency_estimator.rs:27-42).
+pub fn frequency_offset_estimate(samples: &[num::Complex<f64>]) -> Result<f64, NodeError> {
+    let mut est = 0.0f64;
+    check(unsafe { ffi::cb_freq_estimate(samples.as_ptr() as *const f64, samples.len(), &mut est) })?;
+    Ok(est)
+}
