@@ -86,6 +86,18 @@ def test_rrc_taps_host_entry(cb, oracle):
             cb.rrc_taps(8, 4.0, bad)
 
 
+def test_qfilt_taps_host_entry(cb, oracle):
+    # cb_qfilt_taps_f64 restates qfilt_taps (src/util/math.rs:307-342) on the host side of the C ABI (no device): the
+    # oracle bit for bit, including the L'Hospital branch (|2 alpha t| == 1) and the even -> odd length rule
+    for n, alpha, sps in [(21, 0.25, 2), (101, 0.5, 10), (20, 0.25, 2), (33, 0.234, 3), (9, 1.0, 2), (5, 0.0, 4), (65, 0.5, 4),
+                          (1, 0.3, 2)]:
+        a, b = cb.qfilt_taps(n, alpha, sps), oracle.qfilt_taps(n, alpha, sps)
+        assert len(a) == (n if n % 2 else n + 1) and a.tobytes() == np.asarray(b, np.float64).tobytes()
+    for bad in (-0.1, 1.5):
+        with pytest.raises(ValueError):
+            cb.qfilt_taps(9, bad, 2)
+
+
 def test_product_never_touches_the_oracle():
     # only tests/, __graft_entry__.smoke() and bench.py's CPU legs may use oracle/
     pkg = os.path.join(ROOT, "comms-rs_b200")
