@@ -4,6 +4,14 @@ TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and
 bench.py's cpu_baseline / --impl reference legs, never from the product
 package.  Each wrapper keeps the name of the reference item it restates; the
 file:line citations live beside the C functions.
+
+Restated here in numpy rather than in oracle.c (f64 glue around the C batch_fir):
+frequency_offset_estimate and TimingEstimator (src/demodulation), pinned by the
+reference's own recovery tests (tests/test_oracle_golden.py::test_*_reference_kat;
+the reference draws its symbols from rand's SmallRng, not reproducible here, so the
+pin is the statistic, not a vector).  fft(): lengths that are neither a power of two
+nor <= 4200 are evaluated through numpy's f64 transform (same definition, pinned to
+the C direct sum at n = 1201).
 """
 from __future__ import annotations
 
