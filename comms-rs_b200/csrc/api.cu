@@ -1767,8 +1767,8 @@ int cb_timing_create(uint32_t n, uint32_t d, double alpha, cb_timing **out)
 {
     CB_REQUIRE(out, CB_ERR_INVALID_ARG, "out is NULL");
     CB_REQUIRE(n >= 1, CB_ERR_INVALID_ARG, "timing estimator: samples per symbol must be >= 1");
-    CB_REQUIRE((uint64_t)2 * n * d + 1 <= 8193, CB_ERR_UNSUPPORTED,
-               "timing estimator: filter length 2*n*d+1 = %llu > 8193 is not provided", (unsigned long long)2 * n * d + 1);
+    CB_REQUIRE((uint64_t)2 * n * d + 1 <= 4097, CB_ERR_UNSUPPORTED,
+               "timing estimator: filter length 2*n*d+1 = %llu > 4097 is not provided", (unsigned long long)2 * n * d + 1);
     int rc = ensure_device();
     if (rc) return rc;
     std::vector<double> taps((size_t)2 * n * d + 2);

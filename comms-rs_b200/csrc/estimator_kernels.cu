@@ -84,7 +84,8 @@ static TimingGeo timing_geo(unsigned ntaps)
     unsigned q = (TILE + g.h4) / 4;  // h4 and TILE are multiples of four
     while (q % 8 != 2) ++q;
     g.pitch = q;
-    g.smem = (size_t)g.ntaps4 * sizeof(double) + (size_t)4 * g.pitch * sizeof(double2);
+    // taps, the de-interleaved qin tile, and din = x r for the same samples (linear; read once per output)
+    g.smem = (size_t)g.ntaps4 * sizeof(double) + (size_t)4 * g.pitch * sizeof(double2) + (size_t)(TILE + g.h4) * sizeof(double2);
     return g;
 }
 
@@ -97,6 +98,7 @@ timing_partial_kernel(const double2 *__restrict__ x, size_t n, const double *__r
     __shared__ double2 red[NT / 32];
     double *tsm = reinterpret_cast<double *>(esm);
     double2 *qsm = reinterpret_cast<double2 *>(esm + (size_t)ntaps4 * sizeof(double));
+    double2 *dsm = qsm + 4 * (size_t)pitch;  // din[i0 - h4 + e] = x r
     const double pi = 3.14159265358979323846;
     for (unsigned k = threadIdx.x; k < ntaps4; k += NT) tsm[k] = k < ntaps ? taps[k] : 0.0;
     double2 acc = make_double2(0.0, 0.0);
@@ -107,14 +109,16 @@ timing_partial_kernel(const double2 *__restrict__ x, size_t n, const double *__r
         __syncthreads();  // the previous tile's reads are done (and the taps are in)
         for (unsigned e = threadIdx.x; e < TILE + h4; e += NT) {
             const long long m = i0 - (long long)h4 + e;
-            double2 q = make_double2(0.0, 0.0);
+            double2 q = make_double2(0.0, 0.0), d = q;
             if (e >= lead && m >= 0 && m < (long long)n) {
                 double sn, cs;
                 sincos(-pi * (double)m / sps, &sn, &cs);  // r = e^{-j pi m / N}, the reference's operation order
-                const double2 s = x[m];
-                q = cmul64(make_double2(s.x, -s.y), make_double2(cs, sn));
+                const double2 s = x[m], r = make_double2(cs, sn);
+                q = cmul64(make_double2(s.x, -s.y), r);
+                d = cmul64(s, r);
             }
             qsm[(e & 3) * pitch + (e >> 2)] = q;
+            dsm[e] = d;
         }
         __syncthreads();
         // window W[w + 3] = L[base + w], w = -3 .. 3, base = h4 + 4 t - 4 j for tap group j
@@ -157,9 +161,7 @@ timing_partial_kernel(const double2 *__restrict__ x, size_t n, const double *__r
             const long long i = i0 + 4 * t + u;
             const long long m = i - (long long)nd;  // dout[i] = din[i - ND]
             if (i < (long long)n && m >= 0) {
-                double sn, cs;
-                sincos(-pi * (double)m / sps, &sn, &cs);
-                const double2 d = cmul64(x[m], make_double2(cs, sn));
+                const double2 d = dsm[h4 + 4 * t + u - nd];  // nd <= halo: inside the tile's look-back
                 const double2 p = cmul64(y[u], d);
                 acc.x += p.x;
                 acc.y += p.y;

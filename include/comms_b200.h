@@ -275,7 +275,7 @@ CB_API int cb_quantize_i16_dev(const float *d_in, size_t nfloats, float scale, i
  *   arg(sum_{i<n-1} x[i+1] conj(x[i])); n < 2 gives 0.
  * cb_timing_*: TimingEstimator::new / push (src/demodulation/timing_estimator.rs:43-58, 85-112), result in
  *   samples; alpha outside [0, 1] -> CB_ERR_INVALID_ARG (MathError::InvalidRolloffError); the internal filter
- *   length 2*n*d+1 is limited to 8193 (CB_ERR_UNSUPPORTED beyond).
+ *   length 2*n*d+1 is limited to 4097 (CB_ERR_UNSUPPORTED beyond).
  * cb_qfilt_taps_f64: qfilt_taps (src/util/math.rs:307-342); taps must hold n_taps + 1 doubles (an even n_taps is
  *   incremented by one); *n_out receives the count written. */
 typedef struct cb_timing cb_timing;

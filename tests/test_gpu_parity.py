@@ -569,6 +569,17 @@ def test_timing_estimator_matches_oracle(cb, oracle, n, d, alpha, nsym, drop):
         cb.TimingEstimator(n, d, 1.5)
 
 
+def test_timing_estimator_longest_filter(cb, oracle):
+    # 2 N D + 1 = 4097 taps: the largest shared-memory tile; one more symbol of delay is refused
+    n, d, alpha = 8, 256, 0.3
+    rng = np.random.default_rng(4097)
+    x = _shaped_qpsk_f64(oracle, rng, 2000, n, 10 * n + 1, alpha)
+    want = oracle.TimingEstimator(n, d, alpha).push(x)
+    assert abs(cb.TimingEstimator(n, d, alpha).push(x) - want) < 1e-9
+    with pytest.raises(cb.CbError):
+        cb.TimingEstimator(n, d + 1, alpha)
+
+
 def test_frequency_estimator_matches_oracle(cb, oracle):
     # frequency_offset_estimate (src/demodulation/frequency_estimator.rs:27-42) and its test (:56-100)
     rng = np.random.default_rng(7)
