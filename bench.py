@@ -44,6 +44,9 @@ WORKLOADS = {
     "fir63d5": ("firdec", 1 << 28, 9.6, "63-tap real-valued FIR + DecimateNode(5) (fm_radio.rs filt1 -> dec1) fused, one 2^28-sample stream per GPU"),
     "fir63d5_real": ("firreal", 1 << 28, 4.8, "fm_radio second stage (fm_radio.rs:98-164): real f32 samples -> Complex(x,0) -> 63-tap FIR -> .re -> "
                      "DecimateNode(5), fused, one 2^28-sample real stream per GPU"),
+    "fm_radio": ("graph", 1 << 28, 2.16, "examples/fm_radio.rs end to end, one stream per GPU: u8 IQ -> ConvertNode -> filt1 (63 taps) -> /5 -> "
+                 "FMDemodNode -> Convert2Node -> filt2 (63 taps) -> Convert3Node -> /5 -> f32 audio; two kernels "
+                 "(fused byte front end, fused real second stage), 2^28 IQ samples per step"),
     "fft1024": ("fft", 1 << 28, 16.0, "batched 1024-point FFT over 2^28 complex-f32 samples per GPU"),
     "fft2048": ("fft", 1 << 28, 16.0, "batched 2048-point FFT over 2^28 complex-f32 samples per GPU"),
     "fft16384": ("fft", 1 << 28, 16.0, "batched 16384-point FFT over 2^28 complex-f32 samples per GPU"),
@@ -200,6 +203,16 @@ def cpu_rate(workload, samples, threads):
             xr = x.view(np.float32)[:per].astype(np.complex64)  # Convert2Node
             jobs.append(lambda xr=xr, t=t: oracle.decimate(
                 oracle.batch_fir(xr, t, np.zeros(63, np.complex64), literal=True, native=True)[0].real.copy(), 5))
+        elif kind == "graph":
+            t = fm_radio_lowpass()
+            b8 = np.clip(x.view(np.float32) * 127.5 + 127.5, 0, 255).astype(np.uint8)
+
+            def whole(b8=b8, t=t):
+                z = oracle.u8_to_f32(b8).view(np.complex64)                                  # ConvertNode
+                fm = oracle.FmChain(0.0, 0.0, t, 5, do_mix=False, do_fm=True, native=True).run(z)  # filt1, dec1, fm
+                f2 = oracle.batch_fir(fm.astype(np.complex64), t, np.zeros(63, np.complex64), literal=True, native=True)[0]
+                return oracle.decimate(f2.real.copy(), 5)                                   # Convert3Node, dec2
+            jobs.append(whole)
         elif kind == "est":
             x = x.astype(np.complex128)
             if workload == "freqest":
@@ -236,7 +249,7 @@ def run_reference(args, rank):
         return
     threads = os.cpu_count() or 1
     kind, _, _, desc = WORKLOADS[args.workload]
-    rate1 = {"fir": 8e6, "fft": 30e6, "chain": 20e6, "interp": 2e6, "mixer": 30e6, "fm": 60e6, "firdec": 8e6, "est": 3e6, "firreal": 8e6}[kind]
+    rate1 = {"fir": 8e6, "fft": 30e6, "chain": 20e6, "interp": 2e6, "mixer": 30e6, "fm": 60e6, "firdec": 8e6, "est": 3e6, "firreal": 8e6, "graph": 8e6}[kind]
     if args.workload.startswith("poly8x1024"):
         rate1 = 1e4
     per_thread = int(min(max(150.0 * rate1 / (args.steps + args.warmup), 1 << 12), 1 << 23))
@@ -315,6 +328,40 @@ class Job:
             self.kernels_per_step = 1  # + the 128-sample history update
             self.step = lambda: self.node.run_dev_real(self.x.data_ptr(), n, self.y.data_ptr(), no, self.stream)
             self.host_call = lambda hin, hout: cb.load().cb_fir_run_real(self.node._h, hin, n, hout, no, None)
+        elif self.kind == "graph":
+            taps = fm_radio_lowpass()
+            self.front = cb.ChainBank(1, taps, 5, dphase=None, with_fm=True)
+            self.back = cb.BatchFirNode(taps, None, decim=5)
+            n1 = -(-n // 5)
+            n2 = -(-n1 // 5)
+            self.x8 = (torch.view_as_real(self.x) * 127.5 + 127.5).clamp_(0, 255).to(torch.uint8).contiguous()
+            self.mid = torch.empty(n1, dtype=torch.float32, device="cuda")
+            self.y = torch.empty(n2, dtype=torch.float32, device="cuda")
+            self.in_bytes_override = 2 * n
+            self.out_bytes = 4 * n2
+            self.kernels_per_step = 1  # roofline over the whole step (two kernels + the 128-sample history update)
+
+            def step():
+                self.front.run_dev_u8(self.x8.data_ptr(), n, self.mid.data_ptr(), n1, self.stream)
+                self.back.run_dev_real(self.mid.data_ptr(), n1, self.y.data_ptr(), n2, self.stream)
+            self.step = step
+            # end to end: host bytes in, host audio out, the two GPU nodes chained through device buffers (the DeviceBuf
+            # edge of INTEGRATION.md section 3) -- only the graph's outer edges cross PCIe
+            self.x8_e2e = torch.empty_like(self.x8)
+            self.e2e_api = ("cb_copy_h2d_async -> cb_chain_run_u8_dev -> cb_fir_run_real_dev -> cb_copy_d2h_async on one stream, "
+                            "pinned host buffers: nodes chained through device buffers, only the graph's outer edges cross PCIe")
+
+            def host_call(hin, hout):
+                lib = cb.load()
+                rc = lib.cb_copy_h2d_async(self.x8_e2e.data_ptr(), hin, 2 * n, self.stream)
+                if rc:
+                    return rc
+                self.front.run_dev_u8(self.x8_e2e.data_ptr(), n, self.mid.data_ptr(), n1, self.stream)
+                self.back.run_dev_real(self.mid.data_ptr(), n1, self.y.data_ptr(), n2, self.stream)
+                rc = lib.cb_copy_d2h_async(hout, self.y.data_ptr(), 4 * n2, self.stream)
+                self.tstream.synchronize()
+                return rc
+            self.host_call = host_call
         elif self.kind == "est":
             import ctypes as C
             self.x = self.x.to(torch.complex128)  # the same synthetic stream, widened once outside the timed region
@@ -461,7 +508,7 @@ def run_b200(args, rank, world, local_rank):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * job.n * k_e2e / float(tt.item()) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": job.in_bytes, "d2h_bytes_per_step": job.out_bytes, "steps": k_e2e,
-               "api": "host-pointer C-ABI call, pinned buffers, 2-lane chunked H2D/kernel/D2H pipeline"}
+               "api": getattr(job, "e2e_api", "host-pointer C-ABI call, pinned buffers, 2-lane chunked H2D/kernel/D2H pipeline")}
         lib.cb_buf_release(hin)
         lib.cb_buf_release(hout)
     sampler.stop()
@@ -502,7 +549,7 @@ def run_b200(args, rank, world, local_rank):
         }
         if world == 1 and not args.no_cpu:
             kind = job.kind
-            sample = {"fir": 1 << 26, "fft": 1 << 27, "chain": 1 << 26, "interp": 1 << 23, "mixer": 1 << 26, "fm": 1 << 27, "firdec": 1 << 26, "est": 1 << 24, "firreal": 1 << 26}[kind]
+            sample = {"fir": 1 << 26, "fft": 1 << 27, "chain": 1 << 26, "interp": 1 << 23, "mixer": 1 << 26, "fm": 1 << 27, "firdec": 1 << 26, "est": 1 << 24, "firreal": 1 << 26, "graph": 1 << 26}[kind]
             if args.workload == "timing10x5":
                 sample = 1 << 22
             if args.workload.startswith("poly8x1024"):
