@@ -388,10 +388,11 @@ static int launch_chain2(const ChainArgs &args, const ChainTaps &taps, size_t ch
 // the first tile of a channel needs no special path; chunks past n_in are simply not copied.
 // Numerics: identical algebra, different rounding points (rel-L2 ~2e-7 vs the sequential f32 form).
 // ============================================================================
-// U8: the input is the RTL-SDR byte stream of examples/fm_radio.rs (u8 I, u8 Q); ConvertNode's
-// (x - 127.5) / 127.5 (fm_radio.rs:84-87) is applied on the way from the raw TMA stage into the f32 span through
-// a 256-entry table of exactly rounded quotients, so the filter sees the same f32 values as after a separate
-// conversion pass while HBM carries 2 instead of 8 bytes per input sample.
+// U8: the input is the RTL-SDR byte stream of examples/fm_radio.rs (u8 I, u8 Q).  ConvertNode's
+// (x - 127.5) / 127.5 (fm_radio.rs:84-87) is split by linearity: the span holds b - 127.5 (exact: a byte permute
+// that splices the exponent of 2^23 above the byte, and two packed adds -- no table look-ups, no I2F) and the launch
+// scales the taps by 1 / 127.5, so the outputs differ from convert-then-filter only in rounding (~1e-7 relative)
+// while HBM carries 2 instead of 8 bytes per input sample.  The carried history stays ConvertNode's exact values.
 template <bool MIX, bool FM, bool U8, int D, int R, int NT, int NSTAGE, int MINB>
 __global__ void __launch_bounds__(NT + 32, MINB)
 chain3_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ ChainTaps taps, const unsigned tiles_per_ch,
@@ -414,7 +415,6 @@ chain3_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
     unsigned char *stages = c3sm;                                     // ring of raw spans (f32, or bytes when U8)
     unsigned char *span8 = c3sm + NSTAGE * RAWSTAGE;                  // U8: the one converted f32 span
     constexpr int RING = U8 ? NSTAGE * RAWSTAGE + STAGE + 1024 : NSTAGE * STAGE;
-    float *lut = reinterpret_cast<float *>(c3sm + NSTAGE * RAWSTAGE + STAGE);  // U8: (b - 127.5) / 127.5
     float2 *tsm = reinterpret_cast<float2 *>(c3sm + RING);            // tsm[k + 1] = h'[k], tsm[0] = tsm[65] = 0
     float2 *cst = tsm + KP + 2;                                       // e^{j r D dphi} (r < R), then e^{-j D dphi}
     float2 *basep = cst + 8;                                          // per stage: e^{j (phi0 + m0 D dphi)}
@@ -435,8 +435,6 @@ chain3_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
     // stage memory starts out finite (chunks past the end of a batch are never copied)
     for (int i = tid; i < (U8 ? NSTAGE * RAWSTAGE + STAGE : NSTAGE * STAGE) / 16; i += NT + 32)
         reinterpret_cast<uint4 *>(stages)[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (U8)
-        for (int i = tid; i < 256; i += NT + 32) lut[i] = __fdiv_rn(__fsub_rn((float)i, 127.5f), 127.5f);
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; ++i) mbar_init(&full[i], 1);
         fence_mbar_init();
@@ -522,11 +520,19 @@ chain3_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
                     const int p = tid + it * NT;
                     const long long g = g_base + 2 * p;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (g < 0) {
+                    if (g < 0) {  // carried history is in the converted domain: back to b - 127.5
                         v = *reinterpret_cast<const float4 *>(hc + g);
+                        v = make_float4(v.x * 127.5f, v.y * 127.5f, v.z * 127.5f, v.w * 127.5f);
                     } else if (g < (long long)a.n_in && p < SPAN / 2) {
+                        // byte b -> 2^23 + b (exponent byte spliced in by PRMT) -> b -> b - 127.5, every step exact
                         const uint32_t w = raw[p];
-                        v = make_float4(lut[w & 255u], lut[(w >> 8) & 255u], lut[(w >> 16) & 255u], lut[w >> 24]);
+                        const float2 big = make_float2(-8388608.f, -8388608.f), half = make_float2(-127.5f, -127.5f);
+                        const float2 s0 = make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440)),
+                                                      __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7441)));
+                        const float2 s1 = make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7442)),
+                                                      __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7443)));
+                        const float2 c0 = __fadd2_rn(__fadd2_rn(s0, big), half), c1 = __fadd2_rn(__fadd2_rn(s1, big), half);
+                        v = make_float4(c0.x, c0.y, c1.x, c1.y);
                     }
                     if (p < SPAN / 2) reinterpret_cast<float4 *>(span8)[p] = v;
                 }
@@ -630,8 +636,8 @@ chain3_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
                 if (g < 0) {
                     v = hc[H + g];
                 } else if (U8) {
-                    const unsigned char *b = a.x8 + 2 * (c * a.n_in + g);
-                    v = make_float2(lut[b[0]], lut[b[1]]);
+                    const unsigned char *b = a.x8 + 2 * (c * a.n_in + g);  // the state keeps ConvertNode's exact values
+                    v = make_float2(__fdiv_rn(__fsub_rn((float)b[0], 127.5f), 127.5f), __fdiv_rn(__fsub_rn((float)b[1], 127.5f), 127.5f));
                 } else {
                     v = a.x[c * a.n_in + g];
                 }
@@ -668,6 +674,10 @@ static int launch_chain3(const ChainArgs &args, const ChainTaps &taps, size_t ch
     constexpr int SMEM = (U8 ? NSTAGE * RAWSPAN + F32SPAN + 1024 : NSTAGE * F32SPAN) + (66 + 8 + 8) * 8 + 2 * (TO + 1) * 8;
     auto kern = chain3_kernel<MIX, FM, U8, D, R, NT, NSTAGE, MINB>;
     CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    ChainTaps scaled = taps;
+    if (U8)  // the span holds b - 127.5: ConvertNode's division moves into the taps
+        for (int k = 0; k < CHAIN_MAX_TAP_SLOTS; ++k)
+            scaled.t[k] = make_float2((float)((double)taps.t[k].x / 127.5), (float)((double)taps.t[k].y / 127.5));
     const unsigned tiles = (unsigned)ceil_div(args.n_out, (size_t)TO);
     const unsigned long long nitems = (unsigned long long)tiles * channels;
     int dev = 0, sms = 148, per_sm = 1;
@@ -677,7 +687,7 @@ static int launch_chain3(const ChainArgs &args, const ChainTaps &taps, size_t ch
     if (per_sm < 1) per_sm = 1;
     const unsigned long long cap = (unsigned long long)sms * per_sm;
     const unsigned grid = (unsigned)(nitems < cap ? nitems : cap);
-    kern<<<grid, NT + 32, SMEM, s>>>(args, taps, tiles, nitems);
+    kern<<<grid, NT + 32, SMEM, s>>>(args, scaled, tiles, nitems);
     count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;

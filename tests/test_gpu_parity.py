@@ -436,7 +436,17 @@ def test_chain_bank_u8_input_fused_convert(cb, oracle, mix, fm, D, n):
         got = a.run_u8(iq)
         same = b.run(xf)
         assert got.shape == same.shape == (C, -(-n // D))
-        assert got.tobytes() == same.tobytes()  # the fused kernel feeds the filter the very same f32 values
+        if D in (5, 10) and n % 8 == 0:
+            # fused kernel: the span holds b - 127.5 (exact) and ConvertNode's division sits in the taps -- the same
+            # algebra as convert-then-filter, different rounding points
+            if fm:
+                dd = np.abs(got.astype(np.float64) - same.astype(np.float64))
+                dd = np.minimum(dd, 2 * np.pi - dd)
+                assert np.median(dd) < 1e-6 and np.mean(dd > 1e-3) < 2e-3
+            else:
+                assert rel_l2(got, same) <= 1e-6
+        else:  # other shapes convert into a scratch first: the very same f32 values reach the filter
+            assert got.tobytes() == same.tobytes()
         for c in range(C):
             want = refs[c].run(xf[c])
             if fm:
