@@ -21,11 +21,15 @@ fn main() {
         cmd.args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17"])
             .args(["-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "-cudart", "static", "-o"])
             .arg(&lib);
-        for f in ["api.cu", "fir_kernels.cu", "fir_tc_kernel.cu", "fft_kernels.cu", "chain_kernels.cu", "misc_kernels.cu"] {
+        // the same list as comms-rs_b200/build.py (SOURCES)
+        for f in ["api.cu", "comm.cu", "fir_kernels.cu", "fir_tc_kernel.cu", "fir_ptc_kernel.cu", "fir_real_kernel.cu", "fft_kernels.cu",
+                  "fft_cluster_kernel.cu", "fft_rows_kernel.cu", "fft_big_kernel.cu", "chain_kernels.cu", "misc_kernels.cu",
+                  "estimator_kernels.cu"] {
             let p = csrc.join(f);
             println!("cargo:rerun-if-changed={}", p.display());
             cmd.arg(p);
         }
+        cmd.args(["-DCB_BUILD", "-ldl"]); // comm.cu binds NCCL with dlopen
         let st = cmd.status().expect("failed to run nvcc");
         assert!(st.success(), "nvcc failed");
         println!("cargo:rustc-link-search=native={}", out.display());

@@ -40,6 +40,20 @@ def test_library_exports_every_header_symbol(cb):
     assert exported == names  # nothing else leaks out of the .so
 
 
+def test_rust_shim_sources_track_the_library(cb):
+    # the Rust crate cannot be compiled in this image; keep its hand-written parts honest at least: build.rs compiles
+    # the same sources as build.py, and ffi.rs declares every entry of the header (and nothing that does not exist)
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_cb_build", os.path.join(ROOT, "comms-rs_b200", "build.py"))
+    bld = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bld)
+    rs = open(os.path.join(ROOT, "comms-rs_b200", "rust", "build.rs")).read()
+    assert sorted(set(re.findall(r'"(\w+\.cu)"', rs))) == sorted(bld.SOURCES)
+    ffi = open(os.path.join(ROOT, "comms-rs_b200", "rust", "src", "ffi.rs")).read()
+    assert sorted(set(re.findall(r"pub fn (cb_\w+)\(", ffi))) == _header_symbols()
+
+
 def test_every_header_entry_cites_the_reference():
     src = open(os.path.join(ROOT, "include", "comms_b200.h")).read()
     for cite in ("src/filter/fir.rs:87-102", "src/util/resample_node.rs:53-65", "src/mixer.rs:43-51",
