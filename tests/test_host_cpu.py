@@ -169,6 +169,22 @@ assert full2.tobytes() == ref2.tobytes()
 # (2) independent channels: block shard, no exchange needed for compute
 c0, c1 = sh.block_shard(6, world, rank)
 assert (c1 - c0) == 3
+# (3) batched FFT: frames block-sharded, ordered gather = the transform of the whole batch, bit for bit
+N, frames = 256, 11
+f0, f1 = sh.block_shard(frames, world, rank)
+xf = oracle.synth_uniform_c32(9, 0, frames * N)
+yf = oracle.fft(xf[f0 * N:f1 * N], N, False)
+fsz = [N * len(range(*sh.block_shard(frames, world, r))) for r in range(world)]
+assert sh.gather_ordered(torch.from_numpy(yf), fsz).numpy().tobytes() == oracle.fft(xf, N, False).tobytes()
+# (4) the real second stage of fm_radio (Complex(x, 0) -> FIR -> .re -> /5): segments on the decimation grid, halo as state
+xr = oracle.synth_uniform_c32(11, 0, total).real.copy()
+a5, b5 = sh.segment_bounds(total, world, rank, 5)
+lo5 = max(a5 - K, 0)
+y5, _ = oracle.batch_fir(xr[a5:b5].astype(np.complex64), taps, sh.halo_state(xr[lo5:a5].astype(np.complex64), K))
+y5 = oracle.decimate(y5.real.copy(), 5)
+sz5 = [-(-len(range(*sh.segment_bounds(total, world, r, 5))) // 5) for r in range(world)]
+ref5, _ = oracle.batch_fir(xr.astype(np.complex64), taps, np.zeros(K, np.complex64))
+assert sh.gather_ordered(torch.from_numpy(y5), sz5).numpy().tobytes() == oracle.decimate(ref5.real.copy(), 5).tobytes()
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")
