@@ -414,7 +414,7 @@ chain3_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
     extern __shared__ __align__(128) unsigned char c3sm[];
     unsigned char *stages = c3sm;                                     // ring of raw spans (f32, or bytes when U8)
     unsigned char *span8 = c3sm + NSTAGE * RAWSTAGE;                  // U8: the one converted f32 span
-    constexpr int RING = U8 ? NSTAGE * RAWSTAGE + STAGE + 1024 : NSTAGE * STAGE;
+    constexpr int RING = U8 ? NSTAGE * RAWSTAGE + STAGE : NSTAGE * STAGE;
     float2 *tsm = reinterpret_cast<float2 *>(c3sm + RING);            // tsm[k + 1] = h'[k], tsm[0] = tsm[65] = 0
     float2 *cst = tsm + KP + 2;                                       // e^{j r D dphi} (r < R), then e^{-j D dphi}
     float2 *basep = cst + 8;                                          // per stage: e^{j (phi0 + m0 D dphi)}
@@ -484,7 +484,10 @@ chain3_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
     for (unsigned long long item = item0; item < item_end; ++item, ++li) {
         const int st = (int)(li % NSTAGE);
         const uint32_t parity = (uint32_t)((li / NSTAGE) & 1);
-        const int yb = (int)(li & 1) * (TO + 1);
+        // output staging: two buffers so that the stores of one tile overlap the filter of the next; with byte input the
+        // conversion barrier (every thread arrives after its own output reads of the previous tile) already separates
+        // them, so one buffer is enough -- which is what lets a fourth CTA fit per SM
+        const int yb = U8 ? 0 : (int)(li & 1) * (TO + 1);
         const size_t c = (size_t)(item / tiles_per_ch);
         const unsigned tile = (unsigned)(item % tiles_per_ch);
         const long long m0 = (long long)tile * TO;
@@ -671,7 +674,7 @@ static int launch_chain3(const ChainArgs &args, const ChainTaps &taps, size_t ch
 {
     constexpr int TO = NT * R, OFF = U8 ? (64 + D + 7) / 8 * 8 : (64 + D + 1) / 2 * 2;
     constexpr int F32SPAN = ((TO * D + OFF) * 8 + 127) / 128 * 128, RAWSPAN = ((TO * D + OFF) * 2 + 127) / 128 * 128;
-    constexpr int SMEM = (U8 ? NSTAGE * RAWSPAN + F32SPAN + 1024 : NSTAGE * F32SPAN) + (66 + 8 + 8) * 8 + 2 * (TO + 1) * 8;
+    constexpr int SMEM = (U8 ? NSTAGE * RAWSPAN + F32SPAN : NSTAGE * F32SPAN) + (66 + 8 + 8) * 8 + (U8 ? 1 : 2) * (TO + 1) * 8;
     auto kern = chain3_kernel<MIX, FM, U8, D, R, NT, NSTAGE, MINB>;
     CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     ChainTaps scaled = taps;
@@ -730,7 +733,14 @@ static int launch_chain2_d(const ChainArgs &args, const ChainTaps &taps, bool mi
     }();
     if (args.x8 != nullptr && args.hist_len >= 128) {  // byte input: one f32 span + a small raw ring -> more CTAs per SM
         if constexpr (D == 10) return launch_chain3_shape<D, 3, 128, 2, 4>(args, taps, mix, fm, channels, s);
-        if constexpr (D == 5) return launch_chain3_shape<D, 6, 128, 2, 3>(args, taps, mix, fm, channels, s);
+        if constexpr (D == 5) {
+            // without the mixer (fm_radio as shipped) the kernel fits 4 CTAs per SM; the rotated-tap variants need more
+            // than the 102 registers that would leave them and stay at 3
+            if (!mix)
+                return fm ? launch_chain3<false, true, true, D, 6, 128, 2, 4>(args, taps, channels, s)
+                          : launch_chain3<false, false, true, D, 6, 128, 2, 4>(args, taps, channels, s);
+            return launch_chain3_shape<D, 6, 128, 2, 3>(args, taps, mix, fm, channels, s);
+        }
     }
     if (path != 2 && args.hist_len >= 128) {
         if constexpr (D == 10) return launch_chain3_shape<D, 3, 128, 2, 3>(args, taps, mix, fm, channels, s);
