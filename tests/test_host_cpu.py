@@ -210,3 +210,21 @@ def test_bench_reference_arm_prints_contract_line():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "Msamples/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_bench_cpu_leg_runs_for_every_workload_kind():
+    # the reference arm / cpu_baseline leg of bench.py for one workload of every kind, on a small sample
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    kinds = {}
+    for name, (kind, *_rest) in bench.WORKLOADS.items():
+        kinds.setdefault(kind, name)
+    assert set(kinds) == {"fir", "firdec", "firreal", "graph", "fft", "est", "mixer", "fm", "chain", "interp"}
+    for kind, name in kinds.items():
+        rate, dt, n = bench.cpu_rate(name, 1 << 15, 2)
+        assert rate > 0 and n > 0, name
+    rate, _, _ = bench.cpu_rate("timing10x5", 1 << 14, 1)
+    assert rate > 0
