@@ -228,3 +228,98 @@ def test_bench_cpu_leg_runs_for_every_workload_kind():
         assert rate > 0 and n > 0, name
     rate, _, _ = bench.cpu_rate("timing10x5", 1 << 14, 1)
     assert rate > 0
+
+
+@pytest.mark.parametrize("D", [2, 4, 5, 8, 10])
+def test_real_fir_kernel_index_algebra(D, oracle):
+    # The polyphase bookkeeping of fir_real_decim_kernel<D> (csrc/fir_real_kernel.cu), restated index for index in numpy:
+    #   A_p[i] = x[(J0 - LB + i) D - p]  filled from the linear range g = G0 + e with i = e / D, p = D - 1 - e % D,
+    #   thread t / output u reads w[u - q + LB] = A_p[4 t + u - q + LB]  for tap k = q D + p.
+    # It must reproduce y[J] = sum_k h[k] x[J D - k] (history for negative indices) -- checked against the oracle.
+    rng = np.random.default_rng(D)
+    NT, TO = 256, 1024
+    Q = (64 + D - 1) // D
+    LB = (Q - 1 + 3) // 4 * 4
+    LEN = TO + LB
+    ntaps, H = 63, 64
+    h = rng.uniform(-1, 1, ntaps).astype(np.float32)
+    n_in = 2 * TO * D + 3 * D + 1  # two full tiles and a ragged third
+    x = rng.uniform(-1, 1, n_in).astype(np.float32)
+    hist = rng.uniform(-1, 1, H).astype(np.float32)  # chronological, hist[H - 1] = x[-1]
+    n_out = -(-n_in // D)
+    taps = np.zeros(80, np.float32)
+    taps[:ntaps] = h
+
+    def sample(g):
+        if g >= 0:
+            return x[g] if g < n_in else np.float32(0)
+        return hist[H + g] if g + H >= 0 else np.float32(0)
+
+    y = np.zeros(n_out, np.float64)
+    for tile in range(-(-n_out // TO)):
+        J0 = tile * TO
+        G0 = (J0 - LB) * D - (D - 1)
+        A = np.zeros((D, LEN), np.float64)
+        for e in range(LEN * D):
+            A[D - 1 - e % D, e // D] = sample(G0 + e)
+        for t in range(NT):
+            for u in range(4):
+                J = J0 + 4 * t + u
+                if J >= n_out:
+                    continue
+                acc = 0.0
+                for p in range(D):
+                    w = A[p, 4 * t:4 * t + LB + 4]
+                    for q in range(Q):
+                        if q * D + p < 64:
+                            acc += float(taps[q * D + p]) * w[u - q + LB]
+                y[J] = acc
+    state = np.concatenate([hist[::-1], np.zeros(max(0, ntaps - H))]).astype(np.complex64)[:ntaps]
+    full, _ = oracle.batch_fir(x.astype(np.complex64), h.astype(np.complex64), state)
+    want = oracle.decimate(full.real.copy(), D)
+    assert y.shape == want.shape
+    assert np.linalg.norm(y - want) <= 1e-6 * np.linalg.norm(want)
+
+
+@pytest.mark.parametrize("ntaps", [1, 3, 5, 21, 101, 103])
+def test_timing_kernel_window_algebra(ntaps):
+    # The shared-memory geometry of timing_partial_kernel (csrc/estimator_kernels.cu: timing_geo, the mod-4
+    # de-interleaved tile, the 7-sample sliding register window, four taps per step), restated index for index:
+    # it must give y[i] = sum_k h[k] q[i - k] for every output of a tile, whatever ntaps mod 4 is.
+    rng = np.random.default_rng(ntaps)
+    NT, TILE = 256, 1024
+    halo = ntaps - 1
+    ntaps4 = (ntaps + 3) & ~3
+    lead = 4 + ((4 - halo % 4) % 4)
+    h4 = halo + lead
+    assert h4 % 4 == 0 and 4 <= lead <= 7
+    pitch = (TILE + h4) // 4
+    while pitch % 8 != 2:
+        pitch += 1
+    taps = np.zeros(ntaps4)
+    taps[:ntaps] = rng.uniform(-1, 1, ntaps)
+    n = 2 * TILE + 37
+    q = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    want = np.convolve(q, taps[:ntaps])[:n]
+    for tile in range(-(-n // TILE)):
+        i0 = tile * TILE
+        sm = np.full(4 * pitch, np.nan + 0j)  # anything not written must not be used with a non-zero tap
+        for e in range(TILE + h4):
+            m = i0 - h4 + e
+            sm[(e & 3) * pitch + (e >> 2)] = q[m] if (e >= lead and 0 <= m < n) else 0.0
+        for t in range(NT):
+            c = [(h4 >> 2) + t + k * pitch for k in range(4)]  # class k: L[base + k]
+            W = [sm[c[1] - 1], sm[c[2] - 1], sm[c[3] - 1], sm[c[0]], sm[c[1]], sm[c[2]], sm[c[3]]]
+            y = [0j] * 4
+            for k in range(0, ntaps4, 4):
+                for u in range(4):
+                    for r in range(4):
+                        if taps[k + r] != 0.0:
+                            y[u] += taps[k + r] * W[u - r + 3]
+                back = (k >> 2) + 1
+                idx = [c[1] - 1 - back, c[2] - 1 - back, c[3] - 1 - back, c[0] - back]
+                W = [sm[j] if 0 <= j < len(sm) else np.nan for j in idx] + W[:3]
+            for u in range(4):
+                i = i0 + 4 * t + u
+                if i < n:
+                    assert abs(y[u] - want[i]) <= 1e-12 * (1 + abs(want[i])), (tile, t, u)
