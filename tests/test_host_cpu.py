@@ -323,3 +323,53 @@ def test_timing_kernel_window_algebra(ntaps):
                 i = i0 + 4 * t + u
                 if i < n:
                     assert abs(y[u] - want[i]) <= 1e-12 * (1 + abs(want[i])), (tile, t, u)
+
+
+@pytest.mark.parametrize("L1,L2", [(7, 8), (8, 8), (8, 9), (9, 9)])
+def test_two_step_fft_split_algebra(L1, L2):
+    # the N1 x N2 split of fft_big_kernel.cu / fft_rows_kernel.cu: n = N2 n1 + n2, k = k1 + N1 k2,
+    # X[k1 + N1 k2] = sum_n2 W_N2^{n2 k2} { W_N^{n2 k1} sum_n1 x[N2 n1 + n2] W_N1^{n1 k1} }
+    N1, N2 = 1 << L1, 1 << L2
+    N = N1 * N2
+    rng = np.random.default_rng(L1 * 16 + L2)
+    x = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    for inverse in (False, True):
+        sgn = 1.0 if inverse else -1.0
+        f = (lambda a, axis: np.fft.ifft(a, axis=axis) * a.shape[axis]) if inverse else (lambda a, axis: np.fft.fft(a, axis=axis))
+        Y = f(x.reshape(N1, N2), 0)                                   # step A: [k1][n2], stored in place
+        k1, n2 = np.meshgrid(np.arange(N1), np.arange(N2), indexing="ij")
+        Z = Y * np.exp(sgn * 2j * np.pi * (k1 * n2 % N) / N)          # twiddle on the way into step B
+        X = f(Z, 1)                                                   # step B: rows; X[k1 + N1 k2]
+        got = X.T.reshape(-1)                                         # index k1 + N1 k2 -> k2-major
+        want = f(x, 0)
+        assert np.linalg.norm(got - want) <= 1e-11 * np.linalg.norm(want)
+
+
+@pytest.mark.parametrize("nframes,ring", [(1, 4), (5, 4), (33, 32), (100, 8), (7, 2)])
+def test_fused_fft_ticket_order_cannot_wait_on_a_later_ticket(nframes, ring):
+    # the work order of the fused two-step FFT kernels: A(0 .. lag-1), then A(lag + u), B(u) alternating, ITEMS items per
+    # (frame, step), handed out by one ticket counter.  An item waits for: B(f) on all A(f) items; A(f >= ring) on all
+    # B(f - ring) items.  Every such dependency must carry a SMALLER ticket -- then the earliest unfinished item can
+    # always run and the kernel cannot deadlock however few CTAs are resident.
+    ITEMS = 8
+    lag = max(ring // 2, 1)
+    nchunks = lag + 2 * nframes
+    first, last = {}, {}
+    for item in range(nchunks * ITEMS):
+        chunk = item // ITEMS
+        if chunk < lag:
+            is_a, frame = True, chunk
+        else:
+            t = chunk - lag
+            is_a = t % 2 == 0
+            frame = lag + t // 2 if is_a else t // 2
+        if frame >= nframes:
+            continue
+        key = ("A" if is_a else "B", frame)
+        first.setdefault(key, item)
+        last[key] = item
+    assert sorted(first) == sorted([(s, f) for s in "AB" for f in range(nframes)])  # every (step, frame) exactly once
+    for f in range(nframes):
+        assert last[("A", f)] < first[("B", f)]
+        if f >= ring:
+            assert last[("B", f - ring)] < first[("A", f)]
