@@ -133,5 +133,6 @@ int main()
     bad += check<12, false>();
     bad += check<12, true>();
     bad += check<13, false>();
+    bad += check<14, true>();  // the largest one-CTA size (4 passes: 16 16 16 4)
     return bad;
 }
