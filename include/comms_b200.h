@@ -225,7 +225,9 @@ CB_API int cb_chain_run(cb_chain *h, const float *in, size_t n_in, float *out, s
 /* Same bank fed with the raw RTL-SDR byte stream (channel-major, n_in byte pairs per channel): ConvertNode
  * (examples/fm_radio.rs:84-87) fused in front, so HBM carries 2 instead of 8 bytes per input sample.  Fused
  * inside the TMA-staged kernel for real taps <= 64, decimation 5 or 10, n_in % 8 == 0 and a 16-byte aligned
- * input; any other shape converts into an internal f32 scratch first.  Same results either way. */
+ * input (there the span holds b - 127.5 exactly and the division by 127.5 sits in the taps: results equal to
+ * convert-then-filter up to rounding, ~1e-7 relative); any other shape converts into an internal f32 scratch first
+ * (bit-identical to convert-then-filter).  The carried state is ConvertNode's exact output either way. */
 CB_API int cb_chain_run_u8(cb_chain *h, const uint8_t *in, size_t n_in, float *out, size_t out_cap_per_channel,
                            size_t *n_out_per_channel);
 CB_API int cb_chain_run_u8_dev(cb_chain *h, const uint8_t *d_in, size_t n_in, float *d_out,
