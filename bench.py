@@ -73,12 +73,15 @@ WORKLOADS = {
     "chain5_u8": ("chain", 1024 * 131072, 2.8, "fm_radio as shipped from raw RTL-SDR bytes x1024 channels per GPU: u8 IQ -> (x-127.5)/127.5 -> "
                   "63-tap FIR -> /5 -> FM demod, fused, 131072-sample batches"),
     "pulse4": ("interp", 1 << 26, 40.0, "BPSK pulse shaping: x4 polyphase 32-tap RRC over 2^26 symbols per GPU (unit = symbols)"),
+    "pulse4_b4096": ("interp", 1 << 20, 40.0, "BASELINE configs[0] as specified (examples/single_thread_bpsk.rs:19,39): 2^20 BPSK symbols in 256 "
+                     "messages of 4096, x4 / 32-tap RRC pulse shaping, state carried across messages; one step = 256 "
+                     "cb_fir_run_dev calls (launch-latency regime; unit = symbols)"),
     "pulse4_i16": ("interp", 1 << 26, 24.0, "BPSK pulse shaping with the example's i16 quantiser fused: x4 polyphase 32-tap RRC -> (8192 x) as i16 "
                    "IQ over 2^26 symbols per GPU (unit = symbols)"),
     "poly8x1024c": ("interp", 1 << 26, 72.0, "x8 polyphase with a fully complex 1024-tap bank (tcgen05, 54 MMAs per tile) over 2^26 symbols "
                     "per GPU (unit = symbols)"),
-    "poly8x1024": ("interp", 1 << 27, 72.0, "QPSK x8 polyphase, 1024-tap RRC bank (tcgen05 Toeplitz GEMM) over 2^27 symbols per GPU "
-                   "= one of the 8 segments of the 2^30-symbol stream (unit = symbols)"),
+    "poly8x1024": ("interp", 1 << 27, 72.0, "QPSK symbols -> x8 polyphase, 1024-tap RRC bank (tcgen05 Toeplitz GEMM) over 2^27 symbols per GPU "
+                   "= one of the 8 segments of the 2^30-symbol stream, each rank seeded with its 127-symbol halo (unit = symbols)"),
 }
 
 
@@ -91,9 +94,24 @@ def parse_args():
     ap.add_argument("--workload", default="fir64", choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--also", default=None,
+                    help="comma-separated extra workloads reported under 'also' on the same line; default: the other BASELINE "
+                         "configs when --workload is the default, none otherwise; 'none' disables")
+    ap.add_argument("--no-gather", dest="gather", action="store_false",
+                    help="N > 1: skip the ordered gather of the output segments (timed apart from the kernels)")
+    ap.add_argument("--pageable", action="store_true", help="also time the host-pointer call with pageable host buffers")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
     a.steps = max(a.steps, 1)
+    if a.also is None:
+        a.also = list(ALSO_DEFAULT) if a.workload == "fir64" and a.impl == "b200" else []
+    elif a.also.strip().lower() in ("", "none"):
+        a.also = []
+    else:
+        a.also = [w.strip() for w in a.also.split(",") if w.strip()]
+        for w in a.also:
+            if w not in WORKLOADS:
+                ap.error(f"unknown workload in --also: {w}")
     return a
 
 
@@ -103,16 +121,21 @@ def fm_radio_lowpass(n=63):
     return (np.sinc(k / 5) * np.hamming(n) / 5).astype(np.float32).astype(np.complex64)
 
 
-def rrc_taps(n, sps, beta):
-    """rrc_taps (src/util/math.rs:221-280) from the product's host entry (cb_rrc_taps; needs no GPU)."""
+def rrc_taps(n, sps, beta, cpu=False):
+    """rrc_taps (src/util/math.rs:221-280).  GPU arm: the product's host entry (cb_rrc_taps).  CPU legs
+    (cpu_baseline, --impl reference): the oracle's restatement, so that the reference arm never maps the product."""
+    if cpu:
+        import oracle
+
+        return oracle.rrc_taps(n, sps, beta)
     import comms_rs_b200 as cb
 
     return cb.rrc_taps(n, sps, beta)
 
 
-def fir_taps(workload):
+def fir_taps(workload, cpu=False):
     nt = 1024 if workload == "fir1024" else 64
-    t = rrc_taps(nt, 4.0, 0.25)
+    t = rrc_taps(nt, 4.0, 0.25, cpu)
     if workload in ("fir64", "fir1024"):
         t = (t * np.exp(0.1j * np.arange(nt))).astype(np.complex64)
     return t
@@ -190,7 +213,7 @@ def cpu_rate(workload, samples, threads):
     for i in range(threads):
         x = oracle.synth_uniform_c32(SEED, i * per, per)
         if kind == "fir":
-            t = fir_taps(workload)
+            t = fir_taps(workload, cpu=True)
             # reference form: per-sample rotate + ordered MACs (src/filter/fir.rs:87-102), release flags
             jobs.append(lambda x=x, t=t: oracle.batch_fir(x, t, np.zeros(len(t), np.complex64), literal=True, native=True))
         elif kind == "fft":
@@ -231,7 +254,9 @@ def cpu_rate(workload, samples, threads):
             jobs.append(lambda x=x, ch=ch: [ch.run(x[j:j + 131072]) for j in range(0, len(x), 131072)])
         else:
             L, nt = (4, 32) if workload.startswith("pulse4") else (8, 1024)
-            t = rrc_taps(nt, float(L), 0.25)
+            if workload == "poly8x1024":
+                x = (np.where(x.real >= 0, 1.0, -1.0) + 1j * np.where(x.imag >= 0, 1.0, -1.0)).astype(np.complex64)
+            t = rrc_taps(nt, float(L), 0.25, cpu=True)
             st = np.zeros(nt, np.complex64)
             jobs.append(lambda x=x, t=t, st=st: oracle.batch_fir(oracle.upsample(x, L), t, st, literal=True, native=True))
     ths = [threading.Thread(target=j) for j in jobs]
@@ -301,6 +326,7 @@ class Job:
             self.y = torch.empty(n, dtype=torch.complex64, device="cuda")
             self.out_bytes = 8 * n
             self.step = lambda: self.node.run_dev(self.x.data_ptr(), n, self.y.data_ptr(), n, self.stream)
+            self.step_to = lambda dst: self.node.run_dev(self.x.data_ptr(), n, dst, n, self.stream)
             self.host_call = lambda hin, hout: cb.load().cb_fir_run(self.node._h, hin, n, hout, n, None)
         elif self.kind == "firdec":
             self.taps = fm_radio_lowpass()
@@ -410,8 +436,38 @@ class Job:
             self.taps = rrc_taps(nt, float(L), 0.25)
             if workload == "poly8x1024c":
                 self.taps = (self.taps * np.exp(0.01j * np.arange(nt))).astype(np.complex64)
-            self.node = cb.BatchFirNode(self.taps, None, interp=L)
-            if workload == "pulse4_i16":
+            if workload == "poly8x1024":  # QPSK symbols (+-1 +- 1j): the sign bits of the counter-hash stream
+                torch.cuda.current_stream().wait_stream(self.tstream)
+                xr = torch.view_as_real(self.x)
+                xr.copy_(torch.where(xr >= 0, 1.0, -1.0))
+                torch.cuda.synchronize()
+            # this rank's segment of the symbol stream: the nt/L - 1 symbols before it are the reference `state`
+            # (zero-stuffed domain, src/filter/fir_node.rs:193-200)
+            self.halo = self._halo(nt // L, interp=L, nstate=nt, qpsk=workload == "poly8x1024")
+            self.node = cb.BatchFirNode(self.taps, self.halo, interp=L)
+            if workload == "pulse4_b4096":
+                nb = 4096
+                self.messages_per_step = n // nb
+                self.y = torch.empty(n * L, dtype=torch.complex64, device="cuda")
+                self.out_bytes = 8 * n * L
+                xp, yp = self.x.data_ptr(), self.y.data_ptr()
+
+                def step():
+                    for m in range(n // nb):
+                        self.node.run_dev(xp + 8 * m * nb, nb, yp + 8 * m * nb * L, nb * L, self.stream)
+                self.step = step
+                self.kernels_per_step = n // nb
+                self.e2e_api = "256 host-pointer cb_fir_run calls per step, one per 4096-symbol message (Vec in, Vec out)"
+
+                def host_call(hin, hout):
+                    lib = cb.load()
+                    for m in range(n // nb):
+                        rc = lib.cb_fir_run(self.node._h, hin + 8 * m * nb, nb, hout + 8 * m * nb * L, nb * L, None)
+                        if rc:
+                            return rc
+                    return 0
+                self.host_call = host_call
+            elif workload == "pulse4_i16":
                 self.y = torch.empty(2 * n * L, dtype=torch.int16, device="cuda")
                 self.out_bytes = 4 * n * L
                 self.step = lambda: self.node.run_dev_i16(self.x.data_ptr(), n, 8192.0, self.y.data_ptr(), n * L, self.stream)
@@ -420,18 +476,279 @@ class Job:
                 self.y = torch.empty(n * L, dtype=torch.complex64, device="cuda")
                 self.out_bytes = 8 * n * L
                 self.step = lambda: self.node.run_dev(self.x.data_ptr(), n, self.y.data_ptr(), n * L, self.stream)
+                self.step_to = lambda dst: self.node.run_dev(self.x.data_ptr(), n, dst, n * L, self.stream)
                 self.host_call = lambda hin, hout: cb.load().cb_fir_run(self.node._h, hin, n, hout, n * L, None)
         self.in_bytes = getattr(self, "in_bytes_override", 8 * n)
 
-    def _halo(self, k):
-        """The k samples before this rank's segment, newest first: the reference `state`
-        (src/filter/fir_node.rs:193-200) that makes segment + halo partitioning exact."""
+    def _halo(self, k, interp=1, nstate=None, qpsk=False):
+        """The k samples before this rank's segment as the reference `state` (newest first; zero-stuffed domain when
+        interp > 1; src/filter/fir_node.rs:193-200): what makes segment + halo partitioning exact."""
         if self.first == 0:
             return None
+        from comms_rs_b200 import sharding
         t = self.torch.empty(k, dtype=self.torch.complex64, device="cuda")
         self.cb.synth_uniform_dev(SEED, self.first - k, k, t.data_ptr(), self.stream)
         self.torch.cuda.synchronize()
-        return t.cpu().numpy()[::-1].copy()
+        prev = t.cpu().numpy()
+        if qpsk:
+            prev = (np.where(prev.real >= 0, 1.0, -1.0) + 1j * np.where(prev.imag >= 0, 1.0, -1.0)).astype(np.complex64)
+        return sharding.halo_state(prev, nstate if nstate is not None else k, interp)
+
+
+ALSO_DEFAULT = ["fft1024", "fft4096", "ifft4096", "fft65536", "chain", "pulse4_b4096", "poly8x1024"]
+NVLINK_GBS_PER_DIR = 900.0  # NVLink 5, per GPU and direction (B200_PROFILING.md)
+
+
+class PinnedPair:
+    """One pinned input / output buffer pair, grown on demand and shared by all workloads of a run."""
+
+    def __init__(self, cb):
+        self.cb, self.h = cb, [None, None]
+        self.cap = [0, 0]
+
+    def get(self, in_bytes, out_bytes):
+        import ctypes as C
+        lib = self.cb.load()
+        for i, need in enumerate((in_bytes, out_bytes)):
+            if need > self.cap[i]:
+                if self.h[i] is not None:
+                    lib.cb_buf_release(self.h[i])
+                self.h[i] = C.c_void_p()
+                self.cb._lib.check(lib.cb_buf_alloc_pinned(need, C.byref(self.h[i])))
+                self.cap[i] = need
+        return lib.cb_buf_ptr(self.h[0]), lib.cb_buf_ptr(self.h[1])
+
+    def close(self):
+        for h in self.h:
+            if h is not None:
+                self.cb.load().cb_buf_release(h)
+        self.h = [None, None]
+        self.cap = [0, 0]
+
+
+def gather_leg(cb, torch, dist, job, rank, world, reps=3):
+    """The one collective of the design, timed apart from the kernels: every rank's output segment back into ONE ordered
+    stream on rank 0.  (i) cb_gather_segments_to_root_dev (grouped ncclSend/ncclRecv) after the kernels; (ii) the gather
+    fused into the producing kernel: rank 0 exports the stream buffer (CUDA IPC), every rank's kernel stores its segment
+    straight into it over NVLink.  CUDA events on the launch stream, max over ranks."""
+    import ctypes as C
+
+    from comms_rs_b200 import sharding
+    lib = cb.load()
+    seg_bytes = job.out_bytes
+    counts = [seg_bytes] * world
+    ids = [sharding.SegmentGather.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    g = sharding.SegmentGather(world, rank, ids[0])
+    root = C.c_void_p()
+    base = 0
+    if rank == 0:
+        cb._lib.check(lib.cb_buf_alloc_device(seg_bytes * world, C.byref(root)))
+        base = lib.cb_buf_ptr(root)
+
+    def timed(fn, n):
+        fn()  # warm-up (NCCL connection set-up, peer mapping faults)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(job.tstream)
+        for _ in range(n):
+            fn()
+        e1.record(job.tstream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / n], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms = timed(lambda: g.gather_to_root_dev(job.y.data_ptr(), counts, 1, 0, base, job.stream), reps)
+    remote = seg_bytes * (world - 1)
+    out = {"algorithm": "gather-to-root: one grouped ncclSend/ncclRecv (cb_gather_segments_to_root_dev), after the kernels",
+           "ms": ms, "bytes_into_root": remote, "root_ingress_GBps": remote / (ms * 1e-3) / 1e9,
+           "nvlink_GBps_per_dir": NVLINK_GBS_PER_DIR, "frac_of_nvlink": remote / (ms * 1e-3) / 1e9 / NVLINK_GBS_PER_DIR,
+           "segments": world, "segment_bytes": seg_bytes}
+    # fused: d_out = the root's buffer (peer-mapped) + this rank's offset
+    hnd, err = [None], ""
+    if rank == 0:
+        try:
+            hnd[0] = sharding.peer_export(base)
+        except Exception as e:  # noqa: BLE001
+            err = repr(e)[:200]
+    dist.broadcast_object_list(hnd, src=0)
+    mapped = base
+    if rank != 0 and hnd[0] is not None:
+        try:
+            mapped = sharding.peer_open(hnd[0])
+        except Exception as e:  # noqa: BLE001
+            err, mapped = repr(e)[:200], 0
+    okt = torch.tensor([1 if (hnd[0] is not None and mapped) else 0], dtype=torch.int32, device="cuda")
+    dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    if int(okt.item()) == 1:  # every rank mapped the buffer: all of them run the timed loop
+        dst = mapped + rank * seg_bytes
+        ms_f = timed(lambda: job.step_to(dst), reps)
+        out["fused_store"] = {"algorithm": "kernel stores straight into rank 0's stream buffer (cb_peer_export/open, NVLink P2P); "
+                                           "no collective call, no second pass", "ms_per_step": ms_f,
+                              "root_ingress_GBps": remote / (ms_f * 1e-3) / 1e9,
+                              "vs_kernel_then_gather_ms": None}
+    else:
+        out["fused_store"] = {"unavailable": err or "a peer rank could not map the exported buffer"}
+    if rank != 0 and mapped:
+        try:
+            sharding.peer_close(mapped)
+        except Exception:  # noqa: BLE001
+            pass
+    dist.barrier()
+    g.close()
+    if rank == 0:
+        lib.cb_buf_release(root)
+    return out
+
+
+def measure(cb, torch, dist, args, workload, rank, world, local_rank, steps, warmup, pinned, cpu_sample_scale=1.0):
+    """One workload on this rank's GPU: device-resident timing, end-to-end timing, roofline, CPU baseline."""
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    job = Job(cb, torch, workload, rank)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- device-resident: W warm-up steps, then exactly K timed steps
+    for _ in range(warmup):
+        job.step()
+    barrier()
+    launches0 = cb.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    t_wall0 = time.perf_counter()
+    for i in range(steps):
+        ev[i].record(job.tstream)
+        job.step()
+    ev[steps].record(job.tstream)
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches_dev = cb.launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[steps])
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    clocks = sampler.summary(t_wall0, t_wall1)
+
+    # ---- end to end: host buffers, H2D + kernels + D2H inside the timed region
+    e2e = None
+    launches_e2e = 0
+    if not args.no_e2e:
+        lib = cb.load()
+        pin, pout = pinned.get(job.in_bytes, job.out_bytes)
+        src = job.x8 if hasattr(job, "x8") else job.x
+        cb._lib.check(lib.cb_copy_d2h_async(pin, src.data_ptr(), job.in_bytes, job.stream))
+        torch.cuda.synchronize()
+        k_e2e = max(3, min(steps, 10))
+
+        def time_host(hin, hout, k):
+            for _ in range(2):
+                cb._lib.check(job.host_call(hin, hout))
+            barrier()
+            l0 = cb.launch_count()
+            t0 = time.perf_counter()
+            for _ in range(k):
+                cb._lib.check(job.host_call(hin, hout))  # returns when the host output buffer is filled
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return world * job.n * k / float(tt.item()) / 1e6, cb.launch_count() - l0, float(tt.item())
+
+        v, launches_e2e, dt = time_host(pin, pout, k_e2e)
+        e2e = {"value": v, "unit": UNIT,
+               "h2d_bytes_per_step": job.in_bytes, "d2h_bytes_per_step": job.out_bytes, "steps": k_e2e,
+               "h2d_GBps_per_gpu": job.in_bytes * k_e2e / dt / 1e9, "d2h_GBps_per_gpu": job.out_bytes * k_e2e / dt / 1e9,
+               "api": getattr(job, "e2e_api", "host-pointer C-ABI call, pinned buffers, 2-lane chunked H2D/kernel/D2H pipeline")}
+        if args.pageable and workload == args.workload:
+            # what a Rust Vec is: pageable memory on both sides of the same call
+            hin = np.empty(job.in_bytes, dtype=np.uint8)
+            hout = np.empty(job.out_bytes, dtype=np.uint8)
+            import ctypes as C
+            C.memmove(hin.ctypes.data, pin, job.in_bytes)
+            vp, lp, _ = time_host(hin.ctypes.data, hout.ctypes.data, 3)
+            launches_e2e += lp
+            e2e["pageable"] = {"value": vp, "unit": UNIT, "steps": 3,
+                               "note": "same call with pageable (malloc) host buffers, the memory of a Rust Vec"}
+            del hin, hout
+    sampler.stop()
+
+    gather = None
+    if world > 1 and args.gather and job.kind in ("fir", "interp") and hasattr(job, "step_to"):
+        gather = gather_leg(cb, torch, dist, job, rank, world)
+        if "fused_store" in gather and "ms_per_step" in gather["fused_store"]:
+            gather["fused_store"]["vs_kernel_then_gather_ms"] = total_ms_max / steps + gather["ms"]
+
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        peak = peaks.get("hbm_gbs")
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        if not peak:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        ms_launch = total_ms / steps / job.kernels_per_step
+        alg_bytes = job.bytes_per_unit * job.n / job.kernels_per_step
+        achieved = alg_bytes / (ms_launch * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj.get(workload)
+            if traffic is not None:
+                traffic_src = "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (" + \
+                              tj.get("_sources", {}).get(workload, "see its _comment") + "); not measured in this run"
+        except Exception:  # noqa: BLE001
+            pass
+        line = {
+            "metric": METRIC, "value": world * job.n * steps / (total_ms_max * 1e-3) / 1e6, "unit": UNIT,
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": total_ms_max / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if job.kind == "est" else "f32", "data": "synthetic",
+            "config": {"workload": workload, "description": job.desc, "units_per_step_per_gpu": job.n,
+                       "l2": "inputs larger than L2 (%.2f GiB read + %.2f GiB written per step, L2 = 126 MB)"
+                             % (job.in_bytes / 2 ** 30, job.out_bytes / 2 ** 30),
+                       "parallelism": "one overlap-save segment (or channel/frame block) per GPU with its true halo as the "
+                                      "initial state, no data-path collective",
+                       "seed": SEED},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": int(launches_dev + launches_e2e),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "kernels_per_step": job.kernels_per_step,
+                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_launch},
+        }
+        if getattr(job, "messages_per_step", 0):
+            line["messages"] = {"per_step": job.messages_per_step, "units_per_message": job.n // job.messages_per_step,
+                                "us_per_message": 1e3 * total_ms_max / steps / job.messages_per_step,
+                                "messages_per_s": job.messages_per_step * steps / (total_ms_max * 1e-3)}
+        if gather is not None:
+            line["gather"] = gather
+        if world == 1 and not args.no_cpu:
+            kind = job.kind
+            sample = {"fir": 1 << 26, "fft": 1 << 27, "chain": 1 << 26, "interp": 1 << 23, "mixer": 1 << 26, "fm": 1 << 27, "firdec": 1 << 26, "est": 1 << 24, "firreal": 1 << 26, "graph": 1 << 26}[kind]
+            if workload == "timing10x5":
+                sample = 1 << 22
+            if workload.startswith("poly8x1024"):
+                sample = 1 << 17
+            sample = max(int(sample * cpu_sample_scale), 1 << 12)
+            v, dt, n = cpu_rate(workload, sample, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"first {n} units of the same synthetic stream, {dt:.1f} s, one thread "
+                                              "(the reference runs one thread per node)",
+                                    "host_cores": os.cpu_count()}
+    del job
+    torch.cuda.empty_cache()
+    return line
 
 
 def run_b200(args, rank, world, local_rank):
@@ -447,118 +764,28 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    job = Job(cb, torch, args.workload, rank)
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-
-    # ---- device-resident: W warm-up steps, then exactly K timed steps
-    for _ in range(args.warmup):
-        job.step()
-    barrier()
-    launches0 = cb.launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    t_wall0 = time.perf_counter()
-    for i in range(args.steps):
-        ev[i].record(job.tstream)
-        job.step()
-    ev[args.steps].record(job.tstream)
-    barrier()
-    t_wall1 = time.perf_counter()
-    launches_dev = cb.launch_count() - launches0
-    total_ms = ev[0].elapsed_time(ev[args.steps])
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
-    clocks = sampler.summary(t_wall0, t_wall1)
-
-    # ---- end to end: host buffers (pinned), H2D + kernels + D2H inside the timed region
-    e2e = None
-    launches_e2e = 0
-    if not args.no_e2e:
-        import ctypes as C
-        lib = cb.load()
-        hin, hout = C.c_void_p(), C.c_void_p()
-        cb._lib.check(lib.cb_buf_alloc_pinned(job.in_bytes, C.byref(hin)))
-        cb._lib.check(lib.cb_buf_alloc_pinned(job.out_bytes, C.byref(hout)))
-        pin, pout = lib.cb_buf_ptr(hin), lib.cb_buf_ptr(hout)
-        src = job.x8 if hasattr(job, "x8") else job.x
-        cb._lib.check(lib.cb_copy_d2h_async(pin, src.data_ptr(), job.in_bytes, job.stream))
-        torch.cuda.synchronize()
-        k_e2e = max(3, min(args.steps, 10))
-        for _ in range(2):
-            cb._lib.check(job.host_call(pin, pout))
-        barrier()
-        l0 = cb.launch_count()
-        t0 = time.perf_counter()
-        for _ in range(k_e2e):
-            cb._lib.check(job.host_call(pin, pout))  # returns when the host output buffer is filled
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        launches_e2e = cb.launch_count() - l0
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * job.n * k_e2e / float(tt.item()) / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": job.in_bytes, "d2h_bytes_per_step": job.out_bytes, "steps": k_e2e,
-               "api": getattr(job, "e2e_api", "host-pointer C-ABI call, pinned buffers, 2-lane chunked H2D/kernel/D2H pipeline")}
-        lib.cb_buf_release(hin)
-        lib.cb_buf_release(hout)
-    sampler.stop()
-
+    pinned = PinnedPair(cb)
+    line = measure(cb, torch, dist, args, args.workload, rank, world, local_rank, args.steps, args.warmup, pinned)
+    also = {}
+    for w in args.also:
+        if w == args.workload:
+            continue
+        sub = measure(cb, torch, dist, args, w, rank, world, local_rank, max(3, min(args.steps, 10)), 3, pinned,
+                      cpu_sample_scale=1.0 / 8)
+        if rank == 0:
+            keep = ("value", "unit", "ms_per_step", "steps", "warmup", "roofline", "e2e", "cpu_baseline", "clocks", "gpu_launches",
+                    "messages", "gather", "dtype")
+            also[w] = {k: sub[k] for k in keep if k in sub}
+            also[w]["description"] = sub["config"]["description"]
+            also[w]["units_per_step_per_gpu"] = sub["config"]["units_per_step_per_gpu"]
+    pinned.close()
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:  # noqa: BLE001
-            pass
-        peak = peaks.get("hbm_gbs")
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
-        if not peak:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        ms_launch = total_ms / args.steps / job.kernels_per_step
-        alg_bytes = job.bytes_per_unit * job.n / job.kernels_per_step
-        achieved = alg_bytes / (ms_launch * 1e-3) / 1e9
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
-        except Exception:  # noqa: BLE001
-            pass
-        line = {
-            "metric": METRIC, "value": world * job.n * args.steps / (total_ms_max * 1e-3) / 1e6, "unit": UNIT,
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if job.kind == "est" else "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "description": job.desc, "units_per_step_per_gpu": job.n,
-                       "l2": "inputs larger than L2 (%.1f GiB read + %.1f GiB written per step, L2 = 126 MB)"
-                             % (job.in_bytes / 2 ** 30, job.out_bytes / 2 ** 30),
-                       "parallelism": "one overlap-save segment (or channel/frame block) per GPU, no data-path collective",
-                       "seed": SEED},
-            "clocks": clocks,
-            "e2e": e2e,
-            "gpu_launches": int(launches_dev + launches_e2e),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernels_per_step": job.kernels_per_step,
-                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_launch},
-        }
-        if world == 1 and not args.no_cpu:
-            kind = job.kind
-            sample = {"fir": 1 << 26, "fft": 1 << 27, "chain": 1 << 26, "interp": 1 << 23, "mixer": 1 << 26, "fm": 1 << 27, "firdec": 1 << 26, "est": 1 << 24, "firreal": 1 << 26, "graph": 1 << 26}[kind]
-            if args.workload == "timing10x5":
-                sample = 1 << 22
-            if args.workload.startswith("poly8x1024"):
-                sample = 1 << 17
-            v, dt, n = cpu_rate(args.workload, sample, 1)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": f"first {n} units of the same synthetic stream, {dt:.1f} s, one thread "
-                                              "(the reference runs one thread per node)",
-                                    "host_cores": os.cpu_count()}
+        if also:
+            line["also"] = also
+            line["gpu_launches"] += sum(v.get("gpu_launches", 0) for v in also.values())
+            line["also_note"] = ("the other BASELINE.json configs, same protocol as the headline (CUDA events on the launch "
+                                 "stream, max over ranks; e2e through the host-pointer C-ABI call; CPU port on one thread on a "
+                                 "smaller sample); top-level value / ms_per_step / roofline are the headline workload's alone")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

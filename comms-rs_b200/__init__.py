@@ -6,7 +6,7 @@ reference's node structs used by tests and bench.  No CPU fallback exists.
 from . import _lib
 from ._lib import CbError, NodeError, load
 from .nodes import (BatchFirNode, ChainBank, DecimateNode, FFTBatchNode, FFTSampleNode, FirNode, FMDemodNode,
-                    MixerNode, PulseNode, UpsampleNode, bits_to_symbols_dev, complex_real_dev, convert_i16_dev, convert_u8_dev,
+                    MixerNode, NcoNode, PulseNode, UpsampleNode, bits_to_symbols_dev, complex_real_dev, convert_i16_dev, convert_u8_dev,
                     prn_bits, real_to_complex_dev,
                     quantize_i16_dev,
                     rrc_taps, synth_uniform_dev, TimingEstimator, TimingEstimatorNode, frequency_offset_estimate,

@@ -109,6 +109,12 @@ SIGNATURES = {
     "cb_comm_init": (_i, [C.c_int, C.c_int, _vp, C.POINTER(_vp)]),
     "cb_comm_destroy": (_i, [_vp]),
     "cb_gather_segments_dev": (_i, [_vp, _vp, _sz, _vp, _vp]),
+    "cb_comm_rank": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
+    "cb_gather_segments_to_root_dev": (_i, [_vp, _vp, _psz, _sz, _i, _vp, _vp]),
+    "cb_allgather_segments_var_dev": (_i, [_vp, _vp, _psz, _sz, _vp, _vp]),
+    "cb_peer_export": (_i, [_vp, _vp]),
+    "cb_peer_open": (_i, [_vp, _pp]),
+    "cb_peer_close": (_i, [_vp]),
     "cb_real_to_complex_dev": (_i, [_vp, _sz, _vp, _vp]),
     "cb_complex_real_dev": (_i, [_vp, _sz, _vp, _vp]),
     "cb_convert_u8_dev": (_i, [_vp, _sz, _vp, _vp]),
@@ -120,6 +126,12 @@ SIGNATURES = {
     "cb_timing_destroy": (_i, [_vp]),
     "cb_timing_push": (_i, [_vp, _vp, _sz, C.POINTER(_dbl)]),
     "cb_timing_push_dev": (_i, [_vp, _vp, _sz, C.POINTER(_dbl), _vp]),
+    "cb_nco_create": (_i, [_dbl, _dbl, _pp]),
+    "cb_nco_destroy": (_i, [_vp]),
+    "cb_nco_run": (_i, [_vp, _vp, _sz, _vp]),
+    "cb_nco_run_dev": (_i, [_vp, _vp, _sz, _vp, _vp]),
+    "cb_nco_get_phase": (_i, [_vp, C.POINTER(_dbl), C.POINTER(_dbl)]),
+    "cb_nco_set_phase": (_i, [_vp, _dbl]),
     "cb_rrc_taps": (_i, [C.c_uint32, C.c_double, C.c_double, _vp]),
     "cb_rrc_taps_f64": (_i, [C.c_uint32, C.c_double, C.c_double, _vp]),
     "cb_prn_bits": (_i, [C.c_uint64, C.POINTER(C.c_uint64), C.c_uint, _sz, _vp]),

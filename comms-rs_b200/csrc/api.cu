@@ -108,6 +108,55 @@ struct HostPipe {
     }
 };
 
+// Per-handle ordering of carried state across streams.  *_run_dev may be given any stream, while the handle's carried
+// state (history / phase / prev double buffers, the FFT scratch ring and its counters) is one set of device buffers:
+// every launch records `ev` behind itself, and the next use on ANOTHER stream (or a host-side get/set/destroy) waits
+// for it, so two calls on different streams are ordered exactly like two calls on one stream.
+struct LastUse {
+    cudaEvent_t ev = nullptr;
+    cudaStream_t s = nullptr;
+    bool has = false;
+    int begin(cudaStream_t cur)
+    {
+        if (has && cur != s) CB_CUDA(cudaStreamWaitEvent(cur, ev, 0));
+        return CB_OK;
+    }
+    int end(cudaStream_t cur)
+    {
+        if (!ev) CB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CB_CUDA(cudaEventRecord(ev, cur));
+        s = cur;
+        has = true;
+        return CB_OK;
+    }
+    int sync()
+    {
+        if (has) CB_CUDA(cudaEventSynchronize(ev));
+        return CB_OK;
+    }
+    void destroy()
+    {
+        if (ev) {
+            if (has) cudaEventSynchronize(ev);
+            cudaEventDestroy(ev);
+            ev = nullptr;
+        }
+    }
+};
+
+// [a, a+na) and [b, b+nb) share a byte.  The filter / chain / FM kernels read halo samples that other CTAs own and
+// rebuild the carried history from the input after other CTAs may have stored their outputs, so an in-place (or
+// overlapping) call would silently corrupt both the samples and the state of every later batch.
+static inline bool ranges_overlap(const void *a, size_t na, const void *b, size_t nb)
+{
+    const uintptr_t a0 = (uintptr_t)a, b0 = (uintptr_t)b;
+    return a0 < b0 + nb && b0 < a0 + na;
+}
+#define CB_NO_ALIAS(in, in_bytes, out, out_bytes, who)                                                       \
+    CB_REQUIRE(!ranges_overlap((in), (in_bytes), (out), (out_bytes)), CB_ERR_INVALID_ARG,                    \
+               who ": input and output ranges overlap (in-place calls are not provided: the kernel reads "   \
+                   "neighbouring tiles' samples and rebuilds the carried state from the input)")
+
 // complex samples per pipelined chunk of the host-pointer entries (default 2^22 = 32 MiB; COMMS_B200_HOST_CHUNK_LOG2)
 static const size_t HOST_CHUNK = [] {
     const char *e = getenv("COMMS_B200_HOST_CHUNK_LOG2");
@@ -157,6 +206,7 @@ struct cb_fir {
     // overlap-save path for 129 .. 1025 taps: taps' spectrum, the two 4096-point twiddle tables, frame spectra
     float2 *ols_hf, *ols_twf, *ols_twi, *ols_spec;
     size_t ols_spec_frames;
+    LastUse last;
 };
 
 struct cb_mixer {
@@ -177,6 +227,7 @@ struct cb_fft {
     cb_fft *sub_f, *sub_i;
     float2 *chirp, *bspec, *bufa, *bufb;
     size_t bl_m, bl_frames;
+    LastUse last;
 };
 
 struct cb_fm {
@@ -185,6 +236,7 @@ struct cb_fm {
     HostPipe pipe;
     float2 *prev[2];
     int cur;
+    LastUse last;
 };
 
 struct cb_chain {
@@ -200,6 +252,7 @@ struct cb_chain {
     int cur;
     float2 *cscratch;   // converted input of the unfused cb_chain_run_u8 path, grown on demand
     size_t cscratch_len;
+    LastUse last;
 };
 
 static inline cudaStream_t pick_stream(void *user, cudaStream_t own) { return user ? (cudaStream_t)user : own; }
@@ -542,6 +595,7 @@ int cb_fir_destroy(cb_fir *h)
     if (!h) return CB_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    h->last.destroy();
     h->pipe.destroy();
     if (h->taps_dev) cudaFree(h->taps_dev);
     if (h->tc_img) cudaFree(h->tc_img);
@@ -604,12 +658,16 @@ int cb_fir_run_dev(cb_fir *h, const float *d_in, size_t n_in, float *d_out, size
     if (n_in == 0) return CB_OK;
     CB_REQUIRE(d_in && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
     CB_REQUIRE(out_cap >= no, CB_ERR_SIZE, "fir: out_cap %zu < %zu outputs", out_cap, no);
+    CB_NO_ALIAS(d_in, n_in * sizeof(float2), d_out, no * sizeof(float2), "fir");
     CB_CUDA(cudaSetDevice(h->device));
-    int rc = fir_launch_segment(h, reinterpret_cast<const float2 *>(d_in), n_in, h->hist[h->cur], h->hist[h->cur ^ 1],
-                                reinterpret_cast<float2 *>(d_out), pick_stream(stream, h->stream));
+    cudaStream_t s = pick_stream(stream, h->stream);
+    int rc = h->last.begin(s);
+    if (rc) return rc;
+    rc = fir_launch_segment(h, reinterpret_cast<const float2 *>(d_in), n_in, h->hist[h->cur], h->hist[h->cur ^ 1],
+                            reinterpret_cast<float2 *>(d_out), s);
     if (rc) return rc;
     h->cur ^= 1;
-    return CB_OK;
+    return h->last.end(s);
 }
 
 int cb_fir_run_dev_i16(cb_fir *h, const float *d_in, size_t n_in, float scale, int16_t *d_out, size_t out_cap,
@@ -621,6 +679,7 @@ int cb_fir_run_dev_i16(cb_fir *h, const float *d_in, size_t n_in, float scale, i
     if (n_in == 0) return CB_OK;
     CB_REQUIRE(d_in && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
     CB_REQUIRE(out_cap >= no, CB_ERR_SIZE, "fir: out_cap %zu < %zu outputs", out_cap, no);
+    CB_NO_ALIAS(d_in, n_in * sizeof(float2), d_out, no * 2 * sizeof(int16_t), "fir");
     CB_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = pick_stream(stream, h->stream);
     FirSeg seg{reinterpret_cast<const float2 *>(d_in), h->hist[h->cur], h->hist[h->cur ^ 1], nullptr, n_in, no,
@@ -628,7 +687,8 @@ int cb_fir_run_dev_i16(cb_fir *h, const float *d_in, size_t n_in, float scale, i
     seg.y16 = d_out;
     seg.qscale = scale;
     seg.y = reinterpret_cast<float2 *>(d_out);  // unused by the fused kernel (alignment checks only)
-    int rc;
+    int rc = h->last.begin(s);
+    if (rc) return rc;
     if (fir_fuses_i16(seg, h->taps_real, h->tc_img ? &h->tc : nullptr)) {
         rc = launch_fir(seg, h->taps_dev, h->taps.data(), h->taps_real, &h->tc, s);
     } else {  // filter into an f32 scratch, then the stand-alone quantiser
@@ -646,7 +706,7 @@ int cb_fir_run_dev_i16(cb_fir *h, const float *d_in, size_t n_in, float scale, i
     }
     if (rc) return rc;
     h->cur ^= 1;
-    return CB_OK;
+    return h->last.end(s);
 }
 
 // Real samples in, real parts out: the Convert2Node -> BatchFirNode -> Convert3Node [-> DecimateNode] run of
@@ -660,9 +720,11 @@ int cb_fir_run_real_dev(cb_fir *h, const float *d_in, size_t n_in, float *d_out,
     if (n_in == 0) return CB_OK;
     CB_REQUIRE(d_in && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
     CB_REQUIRE(out_cap >= no, CB_ERR_SIZE, "fir: out_cap %zu < %zu outputs", out_cap, no);
+    CB_NO_ALIAS(d_in, n_in * sizeof(float), d_out, no * sizeof(float), "fir");
     CB_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = pick_stream(stream, h->stream);
-    int rc;
+    int rc = h->last.begin(s);
+    if (rc) return rc;
     if (fir_real_applicable(h->k_eff, h->interp, h->decim) && h->hist_len >= h->k_eff) {
         rc = launch_fir_real(d_in, n_in, h->hist[h->cur], h->hist[h->cur ^ 1], h->hist_len, h->taps.data(), h->k_eff,
                              h->decim, d_out, s);
@@ -681,7 +743,7 @@ int cb_fir_run_real_dev(cb_fir *h, const float *d_in, size_t n_in, float *d_out,
     }
     if (rc) return rc;
     h->cur ^= 1;
-    return CB_OK;
+    return h->last.end(s);
 }
 
 int cb_fir_run_real(cb_fir *h, const float *in, size_t n_in, float *out, size_t out_cap, size_t *n_out)
@@ -741,7 +803,9 @@ int cb_fir_run(cb_fir *h, const float *in, size_t n_in, float *out, size_t out_c
     // chunk starts must keep the decimation grid: multiples of D input samples
     size_t chunk = HOST_CHUNK / h->decim * h->decim;
     if (chunk < 4 * H || n_in <= chunk) chunk = n_in;
-    int rc = h->pipe.reserve((chunk + H) * sizeof(float2), fir_out_len(h, chunk) * sizeof(float2));
+    int rc = h->last.sync();  // a *_run_dev on a caller's stream may still be using the carried state
+    if (rc) return rc;
+    rc = h->pipe.reserve((chunk + H) * sizeof(float2), fir_out_len(h, chunk) * sizeof(float2));
     if (rc) return rc;
     size_t done = 0, out_done = 0;
     for (int i = 0; done < n_in; ++i) {
@@ -785,6 +849,10 @@ int cb_fir_get_state(cb_fir *h, float *state, size_t nstate)
     CB_REQUIRE(nstate == h->nstate, CB_ERR_SIZE, "fir: state length %zu != %zu", nstate, h->nstate);
     CB_CUDA(cudaSetDevice(h->device));
     CB_CUDA(cudaStreamSynchronize(h->stream));
+    {
+        const int rcl = h->last.sync();
+        if (rcl) return rcl;
+    }
     std::vector<float2> hist(h->hist_len);
     CB_CUDA(cudaMemcpy(hist.data(), h->hist[h->cur], h->hist_len * sizeof(float2), cudaMemcpyDeviceToHost));
     float2 *st = reinterpret_cast<float2 *>(state);
@@ -809,6 +877,8 @@ int cb_fir_set_state(cb_fir *h, const float *state, size_t nstate)
     int rc = fir_state_to_hist(h, reinterpret_cast<const float2 *>(state), nstate, hist);
     if (rc) return rc;
     CB_CUDA(cudaStreamSynchronize(h->stream));
+    rc = h->last.sync();
+    if (rc) return rc;
     CB_CUDA(cudaMemcpy(h->hist[h->cur], hist.data(), h->hist_len * sizeof(float2), cudaMemcpyHostToDevice));
     return CB_OK;
 }
@@ -1215,6 +1285,7 @@ int cb_fft_destroy(cb_fft *h)
     if (!h) return CB_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    h->last.destroy();
     h->pipe.destroy();
     if (h->tw) cudaFree(h->tw);
     if (h->tw1) cudaFree(h->tw1);
@@ -1318,10 +1389,16 @@ int cb_fft_run_dev(cb_fft *h, const float *d_in, size_t n_in, float *d_out, void
     CB_REQUIRE(n_in > 0 && n_in % h->plan.n == 0, CB_ERR_SIZE, "fft: input length %zu is not a multiple of fft_size %zu",
                n_in, h->plan.n);
     CB_REQUIRE(d_in && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
-    CB_REQUIRE(d_in != d_out, CB_ERR_INVALID_ARG, "fft: in-place transform is not provided");
+    CB_NO_ALIAS(d_in, n_in * sizeof(float2), d_out, n_in * sizeof(float2), "fft");
     CB_CUDA(cudaSetDevice(h->device));
-    return fft_exec(h, reinterpret_cast<const float2 *>(d_in), reinterpret_cast<float2 *>(d_out), n_in / h->plan.n,
-                    pick_stream(stream, h->stream));
+    cudaStream_t s = pick_stream(stream, h->stream);
+    // the scratch ring, its counters and the chirp-z work buffers are per handle: order calls across streams
+    const bool shared = h->plan.kind == FFT_FOURSTEP || h->plan.kind == FFT_BLUESTEIN;
+    int rc = shared ? h->last.begin(s) : CB_OK;
+    if (rc) return rc;
+    rc = fft_exec(h, reinterpret_cast<const float2 *>(d_in), reinterpret_cast<float2 *>(d_out), n_in / h->plan.n, s);
+    if (rc) return rc;
+    return shared ? h->last.end(s) : CB_OK;
 }
 
 int cb_fft_run(cb_fft *h, const float *in, size_t n_in, float *out)
@@ -1335,7 +1412,9 @@ int cb_fft_run(cb_fft *h, const float *in, size_t n_in, float *out)
     size_t chunk = HOST_CHUNK / N * N;
     if (chunk == 0) chunk = N;
     if (n_in < chunk) chunk = n_in;
-    int rc = h->pipe.reserve(chunk * sizeof(float2), chunk * sizeof(float2));
+    int rc = h->last.sync();
+    if (rc) return rc;
+    rc = h->pipe.reserve(chunk * sizeof(float2), chunk * sizeof(float2));
     if (rc) return rc;
     const float2 *hin = reinterpret_cast<const float2 *>(in);
     float2 *hout = reinterpret_cast<float2 *>(out);
@@ -1388,6 +1467,7 @@ int cb_fm_destroy(cb_fm *h)
     if (!h) return CB_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    h->last.destroy();
     h->pipe.destroy();
     for (int i = 0; i < 2; ++i)
         if (h->prev[i]) cudaFree(h->prev[i]);
@@ -1401,12 +1481,15 @@ int cb_fm_run_dev(cb_fm *h, const float *d_in, size_t n, float *d_out, void *str
     CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
     if (n == 0) return CB_OK;
     CB_REQUIRE(d_in && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_NO_ALIAS(d_in, n * sizeof(float2), d_out, n * sizeof(float), "fm");
     CB_CUDA(cudaSetDevice(h->device));
-    int rc = launch_fm(reinterpret_cast<const float2 *>(d_in), d_out, n, h->prev[h->cur], h->prev[h->cur ^ 1],
-                       pick_stream(stream, h->stream));
+    cudaStream_t s = pick_stream(stream, h->stream);
+    int rc = h->last.begin(s);
+    if (rc) return rc;
+    rc = launch_fm(reinterpret_cast<const float2 *>(d_in), d_out, n, h->prev[h->cur], h->prev[h->cur ^ 1], s);
     if (rc) return rc;
     h->cur ^= 1;
-    return CB_OK;
+    return h->last.end(s);
 }
 
 int cb_fm_run(cb_fm *h, const float *in, size_t n, float *out)
@@ -1500,6 +1583,7 @@ int cb_chain_destroy(cb_chain *h)
     if (!h) return CB_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    h->last.destroy();
     h->pipe.destroy();
     for (int i = 0; i < 2; ++i) {
         if (h->hist[i]) cudaFree(h->hist[i]);
@@ -1530,6 +1614,8 @@ static int chain_run_dev_impl(cb_chain *h, const float *d_in, const uint8_t *d_i
     if (n_in == 0) return CB_OK;
     CB_REQUIRE((d_in || d_in8) && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
     CB_REQUIRE(out_cap >= no, CB_ERR_SIZE, "chain: out_cap %zu < %zu outputs per channel", out_cap, no);
+    CB_NO_ALIAS(d_in ? (const void *)d_in : (const void *)d_in8, h->channels * n_in * (d_in ? sizeof(float2) : 2), d_out,
+                h->channels * no * (h->fm ? sizeof(float) : sizeof(float2)), "chain");
     CB_CUDA(cudaSetDevice(h->device));
     ChainArgs a;
     a.x = reinterpret_cast<const float2 *>(d_in);
@@ -1557,6 +1643,10 @@ static int chain_run_dev_impl(cb_chain *h, const float *d_in, const uint8_t *d_i
     CB_REQUIRE(ceil_div((size_t)a.span_max, (size_t)256) <= 64, CB_ERR_UNSUPPORTED,
                "chain: decimation %u with %u taps needs a span beyond the staged window", h->decim, h->ntaps);
     cudaStream_t s = pick_stream(stream, h->stream);
+    {
+        const int rcl = h->last.begin(s);
+        if (rcl) return rcl;
+    }
     if (d_in8 != nullptr && !chain_fuses_u8(a, h->cplx)) {  // no fused kernel for this shape: convert, then filter
         const size_t total = h->channels * n_in;
         if (h->cscratch_len < total) {
@@ -1574,7 +1664,7 @@ static int chain_run_dev_impl(cb_chain *h, const float *d_in, const uint8_t *d_i
     int rc = launch_chain(a, h->taps, h->mix, h->fm, h->cplx, h->channels, s);
     if (rc) return rc;
     h->cur ^= 1;
-    return CB_OK;
+    return h->last.end(s);
 }
 
 int cb_chain_run_dev(cb_chain *h, const float *d_in, size_t n_in, float *d_out, size_t out_cap, size_t *n_out,
@@ -1836,6 +1926,133 @@ int cb_timing_push_dev(cb_timing *h, const double *d_samples, size_t n, double *
 {
     return timing_push_impl(h, reinterpret_cast<const double2 *>(d_samples), false, n, estimate,
                             h ? pick_stream(stream, h->stream) : nullptr);
+}
+
+// ============================================================================ NCO
+// Nco::new / Nco::push (src/demodulation/nco.rs:41-49, 71-77) and NcoNode::new(dphase, phase) (:112-127) over a batch
+// of phase errors: out[k] = exp(j * phase_k), phase_k = phase_{k-1} + dphase + perr[k] (mod 2 pi), carried across calls.
+struct cb_nco {
+    int device;
+    cudaStream_t stream;
+    HostPipe pipe;
+    double dphase;
+    double *phase[2];
+    int cur;
+    double *scratch;
+    size_t scratch_len;
+    LastUse last;
+};
+
+int cb_nco_create(double dphase, double phase, cb_nco **out)
+{
+    CB_REQUIRE(out, CB_ERR_INVALID_ARG, "out is NULL");
+    CB_REQUIRE(std::isfinite(dphase) && std::isfinite(phase), CB_ERR_INVALID_ARG, "nco: non-finite phase");
+    int rc = ensure_device();
+    if (rc) return rc;
+    cb_nco *h = new (std::nothrow) cb_nco();
+    CB_REQUIRE(h, CB_ERR_OOM, "host allocation failed");
+    h->device = g_dev;
+    h->dphase = wrap_dphase(dphase);  // the same wrap loop as Mixer::new (nco.rs:41-49)
+    h->cur = 0;
+    h->phase[0] = h->phase[1] = nullptr;
+    h->scratch = nullptr;
+    h->scratch_len = 0;
+    h->stream = nullptr;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaMalloc(&h->phase[i], sizeof(double));
+        if (e == cudaSuccess) e = cudaMemcpy(h->phase[i], &phase, sizeof(double), cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess || h->pipe.init(h->stream)) {
+        cb_nco_destroy(h);
+        return e != cudaSuccess ? cuda_fail(e, "nco create", __FILE__, __LINE__) : CB_ERR_CUDA;
+    }
+    *out = h;
+    return CB_OK;
+}
+
+int cb_nco_destroy(cb_nco *h)
+{
+    if (!h) return CB_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    h->last.destroy();
+    h->pipe.destroy();
+    for (int i = 0; i < 2; ++i)
+        if (h->phase[i]) cudaFree(h->phase[i]);
+    if (h->scratch) cudaFree(h->scratch);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return CB_OK;
+}
+
+int cb_nco_run_dev(cb_nco *h, const double *d_perr, size_t n, double *d_out, void *stream)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    if (n == 0) return CB_OK;
+    CB_REQUIRE(d_perr && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_REQUIRE((reinterpret_cast<uintptr_t>(d_out) & 15) == 0, CB_ERR_INVALID_ARG, "nco: d_out must be 16-byte aligned");
+    CB_NO_ALIAS(d_perr, n * sizeof(double), d_out, n * 2 * sizeof(double), "nco");
+    CB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = pick_stream(stream, h->stream);
+    int rc = h->last.begin(s);
+    if (rc) return rc;
+    const size_t need = nco_scratch_doubles(n);
+    if (h->scratch_len < need) {
+        if (h->scratch) CB_CUDA(cudaFree(h->scratch));  // waits for earlier launches that use it
+        h->scratch = nullptr;
+        h->scratch_len = 0;
+        CB_CUDA(cudaMalloc(&h->scratch, need * sizeof(double)));
+        h->scratch_len = need;
+    }
+    rc = launch_nco(d_perr, n, h->scratch, h->phase[h->cur], h->phase[h->cur ^ 1], h->dphase,
+                    reinterpret_cast<double2 *>(d_out), s);
+    if (rc) return rc;
+    h->cur ^= 1;
+    return h->last.end(s);
+}
+
+int cb_nco_run(cb_nco *h, const double *perr, size_t n, double *out)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    if (n == 0) return CB_OK;
+    CB_REQUIRE(perr && out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_CUDA(cudaSetDevice(h->device));
+    int rc = h->pipe.reserve(n * sizeof(double), n * 2 * sizeof(double));
+    if (rc) return rc;
+    cudaStream_t s = h->pipe.lane[0];
+    CB_CUDA(cudaMemcpyAsync(h->pipe.in[0], perr, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    rc = cb_nco_run_dev(h, reinterpret_cast<const double *>(h->pipe.in[0]), n, reinterpret_cast<double *>(h->pipe.out[0]), s);
+    if (rc) return rc;
+    CB_CUDA(cudaMemcpyAsync(out, h->pipe.out[0], n * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaStreamSynchronize(s));
+    return CB_OK;
+}
+
+int cb_nco_get_phase(cb_nco *h, double *phase, double *dphase)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    if (dphase) *dphase = h->dphase;
+    if (phase) {
+        CB_CUDA(cudaSetDevice(h->device));
+        CB_CUDA(cudaStreamSynchronize(h->stream));
+        int rc = h->last.sync();
+        if (rc) return rc;
+        CB_CUDA(cudaMemcpy(phase, h->phase[h->cur], sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return CB_OK;
+}
+
+int cb_nco_set_phase(cb_nco *h, double phase)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    CB_REQUIRE(std::isfinite(phase), CB_ERR_INVALID_ARG, "nco: non-finite phase");
+    CB_CUDA(cudaSetDevice(h->device));
+    CB_CUDA(cudaStreamSynchronize(h->stream));
+    int rc = h->last.sync();
+    if (rc) return rc;
+    CB_CUDA(cudaMemcpy(h->phase[h->cur], &phase, sizeof(double), cudaMemcpyHostToDevice));
+    return CB_OK;
 }
 
 // ============================================================================ bit-exact edges

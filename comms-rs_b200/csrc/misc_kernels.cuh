@@ -15,6 +15,10 @@ int launch_complex_real(const float2 *in, float *out, size_t n, cudaStream_t s);
 int launch_convert_u8(const uint8_t *in, float *out, size_t nfloats, cudaStream_t s);
 int launch_convert_i16(const int16_t *in, float *out, size_t nfloats, float scale, cudaStream_t s);
 int launch_synth(float *out, size_t nfloats, unsigned long long base, cudaStream_t s);
+// Nco::push over a batch (nco_kernel.cu): tile_scratch holds nco_scratch_doubles(n) doubles
+size_t nco_scratch_doubles(size_t n);
+int launch_nco(const double *perr, size_t n, double *tile_scratch, const double *phase_in, double *phase_out, double dphase,
+               double2 *out, cudaStream_t s);
 
 #ifdef __CUDACC__
 __device__ __forceinline__ float2 cmul(float2 a, float2 b)

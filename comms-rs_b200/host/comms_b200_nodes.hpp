@@ -247,6 +247,41 @@ struct MixerNode : Node1<MixerNode, c32, c32> {
     }
 };
 
+// NcoNode::new(dphase, phase) / run(f64) -> Complex<f64>          src/demodulation/nco.rs:112-133
+struct c64 {
+    double re, im;
+};
+struct NcoNode : Node1<NcoNode, double, c64> {
+    cb_nco *h_ = nullptr;
+    explicit NcoNode(double dphase, std::optional<double> phase = std::nullopt)
+    {
+        if (cb_nco_create(dphase, phase.value_or(0.0), &h_)) throw std::runtime_error(cb_last_error());
+    }
+    ~NcoNode() { cb_nco_destroy(h_); }
+    Result<c64> run(const double &perr)
+    {
+        c64 out;
+        int st = cb_nco_run(h_, &perr, 1, reinterpret_cast<double *>(&out));
+        return st ? Result<c64>::Err(map_status(st)) : Result<c64>::Ok(out);
+    }
+};
+
+// Batching shim in front of GPU nodes: a vector of phase errors per message, the recurrence applied in order
+struct NcoBatchNode : Node1<NcoBatchNode, std::vector<double>, std::vector<c64>> {
+    cb_nco *h_ = nullptr;
+    explicit NcoBatchNode(double dphase, std::optional<double> phase = std::nullopt)
+    {
+        if (cb_nco_create(dphase, phase.value_or(0.0), &h_)) throw std::runtime_error(cb_last_error());
+    }
+    ~NcoBatchNode() { cb_nco_destroy(h_); }
+    Result<std::vector<c64>> run(const std::vector<double> &perr)
+    {
+        std::vector<c64> out(perr.size());
+        int st = cb_nco_run(h_, perr.data(), perr.size(), reinterpret_cast<double *>(out.data()));
+        return st ? Result<std::vector<c64>>::Err(map_status(st)) : Result<std::vector<c64>>::Ok(std::move(out));
+    }
+};
+
 // FFTBatchNode::new(fft_size, ifft) / run(&[Complex<T>])      src/fft/fft_node.rs:65-83
 struct FFTBatchNode : Node1<FFTBatchNode, std::vector<c32>, std::vector<c32>> {
     cb_fft *h_ = nullptr;

@@ -240,6 +240,48 @@ class MixerNode(_Handle):
         return d.value
 
 
+class NcoNode(_Handle):
+    """NcoNode::new(dphase, phase) (src/demodulation/nco.rs:112-127).  run(perr) takes one phase error (the reference
+    contract: f64 in, Complex<f64> out) or a batch of them -- the batching shim that lets a vector of loop-filter
+    outputs feed GPU nodes: out[k] = exp(j * phase_k) with Nco::push applied in order (nco.rs:71-77)."""
+
+    _destroy = "cb_nco_destroy"
+
+    def __init__(self, dphase: float, phase: float | None = None):
+        super().__init__()
+        check(_lib.load().cb_nco_create(float(dphase), 0.0 if phase is None else float(phase), C.byref(self._h)))
+
+    def run(self, perr):
+        scalar = np.ndim(perr) == 0
+        e = np.ascontiguousarray(np.atleast_1d(np.asarray(perr, dtype=np.float64)))
+        out = np.empty(len(e), dtype=np.complex128)
+        try:
+            check(_lib.load().cb_nco_run(self._h, _ptr(e), len(e), _ptr(out)))
+        except CbError as ex:
+            raise node_error(ex) from ex
+        return out[0] if scalar else out
+
+    def run_dev(self, d_perr: int, n: int, d_out: int, stream: int = 0) -> None:
+        """n doubles in, n complex f64 out, device pointers."""
+        check(_lib.load().cb_nco_run_dev(self._h, d_perr, n, d_out, stream))
+
+    @property
+    def phase(self) -> float:
+        p = C.c_double()
+        check(_lib.load().cb_nco_get_phase(self._h, C.byref(p), None))
+        return p.value
+
+    @phase.setter
+    def phase(self, v: float):
+        check(_lib.load().cb_nco_set_phase(self._h, float(v)))
+
+    @property
+    def dphase(self) -> float:
+        d = C.c_double()
+        check(_lib.load().cb_nco_get_phase(self._h, None, C.byref(d)))
+        return d.value
+
+
 class FFTBatchNode(_Handle):
     """FFTBatchNode::new(fft_size, ifft) (src/fft/fft_node.rs:65-74).  run() takes
     one frame (the reference contract) or several contiguous frames."""

@@ -3,7 +3,7 @@
 use std::os::raw::{c_char, c_double, c_float, c_int, c_uint, c_void};
 
 macro_rules! opaque { ($($n:ident),*) => { $(#[repr(C)] pub struct $n { _p: [u8; 0] })* } }
-opaque!(cb_stream, cb_buf, cb_fir, cb_mixer, cb_fft, cb_fm, cb_chain, cb_comm, cb_timing);
+opaque!(cb_stream, cb_buf, cb_fir, cb_mixer, cb_fft, cb_fm, cb_chain, cb_comm, cb_timing, cb_nco);
 
 pub const CB_OK: c_int = 0;
 pub const CB_ERR_INVALID_ARG: c_int = 1;
@@ -97,6 +97,18 @@ extern "C" {
     pub fn cb_comm_init(nranks: c_int, rank: c_int, id128: *const c_void, out: *mut *mut cb_comm) -> c_int;
     pub fn cb_comm_destroy(c: *mut cb_comm) -> c_int;
     pub fn cb_gather_segments_dev(c: *mut cb_comm, d_seg: *const f32, n_samples: usize, d_all: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn cb_comm_rank(c: *const cb_comm, rank: *mut c_int, nranks: *mut c_int) -> c_int;
+    pub fn cb_gather_segments_to_root_dev(c: *mut cb_comm, d_seg: *const c_void, counts: *const usize, elem_bytes: usize, root: c_int, d_all: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn cb_allgather_segments_var_dev(c: *mut cb_comm, d_seg: *const c_void, counts: *const usize, elem_bytes: usize, d_all: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn cb_peer_export(d_ptr: *mut c_void, handle64: *mut c_void) -> c_int;
+    pub fn cb_peer_open(handle64: *const c_void, d_mapped: *mut *mut c_void) -> c_int;
+    pub fn cb_peer_close(d_mapped: *mut c_void) -> c_int;
+    pub fn cb_nco_create(dphase: f64, phase: f64, out: *mut *mut cb_nco) -> c_int;
+    pub fn cb_nco_destroy(h: *mut cb_nco) -> c_int;
+    pub fn cb_nco_run(h: *mut cb_nco, perr: *const f64, n: usize, out: *mut f64) -> c_int;
+    pub fn cb_nco_run_dev(h: *mut cb_nco, d_perr: *const f64, n: usize, d_out: *mut f64, stream: *mut c_void) -> c_int;
+    pub fn cb_nco_get_phase(h: *mut cb_nco, phase: *mut f64, dphase: *mut f64) -> c_int;
+    pub fn cb_nco_set_phase(h: *mut cb_nco, phase: f64) -> c_int;
     pub fn cb_fir_run_real(h: *mut cb_fir, input: *const f32, n_in: usize, out: *mut f32, out_cap: usize, n_out: *mut usize) -> c_int;
     pub fn cb_fir_run_real_dev(h: *mut cb_fir, d_in: *const f32, n_in: usize, d_out: *mut f32, out_cap: usize, n_out: *mut usize, stream: *mut c_void) -> c_int;
     pub fn cb_qfilt_taps_f64(n_taps: u32, alpha: f64, sam_per_sym: u32, taps: *mut f64, n_out: *mut u32) -> c_int;

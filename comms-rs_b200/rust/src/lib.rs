@@ -249,6 +249,61 @@ impl GpuBatchMixerNode {
     }
 }
 
+/// Drop-in for `NcoNode` (src/demodulation/nco.rs:82-133): one phase error in, one `Complex<f64>` out.
+#[derive(Node)]
+pub struct GpuNcoNode {
+    pub input: NodeReceiver<f64>,
+    nco: Nco,
+    pub output: NodeSender<Complex<f64>>,
+}
+
+struct Nco(*mut ffi::cb_nco);
+unsafe impl Send for Nco {}
+impl Drop for Nco {
+    fn drop(&mut self) {
+        unsafe { ffi::cb_nco_destroy(self.0) };
+    }
+}
+
+fn nco_new(dphase: f64, phase: Option<f64>) -> Nco {
+    let mut h = ptr::null_mut();
+    let st = unsafe { ffi::cb_nco_create(dphase, phase.unwrap_or(0.0), &mut h) };
+    assert_eq!(st, ffi::CB_OK, "cb_nco_create failed");
+    Nco(h)
+}
+
+impl GpuNcoNode {
+    pub fn new(dphase: f64, phase: Option<f64>) -> Self {
+        GpuNcoNode { nco: nco_new(dphase, phase), input: Default::default(), output: Default::default() }
+    }
+    pub fn run(&mut self, input: f64) -> Result<Complex<f64>, NodeError> {
+        let mut out = Complex::new(0.0f64, 0.0f64);
+        check(unsafe { ffi::cb_nco_run(self.nco.0, &input, 1, &mut out as *mut Complex<f64> as *mut f64) })?;
+        Ok(out)
+    }
+}
+
+/// Batching shim: a vector of phase errors per message, `Nco::push` applied in order on the device (one scan).
+#[derive(Node)]
+#[pass_by_ref]
+pub struct GpuNcoBatchNode {
+    pub input: NodeReceiver<Vec<f64>>,
+    nco: Nco,
+    pub output: NodeSender<Vec<Complex<f64>>>,
+}
+
+impl GpuNcoBatchNode {
+    pub fn new(dphase: f64, phase: Option<f64>) -> Self {
+        GpuNcoBatchNode { nco: nco_new(dphase, phase), input: Default::default(), output: Default::default() }
+    }
+    pub fn run(&mut self, input: &[f64]) -> Result<Vec<Complex<f64>>, NodeError> {
+        let mut out: Vec<Complex<f64>> = Vec::with_capacity(input.len());
+        check(unsafe { ffi::cb_nco_run(self.nco.0, input.as_ptr(), input.len(), out.as_mut_ptr() as *mut f64) })?;
+        unsafe { out.set_len(input.len()) };
+        Ok(out)
+    }
+}
+
 /// Drop-in for `FFTBatchNode<f32>` (src/fft/fft_node.rs:26-84).
 #[derive(Node)]
 #[pass_by_ref]

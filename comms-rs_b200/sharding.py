@@ -32,22 +32,36 @@ def block_shard(items: int, world: int, rank: int) -> tuple[int, int]:
     return start, start + base + (1 if rank < extra else 0)
 
 
-def halo_state(prev_samples, k: int):
-    """Reference `state` for a segment: the k samples before it, newest first, zero
-    padded when fewer exist (start of stream)."""
+def halo_state(prev_samples, k: int, interp: int = 1):
+    """Reference `state` for a segment: the k entries of the delay line before it, newest first, zero padded when
+    fewer exist (start of stream).  interp = L > 1: the delay line is in the zero-stuffed domain
+    (UpsampleNode -> BatchFirNode, PulseNode): the i-th most recent input symbol sits at index i*L - 1, zeros
+    between -- a 1024-tap x8 bank needs the 127 symbols before the segment."""
     import numpy as np
 
     prev = np.asarray(prev_samples)
     st = np.zeros(k, dtype=prev.dtype if prev.size else np.complex64)
-    m = min(k, len(prev))
+    L = max(int(interp), 1)
+    m = min(k // L, len(prev))
     if m:
-        st[:m] = prev[len(prev) - m:][::-1]
+        st[L - 1: m * L: L] = prev[len(prev) - m:][::-1]
     return st
 
 
+_TWO_PI_50 = "6.28318530717958647692528676655900576839433879875021"
+
+
 def segment_phase(phase0: float, dphase: float, start: int) -> float:
-    """Mixer phase at sample `start` of the stream, wrapped to [0, 2 pi)."""
-    return math.fmod(phase0 + math.fmod(start * dphase, 2 * math.pi), 2 * math.pi) % (2 * math.pi)
+    """Mixer phase at sample `start` of the stream, wrapped to [0, 2 pi).  start * dphase is formed exactly
+    (both are rationals) and reduced against 2 pi to 50 digits, so the result is the correctly rounded phase for
+    any stream position (a plain f64 product is already 2e-6 rad off at 2^31 samples)."""
+    from fractions import Fraction
+
+    two_pi = Fraction(_TWO_PI_50)
+    p = Fraction(phase0) + Fraction(int(start)) * Fraction(dphase)
+    p -= (p // two_pi) * two_pi
+    v = float(p)
+    return v if v < 2 * math.pi else 0.0
 
 
 def gather_ordered(local, sizes=None, group=None):
@@ -102,6 +116,25 @@ class SegmentGather:
         """d_all (device, nranks * n_samples complex f32) <- every rank's n_samples-sample segment, in rank order."""
         self._lib.check(self._lib.load().cb_gather_segments_dev(self._h, d_seg, n_samples, d_all, stream))
 
+    def _counts(self, counts):
+        import ctypes as C
+
+        if len(counts) != self.nranks:
+            raise ValueError("counts must have one entry per rank")
+        return (C.c_size_t * self.nranks)(*[int(c) for c in counts])
+
+    def gather_to_root_dev(self, d_seg: int, counts, elem_bytes: int, root: int, d_all: int, stream: int = 0) -> None:
+        """Ordered gather of per-rank segments of any lengths onto `root` only (grouped ncclSend / ncclRecv):
+        counts[r] elements of elem_bytes from rank r land at d_all + sum(counts[:r]).  Every rank passes the same
+        counts, so empty segments are skipped consistently."""
+        self._lib.check(self._lib.load().cb_gather_segments_to_root_dev(
+            self._h, d_seg, self._counts(counts), int(elem_bytes), int(root), d_all, stream))
+
+    def allgather_var_dev(self, d_seg: int, counts, elem_bytes: int, d_all: int, stream: int = 0) -> None:
+        """The same ordered stream on every rank (segments of any lengths)."""
+        self._lib.check(self._lib.load().cb_allgather_segments_var_dev(
+            self._h, d_seg, self._counts(counts), int(elem_bytes), d_all, stream))
+
     def close(self) -> None:
         if self._h:
             self._lib.load().cb_comm_destroy(self._h)
@@ -112,3 +145,31 @@ class SegmentGather:
             self.close()
         except Exception:  # noqa: BLE001
             pass
+
+
+def peer_export(d_ptr: int) -> bytes:
+    """64-byte CUDA IPC handle of a device allocation (its base pointer) for cb_peer_open on another rank."""
+    import ctypes as C
+
+    from . import _lib
+
+    buf = C.create_string_buffer(64)
+    _lib.check(_lib.load().cb_peer_export(d_ptr, buf))
+    return buf.raw
+
+
+def peer_open(handle: bytes) -> int:
+    """Maps another rank's exported allocation; the returned device pointer is valid as d_out of any *_run_dev."""
+    import ctypes as C
+
+    from . import _lib
+
+    out = C.c_void_p()
+    _lib.check(_lib.load().cb_peer_open(C.create_string_buffer(bytes(handle), 64), C.byref(out)))
+    return out.value
+
+
+def peer_close(d_mapped: int) -> None:
+    from . import _lib
+
+    _lib.check(_lib.load().cb_peer_close(d_mapped))

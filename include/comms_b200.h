@@ -23,6 +23,15 @@
  *     `out` is filled.  `*_run_dev` takes device pointers (16-byte aligned for
  *     full speed) and a cudaStream_t (NULL = the handle's stream), is
  *     asynchronous, and lets nodes chain on the device.
+ *   - input and output ranges of a `*_run_dev` call must not overlap
+ *     (CB_ERR_INVALID_ARG): the filter, chain, FM and FFT kernels read samples
+ *     owned by neighbouring tiles and rebuild the carried state from the input.
+ *     Only the element-wise entries (mixer, converters, quantiser) may run
+ *     in place.
+ *   - a handle's carried state is ordered across streams: each `*_run_dev`
+ *     records an event behind its launch and the handle's next use on any other
+ *     stream (and get/set_state, destroy) waits for it, so calls on different
+ *     streams behave like calls on one stream, in host call order.
  *   - there is no CPU fallback: without a CUDA device every compute call
  *     fails with CB_ERR_NO_DEVICE.
  */
@@ -289,6 +298,21 @@ CB_API int cb_timing_destroy(cb_timing *h);
 CB_API int cb_timing_push(cb_timing *h, const double *samples, size_t n, double *estimate);
 CB_API int cb_timing_push_dev(cb_timing *h, const double *d_samples, size_t n, double *estimate, void *stream);
 
+/* ------------------------------------------------------------------ NCO
+ * NcoNode::new(dphase, phase) / Nco::push (src/demodulation/nco.rs:41-49, 71-77, 112-127) over a batch of phase errors:
+ *   phase_k = phase_{k-1} + dphase + perr[k]  (one conditional wrap when > 2 pi),  out[k] = exp(j * phase_k),
+ * i.e. phase_k = phase_0 + (k+1)*dphase + sum_{i<=k} perr[i] (mod 2 pi): a prefix sum, evaluated as a device scan in
+ * f64 with the ramp term reduced exactly; the wrap only picks the representative of the phase, never the output.
+ * n doubles in -> n complex f64 (2n doubles) out; dphase wrapped into [0, 2 pi) like Nco::new; phase carried across
+ * calls (cb_nco_get_phase returns it reduced to [0, 2 pi)).  At most 2^29 - 1 errors per call. */
+typedef struct cb_nco cb_nco;
+CB_API int cb_nco_create(double dphase, double phase, cb_nco **out);
+CB_API int cb_nco_destroy(cb_nco *h);
+CB_API int cb_nco_run(cb_nco *h, const double *perr, size_t n, double *out);
+CB_API int cb_nco_run_dev(cb_nco *h, const double *d_perr, size_t n, double *d_out, void *stream);
+CB_API int cb_nco_get_phase(cb_nco *h, double *phase, double *dphase);
+CB_API int cb_nco_set_phase(cb_nco *h, double phase);
+
 /* Real <-> complex glue of examples/fm_radio.rs, device side, so the whole shipped graph can stay on the GPU:
  * cb_real_to_complex: Convert2Node (fm_radio.rs:98-118), x -> Complex(x, 0); cb_complex_real: Convert3Node
  * (fm_radio.rs:122-142), z -> z.re.  n elements each. */
@@ -309,7 +333,28 @@ typedef struct cb_comm cb_comm;
 CB_API int cb_comm_unique_id(void *id128);
 CB_API int cb_comm_init(int nranks, int rank, const void *id128, cb_comm **out);
 CB_API int cb_comm_destroy(cb_comm *c);
+CB_API int cb_comm_rank(const cb_comm *c, int *rank, int *nranks);
+/* Equal-length segments onto EVERY rank (ncclAllGather).  A collective: every rank must call it with the same
+ * n_samples (0 everywhere is a no-op everywhere; one rank may not skip the call on its own). */
 CB_API int cb_gather_segments_dev(cb_comm *c, const float *d_seg, size_t n_samples, float *d_all, void *stream);
+/* Ordered gather of segments of ANY lengths onto ONE rank (what a single ordered output stream needs): counts[r]
+ * elements of elem_bytes bytes from rank r land at d_all + sum_{q<r} counts[q] on `root`.  Every rank passes the
+ * same counts[nranks] (the segment table is host knowledge, sharding.segment_bounds), so empty trailing segments are
+ * skipped consistently and no rank blocks alone.  One grouped ncclSend/ncclRecv: the root's NVLink ingress carries
+ * each remote byte once -- 1/nranks of the switch traffic of an all-gather.  d_all may be NULL off the root. */
+CB_API int cb_gather_segments_to_root_dev(cb_comm *c, const void *d_seg, const size_t *counts, size_t elem_bytes,
+                                          int root, void *d_all, void *stream);
+/* The same ordered stream on every rank, segments of any lengths (one grouped broadcast per non-empty segment). */
+CB_API int cb_allgather_segments_var_dev(cb_comm *c, const void *d_seg, const size_t *counts, size_t elem_bytes,
+                                         void *d_all, void *stream);
+/* Gather fused into the producing kernel: the root exports its gathered-stream buffer (64-byte CUDA IPC handle, passed
+ * by any host channel; the pointer must be the base of a cb_buf_alloc_device / cudaMalloc allocation), the other
+ * ranks map it and pass `mapped + byte offset of their segment` as d_out of cb_fir_run_dev / cb_chain_run_dev /
+ * cb_fft_run_dev: the kernel's stores travel over NVLink / NVSwitch into the root's HBM tile by tile while the
+ * filter runs; there is no second pass over the data and no collective call. */
+CB_API int cb_peer_export(void *d_ptr, void *handle64);
+CB_API int cb_peer_open(const void *handle64, void **d_mapped);
+CB_API int cb_peer_close(void *d_mapped);
 
 /* ------------------------------------------------------------------ synthetic input
  * splitmix64 counter generator shared with the oracle (oracle.c

@@ -166,6 +166,24 @@ class Mixer:
         return out
 
 
+class Nco:
+    """Nco (src/demodulation/nco.rs:15-78); NcoNode::new(dphase, phase) order is the node's (:112-127)."""
+
+    def __init__(self, phase: float, dphase: float):
+        self.phase = float(phase)
+        self.dphase = float(lib().orc_mixer_wrap_dphase(C.c_double(dphase)))  # same wrap loop as Mixer::new (nco.rs:41-49)
+
+    def push(self, perr):
+        """One sample (float) or a batch (array): the per-sample recurrence applied in order."""
+        scalar = np.isscalar(perr)
+        e = np.ascontiguousarray(np.atleast_1d(np.asarray(perr, dtype=np.float64)))
+        out = np.empty(len(e), dtype=np.complex128)
+        ph = C.c_double(self.phase)
+        lib().orc_nco_push(_p(e), _SZ(len(e)), C.byref(ph), C.c_double(self.dphase), _p(out))
+        self.phase = ph.value
+        return out[0] if scalar else out
+
+
 class FM:
     """FM (src/modulation/analog.rs:7-47); prev starts at 0."""
 

@@ -180,6 +180,24 @@ DEF_MIX(orc_mix_c32, c32, float)
 DEF_MIX(orc_mix_c64, c64, double)
 
 /* ------------------------------------------------------------------ */
+/* Nco::push: src/demodulation/nco.rs:71-77 (Nco::new :41-49 wraps     */
+/* dphase like Mixer::new).  phase += dphase + perr; ONE conditional   */
+/* wrap when phase > 2pi; out = exp(j*phase) of the UPDATED phase.     */
+/* PARITY UNPINNED: the reference has no test for the NCO.             */
+/* ------------------------------------------------------------------ */
+ORC_API void orc_nco_push(const double *perr, size_t n, double *phase, double dphase, c64 *out)
+{
+    double ph = *phase;
+    for (size_t i = 0; i < n; ++i) {
+        ph += dphase + perr[i];
+        if (ph > 2.0 * M_PI) ph -= 2.0 * M_PI;
+        out[i].re = 1.0 * cos(ph);
+        out[i].im = 1.0 * sin(ph);
+    }
+    *phase = ph;
+}
+
+/* ------------------------------------------------------------------ */
 /* FM demod: src/modulation/analog.rs:22-34; prev starts at 0 (:43-47) */
 /* theta = samp * conj(prev); out = atan2(theta.im, theta.re).         */
 /* ------------------------------------------------------------------ */

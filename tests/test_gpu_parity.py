@@ -767,6 +767,126 @@ def test_comm_gather_single_rank(cb):
     g.close()
 
 
+def test_comm_single_rank_root_and_var_gather(cb):
+    # the variable-length forms with one rank: a device copy into place (root) / the identity (all ranks)
+    import torch
+
+    g = cb.sharding.SegmentGather(1, 0, cb.sharding.SegmentGather.unique_id())
+    x = torch.randn(2 * 4099, device="cuda")
+    y, z = torch.zeros_like(x), torch.zeros_like(x)
+    ts = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    g.gather_to_root_dev(x.data_ptr(), [4099], 8, 0, y.data_ptr(), ts.cuda_stream)
+    g.allgather_var_dev(x.data_ptr(), [4099], 8, z.data_ptr(), ts.cuda_stream)
+    g.gather_to_root_dev(0, [0], 8, 0, 0, ts.cuda_stream)  # empty segment: a no-op, not a hang
+    torch.cuda.synchronize()
+    assert torch.equal(x, y) and torch.equal(x, z)
+    with pytest.raises(cb.CbError):
+        g.gather_to_root_dev(x.data_ptr(), [4099], 8, 3, y.data_ptr(), ts.cuda_stream)  # root out of range
+    g.close()
+
+
+def test_in_place_run_dev_is_rejected(cb):
+    # include/comms_b200.h: input and output ranges of a *_run_dev call must not overlap (the kernels read neighbouring
+    # tiles and rebuild the carried state from the input) -> CB_ERR_INVALID_ARG, state untouched
+    import torch
+
+    n = 1 << 14
+    x = torch.randn(2 * n, device="cuda")
+    y = torch.empty(2 * n, device="cuda")
+    taps = np.ones(8, np.complex64)
+    fir = cb.BatchFirNode(taps)
+    st0 = fir.state.copy()
+    for dst in (x.data_ptr(), x.data_ptr() + 8 * (n - 1), x.data_ptr() - 8 * (n - 1)):
+        with pytest.raises(cb.CbError) as e:
+            fir.run_dev(x.data_ptr(), n, dst, n, 0)
+        assert e.value.status == cb._lib.CB_ERR_INVALID_ARG and "overlap" in str(e.value)
+    assert fir.state.tobytes() == st0.tobytes()
+    fir.run_dev(x.data_ptr(), n, y.data_ptr(), n, 0)  # disjoint: fine
+    with pytest.raises(cb.CbError):
+        cb.FMDemodNode().run_dev(x.data_ptr(), n, x.data_ptr(), 0)
+    with pytest.raises(cb.CbError):
+        cb.FFTBatchNode(1024).run_dev(x.data_ptr(), n, x.data_ptr() + 8 * 1024, 0)
+    with pytest.raises(cb.CbError):
+        cb.ChainBank(2, taps, 2, dphase=[0.1, 0.2]).run_dev(x.data_ptr(), n // 2, x.data_ptr(), n // 4, 0)
+    with pytest.raises(cb.CbError):
+        cb.BatchFirNode(taps, None, decim=5).run_dev_real(x.data_ptr(), n, x.data_ptr() + 64, n, 0)
+    m = cb.MixerNode(0.1)
+    m.run_dev(x.data_ptr(), n, x.data_ptr(), 0)  # element-wise: in place is allowed
+    torch.cuda.synchronize()
+
+
+def test_handle_state_is_ordered_across_streams(cb):
+    # a handle used on two caller streams back to back (the Rust GpuBatchFirDevNode / C++ mirror pattern): the second
+    # launch must see the history the first one is still writing, get_state must wait for both
+    import oracle
+    import torch
+
+    rng = np.random.default_rng(11)
+    taps = rnd_c32(rng, 48)
+    n1, n2 = 1 << 22, 300
+    xh = rnd_c32(rng, n1 + n2)
+    want, st = oracle.batch_fir(xh[-4096:], taps, xh[-4096 - 48:-4096][::-1].copy())
+    x = torch.from_numpy(xh).cuda()
+    y = torch.empty_like(x)
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for _ in range(3):
+        node = cb.BatchFirNode(taps)
+        node.run_dev(x.data_ptr(), n1, y.data_ptr(), n1, sa.cuda_stream)
+        node.run_dev(x.data_ptr() + 8 * n1, n2, y.data_ptr() + 8 * n1, n2, sb.cuda_stream)
+        state = node.state  # cb_fir_get_state: waits for the last use on any stream
+        assert state.tobytes() == st.tobytes()
+        torch.cuda.synchronize()
+        assert rel_l2(y[-4096:].cpu().numpy(), want) <= FIR_TOL
+    # two 65536-point transforms on different streams share the handle's scratch ring and counters
+    f = cb.FFTBatchNode(65536)
+    xf = torch.from_numpy(rnd_c32(rng, 8 * 65536)).cuda()
+    o1, o2, o3 = torch.empty_like(xf), torch.empty_like(xf), torch.empty_like(xf)
+    torch.cuda.synchronize()
+    f.run_dev(xf.data_ptr(), xf.numel(), o3.data_ptr(), sa.cuda_stream)
+    torch.cuda.synchronize()
+    f.run_dev(xf.data_ptr(), xf.numel(), o1.data_ptr(), sa.cuda_stream)
+    f.run_dev(xf.data_ptr(), xf.numel(), o2.data_ptr(), sb.cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.view_as_real(o1), torch.view_as_real(o3)) and torch.equal(torch.view_as_real(o2), torch.view_as_real(o3))
+
+
+# ------------------------------------------------------------------ NCO batching shim
+def test_nco_batch_matches_reference_recurrence(cb):
+    # Nco::push (src/demodulation/nco.rs:71-77) applied in order; the product evaluates the same phases as a scan.
+    # Truth = the recurrence in extended precision (phase mod 2 pi is all that reaches the output).  Tolerance: the
+    # oracle's own f64 recurrence drifts by up to ~n * ulp(2 pi); the scan must be at least that close to the truth.
+    import oracle
+
+    rng = np.random.default_rng(5)
+    for n, dphase, phase0, amp in ((1, 0.1, np.pi / 4, 0.01), (1000, 0.1, np.pi / 4, 0.01), (8191, 6.2, 0.0, 0.3),
+                                   (1 << 20, 0.123456789, 1.0, 1e-3), (70001, -0.7, 3.0, 0.05)):
+        perr = rng.uniform(-amp, amp, n)
+        want = oracle.Nco(phase0, dphase).push(perr)
+        node = cb.NcoNode(dphase, phase0)
+        got = node.run(perr)
+        dw = np.float64(oracle.Nco(phase0, dphase).dphase)
+        assert node.dphase == dw
+        ph = np.longdouble(phase0) + np.cumsum(np.longdouble(dw) + perr.astype(np.longdouble))
+        truth = np.exp(1j * (ph % (2 * np.longdouble(np.pi) + np.longdouble(1.2246467991473532e-16) * 2)).astype(np.float64))
+        e_orc = np.abs(want - truth).max()
+        e_gpu = np.abs(got - truth).max()
+        assert e_gpu <= max(2e-13, 2 * e_orc), (n, e_gpu, e_orc)
+        assert np.abs(got - want).max() <= 1e-12 + 2e-16 * n * 8, (n, np.abs(got - want).max())
+        # carried phase: continuing in a second batch equals one long batch
+        node2 = cb.NcoNode(dphase, phase0)
+        h = n // 3
+        again = np.concatenate([node2.run(perr[:h]), node2.run(perr[h:])]) if h else got
+        assert np.abs(again - got).max() <= 1e-12
+        assert 0.0 <= node.phase < 2 * np.pi
+        assert abs(np.exp(1j * node.phase) - got[-1]) <= 1e-12
+    # one sample per call: the reference's NcoNode::run(f64)
+    node, orc = cb.NcoNode(0.1, None), oracle.Nco(0.0, 0.1)
+    for e in (-0.01, 0.02, 0.0, 6.0):
+        assert abs(node.run(e) - orc.push(e)) <= 1e-15
+
+
 # ------------------------------------------------------------------ C++ host mirror (graph-level conformance)
 def test_cpp_host_graph_conformance():
     """comms-rs_b200/host/test_graph.cpp: source -> GPU node -> check graphs with one thread per

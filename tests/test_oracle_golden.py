@@ -302,3 +302,19 @@ def test_synth_generator_is_counter_based(oracle):
     b = oracle.synth_uniform_c32(7, 400, 600)
     assert a[400:].tobytes() == b.tobytes()
     assert np.all(a.real >= -1) and np.all(a.real < 1) and abs(a.real.mean()) < 0.1
+
+
+def test_nco_restatement(oracle):
+    # Nco::push (src/demodulation/nco.rs:71-77): no reference vector exists (PARITY UNPINNED, stated in the oracle);
+    # the restatement is checked against the definition on the doc-test's parameters (nco.rs:62-70) and for its wrap
+    nco = oracle.Nco(np.pi / 4.0, 0.1)
+    out = nco.push(-0.01)
+    assert abs(out - np.exp(1j * (np.pi / 4.0 + 0.09))) < 1e-15
+    nco = oracle.Nco(6.2, 0.1 + 4 * np.pi)  # dphase wrapped into [0, 2 pi) by Nco::new (nco.rs:41-49)
+    assert abs(nco.dphase - 0.1) < 1e-12
+    out = nco.push(np.array([0.0, 0.0]))
+    assert abs(nco.phase - (6.4 - 2 * np.pi)) < 1e-12  # wrapped once after the first push, not after the second
+    assert np.allclose(out, np.exp(1j * np.array([6.3, 6.4])), atol=1e-12)
+    nco = oracle.Nco(0.0, 0.0)
+    nco.push(np.full(3, -1.0))  # the reference never adds 2 pi: negative phases stay negative
+    assert abs(nco.phase + 3.0) < 1e-15
