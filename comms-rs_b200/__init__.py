@@ -36,4 +36,19 @@ def launch_count() -> int:
     _lib.check(load().cb_launch_count(C.byref(n)))
     return n.value
 
+
+
+def pool_configure(is_device: bool, max_live_bytes: int = 0, max_cached_bytes: int = 1 << 30, timeout_ms: int = 10000) -> None:
+    """cb_pool_configure: high-water mark (back-pressure), cache size and blocking timeout of the buffer pool."""
+    _lib.check(load().cb_pool_configure(int(bool(is_device)), int(max_live_bytes), int(max_cached_bytes), int(timeout_ms)))
+
+
+def pool_stats(is_device: bool) -> dict:
+    import ctypes as C
+    live, cached = C.c_size_t(), C.c_size_t()
+    hits, misses, waits = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    _lib.check(load().cb_pool_stats(int(bool(is_device)), C.byref(live), C.byref(cached), C.byref(hits), C.byref(misses), C.byref(waits)))
+    return {"live_bytes": live.value, "cached_bytes": cached.value, "hits": hits.value, "misses": misses.value, "waits": waits.value}
+
+
 from . import sharding  # noqa: E402

@@ -56,6 +56,11 @@ SIGNATURES = {
     "cb_stream_handle": (_vp, [_vp]),
     "cb_buf_alloc_pinned": (_i, [_sz, _pp]),
     "cb_buf_alloc_device": (_i, [_sz, _pp]),
+    "cb_pool_configure": (_i, [_i, _sz, _sz, _i]),
+    "cb_pool_stats": (_i, [_i, _psz, _psz, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "cb_pool_trim": (_i, []),
+    "cb_pool_throttle": (_i, [_i]),
+    "cb_buf_record_done": (_i, [_vp, _vp]),
     "cb_buf_retain": (_i, [_vp]),
     "cb_buf_release": (_i, [_vp]),
     "cb_buf_ptr": (_vp, [_vp]),

@@ -1,11 +1,16 @@
 // C ABI of libcomms_b200.so (see include/comms_b200.h): handles, buffers, streams,
 // host-pointer pipelines.  No torch, no C++ types in any signature, no CPU fallback.
 #include <atomic>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
+#include <map>
+#include <mutex>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "chain_kernels.cuh"
@@ -58,6 +63,108 @@ static int use_device(int dev)
 
 int ensure_device() { return use_device(g_dev); }
 
+// Parallel host memcpy for the pageable-memory path of the host-pointer entries.  A Rust `Vec` (what the reference's
+// run(&[Complex<T>]) -> Vec<Complex<T>> hands over) is pageable: cudaMemcpyAsync from it goes through the driver's own
+// single-threaded staging copy and serialises with the kernels (measured: 0.8 instead of 5.9 Gsamples/s for a 2 GiB
+// call).  Large pageable calls are staged by this pool instead: each chunk is copied into / out of a pinned slot of the
+// handle's lane by COMMS_B200_STAGE_THREADS threads (default min(8, cores/2)) while the previous chunk's DMA and kernel run.
+class StagePool {
+    struct Task {
+        char *dst;
+        const char *src;
+        size_t bytes;
+    };
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv, done_cv;
+    std::vector<Task> q;
+    size_t pending = 0;
+    bool stop = false;
+
+    void worker()
+    {
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> l(m);
+                cv.wait(l, [&] { return stop || !q.empty(); });
+                if (q.empty()) return;
+                t = q.back();
+                q.pop_back();
+            }
+            memcpy(t.dst, t.src, t.bytes);
+            {
+                std::lock_guard<std::mutex> l(m);
+                --pending;
+            }
+            done_cv.notify_all();
+        }
+    }
+
+public:
+    StagePool()
+    {
+        unsigned n = std::thread::hardware_concurrency() / 2;
+        if (n > 8) n = 8;
+        if (const char *e = getenv("COMMS_B200_STAGE_THREADS")) n = (unsigned)atoi(e);
+        if (n < 1) n = 1;
+        if (n > 64) n = 64;
+        for (unsigned i = 1; i < n; ++i) th.emplace_back([this] { worker(); });  // the caller is the n-th copier
+    }
+    ~StagePool()
+    {
+        {
+            std::lock_guard<std::mutex> l(m);
+            stop = true;
+        }
+        cv.notify_all();
+        for (auto &t : th) t.join();
+    }
+    // blocking copy; safe to call from several node threads at once (they share the workers)
+    void copy(void *dst, const void *src, size_t bytes)
+    {
+        const size_t parts = th.size() + 1;
+        const size_t piece = round_up(ceil_div(bytes, parts), (size_t)4096);
+        if (th.empty() || bytes < ((size_t)1 << 20)) {
+            memcpy(dst, src, bytes);
+            return;
+        }
+        size_t mine_off = 0, mine_len = piece < bytes ? piece : bytes, posted = 0;
+        {
+            std::lock_guard<std::mutex> l(m);
+            for (size_t off = mine_len; off < bytes; off += piece) {
+                q.push_back(Task{(char *)dst + off, (const char *)src + off, bytes - off < piece ? bytes - off : piece});
+                ++posted;
+            }
+            pending += posted;
+        }
+        cv.notify_all();
+        memcpy((char *)dst + mine_off, (const char *)src + mine_off, mine_len);
+        std::unique_lock<std::mutex> l(m);
+        // `pending` counts every caller's pieces; waiting for zero is conservative but always correct
+        done_cv.wait(l, [&] { return pending == 0; });
+    }
+};
+
+static StagePool &stage_pool()
+{
+    static StagePool p;
+    return p;
+}
+
+// pageable (unregistered) host memory?  Pinned / registered / managed memory takes the direct DMA path.
+static bool is_pageable(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+static const size_t STAGE_MIN_BYTES = (size_t)8 << 20;  // below this the driver's own staging of a pageable copy is fine
+
 // Two copy/compute lanes used by the host-pointer entry points: chunk i runs
 // H2D -> kernel -> D2H on lane i%2, so the copy engines and the SMs overlap.
 struct HostPipe {
@@ -65,6 +172,14 @@ struct HostPipe {
     void *in[2] = {nullptr, nullptr};
     void *out[2] = {nullptr, nullptr};
     size_t in_cap = 0, out_cap = 0;
+    // pinned staging slots for pageable callers (allocated on first use), one per lane and direction
+    void *pin_in[2] = {nullptr, nullptr}, *pin_out[2] = {nullptr, nullptr};
+    size_t pin_in_cap = 0, pin_out_cap = 0;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    bool in_busy[2] = {false, false};
+    void *pend_dst[2] = {nullptr, nullptr};
+    size_t pend_bytes[2] = {0, 0};
+    bool stage_in = false, stage_out = false;
 
     int init(cudaStream_t first)
     {
@@ -92,8 +207,81 @@ struct HostPipe {
         }
         return CB_OK;
     }
+    // Decide per call whether the caller's buffers are staged (large and pageable) and size the pinned slots.
+    int begin_call(const void *host_in, size_t total_in, size_t chunk_in, void *host_out, size_t total_out, size_t chunk_out)
+    {
+        stage_in = total_in >= STAGE_MIN_BYTES && is_pageable(host_in);
+        stage_out = total_out >= STAGE_MIN_BYTES && is_pageable(host_out);
+        for (int i = 0; i < 2; ++i) {
+            in_busy[i] = false;
+            pend_dst[i] = nullptr;
+        }
+        if (stage_in && chunk_in > pin_in_cap) {
+            for (int i = 0; i < 2; ++i) {
+                if (pin_in[i]) CB_CUDA(cudaFreeHost(pin_in[i]));
+                pin_in[i] = nullptr;
+                CB_CUDA(cudaMallocHost(&pin_in[i], chunk_in));
+            }
+            pin_in_cap = chunk_in;
+        }
+        if (stage_out && chunk_out > pin_out_cap) {
+            for (int i = 0; i < 2; ++i) {
+                if (pin_out[i]) CB_CUDA(cudaFreeHost(pin_out[i]));
+                pin_out[i] = nullptr;
+                CB_CUDA(cudaMallocHost(&pin_out[i], chunk_out));
+            }
+            pin_out_cap = chunk_out;
+        }
+        for (int i = 0; i < 2; ++i) {
+            if ((stage_in || stage_out) && !ev_in[i]) CB_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+            if ((stage_in || stage_out) && !ev_out[i]) CB_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+        }
+        return CB_OK;
+    }
+    int h2d(int l, void *dev_dst, const void *host_src, size_t bytes)
+    {
+        if (!stage_in) {
+            CB_CUDA(cudaMemcpyAsync(dev_dst, host_src, bytes, cudaMemcpyHostToDevice, lane[l]));
+            return CB_OK;
+        }
+        if (in_busy[l]) CB_CUDA(cudaEventSynchronize(ev_in[l]));  // the slot's previous DMA has left it
+        stage_pool().copy(pin_in[l], host_src, bytes);
+        CB_CUDA(cudaMemcpyAsync(dev_dst, pin_in[l], bytes, cudaMemcpyHostToDevice, lane[l]));
+        CB_CUDA(cudaEventRecord(ev_in[l], lane[l]));
+        in_busy[l] = true;
+        return CB_OK;
+    }
+    int flush_out(int l)
+    {
+        if (!pend_dst[l]) return CB_OK;
+        CB_CUDA(cudaEventSynchronize(ev_out[l]));
+        stage_pool().copy(pend_dst[l], pin_out[l], pend_bytes[l]);
+        pend_dst[l] = nullptr;
+        return CB_OK;
+    }
+    int d2h(int l, void *host_dst, const void *dev_src, size_t bytes)
+    {
+        if (!stage_out) {
+            CB_CUDA(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, lane[l]));
+            return CB_OK;
+        }
+        int rc = flush_out(l);
+        if (rc) return rc;
+        CB_CUDA(cudaMemcpyAsync(pin_out[l], dev_src, bytes, cudaMemcpyDeviceToHost, lane[l]));
+        CB_CUDA(cudaEventRecord(ev_out[l], lane[l]));
+        pend_dst[l] = host_dst;
+        pend_bytes[l] = bytes;
+        return CB_OK;
+    }
     int sync()
     {
+        // drain the staged outputs in issue order (the older lane first) while the other lane's DMA still runs
+        if (stage_out) {
+            for (int i = 0; i < 2; ++i) {
+                int rc = flush_out(i);
+                if (rc) return rc;
+            }
+        }
         CB_CUDA(cudaStreamSynchronize(lane[0]));
         CB_CUDA(cudaStreamSynchronize(lane[1]));
         return CB_OK;
@@ -103,6 +291,10 @@ struct HostPipe {
         for (int i = 0; i < 2; ++i) {
             if (in[i]) cudaFree(in[i]);
             if (out[i]) cudaFree(out[i]);
+            if (pin_in[i]) cudaFreeHost(pin_in[i]);
+            if (pin_out[i]) cudaFreeHost(pin_out[i]);
+            if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+            if (ev_out[i]) cudaEventDestroy(ev_out[i]);
         }
         if (lane[1]) cudaStreamDestroy(lane[1]);
     }
@@ -164,6 +356,45 @@ static const size_t HOST_CHUNK = [] {
     return (size_t)1 << (l >= 12 && l <= 30 ? l : 22);
 }();
 
+// ---------------------------------------------------------------------------------------------------- buffer pool
+// cb_buf_alloc_* used to be one cudaMalloc / cudaMallocHost per message and one cudaFree per release: a device
+// synchronisation per message.  Blocks now come from a size-classed, thread-safe free list per (device, kind), and the
+// pool applies BACK-PRESSURE: the reference's channels are unbounded (src/node/mod.rs:152), so a source that runs
+// ahead of a GPU node would otherwise queue pinned / device buffers without limit.  While the bytes handed out and
+// not yet released exceed the high-water mark, cb_pool_throttle() -- called by the nodes where pool buffers start --
+// blocks until releases bring them back under it (or fails with CB_ERR_OOM after the timeout, so that a graph that
+// can never release does not hang forever).
+struct BufPool {
+    struct Block {
+        void *ptr;
+        std::vector<cudaEvent_t> pending;  // uses recorded by the previous owner; waited for when the block is reused
+        cudaEvent_t spare_ready;           // the previous owner's event objects, recycled with the block
+        std::vector<cudaEvent_t> spare_done;
+    };
+    std::mutex m;
+    std::condition_variable cv;
+    std::map<size_t, std::vector<Block>> free_list;  // size class -> blocks
+    size_t live = 0, cached = 0;
+    size_t max_live = 0;      // 0 = unlimited
+    size_t max_cached = (size_t)1 << 30;
+    int timeout_ms = 10000;
+    uint64_t hits = 0, misses = 0, waits = 0;
+};
+static BufPool g_pools[16][2];  // [device][is_device]
+
+static size_t pool_class(size_t bytes)
+{
+    if (bytes <= 256) return 256;
+    if (bytes <= ((size_t)1 << 20)) {
+        size_t c = 256;
+        while (c < bytes) c <<= 1;
+        return c;
+    }
+    return round_up(bytes, (size_t)2 << 20);
+}
+
+static BufPool &pool_of(int device, int is_device) { return g_pools[device & 15][is_device ? 1 : 0]; }
+
 }  // namespace cb
 
 using namespace cb;
@@ -177,11 +408,14 @@ struct cb_stream {
 struct cb_buf {
     std::atomic<int> refs;
     void *ptr;
-    size_t bytes;
+    size_t bytes;      // as requested
+    size_t cls_bytes;  // size class actually allocated (what the pool accounts)
     int is_device;
     int device;
     cudaEvent_t ready;  // recorded by the producing node's stream (cb_buf_record_ready)
     bool has_ready;
+    std::vector<cudaEvent_t> done;  // recorded by consumers behind their last use (cb_buf_record_done)
+    size_t n_done;                  // how many of `done` are recorded for the current owner
 };
 
 struct cb_fir {
@@ -361,15 +595,52 @@ static int buf_alloc(size_t bytes, int is_device, cb_buf **out)
     CB_REQUIRE(b, CB_ERR_OOM, "host allocation failed");
     b->refs.store(1);
     b->bytes = bytes;
+    b->cls_bytes = pool_class(bytes);
     b->is_device = is_device;
     b->device = g_dev;
     b->ptr = nullptr;
     b->ready = nullptr;
     b->has_ready = false;
-    cudaError_t e = is_device ? cudaMalloc(&b->ptr, bytes ? bytes : 1) : cudaMallocHost(&b->ptr, bytes ? bytes : 1);
-    if (e != cudaSuccess) {
-        delete b;
-        return cuda_fail(e, is_device ? "cudaMalloc" : "cudaMallocHost", __FILE__, __LINE__);
+    b->n_done = 0;
+    BufPool &p = pool_of(g_dev, is_device);
+    BufPool::Block blk{nullptr, {}, nullptr, {}};
+    bool have = false;
+    {
+        std::unique_lock<std::mutex> l(p.m);
+        auto it = p.free_list.find(b->cls_bytes);
+        if (it != p.free_list.end() && !it->second.empty()) {
+            blk = std::move(it->second.back());
+            it->second.pop_back();
+            p.cached -= b->cls_bytes;
+            ++p.hits;
+            have = true;
+        } else {
+            ++p.misses;
+        }
+        p.live += b->cls_bytes;
+    }
+    if (have) {
+        // the previous owner's asynchronous uses must be over before the new owner touches the block
+        for (cudaEvent_t e : blk.pending) cudaEventSynchronize(e);
+        b->ptr = blk.ptr;
+        b->ready = blk.spare_ready;
+        b->done = std::move(blk.spare_done);
+    } else {
+        cudaError_t e = is_device ? cudaMalloc(&b->ptr, b->cls_bytes) : cudaMallocHost(&b->ptr, b->cls_bytes);
+        if (e != cudaSuccess) {  // give cached blocks of other classes back to the driver and retry once
+            (void)cudaGetLastError();
+            cb_pool_trim();
+            e = is_device ? cudaMalloc(&b->ptr, b->cls_bytes) : cudaMallocHost(&b->ptr, b->cls_bytes);
+        }
+        if (e != cudaSuccess) {
+            {
+                std::lock_guard<std::mutex> l(p.m);
+                p.live -= b->cls_bytes;
+            }
+            p.cv.notify_all();
+            delete b;
+            return cuda_fail(e, is_device ? "cudaMalloc" : "cudaMallocHost", __FILE__, __LINE__);
+        }
     }
     *out = b;
     return CB_OK;
@@ -385,18 +656,104 @@ int cb_buf_retain(cb_buf *b)
     return CB_OK;
 }
 
+static void block_destroy(BufPool::Block &blk, int is_device)
+{
+    for (cudaEvent_t e : blk.pending) cudaEventSynchronize(e);
+    if (blk.spare_ready) cudaEventDestroy(blk.spare_ready);
+    for (cudaEvent_t e : blk.spare_done) cudaEventDestroy(e);
+    if (is_device) cudaFree(blk.ptr);
+    else cudaFreeHost(blk.ptr);
+}
+
 int cb_buf_release(cb_buf *b)
 {
     if (!b) return CB_OK;
     if (b->refs.fetch_sub(1) == 1) {
         cudaSetDevice(b->device);
-        if (b->ready) {
-            if (b->has_ready) cudaEventSynchronize(b->ready);  // never free under a pending writer
-            cudaEventDestroy(b->ready);
+        BufPool &p = pool_of(b->device, b->is_device);
+        BufPool::Block blk{b->ptr, {}, b->ready, std::move(b->done)};
+        if (b->ready && b->has_ready) blk.pending.push_back(b->ready);  // never reuse (or free) under a pending writer ...
+        for (size_t i = 0; i < b->n_done; ++i) blk.pending.push_back(blk.spare_done[i]);  // ... or a pending reader
+        bool keep;
+        {
+            std::lock_guard<std::mutex> l(p.m);
+            p.live -= b->cls_bytes;
+            keep = p.cached + b->cls_bytes <= p.max_cached;
+            if (keep) {
+                p.free_list[b->cls_bytes].push_back(std::move(blk));
+                p.cached += b->cls_bytes;
+            }
         }
-        if (b->is_device) cudaFree(b->ptr);
-        else cudaFreeHost(b->ptr);
+        p.cv.notify_all();
+        if (!keep) block_destroy(blk, b->is_device);
         delete b;
+    }
+    return CB_OK;
+}
+
+int cb_pool_configure(int is_device, size_t max_live_bytes, size_t max_cached_bytes, int timeout_ms)
+{
+    int rc = ensure_device();
+    if (rc) return rc;
+    BufPool &p = pool_of(g_dev, is_device);
+    {
+        std::lock_guard<std::mutex> l(p.m);
+        p.max_live = max_live_bytes;
+        p.max_cached = max_cached_bytes;
+        if (timeout_ms > 0) p.timeout_ms = timeout_ms;
+    }
+    p.cv.notify_all();
+    return CB_OK;
+}
+
+// The back-pressure gate.  Allocations themselves never block (a node in the middle of a graph that waited for a
+// buffer while holding one could close a cycle of waits); the nodes where pool buffers START -- a source that fills
+// pinned messages, a host->device edge node -- call this once per message before they allocate, holding nothing.
+int cb_pool_throttle(int timeout_ms)
+{
+    for (int kind = 0; kind < 2; ++kind) {
+        BufPool &p = pool_of(g_dev, kind);
+        std::unique_lock<std::mutex> l(p.m);
+        if (!p.max_live || p.live <= p.max_live) continue;
+        ++p.waits;
+        const int ms = timeout_ms > 0 ? timeout_ms : p.timeout_ms;
+        const bool ok = p.cv.wait_for(l, std::chrono::milliseconds(ms), [&] { return !p.max_live || p.live <= p.max_live; });
+        if (!ok) {
+            const size_t live = p.live, lim = p.max_live;
+            l.unlock();
+            set_error("buffer pool: %zu bytes of %s messages still in flight against a high-water mark of %zu after %d ms (no "
+                      "consumer released a buffer)", live, kind ? "device" : "pinned", lim, ms);
+            return CB_ERR_OOM;
+        }
+    }
+    return CB_OK;
+}
+
+int cb_pool_stats(int is_device, size_t *live_bytes, size_t *cached_bytes, uint64_t *hits, uint64_t *misses, uint64_t *waits)
+{
+    BufPool &p = pool_of(g_dev, is_device);
+    std::lock_guard<std::mutex> l(p.m);
+    if (live_bytes) *live_bytes = p.live;
+    if (cached_bytes) *cached_bytes = p.cached;
+    if (hits) *hits = p.hits;
+    if (misses) *misses = p.misses;
+    if (waits) *waits = p.waits;
+    return CB_OK;
+}
+
+int cb_pool_trim(void)
+{
+    for (int kind = 0; kind < 2; ++kind) {
+        BufPool &p = pool_of(g_dev, kind);
+        std::map<size_t, std::vector<BufPool::Block>> take;
+        {
+            std::lock_guard<std::mutex> l(p.m);
+            take.swap(p.free_list);
+            p.cached = 0;
+        }
+        cudaSetDevice(g_dev);
+        for (auto &kv : take)
+            for (auto &blk : kv.second) block_destroy(blk, kind);
     }
     return CB_OK;
 }
@@ -412,6 +769,24 @@ int cb_buf_record_ready(cb_buf *b, void *stream)
     if (!b->ready) CB_CUDA(cudaEventCreateWithFlags(&b->ready, cudaEventDisableTiming));
     CB_CUDA(cudaEventRecord(b->ready, (cudaStream_t)stream));
     b->has_ready = true;
+    return CB_OK;
+}
+
+// A consumer that launched asynchronous work reading (or writing) the buffer records "done" behind it before it drops
+// its reference; the pool waits for every such event before the block goes to its next owner.
+int cb_buf_record_done(cb_buf *b, void *stream)
+{
+    CB_REQUIRE(b, CB_ERR_INVALID_ARG, "buffer is NULL");
+    CB_CUDA(cudaSetDevice(b->device));
+    static std::mutex m;  // several consumers (one per downstream edge) may share the buffer
+    std::lock_guard<std::mutex> l(m);
+    if (b->n_done == b->done.size()) {
+        cudaEvent_t e;
+        CB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        b->done.push_back(e);
+    }
+    CB_CUDA(cudaEventRecord(b->done[b->n_done], (cudaStream_t)stream));
+    ++b->n_done;
     return CB_OK;
 }
 
@@ -807,6 +1182,9 @@ int cb_fir_run(cb_fir *h, const float *in, size_t n_in, float *out, size_t out_c
     if (rc) return rc;
     rc = h->pipe.reserve((chunk + H) * sizeof(float2), fir_out_len(h, chunk) * sizeof(float2));
     if (rc) return rc;
+    rc = h->pipe.begin_call(in, n_in * sizeof(float2), (chunk + H) * sizeof(float2), out, no * sizeof(float2),
+                            fir_out_len(h, chunk) * sizeof(float2));
+    if (rc) return rc;
     size_t done = 0, out_done = 0;
     for (int i = 0; done < n_in; ++i) {
         const int l = i & 1;
@@ -817,16 +1195,18 @@ int cb_fir_run(cb_fir *h, const float *in, size_t n_in, float *out, size_t out_c
         const float2 *hist_in;
         if (done == 0) {
             hist_in = h->hist[h->cur];
-            CB_CUDA(cudaMemcpyAsync(slot + H, hin, n * sizeof(float2), cudaMemcpyHostToDevice, s));
+            rc = h->pipe.h2d(l, slot + H, hin, n * sizeof(float2));
         } else {  // the halo is the tail of the previous chunk, re-sent with this one
             hist_in = slot;
-            CB_CUDA(cudaMemcpyAsync(slot, hin + done - H, (n + H) * sizeof(float2), cudaMemcpyHostToDevice, s));
+            rc = h->pipe.h2d(l, slot, hin + done - H, (n + H) * sizeof(float2));
         }
+        if (rc) return rc;
         float2 *y = reinterpret_cast<float2 *>(h->pipe.out[l]);
         rc = fir_launch_segment(h, slot + H, n, hist_in, last ? h->hist[h->cur ^ 1] : nullptr, y, s);
         if (rc) return rc;
         const size_t m = fir_out_len(h, n);
-        CB_CUDA(cudaMemcpyAsync(hout + out_done, y, m * sizeof(float2), cudaMemcpyDeviceToHost, s));
+        rc = h->pipe.d2h(l, hout + out_done, y, m * sizeof(float2));
+        if (rc) return rc;
         done += n;
         out_done += m;
     }
@@ -1039,6 +1419,8 @@ int cb_mixer_run(cb_mixer *h, const float *in, size_t n, float *out)
     const size_t chunk = n < HOST_CHUNK ? n : HOST_CHUNK;
     int rc = h->pipe.reserve(chunk * sizeof(float2), chunk * sizeof(float2));
     if (rc) return rc;
+    rc = h->pipe.begin_call(in, n * sizeof(float2), chunk * sizeof(float2), out, n * sizeof(float2), chunk * sizeof(float2));
+    if (rc) return rc;
     const float2 *hin = reinterpret_cast<const float2 *>(in);
     float2 *hout = reinterpret_cast<float2 *>(out);
     size_t done = 0;
@@ -1047,11 +1429,13 @@ int cb_mixer_run(cb_mixer *h, const float *in, size_t n, float *out)
         const size_t m = n - done < chunk ? n - done : chunk;
         cudaStream_t s = h->pipe.lane[l];
         float2 *di = reinterpret_cast<float2 *>(h->pipe.in[l]), *dout = reinterpret_cast<float2 *>(h->pipe.out[l]);
-        CB_CUDA(cudaMemcpyAsync(di, hin + done, m * sizeof(float2), cudaMemcpyHostToDevice, s));
+        rc = h->pipe.h2d(l, di, hin + done, m * sizeof(float2));
+        if (rc) return rc;
         rc = launch_mixer(di, dout, m, h->phase, h->dphase, s);
         if (rc) return rc;
         h->phase = advance_phase(h->phase, h->dphase, m);
-        CB_CUDA(cudaMemcpyAsync(hout + done, dout, m * sizeof(float2), cudaMemcpyDeviceToHost, s));
+        rc = h->pipe.d2h(l, hout + done, dout, m * sizeof(float2));
+        if (rc) return rc;
         done += m;
     }
     return h->pipe.sync();
@@ -1416,6 +1800,8 @@ int cb_fft_run(cb_fft *h, const float *in, size_t n_in, float *out)
     if (rc) return rc;
     rc = h->pipe.reserve(chunk * sizeof(float2), chunk * sizeof(float2));
     if (rc) return rc;
+    rc = h->pipe.begin_call(in, n_in * sizeof(float2), chunk * sizeof(float2), out, n_in * sizeof(float2), chunk * sizeof(float2));
+    if (rc) return rc;
     const float2 *hin = reinterpret_cast<const float2 *>(in);
     float2 *hout = reinterpret_cast<float2 *>(out);
     size_t done = 0;
@@ -1424,14 +1810,16 @@ int cb_fft_run(cb_fft *h, const float *in, size_t n_in, float *out)
         const size_t m = n_in - done < chunk ? n_in - done : chunk;
         cudaStream_t s = h->pipe.lane[l];
         float2 *di = reinterpret_cast<float2 *>(h->pipe.in[l]), *dout = reinterpret_cast<float2 *>(h->pipe.out[l]);
-        CB_CUDA(cudaMemcpyAsync(di, hin + done, m * sizeof(float2), cudaMemcpyHostToDevice, s));
+        rc = h->pipe.h2d(l, di, hin + done, m * sizeof(float2));
+        if (rc) return rc;
         if ((h->plan.kind == FFT_FOURSTEP || h->plan.kind == FFT_BLUESTEIN) && i > 0) {
             // the scratch / work buffers are shared by both lanes: serialise the kernels
             CB_CUDA(cudaStreamSynchronize(h->pipe.lane[l ^ 1]));
         }
         rc = fft_exec(h, di, dout, m / N, s);
         if (rc) return rc;
-        CB_CUDA(cudaMemcpyAsync(hout + done, dout, m * sizeof(float2), cudaMemcpyDeviceToHost, s));
+        rc = h->pipe.d2h(l, hout + done, dout, m * sizeof(float2));
+        if (rc) return rc;
         done += m;
     }
     return h->pipe.sync();

@@ -18,6 +18,7 @@
 #include <memory>
 #include <mutex>
 #include <optional>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <vector>
@@ -330,6 +331,122 @@ struct FMDemodNode : Node1<FMDemodNode, std::vector<c32>, std::vector<float>> {
         std::vector<float> out(in.size());
         int st = cb_fm_run(h_, reinterpret_cast<const float *>(in.data()), in.size(), out.data());
         return st ? Result<std::vector<float>>::Err(map_status(st)) : Result<std::vector<float>>::Ok(std::move(out));
+    }
+};
+
+// ------------------------------------------------------------------ device-resident edges
+// What crosses a channel between two GPU nodes instead of a Vec: a ref-counted handle to a pooled pinned-host or
+// device buffer (Clone = cb_buf_retain, Drop = cb_buf_release; the derive macro clones once per downstream edge,
+// node_derive/src/lib.rs:156).  `len` = valid elements.  The producer records `ready` on its stream, the consumer
+// makes its stream wait for it and records `done` behind its own use before dropping the message, so no node ever
+// blocks the host and the pool never hands a block to its next owner early.
+class Buf {
+    cb_buf *b_ = nullptr;
+public:
+    size_t len = 0;
+    Buf() = default;
+    Buf(cb_buf *b, size_t n) : b_(b), len(n) {}
+    Buf(const Buf &o) : b_(o.b_), len(o.len) { if (b_) cb_buf_retain(b_); }
+    Buf(Buf &&o) noexcept : b_(o.b_), len(o.len) { o.b_ = nullptr; }
+    Buf &operator=(const Buf &o) { if (this != &o) { if (b_) cb_buf_release(b_); b_ = o.b_; len = o.len; if (b_) cb_buf_retain(b_); } return *this; }
+    Buf &operator=(Buf &&o) noexcept { if (this != &o) { if (b_) cb_buf_release(b_); b_ = o.b_; len = o.len; o.b_ = nullptr; } return *this; }
+    ~Buf() { if (b_) cb_buf_release(b_); }
+    static Buf device(size_t bytes, size_t n) { cb_buf *b = nullptr; if (cb_buf_alloc_device(bytes, &b)) throw std::runtime_error(cb_last_error()); return Buf(b, n); }
+    static Buf pinned(size_t bytes, size_t n) { cb_buf *b = nullptr; if (cb_buf_alloc_pinned(bytes, &b)) throw std::runtime_error(cb_last_error()); return Buf(b, n); }
+    void *ptr() const { return cb_buf_ptr(b_); }
+    cb_buf *raw() const { return b_; }
+};
+
+struct StreamOwner {
+    cb_stream *st = nullptr;
+    StreamOwner() { if (cb_stream_create(&st)) throw std::runtime_error(cb_last_error()); }
+    ~StreamOwner() { cb_stream_destroy(st); }
+    void *s() const { return cb_stream_handle(st); }
+};
+
+// graph edge host -> device: pinned message in, device message out (elem = bytes per element)
+struct H2DNode : Node1<H2DNode, Buf, Buf>, StreamOwner {
+    size_t elem;
+    explicit H2DNode(size_t elem_bytes) : elem(elem_bytes) {}
+    Result<Buf> run(const Buf &in)
+    {
+        Buf out = Buf::device(in.len * elem, in.len);
+        int st = cb_copy_h2d_async(out.ptr(), in.ptr(), in.len * elem, s());
+        if (!st) st = cb_buf_record_done(in.raw(), s());
+        if (!st) st = cb_buf_record_ready(out.raw(), s());
+        return st ? Result<Buf>::Err(map_status(st)) : Result<Buf>::Ok(std::move(out));
+    }
+};
+
+// graph edge device -> host
+struct D2HNode : Node1<D2HNode, Buf, Buf>, StreamOwner {
+    size_t elem;
+    explicit D2HNode(size_t elem_bytes) : elem(elem_bytes) {}
+    Result<Buf> run(const Buf &in)
+    {
+        Buf out = Buf::pinned(in.len * elem, in.len);
+        int st = cb_buf_wait_ready(in.raw(), s());
+        if (!st) st = cb_copy_d2h_async(out.ptr(), in.ptr(), in.len * elem, s());
+        if (!st) st = cb_buf_record_done(in.raw(), s());
+        if (!st) st = cb_buf_record_ready(out.raw(), s());
+        return st ? Result<Buf>::Err(map_status(st)) : Result<Buf>::Ok(std::move(out));
+    }
+};
+
+// BatchFirNode between device edges (complex f32 in and out; decim / interp fused)
+struct BatchFirDevNode : Node1<BatchFirDevNode, Buf, Buf>, FirHandle {
+    BatchFirDevNode(const std::vector<c32> &taps, const std::vector<c32> *state = nullptr, uint32_t decim = 1, uint32_t interp = 1)
+        : FirHandle(taps, state, decim, interp) {}
+    Result<Buf> run(const Buf &in)
+    {
+        size_t no = 0;
+        cb_fir_out_len(h_, in.len, &no);
+        Buf out = Buf::device(no * sizeof(c32), no);
+        void *s = cb_fir_stream(h_);
+        int st = cb_buf_wait_ready(in.raw(), s);
+        if (!st) st = cb_fir_run_dev(h_, static_cast<const float *>(in.ptr()), in.len, static_cast<float *>(out.ptr()), no, &no, s);
+        if (!st) st = cb_buf_record_done(in.raw(), s);
+        if (!st) st = cb_buf_record_ready(out.raw(), s);
+        return st ? Result<Buf>::Err(map_status(st)) : Result<Buf>::Ok(std::move(out));
+    }
+};
+
+// Convert2Node -> BatchFirNode -> Convert3Node -> DecimateNode of examples/fm_radio.rs:98-164 between device edges
+struct FirRealDevNode : Node1<FirRealDevNode, Buf, Buf>, FirHandle {
+    FirRealDevNode(const std::vector<c32> &taps, uint32_t decim) : FirHandle(taps, nullptr, decim, 1) {}
+    Result<Buf> run(const Buf &in)
+    {
+        size_t no = 0;
+        cb_fir_out_len(h_, in.len, &no);
+        Buf out = Buf::device(no * sizeof(float), no);
+        void *s = cb_fir_stream(h_);
+        int st = cb_buf_wait_ready(in.raw(), s);
+        if (!st) st = cb_fir_run_real_dev(h_, static_cast<const float *>(in.ptr()), in.len, static_cast<float *>(out.ptr()), no, &no, s);
+        if (!st) st = cb_buf_record_done(in.raw(), s);
+        if (!st) st = cb_buf_record_ready(out.raw(), s);
+        return st ? Result<Buf>::Err(map_status(st)) : Result<Buf>::Ok(std::move(out));
+    }
+};
+
+// ConvertNode -> filt1 -> dec1 -> FMDemodNode of examples/fm_radio.rs:84-97,144-160 on raw u8 IQ, one channel
+struct FmFrontDevNode : Node1<FmFrontDevNode, Buf, Buf>, StreamOwner {
+    cb_chain *h_ = nullptr;
+    FmFrontDevNode(const std::vector<c32> &taps, uint32_t decim)
+    {
+        if (cb_chain_create(1, nullptr, nullptr, reinterpret_cast<const float *>(taps.data()), taps.size(), decim, 1, &h_))
+            throw std::runtime_error(cb_last_error());
+    }
+    ~FmFrontDevNode() { cb_chain_destroy(h_); }
+    Result<Buf> run(const Buf &in)  // in.len = IQ byte pairs
+    {
+        size_t no = 0;
+        cb_chain_out_len(h_, in.len, &no);
+        Buf out = Buf::device(no * sizeof(float), no);
+        int st = cb_buf_wait_ready(in.raw(), s());
+        if (!st) st = cb_chain_run_u8_dev(h_, static_cast<const uint8_t *>(in.ptr()), in.len, static_cast<float *>(out.ptr()), no, &no, s());
+        if (!st) st = cb_buf_record_done(in.raw(), s());
+        if (!st) st = cb_buf_record_ready(out.raw(), s());
+        return st ? Result<Buf>::Err(map_status(st)) : Result<Buf>::Ok(std::move(out));
     }
 };
 

@@ -103,6 +103,11 @@ extern "C" {
     pub fn cb_peer_export(d_ptr: *mut c_void, handle64: *mut c_void) -> c_int;
     pub fn cb_peer_open(handle64: *const c_void, d_mapped: *mut *mut c_void) -> c_int;
     pub fn cb_peer_close(d_mapped: *mut c_void) -> c_int;
+    pub fn cb_pool_configure(is_device: c_int, max_live_bytes: usize, max_cached_bytes: usize, timeout_ms: c_int) -> c_int;
+    pub fn cb_pool_stats(is_device: c_int, live_bytes: *mut usize, cached_bytes: *mut usize, hits: *mut u64, misses: *mut u64, waits: *mut u64) -> c_int;
+    pub fn cb_pool_trim() -> c_int;
+    pub fn cb_pool_throttle(timeout_ms: c_int) -> c_int;
+    pub fn cb_buf_record_done(b: *mut cb_buf, stream: *mut c_void) -> c_int;
     pub fn cb_nco_create(dphase: f64, phase: f64, out: *mut *mut cb_nco) -> c_int;
     pub fn cb_nco_destroy(h: *mut cb_nco) -> c_int;
     pub fn cb_nco_run(h: *mut cb_nco, perr: *const f64, n: usize, out: *mut f64) -> c_int;

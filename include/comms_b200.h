@@ -94,6 +94,22 @@ CB_API void *cb_stream_handle(cb_stream *s);       /* the cudaStream_t          
  * nodes are adjacent: the derive macro clones the result once per downstream
  * edge (node_derive/src/lib.rs:156), so Clone must be cb_buf_retain, Drop
  * cb_buf_release. */
+/* Blocks come from a size-classed, thread-safe pool per (device, kind): no cudaMalloc / cudaFree per message.  The
+ * pool applies BACK-PRESSURE for the reference's unbounded channels (src/node/mod.rs:152; Graph::new(Some(n)),
+ * src/node/graph.rs:44-47, is the bounded alternative): with a high-water mark set (cb_pool_configure), the nodes where
+ * pool buffers START (a source filling pinned messages, a host->device edge node) call cb_pool_throttle() once per
+ * message: it blocks while the bytes handed out and not yet released exceed the mark of either kind, and fails with
+ * CB_ERR_OOM after timeout_ms (<= 0: the configured default) if no consumer releases.  Allocations themselves never
+ * block -- a node that waited for a buffer while holding one could close a cycle of waits.
+ * max_live_bytes = 0: no mark (default); max_cached_bytes: released blocks kept for reuse (default 1 GiB).
+ * A consumer that launched asynchronous work on a buffer calls cb_buf_record_done(buf, its stream) before dropping its
+ * reference; the pool waits for those events (and the producer's ready event) before the block's next owner gets it. */
+CB_API int cb_pool_configure(int is_device, size_t max_live_bytes, size_t max_cached_bytes, int timeout_ms);
+CB_API int cb_pool_stats(int is_device, size_t *live_bytes, size_t *cached_bytes, uint64_t *hits, uint64_t *misses,
+                         uint64_t *waits);
+CB_API int cb_pool_trim(void);
+CB_API int cb_pool_throttle(int timeout_ms);
+CB_API int cb_buf_record_done(cb_buf *b, void *stream);
 CB_API int cb_buf_alloc_pinned(size_t bytes, cb_buf **out);
 CB_API int cb_buf_alloc_device(size_t bytes, cb_buf **out);
 CB_API int cb_buf_retain(cb_buf *b);

@@ -627,10 +627,11 @@ def test_convert_i16_bit_exact(cb):
 
 
 # ------------------------------------------------------------------ BASELINE cfg 1 (single_thread_bpsk)
-def test_bpsk_chain_config1(cb, oracle):
+@pytest.mark.parametrize("nsym", [1 << 16, 1 << 20])  # 2^20 symbols in 256 batches of 4096: the config as specified
+def test_bpsk_chain_config1(cb, oracle, nsym):
     import torch
 
-    nsym, batch, sps = 1 << 16, 4096, 4
+    batch, sps = 4096, 4
     bits_ref, shaped_ref, iq_ref, st_ref = oracle.bpsk_chain(nsym, batch=batch, sps=sps)
     bits, _ = cb.prn_bits(0xB8, 0x01, nsym, 8)
     assert bits.tobytes() == bits_ref.tobytes()  # PRN bits: bit-exact
@@ -850,6 +851,144 @@ def test_handle_state_is_ordered_across_streams(cb):
     f.run_dev(xf.data_ptr(), xf.numel(), o2.data_ptr(), sb.cuda_stream)
     torch.cuda.synchronize()
     assert torch.equal(torch.view_as_real(o1), torch.view_as_real(o3)) and torch.equal(torch.view_as_real(o2), torch.view_as_real(o3))
+
+
+def test_large_pageable_host_call_is_staged_and_correct(cb):
+    # a Rust Vec is pageable memory: host-pointer calls of >= 8 MiB stage each chunk through pinned slots with the
+    # parallel copier (api.cu HostPipe::h2d / d2h); results must equal the pinned-buffer call bit for bit
+    import ctypes as C
+    import oracle
+    import torch
+
+    rng = np.random.default_rng(3)
+    n = (1 << 22) * 2 + 12345  # three chunks of the 2-lane pipeline, ragged tail
+    x = rnd_c32(rng, n)
+    taps = rnd_c32(rng, 64)
+    got = cb.BatchFirNode(taps).run(x)  # numpy memory: pageable
+    xp = torch.from_numpy(x).pin_memory()
+    yp = torch.empty(n, dtype=torch.complex64).pin_memory()
+    node = cb.BatchFirNode(taps)
+    cb._lib.check(cb.load().cb_fir_run(node._h, xp.data_ptr(), n, yp.data_ptr(), n, None))
+    assert got.tobytes() == yp.numpy().tobytes()
+    lo = (1 << 22) - 500
+    want, _ = oracle.batch_fir(x[lo:lo + 1000], taps, x[lo - 64:lo][::-1].copy())
+    assert rel_l2(got[lo:lo + 1000], want) <= FIR_TOL
+    nf = (n // 4096) * 4096
+    gf = cb.FFTBatchNode(4096).run(x[:nf])
+    fp = torch.empty(nf, dtype=torch.complex64).pin_memory()
+    f = cb.FFTBatchNode(4096)
+    cb._lib.check(cb.load().cb_fft_run(f._h, xp.data_ptr(), nf, fp.data_ptr()))
+    assert gf.tobytes() == fp.numpy().tobytes()
+    gm = cb.MixerNode(0.37, 0.5).run(x)
+    mp = torch.empty(n, dtype=torch.complex64).pin_memory()
+    m = cb.MixerNode(0.37, 0.5)
+    cb._lib.check(cb.load().cb_mixer_run(m._h, xp.data_ptr(), n, mp.data_ptr()))
+    assert gm.tobytes() == mp.numpy().tobytes()
+
+
+def test_cpp_graph_message_rate_bench_runs(cb):
+    """comms-rs_b200/host/bench_graph.cpp at small message counts: thread-per-node graphs with pooled device edges must
+    deliver every message, and the device-edge cfg-1 graph must equal the host-edge graph bit for bit."""
+    import json
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "comms-rs_b200", "host")
+    subprocess.run(["make", "-C", host, "-s", "all"], check=True)
+    r = subprocess.run([os.path.join(host, "bench_graph"), "512", "48"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "bench_graph ok" in r.stdout
+    lines = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 3 and lines[1]["bit_identical_to_host_edges"] is True
+    assert lines[1]["pool_device"]["hits"] > 0  # blocks are recycled, not cudaMalloc'ed per message
+
+
+# ------------------------------------------------------------------ buffer pool (back-pressure for unbounded channels)
+def test_buffer_pool_reuse_and_back_pressure(cb):
+    # cb_buf_alloc_* come from a size-classed pool (no cudaMalloc / cudaFree per message); with a high-water mark the
+    # source-side gate cb_pool_throttle blocks until a consumer releases (src/node/mod.rs:152: unbounded channels)
+    import ctypes as C
+    import threading
+    import time
+
+    lib = cb.load()
+    for dev in (True, False):
+        alloc = lib.cb_buf_alloc_device if dev else lib.cb_buf_alloc_pinned
+        s0 = cb.pool_stats(dev)
+        a = C.c_void_p()
+        cb._lib.check(alloc(100_000, C.byref(a)))
+        pa = lib.cb_buf_ptr(a)
+        assert lib.cb_buf_bytes(a) == 100_000
+        lib.cb_buf_release(a)
+        b = C.c_void_p()
+        cb._lib.check(alloc(120_000, C.byref(b)))  # same size class (128 KiB): the block comes back from the pool
+        assert lib.cb_buf_ptr(b) == pa
+        s1 = cb.pool_stats(dev)
+        assert s1["hits"] == s0["hits"] + 1 and s1["live_bytes"] == s0["live_bytes"] + (1 << 17)
+        lib.cb_buf_release(b)
+        # high-water mark of three 1 MiB blocks: allocations never block, the gate is cb_pool_throttle (called by sources)
+        cb.pool_configure(dev, max_live_bytes=s0["live_bytes"] + (3 << 20), timeout_ms=300)
+        try:
+            held = []
+            for _ in range(4):
+                h = C.c_void_p()
+                cb._lib.check(alloc(1 << 20, C.byref(h)))
+                held.append(h)
+            t0 = time.perf_counter()
+            rc = lib.cb_pool_throttle(0)  # nobody releases: fails after the configured timeout instead of hanging
+            assert rc == cb._lib.CB_ERR_OOM and time.perf_counter() - t0 >= 0.25
+            assert b"high-water" in lib.cb_last_error()
+            threading.Timer(0.1, lambda: lib.cb_buf_release(held.pop())).start()  # a consumer drops its message
+            t0 = time.perf_counter()
+            cb._lib.check(lib.cb_pool_throttle(2000))  # blocks ~0.1 s, then proceeds
+            assert 0.05 <= time.perf_counter() - t0 < 1.0
+            cb._lib.check(lib.cb_pool_throttle(0))  # under the mark: returns at once
+            assert cb.pool_stats(dev)["waits"] >= s0["waits"] + 2
+            for h in held:
+                lib.cb_buf_release(h)
+        finally:
+            cb.pool_configure(dev)
+        assert cb.pool_stats(dev)["live_bytes"] == s0["live_bytes"]
+    lib.cb_pool_trim()
+    assert cb.pool_stats(True)["cached_bytes"] == 0
+
+
+def test_pooled_buffer_waits_for_previous_owner(cb):
+    # a block released while a kernel still reads it (consumer recorded `done` behind its launch) must not reach its
+    # next owner before that kernel finished: the second owner overwrites it at once, the first result must not change
+    import ctypes as C
+    import torch
+
+    lib = cb.load()
+    n = 1 << 24
+    x = torch.randn(2 * n, device="cuda")
+    want = torch.empty(2 * n, device="cuda")
+    m = cb.MixerNode(0.3)
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    m.run_dev(x.data_ptr(), n, want.data_ptr(), sa.cuda_stream)
+    torch.cuda.synchronize()
+    for _ in range(3):
+        buf = C.c_void_p()
+        cb._lib.check(lib.cb_buf_alloc_device(8 * n, C.byref(buf)))
+        p = lib.cb_buf_ptr(buf)
+        cb._lib.check(lib.cb_decimate_dev(x.data_ptr(), n, 8, 1, p, n, None, sa.cuda_stream))  # producer fills the message
+        cb._lib.check(lib.cb_buf_record_ready(buf, sa.cuda_stream))
+        out = torch.empty(2 * n, device="cuda")
+        torch.cuda.synchronize()
+        m.phase = 0.0
+        cb._lib.check(lib.cb_buf_wait_ready(buf, sb.cuda_stream))
+        m.run_dev(p, n, out.data_ptr(), sb.cuda_stream)  # consumer reads it asynchronously ...
+        cb._lib.check(lib.cb_buf_record_done(buf, sb.cuda_stream))
+        lib.cb_buf_release(buf)  # ... and drops it at once
+        nxt = C.c_void_p()
+        cb._lib.check(lib.cb_buf_alloc_device(8 * n, C.byref(nxt)))  # same block, next owner
+        assert lib.cb_buf_ptr(nxt) == p
+        cb._lib.check(lib.cb_synth_uniform_dev(1, 0, n, p, sa.cuda_stream))  # overwrites immediately on another stream
+        torch.cuda.synchronize()
+        assert torch.equal(out, want)
+        lib.cb_buf_release(nxt)
 
 
 # ------------------------------------------------------------------ NCO batching shim (SURVEY 8(f) rank 4)
