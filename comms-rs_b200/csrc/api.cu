@@ -433,6 +433,7 @@ struct cb_fir {
     int cur;
     void *tc_img;       // tensor-core path: prepacked tap image (device), or NULL
     FirTcPlan tc;
+    FirFix fix[2];      // exact fall-back work lists of the tensor-core path, one per host-pipeline lane
     float2 *qscratch;   // f32 result of the unfused cb_fir_run_dev_i16 path, grown on demand
     size_t qscratch_len;
     float2 *rscratch;   // unfused cb_fir_run_real_dev path: widened input followed by the complex result
@@ -974,6 +975,8 @@ int cb_fir_destroy(cb_fir *h)
     h->pipe.destroy();
     if (h->taps_dev) cudaFree(h->taps_dev);
     if (h->tc_img) cudaFree(h->tc_img);
+    for (int i = 0; i < 2; ++i)
+        if (h->fix[i].dev) cudaFree(h->fix[i].dev);
     if (h->qscratch) cudaFree(h->qscratch);
     if (h->rscratch) cudaFree(h->rscratch);
     if (h->ols_hf) cudaFree(h->ols_hf);
@@ -996,9 +999,34 @@ int cb_fir_out_len(const cb_fir *h, size_t n_in, size_t *n_out)
 
 void *cb_fir_stream(cb_fir *h) { return h ? (void *)h->stream : nullptr; }
 
-static int fir_launch_segment(cb_fir *h, const float2 *x, size_t n, const float2 *hist_in, float2 *hist_out,
-                              float2 *y, cudaStream_t s)
+// the lane's fix-up list, grown to hold every tile a launch over n inputs could flag (NULL when it cannot be allocated:
+// the launch then runs without the fall-back pass, as before)
+static FirFix *fir_fix_for(cb_fir *h, size_t n, int lane)
 {
+    if (!h->tc_img) return nullptr;
+    FirFix &f = h->fix[lane & 1];
+    const size_t need = fir_fix_tiles(n);
+    if (f.cap < need) {
+        if (f.dev) cudaFree(f.dev);  // waits for launches that still use it
+        f.dev = nullptr;
+        f.cap = 0;
+        f.calls = 0;
+        const size_t cap = need < 4096 ? 4096 : need * 2;
+        if (cudaMalloc(&f.dev, (cap + 2) * sizeof(unsigned)) != cudaSuccess || cudaMemset(f.dev, 0, 2 * sizeof(unsigned)) != cudaSuccess) {
+            (void)cudaGetLastError();
+            if (f.dev) cudaFree(f.dev);
+            f.dev = nullptr;
+            return nullptr;
+        }
+        f.cap = (unsigned)cap;
+    }
+    return &f;
+}
+
+static int fir_launch_segment(cb_fir *h, const float2 *x, size_t n, const float2 *hist_in, float2 *hist_out,
+                              float2 *y, cudaStream_t s, int lane = 0)
+{
+    h->tc.fix = fir_fix_for(h, n, lane);
     // long filters and long batches: overlap-save fast convolution (spectra scratch grown on demand; when it
     // cannot be allocated the direct-form kernel below is used)
     // COMMS_B200_FIR_OLS=split: the two-kernel form with the spectra in a scratch (kept for comparison); default: one
@@ -1064,6 +1092,7 @@ int cb_fir_run_dev_i16(cb_fir *h, const float *d_in, size_t n_in, float scale, i
     seg.y = reinterpret_cast<float2 *>(d_out);  // unused by the fused kernel (alignment checks only)
     int rc = h->last.begin(s);
     if (rc) return rc;
+    h->tc.fix = fir_fix_for(h, n_in, 0);
     if (fir_fuses_i16(seg, h->taps_real, h->tc_img ? &h->tc : nullptr)) {
         rc = launch_fir(seg, h->taps_dev, h->taps.data(), h->taps_real, &h->tc, s);
     } else {  // filter into an f32 scratch, then the stand-alone quantiser
@@ -1202,7 +1231,7 @@ int cb_fir_run(cb_fir *h, const float *in, size_t n_in, float *out, size_t out_c
         }
         if (rc) return rc;
         float2 *y = reinterpret_cast<float2 *>(h->pipe.out[l]);
-        rc = fir_launch_segment(h, slot + H, n, hist_in, last ? h->hist[h->cur ^ 1] : nullptr, y, s);
+        rc = fir_launch_segment(h, slot + H, n, hist_in, last ? h->hist[h->cur ^ 1] : nullptr, y, s, l);
         if (rc) return rc;
         const size_t m = fir_out_len(h, n);
         rc = h->pipe.d2h(l, hout + out_done, y, m * sizeof(float2));

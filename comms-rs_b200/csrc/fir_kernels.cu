@@ -394,6 +394,57 @@ static int launch_generic(const FirSeg &seg, const float2 *taps_dev, cudaStream_
     return CB_OK;
 }
 
+// Exact fall-back of the tensor-core filters: flagged tiles recomputed in f32 direct form, taps in order, and
+// overwritten (see FirFix).  y[L m + p] = sum_q h[p + q L] * x[m - q]; x[-1-i] comes from the carried history.
+__device__ __forceinline__ int fix_quant_i16(float v, float scale)  // Rust `(scale * v) as i16`: truncate, saturate, NaN -> 0
+{
+    const float t = v * scale;
+    if (!(t == t)) return 0;
+    return (int)fminf(fmaxf(truncf(t), -32768.f), 32767.f);
+}
+
+__global__ void __launch_bounds__(256) fir_fixup_kernel(const FirFixArgs a)
+{
+    const unsigned nfix = *a.count;
+    const unsigned L = a.interp;
+    for (unsigned t = blockIdx.x; t < nfix; t += gridDim.x) {
+        const unsigned long long in0 = (unsigned long long)a.list[t] * a.tile_in;
+        for (unsigned o = threadIdx.x; o < a.tile_in * L; o += blockDim.x) {
+            const unsigned long long m = in0 + o / L;
+            if (m >= a.n) break;
+            const unsigned p = o % L;
+            float re = 0.f, im = 0.f;
+            long long idx = (long long)m;
+            for (unsigned k = p; k < a.ntaps; k += L, --idx) {
+                float2 xs = make_float2(0.f, 0.f);
+                if (idx >= 0) xs = a.x[idx];
+                else if ((long long)a.hist_len + idx >= 0) xs = a.hist_in[(long long)a.hist_len + idx];
+                const float2 h = __ldg(a.taps + k);
+                re = fmaf(h.x, xs.x, re);
+                re = fmaf(-h.y, xs.y, re);
+                im = fmaf(h.x, xs.y, im);
+                im = fmaf(h.y, xs.x, im);
+            }
+            const unsigned long long j = m * L + p;
+            if (a.y16 != nullptr) {
+                a.y16[2 * j] = (int16_t)fix_quant_i16(re, a.qscale);
+                a.y16[2 * j + 1] = (int16_t)fix_quant_i16(im, a.qscale);
+            } else {
+                a.y[j] = make_float2(re, im);
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.next_count = 0;  // nobody else touches the other counter now
+}
+
+int launch_fir_fixup(const FirFixArgs &a, cudaStream_t stream)
+{
+    fir_fixup_kernel<<<148, 256, 0, stream>>>(a);
+    count_launch();
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+
 bool fir_fuses_i16(const FirSeg &seg, bool taps_real, const FirTcPlan *tcplan)
 {
     return tcplan != nullptr && tcplan->bimg_dev != nullptr && seg.n_in >= tcplan->min_samples && seg.interp > 1 &&
@@ -406,9 +457,9 @@ int launch_fir(const FirSeg &seg, const float2 *taps_dev, const float2 *taps_hos
     if (seg.n_in == 0) return CB_OK;
     if (tcplan != nullptr && tcplan->bimg_dev != nullptr && seg.n_in >= tcplan->min_samples) {
         if (seg.interp == 1 && fir_tc_applicable(seg))
-            return launch_fir_tc(seg, tcplan->bimg_dev, tcplan->tap_inv_scale, stream);
+            return launch_fir_tc(seg, tcplan->bimg_dev, tcplan->tap_inv_scale, tcplan->fix, taps_dev, stream);
         if (seg.interp > 1 && fir_ptc_applicable(seg, taps_real))
-            return launch_fir_ptc(seg, tcplan->bimg_dev, tcplan->tap_inv_scale, taps_real, stream);
+            return launch_fir_ptc(seg, tcplan->bimg_dev, tcplan->tap_inv_scale, taps_real, tcplan->fix, taps_dev, stream);
     }
     if (seg.interp == 1 && seg.decim == 1) {
         const uint32_t K = seg.ntaps;

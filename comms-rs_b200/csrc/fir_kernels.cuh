@@ -26,17 +26,47 @@ struct FirSeg {
     float qscale = 1.f;     //   (only the polyphase tensor-core kernel fuses it; see launch_fir_i16)
 };
 
+// Work list of the tensor-core kernels' exact fall-back.  The tensor-core filters scale a whole tile by one power of
+// two before the two-term fp16 split, which holds f32-level accuracy only while a tile's quiet stretches stay within
+// ~2^-20 of its maximum, and a single Inf / NaN poisons every product of the tile.  The converter warps therefore
+// flag such tiles (non-finite sample, or a pair of adjacent samples below 2^-20 of the tile maximum) and append them
+// here; fir_fixup_kernel, launched behind every tensor-core launch, recomputes exactly those tiles in plain f32 direct
+// form (the reference's arithmetic, src/filter/fir.rs:87-102) and overwrites them.  dev[0], dev[1]: counters used by
+// alternate launches (the fix-up kernel of launch k zeroes the counter of launch k+1); dev[2..]: tile indices.
+struct FirFix {
+    unsigned *dev = nullptr;
+    unsigned cap = 0;       // tile indices the list can hold
+    unsigned calls = 0;     // launches so far (selects the counter)
+};
+
 // Tensor-core path (fir_tc_kernel.cu): prepacked fp16 hi/lo Toeplitz tap image + its scale.
 struct FirTcPlan {
     const void *bimg_dev;   // fir_tc_image_bytes(ntaps) bytes, device
     float tap_inv_scale;
     size_t min_samples;     // use the tensor-core kernel from this batch size on
+    FirFix *fix = nullptr;  // the launch's fix-up list (one per concurrent lane); NULL: no fall-back pass
 };
+// upper bound of the tiles any tensor-core launch over n_in inputs can flag
+static inline size_t fir_fix_tiles(size_t n_in) { return n_in / 512 + 8; }
+
+struct FirFixArgs {
+    const float2 *x, *hist_in, *taps;
+    float2 *y;
+    int16_t *y16;
+    float qscale;
+    unsigned long long n;   // input samples
+    unsigned ntaps, interp, tile_in, hist_len;
+    const unsigned *count;
+    unsigned *next_count;
+    const unsigned *list;
+};
+int launch_fir_fixup(const FirFixArgs &a, cudaStream_t stream);
 size_t fir_tc_image_bytes(uint32_t ntaps);
 int fir_tc_kblocks(uint32_t ntaps);
 void fir_tc_build_image(const float2 *taps, uint32_t ntaps, unsigned char *img, float *tap_inv_scale);
 bool fir_tc_applicable(const FirSeg &seg);
-int launch_fir_tc(const FirSeg &seg, const void *bimg_dev, float tap_inv_scale, cudaStream_t stream);
+int launch_fir_tc(const FirSeg &seg, const void *bimg_dev, float tap_inv_scale, FirFix *fix, const float2 *taps_dev,
+                  cudaStream_t stream);
 
 // Polyphase tensor-core path (fir_ptc_kernel.cu): interp in {4, 8}, decim = 1, real or complex taps.
 // The plan's bimg_dev / tap_inv_scale then hold the polyphase tap image.
@@ -46,7 +76,8 @@ size_t fir_ptc_image_bytes(uint32_t ntaps, uint32_t interp, bool taps_real);
 void fir_ptc_build_image(const float2 *taps, uint32_t ntaps, uint32_t interp, bool taps_real, unsigned char *img,
                          float *tap_inv_scale);
 bool fir_ptc_applicable(const FirSeg &seg, bool taps_real);
-int launch_fir_ptc(const FirSeg &seg, const void *himg_dev, float tap_inv_scale, bool taps_real, cudaStream_t stream);
+int launch_fir_ptc(const FirSeg &seg, const void *himg_dev, float tap_inv_scale, bool taps_real, FirFix *fix,
+                   const float2 *taps_dev, cudaStream_t stream);
 
 // Overlap-save path for long filters (fft_kernels.cu): 129 .. 1025 taps, decim = interp = 1.
 // hf: 4096-point spectrum of the zero-padded taps; tw_fwd / tw_inv: fft2 tables for 4096 points; spec: scratch of

@@ -71,6 +71,8 @@ struct Args {
     float tap_inv_scale;
     int2 *y16;              // OUT16: interleaved i16 IQ output (src/io/raw_iq.rs layout) instead of y
     float qscale;           // OUT16: (qscale * v) as i16, truncating, saturating
+    unsigned *fix_count;    // tiles flagged for the exact fall-back pass (FirFix), or NULL
+    unsigned *fix_list;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
@@ -186,12 +188,15 @@ __global__ void __launch_bounds__(OUT16 ? 512 : 288, 1) fir_ptc_kernel(const __g
     __shared__ __align__(8) uint64_t raw_full[NRAW], raw_empty[NRAW];
     __shared__ uint32_t tmem_slot;
     __shared__ float red_max[4];
+    __shared__ uint32_t red_min[4];
+    __shared__ unsigned fix_seen;  // tile + 1 last appended to the fix-up list
     __shared__ float inv_scale[8];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned long long ntiles = (a.n + (unsigned long long)TS - 1) / (unsigned long long)TS;
 
     if (tid == 0) {
+        fix_seen = 0u;
         for (int i = 0; i < 2; ++i) {
             mbar_init(&a_full[i], NLOAD);
             mbar_init(&a_empty[i], 1);
@@ -266,7 +271,8 @@ __global__ void __launch_bounds__(OUT16 ? 512 : 288, 1) fir_ptc_kernel(const __g
             const long long t0 = (long long)tile * TS;
             const int rs = (int)(it % NRAW);
             float4 raw[NLD];
-            float mx = 0.f;
+            float mx = 0.f;            // tile maximum
+            uint32_t mnu = 0xffffffffu;  // bits of the smallest non-zero pair maximum, minus one (a zero pair wraps to the top)
             if (TMA_LOAD) mbar_wait(&raw_full[rs], (uint32_t)((it / NRAW) & 1));
             const float4 *rawt = reinterpret_cast<const float4 *>(sRaw + rs * RAWB);
 #pragma unroll
@@ -282,15 +288,29 @@ __global__ void __launch_bounds__(OUT16 ? 512 : 288, 1) fir_ptc_kernel(const __g
                     v = make_float4(t.x, t.y, 0.f, 0.f);
                 }
                 raw[i] = v;
-                mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+                const float pm = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+                mx = fmaxf(mx, pm);
+                mnu = min(mnu, __float_as_uint(pm) - 1u);
             }
             if (TMA_LOAD) mbar_arrive(&raw_empty[rs]);  // the raw tile is in registers: the TMA warp may refill the stage
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            if (lane == 0) red_max[gw] = mx;
+            for (int o = 16; o > 0; o >>= 1) {
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                mnu = min(mnu, __shfl_xor_sync(0xffffffffu, mnu, o));
+            }
+            if (lane == 0) {
+                red_max[gw] = mx;
+                red_min[gw] = mnu;
+            }
             asm volatile("bar.sync 1, 128;" ::: "memory");
             mx = fmaxf(fmaxf(red_max[0], red_max[1]), fmaxf(red_max[2], red_max[3]));
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // red_max is reused by the next tile
+            mnu = min(min(red_min[0], red_min[1]), min(red_min[2], red_min[3]));
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // red_max / red_min are reused by the next tile
+            // quiet stretch more than 2^20 below the tile maximum: recomputed in plain f32 by the fix-up pass (FirFix,
+            // fir_kernels.cuh); non-finite symbols are caught in the conversion loop below
+            if (gt == 0 && a.fix_count != nullptr && mnu != 0xffffffffu && __uint_as_float(mnu + 1u) < mx * 9.5367431640625e-7f &&
+                atomicExch(&fix_seen, (unsigned)tile + 1u) != (unsigned)tile + 1u)
+                a.fix_list[atomicAdd(a.fix_count, 1u)] = (unsigned)tile;
             uint32_t eb = (__float_as_uint(mx) >> 23) & 0xFF;
             eb = (eb < 16 || eb == 255) ? 141 : eb;  // all-zero / denormal / non-finite tile: scale 1
             const float sc = __uint_as_float((268u - eb) << 23);
@@ -300,6 +320,7 @@ __global__ void __launch_bounds__(OUT16 ? 512 : 288, 1) fir_ptc_kernel(const __g
             }
             mbar_wait(&a_empty[s], ph ^ 1);  // the MMAs that read this stage two tiles ago are done
             unsigned char *hi = sS + s * G::STAGE, *lo = hi + G::PART;
+            __half2 nanacc = __floats2half2_rn(0.f, 0.f);  // sum of the lo terms: NaN iff a symbol of the tile is Inf / NaN
 #pragma unroll
             for (int i = 0; i < NLD; ++i) {
                 const int q = gt + i * NLOAD;
@@ -308,6 +329,7 @@ __global__ void __launch_bounds__(OUT16 ? 512 : 288, 1) fir_ptc_kernel(const __g
                 const float2 br = __half22float2(hr), bm = __half22float2(hm);
                 const __half2 lr = __floats2half2_rn(v.x - br.x, v.z - br.y);
                 const __half2 lm = __floats2half2_rn(v.y - bm.x, v.w - bm.y);
+                nanacc = __hadd2(nanacc, __hadd2(lr, lm));  // Inf * sc - Inf = NaN, NaN stays NaN; finite |lo| < 16
                 const uint32_t off = swz<ROWB>((uint32_t)q * 4u);
                 *reinterpret_cast<__half2 *>(hi + off) = hr;
                 *reinterpret_cast<__half2 *>(hi + G::COMP + off) = hm;
@@ -320,6 +342,9 @@ __global__ void __launch_bounds__(OUT16 ? 512 : 288, 1) fir_ptc_kernel(const __g
             }
             fence_proxy_async();
             mbar_arrive(&a_full[s]);
+            if (a.fix_count != nullptr && (__hisnan(__low2half(nanacc)) || __hisnan(__high2half(nanacc))) &&
+                atomicExch(&fix_seen, (unsigned)tile + 1u) != (unsigned)tile + 1u)
+                a.fix_list[atomicAdd(a.fix_count, 1u)] = (unsigned)tile;  // non-finite symbol: exact fall-back (FirFix)
         }
     } else if (warp == NEPI + 4) {
         // ------------------------------------------------------------------ MMA issuer
@@ -525,7 +550,17 @@ bool fir_ptc_applicable(const FirSeg &seg, bool taps_real)
            (reinterpret_cast<uintptr_t>(seg.y) & 7) == 0 && (reinterpret_cast<uintptr_t>(seg.y16) & 3) == 0;
 }
 
-int launch_fir_ptc(const FirSeg &seg, const void *himg_dev, float tap_inv_scale, bool taps_real, cudaStream_t stream)
+// symbols per tile of the kernel above (TS in fir_ptc_kernel)
+static unsigned ptc_tile_symbols(uint32_t interp, unsigned ks)
+{
+    const int rs = 128 / (int)interp, nel = 128 * rs, kt = 16 * (int)ks;
+    return (unsigned)(((nel - kt) / rs + 1) * rs);
+}
+
+static int launch_fir_ptc_main(const FirSeg &seg, const ptc::Args &a, bool taps_real, cudaStream_t stream);
+
+int launch_fir_ptc(const FirSeg &seg, const void *himg_dev, float tap_inv_scale, bool taps_real, FirFix *fix,
+                   const float2 *taps_dev, cudaStream_t stream)
 {
     if (seg.n_in == 0) return CB_OK;
     ptc::Args a;
@@ -541,6 +576,20 @@ int launch_fir_ptc(const FirSeg &seg, const void *himg_dev, float tap_inv_scale,
     a.tap_inv_scale = tap_inv_scale;
     a.y16 = reinterpret_cast<int2 *>(seg.y16);
     a.qscale = seg.qscale;
+    const unsigned ts = ptc_tile_symbols(seg.interp, a.ks);
+    const bool fixup = fix != nullptr && fix->dev != nullptr && taps_dev != nullptr && fix->cap >= ceil_div(seg.n_in, (size_t)ts);
+    a.fix_count = fixup ? fix->dev + (fix->calls & 1u) : nullptr;
+    a.fix_list = fixup ? fix->dev + 2 : nullptr;
+    const int rc = launch_fir_ptc_main(seg, a, taps_real, stream);
+    if (rc || !fixup) return rc;
+    FirFixArgs f{seg.x, seg.hist_in, taps_dev, seg.y, seg.y16, seg.qscale, seg.n_in, seg.ntaps, seg.interp, ts, seg.hist_len,
+                 a.fix_count, fix->dev + ((fix->calls + 1) & 1u), a.fix_list};
+    ++fix->calls;
+    return launch_fir_fixup(f, stream);
+}
+
+static int launch_fir_ptc_main(const FirSeg &seg, const ptc::Args &a, bool taps_real, cudaStream_t stream)
+{
     if (seg.y16 != nullptr) {
         switch (seg.interp) {
         case 8: return taps_real ? launch_ptc_l<8, false, true>(a, stream) : launch_ptc_l<8, true, true>(a, stream);

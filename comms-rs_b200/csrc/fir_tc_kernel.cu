@@ -61,6 +61,8 @@ struct Args {
     unsigned long long n;
     unsigned hist_len;
     float tap_inv_scale;    // 2^-(14 - e_h)
+    unsigned *fix_count;    // tiles flagged for the exact fall-back pass (FirFix), or NULL
+    unsigned *fix_list;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
@@ -139,12 +141,15 @@ __global__ void __launch_bounds__(512, 1) fir_tc_kernel(const __grid_constant__ 
     __shared__ __align__(8) uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2], sc_ready[8];
     __shared__ uint32_t tmem_slot;
     __shared__ float red_max[2][4];  // [loader group][warp]
+    __shared__ uint32_t red_min[2][4];
+    __shared__ unsigned fix_seen[2];  // tile + 1 last appended to the fix-up list by each converter group
     __shared__ float inv_scale[8];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned long long ntiles = (a.n + TILE - 1) / TILE;
 
     if (tid == 0) {
+        fix_seen[0] = fix_seen[1] = 0u;
         for (int i = 0; i < 2; ++i) {
             mbar_init(&a_full[i], NCONV);
             mbar_init(&a_empty[i], 1);
@@ -213,7 +218,8 @@ __global__ void __launch_bounds__(512, 1) fir_tc_kernel(const __grid_constant__ 
             const uint32_t ph = (uint32_t)((it >> 1) & 1);
             const long long t0 = (long long)tile * TILE;
             float4 raw[NLD];
-            float mx = 0.f;
+            float mx = 0.f;            // tile maximum
+            uint32_t mnu = 0xffffffffu;  // bits of the smallest non-zero pair maximum, minus one (a zero pair wraps to the top)
             const int rs = (int)(it % NRAW);
             mbar_wait(&raw_full[rs], (uint32_t)((it / NRAW) & 1));
             const float4 *rawt = reinterpret_cast<const float4 *>(sRaw + rs * RAWB);
@@ -231,17 +237,31 @@ __global__ void __launch_bounds__(512, 1) fir_tc_kernel(const __grid_constant__ 
                     }
                 }
                 raw[i] = v;
-                mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+                const float pm = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+                mx = fmaxf(mx, pm);
+                mnu = min(mnu, __float_as_uint(pm) - 1u);
             }
             mbar_arrive(&raw_empty[rs]);  // tile is in registers: the TMA warp may refill the stage
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            if (lane == 0) red_max[s][gw] = mx;
+            for (int o = 16; o > 0; o >>= 1) {
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                mnu = min(mnu, __shfl_xor_sync(0xffffffffu, mnu, o));
+            }
+            if (lane == 0) {
+                red_max[s][gw] = mx;
+                red_min[s][gw] = mnu;
+            }
             asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
             mx = fmaxf(fmaxf(red_max[s][0], red_max[s][1]), fmaxf(red_max[s][2], red_max[s][3]));
+            mnu = min(min(red_min[s][0], red_min[s][1]), min(red_min[s][2], red_min[s][3]));
+            // a quiet stretch more than 2^20 below the tile maximum (its lo terms go denormal): this tile is recomputed
+            // in plain f32 by the fix-up pass (FirFix); non-finite samples are caught in the conversion loop below
+            if (gt == 0 && a.fix_count != nullptr && mnu != 0xffffffffu && __uint_as_float(mnu + 1u) < mx * 9.5367431640625e-7f &&
+                atomicExch(&fix_seen[s], (unsigned)tile + 1u) != (unsigned)tile + 1u)
+                a.fix_list[atomicAdd(a.fix_count, 1u)] = (unsigned)tile;
             // exact power-of-two block scale: max * sc in [2^14, 2^15)
             uint32_t eb = (__float_as_uint(mx) >> 23) & 0xFF;
-            eb = eb < 16 ? 141 : eb;  // all-zero / denormal tile: scale 1
+            eb = (eb < 16 || eb == 255) ? 141 : eb;  // all-zero / denormal / non-finite tile: scale 1
             const float sc = __uint_as_float((268u - eb) << 23);
             if (gt == 0) {  // the epilogue is at most 4 tiles behind: an 8-deep ring cannot wrap
                 inv_scale[it & 7] = __uint_as_float((eb - 14u) << 23);
@@ -250,6 +270,7 @@ __global__ void __launch_bounds__(512, 1) fir_tc_kernel(const __grid_constant__ 
 
             mbar_wait(&a_empty[s], ph ^ 1);  // MMAs that read this stage two tiles ago are done
             unsigned char *hi = sA + s * A_STAGE, *lo = hi + A_PART;
+            __half2 nanacc = __floats2half2_rn(0.f, 0.f);  // sum of the lo terms: NaN iff a sample of the tile is Inf / NaN
 #pragma unroll
             for (int i = 0; i < NLD; ++i) {
                 const int q = gt + i * NCONV;
@@ -259,6 +280,7 @@ __global__ void __launch_bounds__(512, 1) fir_tc_kernel(const __grid_constant__ 
                     const float2 b0 = __half22float2(h0), b1 = __half22float2(h1);
                     const __half2 l0 = __floats2half2_rn(v.x - b0.x, v.y - b0.y);
                     const __half2 l1 = __floats2half2_rn(v.z - b1.x, v.w - b1.y);
+                    nanacc = __hadd2(nanacc, __hadd2(l0, l1));  // Inf * sc - Inf = NaN, NaN stays NaN; finite |lo| < 16
                     const uint32_t off = swz128((uint32_t)q * 8u);
                     uint2 ph2, pl2;
                     ph2.x = *reinterpret_cast<const uint32_t *>(&h0);
@@ -271,6 +293,9 @@ __global__ void __launch_bounds__(512, 1) fir_tc_kernel(const __grid_constant__ 
             }
             fence_proxy_async();
             mbar_arrive(&a_full[s]);
+            if (a.fix_count != nullptr && (__hisnan(__low2half(nanacc)) || __hisnan(__high2half(nanacc))) &&
+                atomicExch(&fix_seen[s], (unsigned)tile + 1u) != (unsigned)tile + 1u)
+                a.fix_list[atomicAdd(a.fix_count, 1u)] = (unsigned)tile;  // non-finite sample: exact fall-back (FirFix)
         }
     } else if (warp == 12) {
         // ------------------------------------------------------------------ MMA issuer
@@ -468,7 +493,8 @@ bool fir_tc_applicable(const FirSeg &seg)
     return ((reinterpret_cast<uintptr_t>(seg.x) | reinterpret_cast<uintptr_t>(seg.y) | reinterpret_cast<uintptr_t>(h)) & 15) == 0;
 }
 
-int launch_fir_tc(const FirSeg &seg, const void *bimg_dev, float tap_inv_scale, cudaStream_t stream)
+int launch_fir_tc(const FirSeg &seg, const void *bimg_dev, float tap_inv_scale, FirFix *fix, const float2 *taps_dev,
+                  cudaStream_t stream)
 {
     if (seg.n_in == 0) return CB_OK;
     const int KB = fir_tc_kblocks(seg.ntaps);
@@ -482,13 +508,23 @@ int launch_fir_tc(const FirSeg &seg, const void *bimg_dev, float tap_inv_scale, 
     a.n = seg.n_in;
     a.hist_len = seg.hist_len;
     a.tap_inv_scale = tap_inv_scale;
+    const bool fixup = fix != nullptr && fix->dev != nullptr && taps_dev != nullptr &&
+                       fix->cap >= ceil_div(seg.n_in, (size_t)tc::TILE);
+    a.fix_count = fixup ? fix->dev + (fix->calls & 1u) : nullptr;
+    a.fix_list = fixup ? fix->dev + 2 : nullptr;
+    int rc;
     switch (KB) {
-    case 2: return launch_tc_kb<2>(a, stream);
-    case 3: return launch_tc_kb<3>(a, stream);
-    case 4: return launch_tc_kb<4>(a, stream);
-    case 5: return launch_tc_kb<5>(a, stream);
+    case 2: rc = launch_tc_kb<2>(a, stream); break;
+    case 3: rc = launch_tc_kb<3>(a, stream); break;
+    case 4: rc = launch_tc_kb<4>(a, stream); break;
+    case 5: rc = launch_tc_kb<5>(a, stream); break;
     default: set_error("fir_tc: unsupported tap count %u", seg.ntaps); return CB_ERR_UNSUPPORTED;
     }
+    if (rc || !fixup) return rc;
+    FirFixArgs f{seg.x, seg.hist_in, taps_dev, seg.y, nullptr, 1.f, seg.n_in, seg.ntaps, 1u, (unsigned)tc::TILE, seg.hist_len,
+                 a.fix_count, fix->dev + ((fix->calls + 1) & 1u), a.fix_list};
+    ++fix->calls;
+    return launch_fir_fixup(f, stream);
 }
 
 }  // namespace cb

@@ -256,6 +256,91 @@ def test_fir_tensor_core_dynamic_range(cb, oracle, cplx, monkeypatch):
         assert rel_l2(got[lo:hi], want[lo:hi]) <= FIR_TOL, (lo, hi)
 
 
+def _windows_ok(got, want, win, tol):
+    """every `win`-sample window on its own (a bad stretch cannot hide in the global norm); all-zero windows must be zero"""
+    n = len(want) // win * win
+    g = got[:n].astype(np.complex128).reshape(-1, win)
+    w = want[:n].astype(np.complex128).reshape(-1, win)
+    num = np.linalg.norm(g - w, axis=1)
+    den = np.linalg.norm(w, axis=1)
+    rel = np.where(den > 0, num / np.where(den > 0, den, 1), num)
+    worst = int(np.argmax(rel))
+    assert rel[worst] <= tol, (worst * win, float(rel[worst]))
+
+
+@pytest.mark.parametrize("exp", [6, 8, 10])
+@pytest.mark.parametrize("cplx", [False, True])
+def test_fir_tensor_core_mixed_tile_windows(cb, oracle, cplx, exp, monkeypatch):
+    # The tile that CONTAINS both the loud and the quiet stretch: one power-of-two scale per 4096-sample tile cannot
+    # hold f32 accuracy there (the quiet samples' lo terms go denormal), the reference (plain f32, fir.rs:87-102) has no
+    # such limit.  Such tiles are flagged by the converter warps and recomputed in f32 direct form (FirFix): every
+    # 64-sample window must keep 1e-5, at in-tile dynamic ranges of 1e6, 1e8 and 1e10.
+    monkeypatch.setenv("COMMS_B200_FIR_PATH", "tc")
+    rng = np.random.default_rng(700 + exp + cplx)
+    t = rnd_c32(rng, 64) if cplx else rng.uniform(-1, 1, 64).astype(np.complex64)
+    x = rnd_c32(rng, 70_000)
+    q = np.float32(10.0 ** -exp)
+    x[9_000:11_000] *= q          # inside tile 2
+    x[20_400:20_700] *= q         # across the edge of tiles 4 / 5
+    x[33_000:41_500] *= q         # two whole tiles and parts of their neighbours
+    x[50_000:50_200] = 0          # exact zeros are not a quiet stretch
+    want, st = oracle.batch_fir(x, t, np.zeros(64, np.complex64))
+    node = cb.BatchFirNode(t)
+    got = node.run(x)
+    _windows_ok(got, want, 64, FIR_TOL)
+    assert node.state.tobytes() == st.tobytes()
+    # batch invariance survives the fall-back: two calls, same stream
+    node2 = cb.BatchFirNode(t)
+    got2 = np.concatenate([node2.run(x[:35_000]), node2.run(x[35_000:])])
+    _windows_ok(got2, want, 64, FIR_TOL)
+
+
+@pytest.mark.parametrize("L,ntaps,cplx", [(8, 1024, False), (4, 32, False), (8, 128, True)])
+@pytest.mark.parametrize("exp", [6, 10])
+def test_polyphase_tensor_core_mixed_tile_windows(cb, oracle, L, ntaps, cplx, exp, monkeypatch):
+    # same for the polyphase bank (fir_ptc_kernel.cu), symbol tiles of ~1900 symbols
+    monkeypatch.setenv("COMMS_B200_FIR_PATH", "tc")
+    rng = np.random.default_rng(900 + L + ntaps + exp)
+    t = rnd_c32(rng, ntaps) if cplx else rng.uniform(-1, 1, ntaps).astype(np.complex64)
+    sym = rnd_c32(rng, 12_000)
+    q = np.float32(10.0 ** -exp)
+    sym[2_500:3_100] *= q
+    sym[5_600:9_900] *= q
+    want, st = oracle.batch_fir(oracle.upsample(sym, L), t, np.zeros(ntaps, np.complex64))
+    node = cb.BatchFirNode(t, None, interp=L)
+    got = node.run(sym)
+    _windows_ok(got, want, 64 * L, FIR_TOL)
+    assert node.state.tobytes() == st.tobytes()
+    if not cplx and L == 4:  # the fused quantiser takes the same fall-back
+        scale = float(2.0 ** exp)
+        i16 = cb.BatchFirNode(t, None, interp=L).run_i16(sym, scale)
+        assert np.array_equal(i16, oracle.quantize_i16(got, scale).reshape(-1, 2))
+
+
+@pytest.mark.parametrize("interp", [1, 8])
+def test_tensor_core_nonfinite_samples_stay_local(cb, oracle, interp, monkeypatch):
+    # an Inf / NaN sample poisons exactly the outputs whose taps reach it (K outputs, fir.rs:99), as in the reference --
+    # not the whole 4096-sample tile that shares its block scale
+    monkeypatch.setenv("COMMS_B200_FIR_PATH", "tc")
+    rng = np.random.default_rng(1234 + interp)
+    ntaps = 64 if interp == 1 else 256
+    t = rnd_c32(rng, ntaps) if interp == 1 else rng.uniform(-1, 1, ntaps).astype(np.complex64)
+    x = rnd_c32(rng, 40_000)
+    x[12_345] = np.complex64(complex(np.inf, 0.5))
+    x[20_479] = np.complex64(complex(np.nan, 0.0))    # last sample of a tile: reaches into the next one
+    x[30_000] = np.complex64(complex(1.0, -np.inf))
+    with np.errstate(all="ignore"):
+        want, _ = oracle.batch_fir(oracle.upsample(x, interp) if interp > 1 else x, t, np.zeros(ntaps, np.complex64))
+    got = cb.BatchFirNode(t, None, interp=interp).run(x)
+    bad_w = ~(np.isfinite(want.real) & np.isfinite(want.imag))
+    bad_g = ~(np.isfinite(got.real) & np.isfinite(got.imag))
+    assert bad_w.sum() == 3 * ntaps
+    assert np.array_equal(bad_g, bad_w)
+    ok = ~bad_w
+    g, w = np.where(ok, got, 0), np.where(ok, want, 0)
+    _windows_ok(g, w, 64 * interp, FIR_TOL)
+
+
 @pytest.mark.parametrize("ntaps,seed", [(129, 1), (500, 2), (1024, 3), (1025, 4)])
 def test_long_fir_overlap_save_batches(cb, oracle, ntaps, seed):
     # 129 .. 1025 taps: fast convolution (4096-point FFT -> x Hf -> IFFT) from 8192 samples per call on, the direct
