@@ -1688,6 +1688,7 @@ int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
         if (path && strcmp(path, "rows") == 0) h->plan.cluster_tpt = 6;       // 256 x 256, fused persistent kernel, L2 ring
         if (path && strcmp(path, "rows2") == 0) h->plan.cluster_tpt = 7;      // 256 x 256, two launches, batch-sized scratch
         if (path && strcmp(path, "big") == 0) h->plan.cluster_tpt = 8;        // the generic fused two-step kernel (K5-B)
+        if (path && strcmp(path, "cpipe") == 0) h->plan.cluster_tpt = 9;      // persistent pipelined 8-CTA clusters (K5-P)
     }
     *out = h;
     return CB_OK;

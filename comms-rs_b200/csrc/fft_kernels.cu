@@ -868,6 +868,8 @@ int launch_fft(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframe
                          : launch_frames_dir<false>(p.log2n, in, out, p.tw, nframes, s);
     }
     if (fft_big_applicable(p, nframes) && (p.n != 65536 || p.cluster_tpt == 8)) return launch_fft_big(p, in, out, nframes, s);
+    if (p.kind == FFT_FOURSTEP && p.n == 65536 && p.cluster_tpt == 9)
+        return launch_fft65536_cpipe(in, out, p.tw, nframes, p.inverse != 0, s);
     if (p.kind == FFT_FOURSTEP && p.n == 65536 && (p.cluster_tpt == 6 || p.cluster_tpt == 7))
         return launch_fft65536_rows(p, in, out, nframes, s);
     if (p.kind == FFT_FOURSTEP && p.n == 65536 && p.cluster_tpt == 5 && p.tw16 != nullptr)

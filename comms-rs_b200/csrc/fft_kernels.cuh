@@ -25,7 +25,8 @@ struct FftPlanDev {
     const float2 *tw16a, *tw16b;  // radix-16 tables of the n1- and n2-point step transforms (fused two-step form), or NULL
     int big;              // 1: sizes 2^15, 2^17 .. 2^20 run the fused two-step kernel (fft_big_kernel.cu); 0: four-step
     int cluster_tpt;      // n = 65536: 0 = four-step, 1 / 2 / 3 = cluster kernel exchange variants, 4 = 16-CTA clusters,
-                          // 5 = 16 x 4096 two-pass, 6 = 256 x 256 two-pass with a batch-sized scratch (default)
+                          // 5 = 16 x 4096 two-pass, 6 = 256 x 256 fused two-step with an L2 ring, 7 = the same as two launches,
+                          // 8 = generic fused two-step, 9 = persistent pipelined clusters (fft_cpipe_kernel.cu)
 };
 
 size_t fft2_table_len(int log2n);
@@ -33,6 +34,7 @@ void fft2_fill_table(int log2n, int inverse, float2 *host_table);
 int fft_plan_split(size_t n, int *log2n1, int *log2n2);
 int launch_fft65536_cluster(const float2 *in, float2 *out, const float2 *twN, size_t nframes, bool inverse, int tpt,
                             cudaStream_t s);
+int launch_fft65536_cpipe(const float2 *in, float2 *out, const float2 *twN, size_t nframes, bool inverse, cudaStream_t s);
 int launch_fft65536_rows(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s);
 bool fft_big_applicable(const FftPlanDev &p, size_t nframes);
 int launch_fft_big(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s);

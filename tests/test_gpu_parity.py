@@ -319,7 +319,7 @@ def test_fft_matches_oracle(cb, oracle, n, inverse):
         assert rel_l2(got[f * n:(f + 1) * n], want[f * n:(f + 1) * n]) <= FFT_TOL
 
 
-@pytest.mark.parametrize("path", ["cluster", "cluster1", "cluster2", "cluster16", "twopass", "rows", "rows2", "big", "fourstep"])
+@pytest.mark.parametrize("path", ["cluster", "cluster1", "cluster2", "cluster16", "twopass", "rows", "rows2", "big", "fourstep", "cpipe"])
 @pytest.mark.parametrize("inverse", [False, True])
 def test_fft65536_paths(cb, oracle, path, inverse, monkeypatch):
     # K5-C: one HBM pass on an 8-CTA cluster (distributed shared memory) vs the four-step fallback
@@ -333,6 +333,24 @@ def test_fft65536_paths(cb, oracle, path, inverse, monkeypatch):
     got = cb.FFTBatchNode(n, inverse).run(x)
     for f in range(frames):
         assert rel_l2(got[f * n:(f + 1) * n], want[f * n:(f + 1) * n]) <= FFT_TOL
+
+
+@pytest.mark.parametrize("frames", [1, 2, 3, 19, 75])
+def test_fft65536_pipelined_cluster_frame_counts(cb, oracle, frames, monkeypatch):
+    # K5-P (fft_cpipe_kernel.cu): persistent clusters, frames round-robin over the resident clusters; fewer frames than
+    # clusters, exactly one or two per cluster (the pipeline's prologue / epilogue iterations) and several per cluster
+    monkeypatch.setenv("COMMS_B200_FFT_PATH", "cpipe")
+    n = 65536
+    rng = np.random.default_rng(frames)
+    x = rnd_c32(rng, frames * n)
+    for inverse in (False, True):
+        got = cb.FFTBatchNode(n, inverse).run(x)
+        for f in sorted({0, frames // 2, frames - 1}):
+            want = oracle.fft(x[f * n:(f + 1) * n], n, inverse)
+            assert rel_l2(got[f * n:(f + 1) * n], want) <= FFT_TOL, (f, inverse)
+        e_in = (np.abs(x.reshape(frames, n).astype(np.complex128)) ** 2).sum(axis=1)
+        e_out = (np.abs(got.reshape(frames, n).astype(np.complex128)) ** 2).sum(axis=1)
+        assert np.all(np.abs(e_out / (n * e_in) - 1) < 1e-5)  # every frame: Parseval
 
 
 @pytest.mark.parametrize("n", [1024, 4096, 65536])
