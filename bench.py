@@ -40,6 +40,9 @@ WORKLOADS = {
     # name: (kind, samples per step per GPU, algorithmic bytes per input sample, description)
     "fir64": ("fir", 1 << 28, 16.0, "64-tap complex-f32 FIR (complex taps) on one 2^28-sample stream per GPU"),
     "fir64_real": ("fir", 1 << 28, 16.0, "64-tap complex-f32 FIR (real-valued rrc taps) on one 2^28-sample stream per GPU"),
+    "fir64_iq16": ("fir16", 1 << 28, 8.0, "64-tap complex FIR with i16 IQ on both edges (IQBatchInput -> filter -> IQBatchOutput, src/io/raw_iq.rs): "
+                   "4 B in + 4 B out per sample; cast and quantiser run as separate kernels around the f32 filter, so the device-resident "
+                   "figure is low against an 8 B/sample roof -- the point of the entry is the PCIe-bound host call"),
     "fir1024": ("fir", 1 << 28, 16.0, "1024-tap complex-f32 FIR (overlap-save fast convolution) on one 2^28-sample stream per GPU"),
     "fir63d5": ("firdec", 1 << 28, 9.6, "63-tap real-valued FIR + DecimateNode(5) (fm_radio.rs filt1 -> dec1) fused, one 2^28-sample stream per GPU"),
     "fir63d5_real": ("firreal", 1 << 28, 4.8, "fm_radio second stage (fm_radio.rs:98-164): real f32 samples -> Complex(x,0) -> 63-tap FIR -> .re -> "
@@ -212,7 +215,13 @@ def cpu_rate(workload, samples, threads):
     jobs = []
     for i in range(threads):
         x = oracle.synth_uniform_c32(SEED, i * per, per)
-        if kind == "fir":
+        if kind == "fir16":
+            t = fir_taps("fir64", cpu=True)
+            iq = (x.view(np.float32) * np.float32(32767.0)).astype(np.int16)
+            jobs.append(lambda iq=iq, t=t: oracle.quantize_i16(oracle.batch_fir(
+                (iq.astype(np.float32) * np.float32(1.0 / 32767.0)).view(np.complex64), t, np.zeros(len(t), np.complex64),
+                literal=True, native=True)[0], 8192.0))
+        elif kind == "fir":
             t = fir_taps(workload, cpu=True)
             # reference form: per-sample rotate + ordered MACs (src/filter/fir.rs:87-102), release flags
             jobs.append(lambda x=x, t=t: oracle.batch_fir(x, t, np.zeros(len(t), np.complex64), literal=True, native=True))
@@ -274,7 +283,7 @@ def run_reference(args, rank):
         return
     threads = os.cpu_count() or 1
     kind, _, _, desc = WORKLOADS[args.workload]
-    rate1 = {"fir": 8e6, "fft": 30e6, "chain": 20e6, "interp": 2e6, "mixer": 30e6, "fm": 60e6, "firdec": 8e6, "est": 3e6, "firreal": 8e6, "graph": 8e6}[kind]
+    rate1 = {"fir16": 8e6, "fir": 8e6, "fft": 30e6, "chain": 20e6, "interp": 2e6, "mixer": 30e6, "fm": 60e6, "firdec": 8e6, "est": 3e6, "firreal": 8e6, "graph": 8e6}[kind]
     if args.workload.startswith("poly8x1024"):
         rate1 = 1e4
     per_thread = int(min(max(150.0 * rate1 / (args.steps + args.warmup), 1 << 12), 1 << 23))
@@ -328,6 +337,19 @@ class Job:
             self.step = lambda: self.node.run_dev(self.x.data_ptr(), n, self.y.data_ptr(), n, self.stream)
             self.step_to = lambda dst: self.node.run_dev(self.x.data_ptr(), n, dst, n, self.stream)
             self.host_call = lambda hin, hout: cb.load().cb_fir_run(self.node._h, hin, n, hout, n, None)
+        elif self.kind == "fir16":
+            self.taps = fir_taps("fir64")
+            self.node = cb.BatchFirNode(self.taps, None)
+            xr = torch.view_as_real(self.x)
+            self.x16 = (xr * 32767.0).to(torch.int16).contiguous()  # the same synthetic stream as i16 IQ
+            self.x8 = self.x16  # (the e2e leg copies `x8` when present)
+            self.y = torch.empty(2 * n, dtype=torch.int16, device="cuda")
+            self.in_bytes_override = 4 * n
+            self.out_bytes = 4 * n
+            self.kernels_per_step = 1  # roofline over the whole step (cast + filter + fix-up + quantiser)
+            sc_in, sc_out = 1.0 / 32767.0, 8192.0
+            self.step = lambda: self.node.run_dev_iq16(self.x16.data_ptr(), n, sc_in, sc_out, self.y.data_ptr(), n, self.stream)
+            self.host_call = lambda hin, hout: cb.load().cb_fir_run_iq16(self.node._h, hin, n, sc_in, sc_out, hout, n, None)
         elif self.kind == "firdec":
             self.taps = fm_radio_lowpass()
             self.node = cb.BatchFirNode(self.taps, None, decim=5)
@@ -735,7 +757,7 @@ def measure(cb, torch, dist, args, workload, rank, world, local_rank, steps, war
             line["gather"] = gather
         if world == 1 and not args.no_cpu:
             kind = job.kind
-            sample = {"fir": 1 << 26, "fft": 1 << 27, "chain": 1 << 26, "interp": 1 << 23, "mixer": 1 << 26, "fm": 1 << 27, "firdec": 1 << 26, "est": 1 << 24, "firreal": 1 << 26, "graph": 1 << 26}[kind]
+            sample = {"fir16": 1 << 26, "fir": 1 << 26, "fft": 1 << 27, "chain": 1 << 26, "interp": 1 << 23, "mixer": 1 << 26, "fm": 1 << 27, "firdec": 1 << 26, "est": 1 << 24, "firreal": 1 << 26, "graph": 1 << 26}[kind]
             if workload == "timing10x5":
                 sample = 1 << 22
             if workload.startswith("poly8x1024"):

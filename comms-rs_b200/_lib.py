@@ -80,6 +80,10 @@ SIGNATURES = {
     "cb_fir_run_real_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _psz, _vp]),
     "cb_fir_run_i16": (_i, [_vp, _vp, _sz, C.c_float, _vp, _sz, C.POINTER(_sz)]),
     "cb_fir_run_dev_i16": (_i, [_vp, _vp, _sz, C.c_float, _vp, _sz, C.POINTER(_sz), _vp]),
+    "cb_fir_run_iq16": (_i, [_vp, _vp, _sz, C.c_float, C.c_float, _vp, _sz, _psz]),
+    "cb_fir_run_dev_iq16": (_i, [_vp, _vp, _sz, C.c_float, C.c_float, _vp, _sz, _psz, _vp]),
+    "cb_fft_run_iq16": (_i, [_vp, _vp, _sz, C.c_float, _vp]),
+    "cb_fft_run_dev_iq16": (_i, [_vp, _vp, _sz, C.c_float, _vp, _vp]),
     "cb_fir_state_len": (_i, [_vp, _psz]),
     "cb_fir_get_state": (_i, [_vp, _vp, _sz]),
     "cb_fir_set_state": (_i, [_vp, _vp, _sz]),

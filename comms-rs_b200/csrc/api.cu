@@ -172,6 +172,8 @@ struct HostPipe {
     void *in[2] = {nullptr, nullptr};
     void *out[2] = {nullptr, nullptr};
     size_t in_cap = 0, out_cap = 0;
+    void *aux_in[2] = {nullptr, nullptr}, *aux_out[2] = {nullptr, nullptr};  // f32 sides of the i16-IQ entries
+    size_t aux_in_cap = 0, aux_out_cap = 0;
     // pinned staging slots for pageable callers (allocated on first use), one per lane and direction
     void *pin_in[2] = {nullptr, nullptr}, *pin_out[2] = {nullptr, nullptr};
     size_t pin_in_cap = 0, pin_out_cap = 0;
@@ -204,6 +206,26 @@ struct HostPipe {
                 CB_CUDA(cudaMalloc(&out[i], out_bytes));
             }
             out_cap = out_bytes;
+        }
+        return CB_OK;
+    }
+    int reserve_aux(size_t in_bytes, size_t out_bytes)
+    {
+        if (in_bytes > aux_in_cap) {
+            for (int i = 0; i < 2; ++i) {
+                if (aux_in[i]) CB_CUDA(cudaFree(aux_in[i]));
+                aux_in[i] = nullptr;
+                CB_CUDA(cudaMalloc(&aux_in[i], in_bytes));
+            }
+            aux_in_cap = in_bytes;
+        }
+        if (out_bytes > aux_out_cap) {
+            for (int i = 0; i < 2; ++i) {
+                if (aux_out[i]) CB_CUDA(cudaFree(aux_out[i]));
+                aux_out[i] = nullptr;
+                CB_CUDA(cudaMalloc(&aux_out[i], out_bytes));
+            }
+            aux_out_cap = out_bytes;
         }
         return CB_OK;
     }
@@ -291,6 +313,8 @@ struct HostPipe {
         for (int i = 0; i < 2; ++i) {
             if (in[i]) cudaFree(in[i]);
             if (out[i]) cudaFree(out[i]);
+            if (aux_in[i]) cudaFree(aux_in[i]);
+            if (aux_out[i]) cudaFree(aux_out[i]);
             if (pin_in[i]) cudaFreeHost(pin_in[i]);
             if (pin_out[i]) cudaFreeHost(pin_out[i]);
             if (ev_in[i]) cudaEventDestroy(ev_in[i]);
@@ -1245,6 +1269,114 @@ int cb_fir_run(cb_fir *h, const float *in, size_t n_in, float *out, size_t out_c
     return CB_OK;
 }
 
+// ---- i16 IQ on both edges (src/io/raw_iq.rs:78-140 IQBatchInput, :185-223 IQBatchOutput): x = in_scale * (i16 as f32),
+// the handle's filter, y16 = (out_scale * y) as i16.  Half the bytes of the f32 entries on every edge.
+// One filter step with f32 input already on the device -> i16 output (fused epilogue for the tensor-core polyphase banks).
+static int fir_segment_to_i16(cb_fir *h, const float2 *x, size_t n, const float2 *hist_in, float2 *hist_out, float out_scale,
+                              int16_t *y16, float2 *yscratch, cudaStream_t s, int lane)
+{
+    const size_t no = fir_out_len(h, n);
+    h->tc.fix = fir_fix_for(h, n, lane);
+    FirSeg seg{x, hist_in, hist_out, nullptr, n, no, h->hist_len, h->k_eff, h->interp, h->decim};
+    seg.y16 = y16;
+    seg.qscale = out_scale;
+    seg.y = reinterpret_cast<float2 *>(y16);
+    if (fir_fuses_i16(seg, h->taps_real, h->tc_img ? &h->tc : nullptr))
+        return launch_fir(seg, h->taps_dev, h->taps.data(), h->taps_real, &h->tc, s);
+    int rc = fir_launch_segment(h, x, n, hist_in, hist_out, yscratch, s, lane);
+    if (rc) return rc;
+    return launch_quantize_i16(reinterpret_cast<const float *>(yscratch), y16, 2 * no, out_scale, s);
+}
+
+int cb_fir_run_dev_iq16(cb_fir *h, const int16_t *d_in, size_t n_in, float in_scale, float out_scale, int16_t *d_out,
+                        size_t out_cap, size_t *n_out, void *stream)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    const size_t no = fir_out_len(h, n_in);
+    if (n_out) *n_out = no;
+    if (n_in == 0) return CB_OK;
+    CB_REQUIRE(d_in && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_REQUIRE(out_cap >= no, CB_ERR_SIZE, "fir: out_cap %zu < %zu outputs", out_cap, no);
+    CB_NO_ALIAS(d_in, n_in * 2 * sizeof(int16_t), d_out, no * 2 * sizeof(int16_t), "fir");
+    CB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = pick_stream(stream, h->stream);
+    int rc = h->last.begin(s);
+    if (rc) return rc;
+    if (h->rscratch_len < n_in + no) {  // widened input followed by the f32 result
+        if (h->rscratch) CB_CUDA(cudaFree(h->rscratch));
+        h->rscratch = nullptr;
+        h->rscratch_len = 0;
+        CB_CUDA(cudaMalloc(&h->rscratch, (n_in + no) * sizeof(float2)));
+        h->rscratch_len = n_in + no;
+    }
+    float2 *wide = h->rscratch, *res = h->rscratch + n_in;
+    rc = launch_convert_i16(d_in, reinterpret_cast<float *>(wide), 2 * n_in, in_scale, s);
+    if (rc == CB_OK)
+        rc = fir_segment_to_i16(h, wide, n_in, h->hist[h->cur], h->hist[h->cur ^ 1], out_scale, d_out, res, s, 0);
+    if (rc) return rc;
+    h->cur ^= 1;
+    return h->last.end(s);
+}
+
+int cb_fir_run_iq16(cb_fir *h, const int16_t *in, size_t n_in, float in_scale, float out_scale, int16_t *out, size_t out_cap,
+                    size_t *n_out)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    const size_t no = fir_out_len(h, n_in);
+    if (n_out) *n_out = no;
+    if (n_in == 0) return CB_OK;
+    CB_REQUIRE(in && out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_REQUIRE(out_cap >= no, CB_ERR_SIZE, "fir: out_cap %zu < %zu outputs", out_cap, no);
+    CB_CUDA(cudaSetDevice(h->device));
+    const size_t H = h->hist_len, IQ = 2 * sizeof(int16_t);
+    size_t chunk = HOST_CHUNK * 2 / h->decim * h->decim;  // twice the samples of an f32 chunk: the same 32 MiB per copy
+    if (chunk < 4 * H || n_in <= chunk) chunk = n_in;
+    const size_t chunk_out = fir_out_len(h, chunk);
+    int rc = h->last.sync();
+    if (rc) return rc;
+    rc = h->pipe.reserve((chunk + H) * IQ, chunk_out * IQ);
+    if (rc) return rc;
+    rc = h->pipe.reserve_aux((chunk + H) * sizeof(float2), chunk_out * sizeof(float2));
+    if (rc) return rc;
+    rc = h->pipe.begin_call(in, n_in * IQ, (chunk + H) * IQ, out, no * IQ, chunk_out * IQ);
+    if (rc) return rc;
+    const char *hin = reinterpret_cast<const char *>(in);
+    char *hout = reinterpret_cast<char *>(out);
+    size_t done = 0, out_done = 0;
+    for (int i = 0; done < n_in; ++i) {
+        const int l = i & 1;
+        const size_t n = n_in - done < chunk ? n_in - done : chunk;
+        const bool last = done + n == n_in;
+        cudaStream_t s = h->pipe.lane[l];
+        char *slot16 = reinterpret_cast<char *>(h->pipe.in[l]);
+        float2 *wide = reinterpret_cast<float2 *>(h->pipe.aux_in[l]);
+        const float2 *hist_in;
+        if (done == 0) {  // the carried history is already f32
+            hist_in = h->hist[h->cur];
+            rc = h->pipe.h2d(l, slot16 + H * IQ, hin, n * IQ);
+            if (rc == CB_OK) rc = launch_convert_i16(reinterpret_cast<const int16_t *>(slot16 + H * IQ), reinterpret_cast<float *>(wide + H), 2 * n, in_scale, s);
+        } else {  // the halo is the tail of the previous chunk, re-sent (and re-converted) with this one
+            hist_in = wide;
+            rc = h->pipe.h2d(l, slot16, hin + (done - H) * IQ, (n + H) * IQ);
+            if (rc == CB_OK) rc = launch_convert_i16(reinterpret_cast<const int16_t *>(slot16), reinterpret_cast<float *>(wide), 2 * (n + H), in_scale, s);
+        }
+        if (rc) return rc;
+        int16_t *y16 = reinterpret_cast<int16_t *>(h->pipe.out[l]);
+        rc = fir_segment_to_i16(h, wide + H, n, hist_in, last ? h->hist[h->cur ^ 1] : nullptr, out_scale, y16,
+                                reinterpret_cast<float2 *>(h->pipe.aux_out[l]), s, l);
+        if (rc) return rc;
+        const size_t m = fir_out_len(h, n);
+        rc = h->pipe.d2h(l, hout + out_done * IQ, y16, m * IQ);
+        if (rc) return rc;
+        done += n;
+        out_done += m;
+    }
+    rc = h->pipe.sync();
+    if (rc) return rc;
+    h->cur ^= 1;
+    return CB_OK;
+}
+
 int cb_fir_state_len(const cb_fir *h, size_t *nstate)
 {
     CB_REQUIRE(h && nstate, CB_ERR_INVALID_ARG, "NULL argument");
@@ -1847,6 +1979,68 @@ int cb_fft_run(cb_fft *h, const float *in, size_t n_in, float *out)
             CB_CUDA(cudaStreamSynchronize(h->pipe.lane[l ^ 1]));
         }
         rc = fft_exec(h, di, dout, m / N, s);
+        if (rc) return rc;
+        rc = h->pipe.d2h(l, hout + done, dout, m * sizeof(float2));
+        if (rc) return rc;
+        done += m;
+    }
+    return h->pipe.sync();
+}
+
+// i16 IQ frames in (IQBatchInput, src/io/raw_iq.rs:78-140), f32 spectra out: x = in_scale * (i16 as f32)
+int cb_fft_run_dev_iq16(cb_fft *h, const int16_t *d_in, size_t n_in, float in_scale, float *d_out, void *stream)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    CB_REQUIRE(n_in > 0 && n_in % h->plan.n == 0, CB_ERR_SIZE, "fft: input length %zu is not a multiple of fft_size %zu",
+               n_in, h->plan.n);
+    CB_REQUIRE(d_in && d_out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_NO_ALIAS(d_in, n_in * 2 * sizeof(int16_t), d_out, n_in * sizeof(float2), "fft");
+    CB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = pick_stream(stream, h->stream);
+    int rc = h->last.begin(s);  // the widened-input scratch is per handle
+    if (rc) return rc;
+    rc = h->pipe.reserve_aux(n_in * sizeof(float2), 0);
+    if (rc) return rc;
+    float2 *wide = reinterpret_cast<float2 *>(h->pipe.aux_in[0]);
+    rc = launch_convert_i16(d_in, reinterpret_cast<float *>(wide), 2 * n_in, in_scale, s);
+    if (rc == CB_OK) rc = fft_exec(h, wide, reinterpret_cast<float2 *>(d_out), n_in / h->plan.n, s);
+    if (rc) return rc;
+    return h->last.end(s);
+}
+
+int cb_fft_run_iq16(cb_fft *h, const int16_t *in, size_t n_in, float in_scale, float *out)
+{
+    CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
+    CB_REQUIRE(n_in > 0 && n_in % h->plan.n == 0, CB_ERR_SIZE, "fft: input length %zu is not a multiple of fft_size %zu",
+               n_in, h->plan.n);
+    CB_REQUIRE(in && out, CB_ERR_INVALID_ARG, "NULL data pointer");
+    CB_CUDA(cudaSetDevice(h->device));
+    const size_t N = h->plan.n, IQ = 2 * sizeof(int16_t);
+    size_t chunk = HOST_CHUNK / N * N;
+    if (chunk == 0) chunk = N;
+    if (n_in < chunk) chunk = n_in;
+    int rc = h->last.sync();
+    if (rc) return rc;
+    rc = h->pipe.reserve(chunk * IQ, chunk * sizeof(float2));
+    if (rc) return rc;
+    rc = h->pipe.reserve_aux(chunk * sizeof(float2), 0);
+    if (rc) return rc;
+    rc = h->pipe.begin_call(in, n_in * IQ, chunk * IQ, out, n_in * sizeof(float2), chunk * sizeof(float2));
+    if (rc) return rc;
+    const char *hin = reinterpret_cast<const char *>(in);
+    float2 *hout = reinterpret_cast<float2 *>(out);
+    size_t done = 0;
+    for (int i = 0; done < n_in; ++i) {
+        const int l = i & 1;
+        const size_t m = n_in - done < chunk ? n_in - done : chunk;
+        cudaStream_t s = h->pipe.lane[l];
+        float2 *wide = reinterpret_cast<float2 *>(h->pipe.aux_in[l]), *dout = reinterpret_cast<float2 *>(h->pipe.out[l]);
+        rc = h->pipe.h2d(l, h->pipe.in[l], hin + done * IQ, m * IQ);
+        if (rc) return rc;
+        rc = launch_convert_i16(reinterpret_cast<const int16_t *>(h->pipe.in[l]), reinterpret_cast<float *>(wide), 2 * m, in_scale, s);
+        if (rc) return rc;
+        if ((h->plan.kind == FFT_FOURSTEP || h->plan.kind == FFT_BLUESTEIN) && i > 0) CB_CUDA(cudaStreamSynchronize(h->pipe.lane[l ^ 1]));
+        rc = fft_exec(h, wide, dout, m / N, s);
         if (rc) return rc;
         rc = h->pipe.d2h(l, hout + done, dout, m * sizeof(float2));
         if (rc) return rc;

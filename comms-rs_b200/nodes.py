@@ -121,6 +121,25 @@ class BatchFirNode(_Handle):
         check(_lib.load().cb_fir_run_dev_i16(self._h, d_in, n_in, float(scale), d_out, out_cap, C.byref(m), stream))
         return m.value
 
+    def run_iq16(self, iq, in_scale: float = 1.0, out_scale: float = 1.0) -> np.ndarray:
+        """i16 IQ in ([n, 2] int16, what IQBatchInput reads: src/io/raw_iq.rs:78-140), i16 IQ out ([n_out, 2]):
+        x = in_scale * (i16 as f32) -> this filter -> (out_scale * y) as i16."""
+        x = np.ascontiguousarray(np.asarray(iq, dtype=np.int16)).reshape(-1, 2)
+        n = _sz()
+        check(_lib.load().cb_fir_out_len(self._h, len(x), C.byref(n)))
+        out = np.empty((n.value, 2), dtype=np.int16)
+        m = _sz()
+        try:
+            check(_lib.load().cb_fir_run_iq16(self._h, _ptr(x), len(x), float(in_scale), float(out_scale), _ptr(out), n.value, C.byref(m)))
+        except CbError as e:
+            raise node_error(e) from e
+        return out[: m.value]
+
+    def run_dev_iq16(self, d_in: int, n_in: int, in_scale: float, out_scale: float, d_out: int, out_cap: int, stream: int = 0) -> int:
+        m = _sz()
+        check(_lib.load().cb_fir_run_dev_iq16(self._h, d_in, n_in, float(in_scale), float(out_scale), d_out, out_cap, C.byref(m), stream))
+        return m.value
+
     @property
     def state(self) -> np.ndarray:
         n = _sz()
@@ -304,6 +323,20 @@ class FFTBatchNode(_Handle):
 
     def run_dev(self, d_in: int, n_in: int, d_out: int, stream: int = 0) -> None:
         check(_lib.load().cb_fft_run_dev(self._h, d_in, n_in, d_out, stream))
+
+
+def _fft_run_iq16(self, iq, in_scale: float = 1.0) -> np.ndarray:
+    """i16 IQ frames in ([n, 2] int16), complex f32 spectra out: x = in_scale * (i16 as f32)."""
+    x = np.ascontiguousarray(np.asarray(iq, dtype=np.int16)).reshape(-1, 2)
+    out = np.empty(len(x), dtype=np.complex64)
+    try:
+        check(_lib.load().cb_fft_run_iq16(self._h, _ptr(x), len(x), float(in_scale), _ptr(out)))
+    except CbError as e:
+        raise node_error(e) from e
+    return out
+
+
+FFTBatchNode.run_iq16 = _fft_run_iq16
 
 
 class FFTSampleNode(FFTBatchNode):

@@ -103,6 +103,10 @@ extern "C" {
     pub fn cb_peer_export(d_ptr: *mut c_void, handle64: *mut c_void) -> c_int;
     pub fn cb_peer_open(handle64: *const c_void, d_mapped: *mut *mut c_void) -> c_int;
     pub fn cb_peer_close(d_mapped: *mut c_void) -> c_int;
+    pub fn cb_fir_run_iq16(h: *mut cb_fir, input: *const i16, n_in: usize, in_scale: f32, out_scale: f32, out: *mut i16, out_cap: usize, n_out: *mut usize) -> c_int;
+    pub fn cb_fir_run_dev_iq16(h: *mut cb_fir, d_in: *const i16, n_in: usize, in_scale: f32, out_scale: f32, d_out: *mut i16, out_cap: usize, n_out: *mut usize, stream: *mut c_void) -> c_int;
+    pub fn cb_fft_run_iq16(h: *mut cb_fft, input: *const i16, n_in: usize, in_scale: f32, out: *mut f32) -> c_int;
+    pub fn cb_fft_run_dev_iq16(h: *mut cb_fft, d_in: *const i16, n_in: usize, in_scale: f32, d_out: *mut f32, stream: *mut c_void) -> c_int;
     pub fn cb_pool_configure(is_device: c_int, max_live_bytes: usize, max_cached_bytes: usize, timeout_ms: c_int) -> c_int;
     pub fn cb_pool_stats(is_device: c_int, live_bytes: *mut usize, cached_bytes: *mut usize, hits: *mut u64, misses: *mut u64, waits: *mut u64) -> c_int;
     pub fn cb_pool_trim() -> c_int;

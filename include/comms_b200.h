@@ -167,6 +167,15 @@ CB_API int cb_fir_run_dev_i16(cb_fir *h, const float *d_in, size_t n_in, float s
                               size_t out_cap, size_t *n_out, void *stream);
 CB_API int cb_fir_run_i16(cb_fir *h, const float *in, size_t n_in, float scale, int16_t *out, size_t out_cap,
                           size_t *n_out);
+/* i16 IQ on both edges -- what IQBatchInput / IQBatchOutput read and write (src/io/raw_iq.rs:78-140, 185-223:
+ * interleaved native-endian i16): x = in_scale * (i16 as f32) (in_scale = 1: the plain cast of a
+ * Vec<Complex<i16>>), this filter, out = (out_scale * y) as i16 (truncating, saturating).  d_in / in: 2*n_in int16,
+ * d_out / out: 2*n_out int16.  Results are identical to cb_convert_i16 -> cb_fir_run -> cb_quantize_i16; every edge
+ * carries 4 instead of 8 bytes per sample (the host-pointer form is PCIe-bound: twice the samples per second). */
+CB_API int cb_fir_run_dev_iq16(cb_fir *h, const int16_t *d_in, size_t n_in, float in_scale, float out_scale,
+                               int16_t *d_out, size_t out_cap, size_t *n_out, void *stream);
+CB_API int cb_fir_run_iq16(cb_fir *h, const int16_t *in, size_t n_in, float in_scale, float out_scale, int16_t *out,
+                           size_t out_cap, size_t *n_out);
 /* Real samples in, real parts out: x -> Complex(x, 0) -> this filter -> .re, i.e. Convert2Node -> BatchFirNode ->
  * Convert3Node [-> DecimateNode] of examples/fm_radio.rs:98-164 in one call (n_in floats in, *n_out floats out; same
  * state, sizes and errors as cb_fir_run).  Fused into one kernel for <= 64 taps and decim in {2, 4, 5, 8, 10}. */
@@ -217,6 +226,9 @@ CB_API int cb_fft_destroy(cb_fft *h);
 CB_API int cb_fft_run(cb_fft *h, const float *in, size_t n_in, float *out);
 CB_API int cb_fft_run_dev(cb_fft *h, const float *d_in, size_t n_in, float *d_out, void *stream);
 CB_API int cb_fft_size(const cb_fft *h, size_t *fft_size, int *inverse);
+/* i16 IQ frames in (IQBatchInput, src/io/raw_iq.rs:78-140): x = in_scale * (i16 as f32); complex f32 spectra out. */
+CB_API int cb_fft_run_iq16(cb_fft *h, const int16_t *in, size_t n_in, float in_scale, float *out);
+CB_API int cb_fft_run_dev_iq16(cb_fft *h, const int16_t *d_in, size_t n_in, float in_scale, float *d_out, void *stream);
 
 /* ------------------------------------------------------------------ FM demod
  * Replaces FM::demod (src/modulation/analog.rs:22-34): out[n] =

@@ -922,6 +922,47 @@ def test_cpp_graph_message_rate_bench_runs(cb):
     assert lines[1]["pool_device"]["hits"] > 0  # blocks are recycled, not cudaMalloc'ed per message
 
 
+# ------------------------------------------------------------------ i16 IQ on both edges (src/io/raw_iq.rs)
+@pytest.mark.parametrize("ntaps,interp,decim,n", [(64, 1, 1, 300_000), (32, 4, 1, 70_000), (63, 1, 5, 100_003), (17, 3, 2, 5_001),
+                                                   (64, 1, 1, (1 << 23) + 4099)])
+def test_fir_iq16_edges_equal_the_separate_nodes(cb, oracle, ntaps, interp, decim, n):
+    # cb_fir_run_iq16: IQBatchInput's i16 samples -> cast -> filter -> `(scale * y) as i16` (IQBatchOutput), 4 bytes per
+    # sample on every edge; must equal convert -> cb_fir_run -> quantise bit for bit (small batches: one chunk; the
+    # last case: three chunks of the 2-lane host pipeline with re-sent halos) and match the oracle chain
+    rng = np.random.default_rng(ntaps * 100 + interp)
+    t = rng.uniform(-1, 1, ntaps).astype(np.complex64) if interp > 1 or decim > 1 else rnd_c32(rng, ntaps)
+    iq = rng.integers(-32768, 32768, size=(n, 2), dtype=np.int16)
+    in_scale, out_scale = 1.0 / 32768.0, 3000.0
+    x = (iq.astype(np.float32) * np.float32(in_scale)).view(np.complex64).ravel()
+    a, b = cb.BatchFirNode(t, None, decim=decim, interp=interp), cb.BatchFirNode(t, None, decim=decim, interp=interp)
+    cut = n // 3
+    got = np.concatenate([a.run_iq16(iq[:cut], in_scale, out_scale), a.run_iq16(iq[cut:], in_scale, out_scale)])
+    f32 = np.concatenate([b.run(x[:cut]), b.run(x[cut:])])
+    assert np.array_equal(got, oracle.quantize_i16(f32, out_scale).reshape(-1, 2))
+    assert a.state.tobytes() == b.state.tobytes()
+    if n <= 300_000:
+        st, parts = np.zeros(ntaps, np.complex64), []
+        for seg in (x[:cut], x[cut:]):  # per call: the decimation phase restarts with every batch (resample_node.rs:53-65)
+            w, st = oracle.batch_fir(oracle.upsample(seg, interp) if interp > 1 else seg, t, st)
+            parts.append(oracle.decimate(w, decim) if decim > 1 else w)
+        want = oracle.quantize_i16(np.concatenate(parts), out_scale).reshape(-1, 2)
+        d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        assert d.max() <= 1 and (d != 0).mean() < 2e-2  # same values up to the filter's rounding: rarely one LSB apart
+
+
+def test_fft_iq16_input_equals_cast_then_fft(cb):
+    rng = np.random.default_rng(9)
+    iq = rng.integers(-32768, 32768, size=(8 * 4096, 2), dtype=np.int16)
+    x = iq.astype(np.float32).view(np.complex64).ravel()
+    f = cb.FFTBatchNode(4096)
+    assert f.run_iq16(iq).tobytes() == f.run(x).tobytes()
+    f2 = cb.FFTBatchNode(65536)
+    iq2 = rng.integers(-2000, 2000, size=(3 * 65536, 2), dtype=np.int16)
+    assert f2.run_iq16(iq2, 0.5).tobytes() == f2.run((iq2.astype(np.float32) * np.float32(0.5)).view(np.complex64).ravel()).tobytes()
+    with pytest.raises(cb.NodeError):
+        f.run_iq16(iq[:100])  # wrong length -> DataError, like the f32 entry
+
+
 # ------------------------------------------------------------------ buffer pool (back-pressure for unbounded channels)
 def test_buffer_pool_reuse_and_back_pressure(cb):
     # cb_buf_alloc_* come from a size-classed pool (no cudaMalloc / cudaFree per message); with a high-water mark the
