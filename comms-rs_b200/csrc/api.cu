@@ -511,6 +511,10 @@ struct cb_chain {
     int cur;
     float2 *cscratch;   // converted input of the unfused cb_chain_run_u8 path, grown on demand
     size_t cscratch_len;
+    void *tc_img;       // tensor-core byte front end: prepacked tap image (device), or NULL
+    float tc_inv_scale, tc_dc;
+    float2 *tc_seam;    // its per-tile first / last outputs, grown on demand
+    size_t tc_seam_len;
     LastUse last;
 };
 
@@ -2162,7 +2166,20 @@ int cb_chain_create(size_t channels, const double *dphase, const double *phase, 
     h->stream = nullptr;
     h->cscratch = nullptr;
     h->cscratch_len = 0;
+    h->tc_img = nullptr;
+    h->tc_seam = nullptr;
+    h->tc_seam_len = 0;
+    h->tc_inv_scale = 1.f;
+    h->tc_dc = 0.f;
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess && chain_tc_supported(h->ntaps, h->decim, h->mix, h->cplx)) {
+        std::vector<unsigned char> img(chain_tc_image_bytes());
+        std::vector<float> re(ntaps);
+        for (size_t k = 0; k < ntaps; ++k) re[k] = t[k].x;
+        chain_tc_build_image(re.data(), (uint32_t)ntaps, img.data(), &h->tc_inv_scale, &h->tc_dc);
+        e = cudaMalloc(&h->tc_img, img.size());
+        if (e == cudaSuccess) e = cudaMemcpy(h->tc_img, img.data(), img.size(), cudaMemcpyHostToDevice);
+    }
     const size_t hb = channels * h->hist_len * sizeof(float2);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaMalloc(&h->hist[i], hb);
@@ -2204,6 +2221,8 @@ int cb_chain_destroy(cb_chain *h)
     }
     if (h->dphase) cudaFree(h->dphase);
     if (h->cscratch) cudaFree(h->cscratch);
+    if (h->tc_img) cudaFree(h->tc_img);
+    if (h->tc_seam) cudaFree(h->tc_seam);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return CB_OK;
@@ -2245,6 +2264,20 @@ static int chain_run_dev_impl(cb_chain *h, const float *d_in, const uint8_t *d_i
     a.ntaps = h->ntaps;
     a.decim = h->decim;
     a.hist_len = h->hist_len;
+    a.tc_img = h->tc_img;
+    a.tc_inv_scale = h->tc_inv_scale;
+    a.tc_dc = h->tc_dc;
+    if (h->tc_img != nullptr && d_in8 != nullptr) {
+        const size_t need = chain_tc_seam_entries(no, h->channels);
+        if (h->tc_seam_len < need) {
+            if (h->tc_seam) cudaFree(h->tc_seam);  // waits for launches that still use it
+            h->tc_seam = nullptr;
+            h->tc_seam_len = 0;
+            if (cudaMalloc(&h->tc_seam, need * sizeof(float2)) == cudaSuccess) h->tc_seam_len = need;
+            else (void)cudaGetLastError();  // without the scratch the CUDA-core kernel runs
+        }
+        a.tc_seam = h->tc_seam;
+    }
     // outputs per CTA: keep the staged span around 48 KiB, whole multiples of 256 when possible
     size_t budget = (6144 > h->ntaps + h->decim ? 6144 - h->ntaps - h->decim : 0) / h->decim;
     size_t to = budget >= 256 ? budget / 256 * 256 : (budget ? budget : 1);

@@ -768,6 +768,7 @@ int launch_chain(const ChainArgs &args, const ChainTaps &taps, bool mix, bool fm
             set_error("chain: no fused u8 kernel for this shape");
             return CB_ERR_UNSUPPORTED;
         }
+        if (!mix && chain_tc_applicable(args, channels)) return launch_chain_tc(args, taps, fm, channels, s);
         return args.decim == 10 ? launch_chain2_d<10, 2>(args, taps, mix, fm, channels, s)
                                 : launch_chain2_d<5, 4>(args, taps, mix, fm, channels, s);
     }

@@ -79,6 +79,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar)
@@ -348,30 +360,34 @@ __global__ void __launch_bounds__(OUT16 ? 512 : 288, 1) fir_ptc_kernel(const __g
         }
     } else if (warp == NEPI + 4) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            unsigned long long it = 0;
-            const uint32_t hbase = smem_u32(sH), hlo = hbase + (uint32_t)KS * 4096u;
-            for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-                const int s = (int)(it & 1);
-                const uint32_t ph = (uint32_t)((it >> 1) & 1);
-                mbar_wait_long(&t_empty[s], ph ^ 1);
-                mbar_wait_long(&a_full[s], ph);
-                tc_fence_after();
-                const uint32_t shi = smem_u32(sS + s * G::STAGE), slo = shi + G::PART;
-                const uint32_t d = tmem_base + (uint32_t)s * 256u;
+        // The whole warp runs the loop, one elected lane issues: warp-uniform code keeps the descriptors in uniform
+        // registers (base descriptor + (byte offset >> 4)); inside `if (lane == 0)` every tcgen05.mma was wrapped in an
+        // ELECT / R2UR.BROADCAST / branch sequence.
+        unsigned long long it = 0;
+        const uint64_t hd0 = kdesc<32>(smem_u32(sH)), sd0 = kdesc<ROWB>(smem_u32(sS));
+        for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int s = (int)(it & 1);
+            const uint32_t ph = (uint32_t)((it >> 1) & 1);
+            mbar_wait_long(&t_empty[s], ph ^ 1);
+            mbar_wait_long(&a_full[s], ph);
+            tc_fence_after();
+            const uint64_t shi = sd0 + (uint64_t)((s * G::STAGE) >> 4), slo = shi + (uint64_t)(G::PART >> 4);
+            const uint64_t hlo = hd0 + (uint64_t)((KS * 4096) >> 4);
+            const uint32_t d = tmem_base + (uint32_t)s * 256u;
+            if (elect_one()) {
                 for (int ks = 0; ks < KS; ++ks) {
-                    const uint64_t ah = kdesc<32>(hbase + (uint32_t)ks * 4096u);
-                    const uint64_t al = kdesc<32>(hlo + (uint32_t)ks * 4096u);
-                    const uint64_t bh = kdesc<ROWB>(shi + (uint32_t)ks * 32u);
-                    const uint64_t bl = kdesc<ROWB>(slo + (uint32_t)ks * 32u);
+                    const uint64_t ah = hd0 + (uint64_t)(ks * 256);          // ks * 4096 bytes
+                    const uint64_t al = hlo + (uint64_t)(ks * 256);
+                    const uint64_t bh = shi + (uint64_t)(ks * 2);            // ks * 32 bytes
+                    const uint64_t bl = slo + (uint64_t)(ks * 2);
                     tc_mma(d, ah, bh, IDESC, ks > 0 ? 1u : 0u);
                     tc_mma(d, al, bh, IDESC, 1u);
                     tc_mma(d, ah, bl, IDESC, 1u);
                     if (CPLX) {  // (-Hi) x [S_im | -S_re]
-                        const uint64_t ch = kdesc<32>(hbase + (uint32_t)(2 * KS + ks) * 4096u);
-                        const uint64_t cl = kdesc<32>(hbase + (uint32_t)(3 * KS + ks) * 4096u);
-                        const uint64_t dh = kdesc<ROWB>(shi + (uint32_t)G::COMP + (uint32_t)ks * 32u);
-                        const uint64_t dl = kdesc<ROWB>(slo + (uint32_t)G::COMP + (uint32_t)ks * 32u);
+                        const uint64_t ch = hd0 + (uint64_t)((2 * KS + ks) * 256);
+                        const uint64_t cl = hd0 + (uint64_t)((3 * KS + ks) * 256);
+                        const uint64_t dh = shi + (uint64_t)((G::COMP >> 4) + ks * 2);
+                        const uint64_t dl = slo + (uint64_t)((G::COMP >> 4) + ks * 2);
                         tc_mma(d, ch, dh, IDESC, 1u);
                         tc_mma(d, cl, dh, IDESC, 1u);
                         tc_mma(d, ch, dl, IDESC, 1u);
@@ -380,8 +396,8 @@ __global__ void __launch_bounds__(OUT16 ? 512 : 288, 1) fir_ptc_kernel(const __g
                 tc_commit(&a_empty[s]);
                 tc_commit(&t_full[s]);
             }
+            __syncwarp();
         }
-        __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue (warps 0 .. NEPI-1)
         const int e = warp & 3;  // TMEM sub-partition = warp % 4; lane m = 32 e + lane

@@ -44,8 +44,14 @@ namespace tc {
 constexpr int ROWS = 128;          // MMA M
 constexpr int RS = 32;             // complex outputs per row
 constexpr int TILE = ROWS * RS;    // 4096 outputs per tile
-constexpr int NCONV = 128;         // loader threads
-constexpr int NTHREADS = 448;     // 2 converter groups (2 x 4 warps) + 4 epilogue warps + MMA warp + TMA warp
+constexpr int NCW = 6;             // warps per converter group
+constexpr int NCONV = 32 * NCW;    // converter threads per group.  The groups' serial chain (wait raw tile -> max / min
+                                   // reduction -> barrier -> scale, split, store) bounds the kernel; six warps instead of
+                                   // four shorten it by a third (11 instead of 17 sample pairs per thread and tile)
+constexpr int W_EPI = 2 * NCW;     // first of the 4 epilogue warps (a multiple of 4: TMEM sub-partition = warp % 4)
+constexpr int W_MMA = W_EPI + 4, W_TMA = W_EPI + 5;
+constexpr int NTHREADS = 32 * (W_TMA + 1);  // 2 converter groups + 4 epilogue warps + MMA warp + TMA warp
+static_assert(W_EPI % 4 == 0, "epilogue warp w must own TMEM sub-partition w % 4");
 constexpr int A_PART = 18432;      // bytes reserved for one fp16 stream part (>= (128+4)*128, 1024-aligned)
 constexpr int A_STAGE = 2 * A_PART;
 constexpr int OUT_PITCH = 272;     // padded row pitch of the output staging (bytes)
@@ -75,6 +81,18 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
+}
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, fp16 operands, fp32 accumulate.  One thread issues.
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
@@ -121,7 +139,7 @@ __device__ __forceinline__ uint32_t swz128(uint32_t o) { return o ^ (((o >> 7) &
 
 // NRAW raw f32 tiles are kept in flight by the TMA warp (2 when shared memory allows, i.e. up to 64 taps, else 1)
 template <int KB, int NRAW>
-__global__ void __launch_bounds__(512, 1) fir_tc_kernel(const __grid_constant__ Args a)  // 512: 128-register cap (14 warps)
+__global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_constant__ Args a)
 {
     constexpr int HALO = RS * (KB - 1);            // complex samples of history per tile
     constexpr int NPAIR = (TILE + HALO) / 2;       // 16-byte pairs of complex samples per tile
@@ -140,8 +158,8 @@ __global__ void __launch_bounds__(512, 1) fir_tc_kernel(const __grid_constant__ 
     __shared__ __align__(8) uint64_t raw_full[NRAW], raw_empty[NRAW];
     __shared__ __align__(8) uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2], sc_ready[8];
     __shared__ uint32_t tmem_slot;
-    __shared__ float red_max[2][4];  // [loader group][warp]
-    __shared__ uint32_t red_min[2][4];
+    __shared__ float red_max[2][NCW];  // [loader group][warp]
+    __shared__ uint32_t red_min[2][NCW];
     __shared__ unsigned fix_seen[2];  // tile + 1 last appended to the fix-up list by each converter group
     __shared__ float inv_scale[8];
 
@@ -163,7 +181,7 @@ __global__ void __launch_bounds__(512, 1) fir_tc_kernel(const __grid_constant__ 
         }
         fence_mbar_init();
     }
-    if (warp == 12) {
+    if (warp == W_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
                      "r"(256)
                      : "memory");
@@ -178,7 +196,7 @@ __global__ void __launch_bounds__(512, 1) fir_tc_kernel(const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
-    if (warp == 13) {
+    if (warp == W_TMA) {
         // ------------------------------------------------------------------ TMA producer: raw f32 tiles, HBM -> shared
         // raw stage rs = it % NRAW holds samples g = t0 - HALO + e, e = 0 .. TILE + HALO - 1; the first tile's halo comes
         // from the history buffer; an odd trailing sample (16-byte copy granularity) is left to the converters
@@ -201,9 +219,9 @@ __global__ void __launch_bounds__(512, 1) fir_tc_kernel(const __grid_constant__ 
                 tma_load_1d(dstb + (g - g0) * 8, a.x + g, (uint32_t)(n * 8), &raw_full[rs]);
             }
         }
-    } else if (warp < 8) {
+    } else if (warp < W_EPI) {
         // ------------------------------------------------------------------ converters (two groups, even / odd tiles)
-        const int grp = warp >> 2, gt = tid & (NCONV - 1), gw = warp & 3;
+        const int grp = warp / NCW, gt = tid - grp * NCONV, gw = warp - grp * NCW;
         if (a.hist_out != nullptr && blockIdx.x == 0 && grp == 0) {
             const long long H = a.hist_len;
             for (long long i = gt; i < H; i += NCONV) {
@@ -251,9 +269,14 @@ __global__ void __launch_bounds__(512, 1) fir_tc_kernel(const __grid_constant__ 
                 red_max[s][gw] = mx;
                 red_min[s][gw] = mnu;
             }
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-            mx = fmaxf(fmaxf(red_max[s][0], red_max[s][1]), fmaxf(red_max[s][2], red_max[s][3]));
-            mnu = min(min(red_min[s][0], red_min[s][1]), min(red_min[s][2], red_min[s][3]));
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(NCONV) : "memory");
+            mx = red_max[s][0];
+            mnu = red_min[s][0];
+#pragma unroll
+            for (int w = 1; w < NCW; ++w) {
+                mx = fmaxf(mx, red_max[s][w]);
+                mnu = min(mnu, red_min[s][w]);
+            }
             // a quiet stretch more than 2^20 below the tile maximum (its lo terms go denormal): this tile is recomputed
             // in plain f32 by the fix-up pass (FirFix); non-finite samples are caught in the conversion loop below
             if (gt == 0 && a.fix_count != nullptr && mnu != 0xffffffffu && __uint_as_float(mnu + 1u) < mx * 9.5367431640625e-7f &&
@@ -297,35 +320,38 @@ __global__ void __launch_bounds__(512, 1) fir_tc_kernel(const __grid_constant__ 
                 atomicExch(&fix_seen[s], (unsigned)tile + 1u) != (unsigned)tile + 1u)
                 a.fix_list[atomicAdd(a.fix_count, 1u)] = (unsigned)tile;  // non-finite sample: exact fall-back (FirFix)
         }
-    } else if (warp == 12) {
+    } else if (warp == W_MMA) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            unsigned long long it = 0;
-            const uint32_t bbase = smem_u32(sB);
-            for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-                const int s = (int)(it & 1);
-                const uint32_t ph = (uint32_t)((it >> 1) & 1);
-                mbar_wait_long(&t_empty[s], ph ^ 1);
-                mbar_wait_long(&a_full[s], ph);
-                tc_fence_after();
-                const uint32_t ahi = smem_u32(sA + s * A_STAGE), alo = ahi + A_PART;
-                const uint32_t d = tmem_base + (uint32_t)s * 128u;
+        // The whole warp runs the loop, one elected lane issues: inside `if (lane == 0)` the compiler cannot prove the
+        // descriptors warp-uniform and wraps every tcgen05.mma in an ELECT / R2UR.BROADCAST / branch sequence (~14
+        // instructions per MMA on a scheduler shared with busy warps); warp-uniform code keeps them in uniform registers
+        // (descriptor = base descriptor + (byte offset >> 4), one UIADD3.64 between two UTCHMMAs).
+        unsigned long long it = 0;
+        const uint64_t bd0 = tc_desc(smem_u32(sB)), ad0 = tc_desc(smem_u32(sA));
+        for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int s = (int)(it & 1);
+            const uint32_t ph = (uint32_t)((it >> 1) & 1);
+            mbar_wait_long(&t_empty[s], ph ^ 1);
+            mbar_wait_long(&a_full[s], ph);
+            tc_fence_after();
+            const uint64_t ahi = ad0 + (uint64_t)((s * A_STAGE) >> 4), alo = ahi + (uint64_t)(A_PART >> 4);
+            const uint32_t d = tmem_base + (uint32_t)s * 128u;
+            if (elect_one()) {
 #pragma unroll
                 for (int t = 0; t < KB * 4; ++t) {
-                    const uint32_t aoff = (uint32_t)(t >> 2) * 128u + (uint32_t)(t & 3) * 32u;
-                    const uint32_t boff = (uint32_t)(t >> 2) * 16384u + (uint32_t)(t & 3) * 32u;
-                    const uint64_t bd = tc_desc(bbase + boff);
-                    tc_mma(d, tc_desc(ahi + aoff), bd, IDESC128, t > 0 ? 1u : 0u);
-                    tc_mma(d, tc_desc(alo + aoff), bd, IDESC64, 1u);
+                    const uint64_t aoff = (uint64_t)(((t >> 2) * 128 + (t & 3) * 32) >> 4);
+                    const uint64_t boff = (uint64_t)(((t >> 2) * 16384 + (t & 3) * 32) >> 4);
+                    tc_mma(d, ahi + aoff, bd0 + boff, IDESC128, t > 0 ? 1u : 0u);
+                    tc_mma(d, alo + aoff, bd0 + boff, IDESC64, 1u);
                 }
                 tc_commit(&a_empty[s]);
                 tc_commit(&t_full[s]);
             }
+            __syncwarp();
         }
-        __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue
-        const int e = warp - 8;  // TMEM sub-partition = warp % 4
+        const int e = warp - W_EPI;  // TMEM sub-partition = warp % 4
         unsigned char *stage = sOut + e * OUT_WARP;
         const bool direct = (reinterpret_cast<uintptr_t>(a.y) & 31) == 0;
         unsigned long long it = 0;
@@ -405,7 +431,7 @@ __global__ void __launch_bounds__(512, 1) fir_tc_kernel(const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 12) {
+    if (warp == W_MMA) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
     }
 }

@@ -475,6 +475,43 @@ def test_chain_bank_u8_input_fused_convert(cb, oracle, mix, fm, D, n):
                 assert rel_l2(got[c], want) <= FIR_TOL, (c, call)
 
 
+@pytest.mark.parametrize("fm", [True, False])
+@pytest.mark.parametrize("ntaps,n", [(63, 131_072), (63, 40_000), (64, 10_240 * 2 + 8), (17, 10_240 * 3 - 40), (5, 2_048), (63, 8)])
+def test_chain_bank_u8_tensor_core_path(cb, oracle, fm, ntaps, n, monkeypatch):
+    # K2-TC (chain_tc_kernel.cu): bytes -> ConvertNode -> <= 64 real taps -> /5 [-> FM] as five polyphase Toeplitz GEMMs on
+    # tcgen05, forced for every batch size; against convert-then-filter of the product's CUDA-core kernel and the oracle
+    # chain (examples/fm_radio.rs:84-97,144-160).  Tiles of 2048 outputs: batch lengths below, at and across tile edges.
+    monkeypatch.setenv("COMMS_B200_CHAIN_PATH", "tc")
+    rng = np.random.default_rng(ntaps * 13 + n)
+    C, taps = 3, _lowpass(ntaps)
+    a = cb.ChainBank(C, taps, 5, dphase=None, with_fm=fm)
+    refs = [oracle.FmChain(0.0, 0.0, taps, 5, do_mix=False, do_fm=fm) for _ in range(C)]
+    for call in range(3):  # history and FM state carried across calls; the decimation phase restarts with each
+        iq = rng.integers(0, 256, (C, n, 2), dtype=np.uint8)
+        if call == 1:
+            iq[0, : n // 2] = 128  # a constant stretch: outputs near the filter's DC response, angles near 0 / pi
+        got = a.run_u8(iq)
+        xf = oracle.u8_to_f32(iq.reshape(-1)).view(np.complex64).reshape(C, n)
+        assert got.shape == (C, -(-n // 5))
+        for c in range(C):
+            want = refs[c].run(xf[c])
+            if fm:
+                d = np.abs(got[c].astype(np.float64) - want.astype(np.float64))
+                d = np.minimum(d, 2 * np.pi - d)
+                assert np.median(d) < 2e-6 and np.mean(d > 1e-3) < 5e-3, (c, call, np.median(d), d.max())
+            else:
+                assert rel_l2(got[c], want) <= FIR_TOL, (c, call, rel_l2(got[c], want))
+    monkeypatch.setenv("COMMS_B200_CHAIN_PATH", "v3")
+    b = cb.ChainBank(C, taps, 5, dphase=None, with_fm=False)
+    monkeypatch.setenv("COMMS_B200_CHAIN_PATH", "tc")
+    t = cb.ChainBank(C, taps, 5, dphase=None, with_fm=False)
+    iq = rng.integers(0, 256, (C, n, 2), dtype=np.uint8)
+    y_tc = t.run_u8(iq)
+    monkeypatch.setenv("COMMS_B200_CHAIN_PATH", "v3")
+    y_cc = b.run_u8(iq)
+    assert rel_l2(y_tc, y_cc) <= 1e-6  # the two kernel families agree far inside the tolerance
+
+
 @pytest.mark.parametrize("decim,ntaps", [(5, 63), (10, 63), (2, 64), (4, 17), (8, 33), (5, 1), (3, 63), (1, 40), (5, 100)])
 def test_real_input_fir_matches_oracle(cb, oracle, decim, ntaps):
     # Convert2Node -> filt2 -> Convert3Node -> dec2 (examples/fm_radio.rs:98-164) as one call: real samples in, real
