@@ -22,12 +22,12 @@
 // block-scaled by a power of two and split into fp16 hi + lo (columns 0-31 / 32-63 of the accumulator): f32-level
 // accuracy (rel-L2 ~1e-7 against convert-then-filter).
 //
-// Roles (18 warps, one persistent CTA per SM; items = (channel, tile) round-robin):
-//   warp 17    TMA producer: the tile's raw bytes incl. 80 samples of halo, 2 KiB bulk copies into a ring of 2 stages
-//   warps 0-3 / 4-7  two converter groups (even / odd items): bytes -> fp16 phase streams, 10 x STS.128 per 40 samples;
+// Roles (20 warps, one persistent CTA per SM; items = (channel, tile) round-robin):
+//   warp 11    TMA producer: the tile's raw bytes incl. 80 samples of halo, 2 KiB bulk copies into a ring of 2 stages
+//   warps 0-4 / 5-9  two converter groups (even / odd items): bytes -> fp16 phase streams, 10 x STS.128 per 40 samples;
 //              warp 0 of a group also evaluates y[first - 1] for the tile's first discriminator step (2 taps per lane)
-//   warp 16    one thread issues the 20 tcgen05.mma per tile, commits a_empty / t_full
-//   warps 8-15 epilogue, two per TMEM sub-partition (lane = row; warps 8-11 take outputs 0-7 of the row, 12-15 outputs
+//   warp 10    one elected lane issues the 20 tcgen05.mma per tile, commits a_empty / t_full
+//   warps 12-19 epilogue, two per TMEM sub-partition (lane = row; warps 12-15 take outputs 0-7 of the row, 16-19 outputs
 //              8-15): tcgen05.ld -> add halves, unscale, + dc -> FM discriminator (the previous output is in the thread,
 //              re-read from TMEM, or the last output of the row below through shared memory / the look-back value)
 //              -> 32 contiguous bytes per lane.  The discriminator is ~35 instructions per output: with four epilogue
@@ -51,11 +51,13 @@ constexpr int TO = ROWS * RS;        // 2048 outputs per tile
 constexpr int TI = TO * D;           // 10240 input samples per tile
 constexpr int HALO = RS;             // history per phase stream (decimated grid): one row >= 14 taps
 constexpr int HIN = HALO * D;        // = 80 input samples of halo
-constexpr int NCONV = 128;           // converter threads per group
-constexpr int W_EPI = 8;             // first of the 8 epilogue warps (two per TMEM sub-partition: outputs 0-7 / 8-15 of a row)
-constexpr int W_MMA = 16, W_TMA = 17;
+constexpr int NCW = 5;               // warps per converter group: 258 units of 40 samples per tile = at most 2 per thread
+constexpr int NCONV = 32 * NCW;      // converter threads per group
+constexpr int W_MMA = 2 * NCW, W_TMA = 2 * NCW + 1;
+constexpr int W_EPI = 12;            // first of the 8 epilogue warps (two per TMEM sub-partition: outputs 0-7 / 8-15 of a row)
 constexpr int NEPI = 256;            // epilogue threads
-constexpr int NTHREADS = 32 * (W_TMA + 1);
+constexpr int NTHREADS = 32 * (W_EPI + 8);
+static_assert(W_EPI % 4 == 0 && W_EPI > W_TMA, "epilogue warp w owns TMEM sub-partition w % 4");
 constexpr int A_PHASE = 17 * 512;    // bytes per phase stream: (128 + 1) rows x 64 B, rounded to the 512-byte swizzle atom
 constexpr int A_STAGE = D * A_PHASE;
 constexpr int B_PHASE = 2 * 4096;    // per phase: 2 K-blocks x (64 rows x 64 B)
@@ -63,7 +65,8 @@ constexpr int B_BYTES = D * B_PHASE;
 constexpr int RAWB = ((TI + HIN) * 2 + 127) / 128 * 128;
 constexpr int NUNIT = (TI + HIN) / 40;  // converter work units of 40 samples (8 per phase)
 constexpr int NRAW = 4;              // raw byte tiles in flight: with two, a stage's cycle (HBM latency + conversion) bounded the kernel
-constexpr int SMEM = B_BYTES + 2 * A_STAGE + NRAW * RAWB + 1024;
+constexpr int OSTAGE = TO * 4;       // FM outputs of one tile, staged when the channel's output row is not 16-byte aligned
+constexpr int SMEM = B_BYTES + 2 * A_STAGE + NRAW * RAWB + 2 * OSTAGE + 1024;
 static_assert(SMEM <= 227 * 1024, "shared memory budget");
 static_assert((TI + HIN) % 40 == 0, "whole units");
 
@@ -182,6 +185,25 @@ __device__ __forceinline__ uint32_t bytes_to_half2(uint32_t w, int odd)
     return *reinterpret_cast<const uint32_t *>(&v);
 }
 
+// (channel, tile) of the items first, first + stride, ... without a 64-bit division per item (each costs ~100 instructions
+// per warp, and every role of the CTA walks the item list)
+struct ItemWalk {
+    unsigned c, tile, dc, dt, tiles;
+    __device__ __forceinline__ ItemWalk(unsigned first, unsigned stride, unsigned tiles_per_ch)
+        : c(first / tiles_per_ch), tile(first % tiles_per_ch), dc(stride / tiles_per_ch), dt(stride % tiles_per_ch), tiles(tiles_per_ch)
+    {
+    }
+    __device__ __forceinline__ void next()
+    {
+        c += dc;
+        tile += dt;
+        if (tile >= tiles) {
+            tile -= tiles;
+            ++c;
+        }
+    }
+};
+
 template <bool FM>
 __global__ void __launch_bounds__(NTHREADS, 1) chain_tc_kernel(const __grid_constant__ Args a, const __grid_constant__ ChainTaps taps)
 {
@@ -192,6 +214,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) chain_tc_kernel(const __grid_cons
     unsigned char *sB = smem;                     // tap image
     unsigned char *sA = sB + B_BYTES;             // 2 stages x 5 phase streams
     unsigned char *sRaw = sA + 2 * A_STAGE;       // NRAW raw byte tiles (TMA destination)
+    float *sOut = reinterpret_cast<float *>(sRaw + NRAW * RAWB);  // 2 x TO floats
     __shared__ __align__(8) uint64_t raw_full[NRAW], raw_empty[NRAW], a_full[2], a_empty[2], t_full[2], t_empty[2];
     __shared__ uint32_t tmem_slot;
     __shared__ float2 ylast[2][ROWS];             // last output of every row of the tile (two tiles deep)
@@ -231,10 +254,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) chain_tc_kernel(const __grid_cons
     if (warp == W_TMA) {
         // ------------------------------------------------------------------ TMA producer
         unsigned long long it = 0;
-        for (unsigned long long item = blockIdx.x; item < a.nitems; item += gridDim.x, ++it) {
+        ItemWalk w(blockIdx.x, gridDim.x, a.tiles_per_ch);
+        for (unsigned long long item = blockIdx.x; item < a.nitems; item += gridDim.x, ++it, w.next()) {
             const int s = (int)(it % NRAW);
-            const unsigned long long c = item / a.tiles_per_ch;
-            const long long tile = (long long)(item % a.tiles_per_ch);
+            const unsigned long long c = w.c;
+            const long long tile = w.tile;
             const long long g0 = tile * TI - HIN;
             const long long g_lo = g0 < 0 ? 0 : g0;
             long long g_hi = g0 + TI + HIN;
@@ -251,23 +275,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) chain_tc_kernel(const __grid_cons
                 tma_load_1d(dst + (g - g0) * 2, xc + 2 * g, (uint32_t)(n * 2), &raw_full[s]);
             }
         }
-    } else if (warp < 8) {
+    } else if (warp < 2 * NCW) {
         // ------------------------------------------------------------------ converters (two groups, even / odd items)
-        const int grp = warp >> 2, gt = tid & (NCONV - 1);
+        const int grp = warp / NCW, gt = tid - grp * NCONV;
         unsigned long long it = grp;
+        ItemWalk w(blockIdx.x + grp * gridDim.x, 2u * gridDim.x, a.tiles_per_ch);
         for (unsigned long long item = blockIdx.x + (unsigned long long)grp * gridDim.x; item < a.nitems;
-             item += 2ull * gridDim.x, it += 2) {
+             item += 2ull * gridDim.x, it += 2, w.next()) {
             const int s = grp;
             const uint32_t ph = (uint32_t)((it >> 1) & 1);
-            const unsigned long long c = item / a.tiles_per_ch;
-            const long long tile = (long long)(item % a.tiles_per_ch);
+            const unsigned long long c = w.c;
+            const long long tile = w.tile;
             const long long g0 = tile * TI - HIN;
 
             const int rs = (int)(it % NRAW);
             CTC_STAMP(gt == 0, 0);
-            mbar_wait(&raw_full[rs], (uint32_t)((it / NRAW) & 1));
+            mbar_wait_long(&raw_full[rs], (uint32_t)((it / NRAW) & 1));
             CTC_STAMP(gt == 0, 1);
-            mbar_wait(&a_empty[s], ph ^ 1);  // the MMAs that read this stage two items ago are done
+            mbar_wait_long(&a_empty[s], ph ^ 1);  // the MMAs that read this stage two items ago are done
             CTC_STAMP(gt == 0, 2);
             const unsigned char *raw = sRaw + rs * RAWB;
             unsigned char *stage = sA + s * A_STAGE;
@@ -326,7 +351,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) chain_tc_kernel(const __grid_cons
             fence_proxy_async();
             mbar_arrive(&a_full[s]);
             CTC_STAMP(gt == 0, 3);
-            CTC_STAMP(gt == 127, 4);
+            CTC_STAMP(gt == NCONV - 1, 4);
             mbar_arrive(&raw_empty[rs]);  // the raw tile has been consumed: the TMA warp may refill the stage
             CTC_STAMP(gt == 0, 5);
             // ---- carried state for the next call (last tile of the channel): ConvertNode's exact values
@@ -387,11 +412,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) chain_tc_kernel(const __grid_cons
         const int half = (warp - W_EPI) >> 2;  // outputs 8 half .. 8 half + 7 of the row
         const int row = 32 * e + lane;
         unsigned long long it = 0;
-        for (unsigned long long item = blockIdx.x; item < a.nitems; item += gridDim.x, ++it) {
+        ItemWalk w(blockIdx.x, gridDim.x, a.tiles_per_ch);
+        for (unsigned long long item = blockIdx.x; item < a.nitems; item += gridDim.x, ++it, w.next()) {
             const int s = (int)(it & 1);
             const uint32_t ph = (uint32_t)((it >> 1) & 1);
-            const unsigned long long c = item / a.tiles_per_ch;
-            const long long tile = (long long)(item % a.tiles_per_ch);
+            const unsigned long long c = w.c;
+            const long long tile = w.tile;
             const long long m0 = tile * TO + (long long)row * RS + 8 * half;  // first output of this thread
             CTC_STAMP(tid == 32 * W_EPI, 12);
             mbar_wait_long(&t_full[s], ph);
@@ -432,15 +458,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) chain_tc_kernel(const __grid_cons
                 if (half && row == ROWS - 1) a.seam[2 * item + 1] = y[7];  // the tile's last output (zeros-only rows: unused)
                 float o[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) o[q] = fm_angle_fast(y[q], q ? y[q - 1] : yp);
-                float *dst = reinterpret_cast<float *>(a.out) + c * a.n_out + m0;
-                if (m0 + 8 <= (long long)a.n_out && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-                    stg_stream(reinterpret_cast<float4 *>(dst), make_float4(o[0], o[1], o[2], o[3]));
-                    stg_stream(reinterpret_cast<float4 *>(dst + 4), make_float4(o[4], o[5], o[6], o[7]));
-                } else {
+                for (int q = 0; q < 8; q += 2) {
+                    const float2 t = fm_angle_fast2(y[q], q ? y[q - 1] : yp, y[q + 1], y[q]);
+                    o[q] = t.x;
+                    o[q + 1] = t.y;
+                }
+                float *chan = reinterpret_cast<float *>(a.out) + c * a.n_out;
+                float *dst = chan + m0;
+                if ((reinterpret_cast<uintptr_t>(chan) & 15) == 0) {  // (the same for every thread of the CTA)
+                    if (m0 + 8 <= (long long)a.n_out) {
+                        stg_stream(reinterpret_cast<float4 *>(dst), make_float4(o[0], o[1], o[2], o[3]));
+                        stg_stream(reinterpret_cast<float4 *>(dst + 4), make_float4(o[4], o[5], o[6], o[7]));
+                    } else {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        if (m0 + q < (long long)a.n_out) dst[q] = o[q];
+                        for (int q = 0; q < 8; ++q)
+                            if (m0 + q < (long long)a.n_out) dst[q] = o[q];
+                    }
+                } else {
+                    // A channel's output row starts wherever c * n_out puts it (n_out = 26215 for fm_radio's reads): lanes
+                    // that own rows would write 4 bytes each at a 64-byte pitch.  Through shared memory instead: every
+                    // store instruction of a warp writes 128 contiguous bytes.  Two buffers, one barrier per tile: a
+                    // buffer is rewritten two tiles later, after every thread has passed the next tile's barrier.
+                    float *st = sOut + (it & 1) * TO;
+                    *reinterpret_cast<float4 *>(st + RS * row + 8 * half) = make_float4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<float4 *>(st + RS * row + 8 * half + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                    asm volatile("bar.sync 6, %0;" ::"n"(NEPI) : "memory");
+                    const int et = tid - 32 * W_EPI;
+                    const long long t0 = tile * TO;
+#pragma unroll
+                    for (int k = 0; k < TO / NEPI; ++k) {
+                        const int idx = et + k * NEPI;
+                        if (t0 + idx < (long long)a.n_out) chan[t0 + idx] = st[idx];
+                    }
                 }
                 CTC_STAMP(tid == 32 * W_EPI, 17);
                 const long long last = (long long)a.n_out - 1 - m0;  // carried FM state: the call's last filter output
@@ -540,6 +589,7 @@ bool chain_tc_applicable(const ChainArgs &args, size_t channels)
     const int path = (e && strcmp(e, "tc") == 0) ? 1 : ((e && (strcmp(e, "v3") == 0 || strcmp(e, "v2") == 0)) ? -1 : 0);
     if (path < 0) return false;
     const size_t tiles = ceil_div(args.n_out, (size_t)ctc::TO);
+    if (tiles * channels >= ((size_t)1 << 31)) return false;  // the kernel walks items with 32-bit arithmetic
     return path > 0 || tiles * channels >= 96;  // small calls: the CUDA-core kernel's 768-output tiles fill the SMs better
 }
 

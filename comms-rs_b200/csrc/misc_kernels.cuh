@@ -82,6 +82,36 @@ __device__ __forceinline__ float fm_angle_fast(float2 s, float2 p)
     r = (__float_as_uint(tr) >> 31) ? 3.14159265358979324f - r : r;
     return __uint_as_float(__float_as_uint(r) | (__float_as_uint(ti) & 0x80000000u));
 }
+// Two discriminator steps at once with the polynomial in packed f32 (FFMA2): out.x = angle(s0, p0), out.y = angle(s1, p1).
+// Same products, rounding points, polynomial and quadrant logic as fm_angle_fast: bit-identical results.
+__device__ __forceinline__ float2 fm_angle_fast2(float2 s0, float2 p0, float2 s1, float2 p1)
+{
+    const float tr0 = __fsub_rn(__fmul_rn(s0.x, p0.x), __fmul_rn(s0.y, -p0.y));
+    const float ti0 = __fadd_rn(__fmul_rn(s0.x, -p0.y), __fmul_rn(s0.y, p0.x));
+    const float tr1 = __fsub_rn(__fmul_rn(s1.x, p1.x), __fmul_rn(s1.y, -p1.y));
+    const float ti1 = __fadd_rn(__fmul_rn(s1.x, -p1.y), __fmul_rn(s1.y, p1.x));
+    const float ax0 = fabsf(tr0), ay0 = fabsf(ti0), ax1 = fabsf(tr1), ay1 = fabsf(ti1);
+    const float mx0 = fmaxf(ax0, ay0), mn0 = fminf(ax0, ay0), mx1 = fmaxf(ax1, ay1), mn1 = fminf(ax1, ay1);
+    const float2 a = make_float2(mx0 > 0.f ? __fdividef(mn0, mx0) : 0.f, mx1 > 0.f ? __fdividef(mn1, mx1) : 0.f);
+    const float2 z = __fmul2_rn(a, a);
+    float2 q = make_float2(0.0028340641874819994f, 0.0028340641874819994f);
+    q = __ffma2_rn(q, z, make_float2(-0.016005029901862144f, -0.016005029901862144f));
+    q = __ffma2_rn(q, z, make_float2(0.042587608098983765f, 0.042587608098983765f));
+    q = __ffma2_rn(q, z, make_float2(-0.07495445758104324f, -0.07495445758104324f));
+    q = __ffma2_rn(q, z, make_float2(0.10636754333972931f, 0.10636754333972931f));
+    q = __ffma2_rn(q, z, make_float2(-0.14202570915222168f, -0.14202570915222168f));
+    q = __ffma2_rn(q, z, make_float2(0.19992484152317047f, 0.19992484152317047f));
+    q = __ffma2_rn(q, z, make_float2(-0.3333306610584259f, -0.3333306610584259f));
+    q = __ffma2_rn(q, z, make_float2(1.0f, 1.0f));
+    const float2 r2 = __fmul2_rn(a, q);
+    float r0 = r2.x, r1 = r2.y;
+    r0 = ay0 > ax0 ? 1.57079632679489662f - r0 : r0;
+    r1 = ay1 > ax1 ? 1.57079632679489662f - r1 : r1;
+    r0 = (__float_as_uint(tr0) >> 31) ? 3.14159265358979324f - r0 : r0;
+    r1 = (__float_as_uint(tr1) >> 31) ? 3.14159265358979324f - r1 : r1;
+    return make_float2(__uint_as_float(__float_as_uint(r0) | (__float_as_uint(ti0) & 0x80000000u)),
+                       __uint_as_float(__float_as_uint(r1) | (__float_as_uint(ti1) & 0x80000000u)));
+}
 #endif
 
 }  // namespace cb
