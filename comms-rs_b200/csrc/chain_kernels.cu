@@ -165,8 +165,8 @@ chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
     // registers while item i is filtered, so HBM loads are always in flight.
     float4 raw[NB];
     auto issue_loads = [&](unsigned long long item, const int b0) {
-        const size_t c = (size_t)(item / tiles_per_ch);
-        const long long g_base = (long long)(item % tiles_per_ch) * TO * D - OFF;  // even
+        const size_t c = (size_t)((unsigned)item / tiles_per_ch);
+        const long long g_base = (long long)((unsigned)item % tiles_per_ch) * TO * D - OFF;  // even
         const float2 *xc = a.x + c * a.n_in;
         if (g_base >= 0 && g_base + SPAN <= (long long)a.n_in) {
             // interior tile (all but the first and last of a channel): no bounds checks
@@ -200,9 +200,9 @@ chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
     // slot 62 = e^{j (phi0 + g_base dphi)} (the item's first staged sample)
     auto fill_ftab = [&](unsigned long long item, int buf) {
         if (MIX && (tid < NIT || tid >= 62) && tid < 64) {
-            const size_t c = (size_t)(item / tiles_per_ch);
+            const size_t c = (size_t)((unsigned)item / tiles_per_ch);
             const double dphi = a.dphase[c];
-            const long long g_base = (long long)(item % tiles_per_ch) * TO * D - OFF;
+            const long long g_base = (long long)((unsigned)item % tiles_per_ch) * TO * D - OFF;
             const double th = tid == 63 ? dphi : (tid == 62 ? fma((double)g_base, dphi, a.phase_in[c]) : (double)(tid * 2 * NT) * dphi);
             ftab[buf * 64 + tid] = phase_rotation(th);
         }
@@ -219,8 +219,8 @@ chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
     size_t t_ch = ~(size_t)0;             // channel for which e_thr is valid
     float2 e_thr = make_float2(1.f, 0.f);  // e^{j (2 tid) dphi}
     for (int cur = 0; item < item_end; ++item, cur ^= 1) {
-        const size_t c = (size_t)(item / tiles_per_ch);
-        const unsigned tile = (unsigned)(item % tiles_per_ch);
+        const size_t c = (size_t)((unsigned)item / tiles_per_ch);
+        const unsigned tile = (unsigned)((unsigned)item % tiles_per_ch);
         const long long m0 = (long long)tile * TO;
         const float2 *xc = a.x + c * a.n_in;
         const float2 *hc = a.hist_in + c * H;
@@ -358,6 +358,7 @@ static int launch_chain2(const ChainArgs &args, const ChainTaps &taps, size_t ch
     CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const unsigned tiles = (unsigned)ceil_div(args.n_out, (size_t)TO);
     const unsigned long long nitems = (unsigned long long)tiles * channels;
+    CB_REQUIRE(nitems < (1ull << 32), CB_ERR_UNSUPPORTED, "chain: more than 2^32 tiles in one call");  // 32-bit item arithmetic in the kernel
     int dev = 0, sms = 148, per_sm = 2;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -444,8 +445,8 @@ chain3_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
 
     // warp 0: bulk-copy the span of `item` into stage `st`
     auto produce = [&](unsigned long long item, int st) {
-        const size_t c = (size_t)(item / tiles_per_ch);
-        const long long tile = (long long)(item % tiles_per_ch);
+        const size_t c = (size_t)((unsigned)item / tiles_per_ch);
+        const long long tile = (long long)((unsigned)item % tiles_per_ch);
         const long long g_base = tile * TO * D - OFF;
         long long g_hi = g_base + SPAN;
         if (g_hi > (long long)a.n_in) g_hi = (long long)a.n_in;
@@ -488,8 +489,8 @@ chain3_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Chain
         // conversion barrier (every thread arrives after its own output reads of the previous tile) already separates
         // them, so one buffer is enough -- which is what lets a fourth CTA fit per SM
         const int yb = U8 ? 0 : (int)(li & 1) * (TO + 1);
-        const size_t c = (size_t)(item / tiles_per_ch);
-        const unsigned tile = (unsigned)(item % tiles_per_ch);
+        const size_t c = (size_t)((unsigned)item / tiles_per_ch);
+        const unsigned tile = (unsigned)((unsigned)item % tiles_per_ch);
         const long long m0 = (long long)tile * TO;
 
         if (MIX && c != cur_c) {  // new channel: rotated taps and the per-channel phasors
@@ -683,6 +684,7 @@ static int launch_chain3(const ChainArgs &args, const ChainTaps &taps, size_t ch
             scaled.t[k] = make_float2((float)((double)taps.t[k].x / 127.5), (float)((double)taps.t[k].y / 127.5));
     const unsigned tiles = (unsigned)ceil_div(args.n_out, (size_t)TO);
     const unsigned long long nitems = (unsigned long long)tiles * channels;
+    CB_REQUIRE(nitems < (1ull << 32), CB_ERR_UNSUPPORTED, "chain: more than 2^32 tiles in one call");  // 32-bit item arithmetic in the kernel
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
