@@ -427,7 +427,74 @@ impl GpuBatchFirDevNode {
         let stream = unsafe { ffi::cb_fir_stream(self.fir.0) };
         check(unsafe { ffi::cb_buf_wait_ready(input.raw, stream) })?; // producer's stream -> ours, no host sync
         check(unsafe { ffi::cb_fir_run_dev(self.fir.0, input.ptr(), input.len, out.ptr(), n_out, &mut n_out, stream) })?;
+        // the pool hands `input`'s block to its next owner only after this launch has read it
+        check(unsafe { ffi::cb_buf_record_done(input.raw, stream) })?;
         check(unsafe { ffi::cb_buf_record_ready(out.raw, stream) })?;
+        Ok(out)
+    }
+}
+
+/// Graph edge host -> device: a `Vec` in, a pooled `DeviceBuf` out.  This is where pool buffers START in a graph, so it
+/// is also where the back-pressure gate sits: `cb_pool_throttle` blocks while more than the configured high-water mark
+/// of device / pinned messages is in flight (comms-rs channels are unbounded, src/node/mod.rs:152).
+#[derive(Node)]
+#[pass_by_ref]
+pub struct GpuUploadNode {
+    pub input: NodeReceiver<Vec<C32>>,
+    stream: Stream,
+    pub output: NodeSender<DeviceBuf>,
+}
+
+struct Stream(*mut ffi::cb_stream);
+unsafe impl Send for Stream {}
+impl Drop for Stream {
+    fn drop(&mut self) {
+        unsafe { ffi::cb_stream_destroy(self.0) };
+    }
+}
+
+impl GpuUploadNode {
+    pub fn new() -> Self {
+        let mut s = ptr::null_mut();
+        let st = unsafe { ffi::cb_stream_create(&mut s) };
+        assert_eq!(st, ffi::CB_OK, "cb_stream_create failed");
+        GpuUploadNode { stream: Stream(s), input: Default::default(), output: Default::default() }
+    }
+    pub fn run(&mut self, input: &[C32]) -> Result<DeviceBuf, NodeError> {
+        check(unsafe { ffi::cb_pool_throttle(0) })?;
+        let out = DeviceBuf::device(input.len())?;
+        let s = unsafe { ffi::cb_stream_handle(self.stream.0) };
+        check(unsafe { ffi::cb_copy_h2d_async(out.ptr() as *mut _, input.as_ptr() as *const _, input.len() * 8, s) })?;
+        // `input` is borrowed for this call only: the copy must have left it before run() returns
+        check(unsafe { ffi::cb_stream_sync(self.stream.0) })?;
+        check(unsafe { ffi::cb_buf_record_ready(out.raw, s) })?;
+        Ok(out)
+    }
+}
+
+/// Graph edge device -> host: a `DeviceBuf` in, a `Vec` out.
+#[derive(Node)]
+#[pass_by_ref]
+pub struct GpuDownloadNode {
+    pub input: NodeReceiver<DeviceBuf>,
+    stream: Stream,
+    pub output: NodeSender<Vec<C32>>,
+}
+
+impl GpuDownloadNode {
+    pub fn new() -> Self {
+        let mut s = ptr::null_mut();
+        let st = unsafe { ffi::cb_stream_create(&mut s) };
+        assert_eq!(st, ffi::CB_OK, "cb_stream_create failed");
+        GpuDownloadNode { stream: Stream(s), input: Default::default(), output: Default::default() }
+    }
+    pub fn run(&mut self, input: &DeviceBuf) -> Result<Vec<C32>, NodeError> {
+        let mut out: Vec<C32> = Vec::with_capacity(input.len);
+        let s = unsafe { ffi::cb_stream_handle(self.stream.0) };
+        check(unsafe { ffi::cb_buf_wait_ready(input.raw, s) })?;
+        check(unsafe { ffi::cb_copy_d2h_async(out.as_mut_ptr() as *mut _, input.ptr() as *const _, input.len * 8, s) })?;
+        check(unsafe { ffi::cb_stream_sync(self.stream.0) })?;
+        unsafe { out.set_len(input.len) };
         Ok(out)
     }
 }

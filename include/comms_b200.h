@@ -147,6 +147,12 @@ CB_API int cb_copy_d2h_async(void *dst_host, const void *src_dev, size_t bytes, 
  * zero-stuffed history (non-zero only every L-th entry, newest = index L-1
  * ... ) or be NULL; otherwise CB_ERR_UNSUPPORTED.
  */
+/* Numerical locality.  Filters of up to 128 taps (and the polyphase banks) keep the reference's locality exactly: a
+ * quiet stretch next to a loud one keeps its own 1e-5, and an Inf / NaN input sample makes exactly the outputs
+ * non-finite whose taps reach it (tiles the tensor-core kernels cannot hold to that are recomputed in plain f32).  The
+ * fast-convolution path for 129..1025 taps (calls of >= 8192 samples) works on frames of 4096 points: its error is
+ * relative to the frame's energy (~4e-7 of it), and one non-finite sample makes the ~3000 outputs of its frame
+ * non-finite.  COMMS_B200_FIR_PATH=cuda selects the direct form for such filters when that matters. */
 CB_API int cb_fir_create(const float *taps, size_t ntaps, const float *state, size_t nstate,
                          uint32_t decim, uint32_t interp, cb_fir **out);
 CB_API int cb_fir_destroy(cb_fir *h);

@@ -373,3 +373,53 @@ def test_fused_fft_ticket_order_cannot_wait_on_a_later_ticket(nframes, ring):
         assert last[("A", f)] < first[("B", f)]
         if f >= ring:
             assert last[("B", f - ring)] < first[("A", f)]
+
+
+def test_halo_state_for_polyphase_segments_matches_the_oracle_state(cb):
+    # the reference `state` (src/filter/fir_node.rs:193-200) a rank hands to its polyphase bank: zero-stuffed domain, the
+    # i-th most recent symbol at index i*L - 1.  Must equal the state the oracle's UpsampleNode -> batch_fir carries.
+    import oracle
+
+    rng = np.random.default_rng(5)
+    for L, ntaps in ((8, 1024), (4, 32), (3, 17), (1, 64)):
+        sym = (rng.uniform(-1, 1, 300) + 1j * rng.uniform(-1, 1, 300)).astype(np.complex64)
+        taps = rng.uniform(-1, 1, ntaps).astype(np.complex64)
+        _, st = oracle.batch_fir(oracle.upsample(sym, L) if L > 1 else sym, taps, np.zeros(ntaps, np.complex64))
+        mine = cb.sharding.halo_state(sym, ntaps, L)
+        if L == 1:
+            assert mine.tobytes() == st.tobytes()
+        else:
+            # after the last stuffed zeros the reference state is shifted by L - 1 slots: entries that hold symbols agree
+            k = np.arange(L - 1, ntaps, L)
+            i = (k + 1) // L
+            assert np.array_equal(mine[k], sym[len(sym) - i])
+            assert np.count_nonzero(np.delete(mine, k)) == 0
+        # segment = suffix: filtering the second half from that state reproduces the one-stream output exactly
+        h = 150
+        full, _ = oracle.batch_fir(oracle.upsample(sym, L) if L > 1 else sym, taps, np.zeros(ntaps, np.complex64))
+        part, _ = oracle.batch_fir(oracle.upsample(sym[h:], L) if L > 1 else sym[h:], taps, cb.sharding.halo_state(sym[:h], ntaps, L))
+        assert part.tobytes() == full[h * L:].tobytes()
+
+
+def test_segment_phase_is_exact_for_long_streams(cb):
+    # phase0 + start * dphase reduced exactly (a plain f64 product is 2e-6 rad off at 2^31 samples)
+    from fractions import Fraction
+    import math
+
+    two_pi = Fraction("6.28318530717958647692528676655900576839433879875021")
+    for phase0, dphase, start in ((0.1, 0.123, 5), (0.0, 6.2, (1 << 31) + 12345), (3.0, 0.7853981633974483, 1 << 40), (0.5, 1e-9, 1 << 33)):
+        got = cb.sharding.segment_phase(phase0, dphase, start)
+        p = Fraction(phase0) + Fraction(start) * Fraction(dphase)
+        want = float(p - (p // two_pi) * two_pi)
+        assert 0.0 <= got < 2 * math.pi
+        assert abs(got - want) < 1e-15 or abs(abs(got - want) - 2 * math.pi) < 1e-12
+    assert cb.sharding.segment_phase(0.25, 0.5, 0) == 0.25
+
+
+def test_segment_bounds_cover_ragged_totals(cb):
+    for total, world, mult in ((7344129, 8, 1 << 20), (10, 4, 4), (5, 8, 1), (1 << 28, 8, 10)):
+        b = [cb.sharding.segment_bounds(total, world, r, mult) for r in range(world)]
+        assert b[0][0] == 0 and b[-1][1] == total
+        for (a0, a1), (b0, b1) in zip(b, b[1:]):
+            assert a1 == b0 and a0 <= a1
+        assert all(s % mult == 0 for s, _ in b if s < total)
