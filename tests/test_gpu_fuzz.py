@@ -432,6 +432,38 @@ def test_no_writes_outside_the_output_buffers(cb, monkeypatch):
         buf, p = guarded(esz * C * no)
         bank.run_dev_u8(b8.data_ptr(), n, p, no, s)
         check(buf, esz * C * no, ("chain u8", D, fm))
+    # round 2: tensor-core byte front end (ragged last tile, odd n_out -> unaligned rows through the staged store path),
+    # NCO scan, i16-IQ edges, the pipelined-cluster FFT
+    monkeypatch.setenv("COMMS_B200_CHAIN_PATH", "tc")
+    for fm in (True, False):
+        C, n = 3, 10_248 * 2 + 40  # n_out = 4107 (odd): channel rows 1 and 2 start unaligned
+        bank = cb.ChainBank(C, taps, 5, dphase=None, with_fm=fm)
+        no = bank.out_len(n)
+        b8 = torch.randint(0, 256, (C * n * 2,), dtype=torch.uint8, device="cuda")
+        esz = 4 if fm else 8
+        buf, p = guarded(esz * C * no)
+        bank.run_dev_u8(b8.data_ptr(), n, p, no, s)
+        check(buf, esz * C * no, ("chain tc", fm))
+    monkeypatch.delenv("COMMS_B200_CHAIN_PATH")
+    for n in (1, 2047, 2049, 70_001):
+        e = torch.randn(n, dtype=torch.float64, device="cuda") * 0.01
+        buf, p = guarded(16 * n)
+        cb.NcoNode(0.3, 0.1).run_dev(e.data_ptr(), n, p, s)
+        check(buf, 16 * n, ("nco", n))
+    for n, L in ((70_001, 1), (66_000, 4)):
+        iq = torch.randint(-3000, 3000, (2 * n,), dtype=torch.int16, device="cuda")
+        t = rnd_c32(rng, 64) if L == 1 else rng.uniform(-1, 1, 32).astype(np.complex64)
+        buf, p = guarded(4 * n * L)
+        cb.BatchFirNode(t, None, interp=L).run_dev_iq16(iq.data_ptr(), n, 1.0 / 4096, 2048.0, p, n * L, s)
+        check(buf, 4 * n * L, ("fir iq16", n, L))
+    monkeypatch.setenv("COMMS_B200_FFT_PATH", "cpipe")
+    for frames in (1, 20):
+        x = torch.empty(65536 * frames, dtype=torch.complex64, device="cuda")
+        cb.synth_uniform_dev(6, 0, 65536 * frames, x.data_ptr(), s)
+        buf, p = guarded(8 * 65536 * frames)
+        cb.FFTBatchNode(65536, False).run_dev(x.data_ptr(), 65536 * frames, p, s)
+        check(buf, 8 * 65536 * frames, ("fft cpipe", frames))
+    monkeypatch.delenv("COMMS_B200_FFT_PATH")
     # FFTs
     for N, frames in ((4096, 5), (16384, 3), (65536, 35)):
         x = torch.empty(N * frames, dtype=torch.complex64, device="cuda")
