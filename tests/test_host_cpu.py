@@ -1,6 +1,7 @@
 """CPU-only checks of the boundary and host logic: the C-ABI library loads and
 exports exactly what include/comms_b200.h declares, fails loudly without a GPU,
 and the multi-GPU partitioning (world_size 2, gloo) reproduces the one-shot result."""
+import json
 import os
 import re
 import subprocess
@@ -423,3 +424,21 @@ def test_segment_bounds_cover_ragged_totals(cb):
         for (a0, a1), (b0, b1) in zip(b, b[1:]):
             assert a1 == b0 and a0 <= a1
         assert all(s % mult == 0 for s, _ in b if s < total)
+
+
+def test_reference_arm_never_maps_the_product():
+    # bench.py --impl reference times the oracle port only: neither the package nor libcomms_b200.so may be loaded
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, runpy\n"
+        "sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '3', '--workload', 'pulse4']\n"
+        f"runpy.run_path({os.path.join(ROOT, 'bench.py')!r}, run_name='__main__')\n"
+        "maps = open('/proc/self/maps').read()\n"
+        "assert 'libcomms_b200' not in maps and 'comms_rs_b200' not in sys.modules, 'product loaded by the reference arm'\n"
+    )
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["gpu_launches"] == 0
