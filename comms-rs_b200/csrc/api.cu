@@ -1784,8 +1784,9 @@ int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
         FFT_TRY(upload_twiddles((size_t)1 << l1, inverse, &h->tw1));
         FFT_TRY(upload_twiddles((size_t)1 << l2, inverse, &h->tw2));
         // the fused two-step kernels keep the intermediate in a ring of scratch frames that stays in L2
-        // (65536: 32 frames measured best); the four-step fallback uses the same buffer in groups of frames
-        size_t scratch_mb = log2n <= 18 ? 16 : (log2n == 19 ? 32 : 64);
+        // (65536: 96 frames measured best, each CTA holding two tickets: profiles/r03h_fft65536_variants.txt); the
+        // four-step fallback uses the same buffer in groups of frames
+        size_t scratch_mb = log2n == 16 ? 48 : (log2n <= 18 ? 16 : (log2n == 19 ? 32 : 64));
         FFT_TRY(upload_fft2_table(l1, inverse, &h->tw16a));
         FFT_TRY(upload_fft2_table(l2, inverse, &h->tw16b));
         h->plan.big = 1;
@@ -1825,6 +1826,7 @@ int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
         if (path && strcmp(path, "rows2") == 0) h->plan.cluster_tpt = 7;      // 256 x 256, two launches, batch-sized scratch
         if (path && strcmp(path, "big") == 0) h->plan.cluster_tpt = 8;        // the generic fused two-step kernel (K5-B)
         if (path && strcmp(path, "cpipe") == 0) h->plan.cluster_tpt = 9;      // persistent pipelined 8-CTA clusters (K5-P)
+        if (path && strcmp(path, "rowspf") == 0) h->plan.cluster_tpt = 10;    // rows with the next item's points prefetched (K5-R2)
     }
     *out = h;
     return CB_OK;
@@ -1873,7 +1875,7 @@ static void fft_prepare_scratch(cb_fft *h, size_t nframes)
 {
     if (h->plan.kind != FFT_FOURSTEP) return;
     const bool big = h->plan.big && (h->plan.n != 65536 || h->plan.cluster_tpt == 8);
-    if ((big || (h->plan.n == 65536 && h->plan.cluster_tpt == 6)) && h->plan.flags_frames < nframes) {
+    if ((big || (h->plan.n == 65536 && (h->plan.cluster_tpt == 6 || h->plan.cluster_tpt == 10))) && h->plan.flags_frames < nframes) {
         if (h->plan.flags) cudaFree(h->plan.flags);
         h->plan.flags = nullptr;
         h->plan.flags_frames = 0;

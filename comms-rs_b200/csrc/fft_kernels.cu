@@ -870,7 +870,7 @@ int launch_fft(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframe
     if (fft_big_applicable(p, nframes) && (p.n != 65536 || p.cluster_tpt == 8)) return launch_fft_big(p, in, out, nframes, s);
     if (p.kind == FFT_FOURSTEP && p.n == 65536 && p.cluster_tpt == 9)
         return launch_fft65536_cpipe(in, out, p.tw, nframes, p.inverse != 0, s);
-    if (p.kind == FFT_FOURSTEP && p.n == 65536 && (p.cluster_tpt == 6 || p.cluster_tpt == 7))
+    if (p.kind == FFT_FOURSTEP && p.n == 65536 && (p.cluster_tpt == 6 || p.cluster_tpt == 7 || p.cluster_tpt == 10))
         return launch_fft65536_rows(p, in, out, nframes, s);
     if (p.kind == FFT_FOURSTEP && p.n == 65536 && p.cluster_tpt == 5 && p.tw16 != nullptr)
         return launch_fft65536_two_pass(in, out, p.scratch, p.scratch_frames, p.tw, p.tw16, nframes, p.inverse != 0, s);

@@ -319,7 +319,7 @@ def test_fft_matches_oracle(cb, oracle, n, inverse):
         assert rel_l2(got[f * n:(f + 1) * n], want[f * n:(f + 1) * n]) <= FFT_TOL
 
 
-@pytest.mark.parametrize("path", ["cluster", "cluster1", "cluster2", "cluster16", "twopass", "rows", "rows2", "big", "fourstep", "cpipe"])
+@pytest.mark.parametrize("path", ["cluster", "cluster1", "cluster2", "cluster16", "twopass", "rows", "rows2", "big", "fourstep", "cpipe", "rowspf"])
 @pytest.mark.parametrize("inverse", [False, True])
 def test_fft65536_paths(cb, oracle, path, inverse, monkeypatch):
     # K5-C: one HBM pass on an 8-CTA cluster (distributed shared memory) vs the four-step fallback
@@ -351,6 +351,30 @@ def test_fft65536_pipelined_cluster_frame_counts(cb, oracle, frames, monkeypatch
         e_in = (np.abs(x.reshape(frames, n).astype(np.complex128)) ** 2).sum(axis=1)
         e_out = (np.abs(got.reshape(frames, n).astype(np.complex128)) ** 2).sum(axis=1)
         assert np.all(np.abs(e_out / (n * e_in) - 1) < 1e-5)  # every frame: Parseval
+
+
+@pytest.mark.parametrize("path", ["rows", "rowspf"])
+@pytest.mark.parametrize("frames", [1, 2, 17, 40, 150, 700])
+def test_fft65536_ring_frame_counts(cb, oracle, frames, path, monkeypatch):
+    # K5-R / K5-R2 (fft_rows_kernel.cu): persistent kernels over tickets with the intermediate in a ring of 96 frames;
+    # fewer frames than the lag, more than the ring (slots reused, both dependency directions exercised), and enough
+    # for every CTA to run many items back to back (the prefetching form's steady state)
+    monkeypatch.setenv("COMMS_B200_FFT_PATH", path)
+    n = 65536
+    rng = np.random.default_rng(1000 + frames)
+    x = rnd_c32(rng, frames * n)
+    for inverse in (False, True):
+        got = cb.FFTBatchNode(n, inverse).run(x)
+        for f in sorted({0, frames // 3, frames // 2, frames - 1}):
+            want = oracle.fft(x[f * n:(f + 1) * n], n, inverse)
+            assert rel_l2(got[f * n:(f + 1) * n], want) <= FFT_TOL, (f, inverse)
+        e_in = (np.abs(x.reshape(frames, n).astype(np.complex128)) ** 2).sum(axis=1)
+        e_out = (np.abs(got.reshape(frames, n).astype(np.complex128)) ** 2).sum(axis=1)
+        assert np.all(np.abs(e_out / (n * e_in) - 1) < 1e-5)  # every frame: Parseval
+    if frames >= 150:  # a repeated run of the same handle gives the same bits (no dependence on who won which ticket)
+        node = cb.FFTBatchNode(n, False)
+        a, b = node.run(x), node.run(x)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
 @pytest.mark.parametrize("n", [1024, 4096, 65536])
