@@ -1784,9 +1784,10 @@ int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
         FFT_TRY(upload_twiddles((size_t)1 << l1, inverse, &h->tw1));
         FFT_TRY(upload_twiddles((size_t)1 << l2, inverse, &h->tw2));
         // the fused two-step kernels keep the intermediate in a ring of scratch frames that stays in L2
-        // (65536: 96 frames measured best, each CTA holding two tickets: profiles/r03h_fft65536_variants.txt); the
-        // four-step fallback uses the same buffer in groups of frames
-        size_t scratch_mb = log2n == 16 ? 48 : (log2n <= 18 ? 16 : (log2n == 19 ? 32 : 64));
+        // (48 MiB measured best at every size, each CTA holding two tickets: profiles/r03h_fft65536_variants.txt; that is
+        // 192 / 96 / 48 / 24 / 12 / 6 frames of 2^15 .. 2^20 points); the four-step fallback uses the same buffer in groups
+        // of frames
+        size_t scratch_mb = 48;
         FFT_TRY(upload_fft2_table(l1, inverse, &h->tw16a));
         FFT_TRY(upload_fft2_table(l2, inverse, &h->tw16b));
         h->plan.big = 1;
@@ -1814,7 +1815,7 @@ int cb_fft_create(size_t fft_size, int inverse, cb_fft **out)
     // 65536 points.  COMMS_B200_FFT_PATH = rows (default: one persistent kernel over a 256 x 256 split, intermediate in
     // an L2-resident ring, K5-R) | rows2 (same two steps as two launches with a batch-sized scratch) | cluster (one HBM
     // pass on 8-CTA clusters, K5-C; also the fallback when an allocation fails) | cluster1 / cluster2 (its other
-    // exchange synchronisations) | cluster16 | twopass | fourstep
+    // exchange synchronisations) | cluster16 | twopass | fourstep | cpipe | rowspf (K5-R2: rows with TMA-prefetched items)
     if (fft_size == 65536) {
         const char *path = getenv("COMMS_B200_FFT_PATH");
         h->plan.cluster_tpt = 6;

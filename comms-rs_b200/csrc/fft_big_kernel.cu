@@ -68,6 +68,10 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned *p)
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void red_release(unsigned *p)
+{
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
 // a whole converged warp waits until *p >= need (see fft_rows_kernel.cu)
 __device__ __forceinline__ void poll_at_least(const unsigned *p, unsigned need, int lane)
 {
@@ -105,15 +109,20 @@ fft_big_fused_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, fl
     using namespace fft2;
     using G = Geo<L1, L2, NT>;
     extern __shared__ __align__(16) float2 bsm[];
-    __shared__ unsigned s_item;
+    __shared__ unsigned s_cur[2];
     const int tid = threadIdx.x, lane = tid & 31;
-    const unsigned long long nchunks = lag + 2ull * nframes;
-    for (;;) {
-        __syncthreads();  // the previous item's shared-memory reads (and its read of s_item) are done
-        if (tid == 0) s_item = atomicAdd(ticket, 1u);
-        __syncthreads();
-        const unsigned long long item = s_item;
-        if (item >= nchunks * G::ITEMS) break;
+    const unsigned long long total = (lag + 2ull * nframes) * G::ITEMS;
+    // as in fft65536_fused_kernel: the next ticket is requested at the top of an item and read after its closing
+    // barrier; the previous item's counter is released by warp 1 (red.release, after that barrier) once this item's
+    // loads have been issued
+    if (tid == 0) s_cur[0] = atomicAdd(ticket, 1u);
+    __syncthreads();
+    unsigned *pending = nullptr;
+    for (int par = 0;; par ^= 1) {
+        const unsigned long long item = s_cur[par];
+        if (item >= total) break;
+        unsigned nxt = 0;
+        if (tid == 0) nxt = atomicAdd(ticket, 1u);
         const unsigned long long chunk = item / G::ITEMS;
         const int part = (int)(item % G::ITEMS);
         bool is_a;
@@ -126,9 +135,9 @@ fft_big_fused_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, fl
             is_a = (t & 1) == 0;
             frame = is_a ? lag + (t >> 1) : (t >> 1);
         }
-        if (frame >= nframes) continue;
+        const bool valid = frame < nframes;
         float2 *slot = scratch + (frame % ring) * G::N;
-        if (is_a) {
+        if (valid && is_a) {
             const int c = tid % G::GA, j = tid / G::GA;
             const float2 *src = in + frame * G::N + part * G::GA + c;
             float2 *dst = slot + part * G::GA + c;
@@ -138,16 +147,13 @@ fft_big_fused_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, fl
             auto gld = [&](int i) { return ld_cs(src + (size_t)i * G::N2); };
             auto gst = [&](int i, float2 v) { __stcg(dst + (size_t)i * G::N2, v); };
             run_pass<L1, INV, 0>(j, twA, gld, gst, sm, sm, nomid);
+            if (tid == 32 && pending != nullptr) red_release(pending);
             // the slot must have been consumed by its last reader before anything is stored into it; the barrier
             // that opens the next pass orders warp 0's observation before every thread's stores
             if (frame >= ring && tid < 32) poll_at_least(flags_b + (frame - ring), (unsigned)G::ITEMS, lane);
             later_passes<L1, INV, 1, true>(j, twA, gst, buf);
-            __syncthreads();
-            if (tid == 0) {
-                __threadfence();
-                atomicAdd(flags_a + frame, 1u);
-            }
-        } else {
+        } else if (valid) {
+            if (tid == 32 && pending != nullptr) red_release(pending);
             if (tid < 32) poll_at_least(flags_a + frame, (unsigned)G::ITEMS, lane);  // every column block is in
             __syncthreads();
             constexpr int T2 = G::PB::T;
@@ -165,18 +171,20 @@ fft_big_fused_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, fl
                 for (int sl = 0; sl < 16; ++sl) row[pad16(16 * j + q16(sl))] = v[sl];
             }
             __syncthreads();  // every thread has consumed its scratch reads
-            if (tid == 0) {
-                __threadfence();
-                atomicAdd(flags_b + frame, 1u);
-            }
             {   // later passes, lanes across the rows: thread (row tid % GB, butterfly index tid / GB)
                 const int r = tid % G::GB, j = tid / G::GB;
                 float2 *dst = out + frame * G::N + part * G::GB + r;
                 auto gst = [&](int i, float2 v) { st_cs(dst + (size_t)i * G::N1, v); };
                 later_passes<L2, INV, 1, false>(j, twB, gst, bsm + r * G::RPB);
             }
+        } else if (tid == 32 && pending != nullptr) {
+            red_release(pending);
         }
+        if (tid == 0) s_cur[par ^ 1] = nxt;
+        __syncthreads();  // shared-memory reads done, the next ticket published, every thread's stores ordered before the release
+        pending = !valid ? nullptr : is_a ? flags_a + frame : flags_b + frame;
     }
+    if (tid == 32 && pending != nullptr) red_release(pending);
 }
 
 template <int L1, int L2, int NT, bool INV>

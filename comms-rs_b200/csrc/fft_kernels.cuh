@@ -26,7 +26,8 @@ struct FftPlanDev {
     int big;              // 1: sizes 2^15, 2^17 .. 2^20 run the fused two-step kernel (fft_big_kernel.cu); 0: four-step
     int cluster_tpt;      // n = 65536: 0 = four-step, 1 / 2 / 3 = cluster kernel exchange variants, 4 = 16-CTA clusters,
                           // 5 = 16 x 4096 two-pass, 6 = 256 x 256 fused two-step with an L2 ring, 7 = the same as two launches,
-                          // 8 = generic fused two-step, 9 = persistent pipelined clusters (fft_cpipe_kernel.cu)
+                          // 8 = generic fused two-step, 9 = persistent pipelined clusters (fft_cpipe_kernel.cu),
+                          // 10 = 6 with the next item's points prefetched by the TMA engine (K5-R2)
 };
 
 size_t fft2_table_len(int log2n);

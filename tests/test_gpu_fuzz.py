@@ -123,9 +123,10 @@ def test_fft65536_frame_counts(cb, oracle, frames):
 
 
 @pytest.mark.parametrize("path", ["default", "fourstep"])
-@pytest.mark.parametrize("log2n,frames", [(15, 1), (15, 70), (17, 3), (17, 40), (18, 11), (19, 9), (20, 2), (20, 10)])
+@pytest.mark.parametrize("log2n,frames", [(15, 1), (15, 70), (15, 400), (17, 3), (17, 40), (17, 100), (18, 11), (18, 50), (19, 9),
+                                          (19, 26), (20, 2), (20, 10)])
 def test_fft_large_sizes(cb, oracle, log2n, frames, path, monkeypatch):
-    # K5-B (fused two-step kernel over an N1 x N2 split, intermediate in an L2 ring of 64 / 16 / 8 / 8 / 8 frames) and
+    # K5-B (fused two-step kernel over an N1 x N2 split, intermediate in an L2 ring of 192 / 48 / 24 / 12 / 6 frames) and
     # the four-step fallback: frame counts below, at and beyond lag and ring; forward and inverse
     if path != "default":
         monkeypatch.setenv("COMMS_B200_FFT_PATH", path)
