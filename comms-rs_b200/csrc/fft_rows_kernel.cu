@@ -134,6 +134,10 @@ __device__ __forceinline__ void poll_at_least(const unsigned *p, unsigned need, 
     }
 }
 
+__device__ __forceinline__ void discard_l2_line(const float2 *p)
+{
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+}
 __device__ __forceinline__ void red_release(unsigned *p)
 {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
@@ -228,6 +232,9 @@ fft65536_fused_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, f
 #pragma unroll
             for (int sl = 0; sl < 16; ++sl) rowp[pad16(16 * lo + q16(sl))] = v[sl];
             __syncthreads();  // every thread has consumed its scratch reads
+            // the 16 rows are dead until step A of frame + ring overwrites them: drop their (dirty) lines from L2 instead
+            // of letting them be written back -- one 128-byte line per thread
+            discard_l2_line(slot + (size_t)(part16 + (threadIdx.x >> 4)) * 256 + (threadIdx.x & 15) * 16);
             const float2 *row = rsm + lo * RP;
 #pragma unroll
             for (int m = 0; m < 16; ++m) v[m] = row[pad16(hi + 16 * m)];
@@ -460,6 +467,9 @@ fft65536_pf_kernel(const __grid_constant__ CUtensorMap in_map, float2 *__restric
                 for (int sl = 0; sl < 16; ++sl) __stcg(dst + 256 * (hi + 16 * q16(sl)), v[sl]);
             } else {
                 const int k1 = part16 + hi;
+                // the rows are on chip and dead in the scratch until frame + ring overwrites them: drop their dirty L2 lines
+                discard_l2_line(scratch + (size_t)((unsigned)frame % ring) * NF + (size_t)(part16 + (threadIdx.x >> 4)) * 256 +
+                                (threadIdx.x & 15) * 16);
                 float2 *sb = reinterpret_cast<float2 *>(buf) + hi * BPITCH + lo;
 #pragma unroll
                 for (int m = 0; m < 16; ++m) v[m] = sb[16 * m];
