@@ -171,6 +171,12 @@ fft_big_fused_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, fl
                 for (int sl = 0; sl < 16; ++sl) row[pad16(16 * j + q16(sl))] = v[sl];
             }
             __syncthreads();  // every thread has consumed its scratch reads
+            {   // the GB rows are dead until step A of frame + ring overwrites them: drop their dirty lines from L2 instead
+                // of letting them be written back (GB * N2 = 16 NT points = NT lines of 128 bytes, one per thread)
+                constexpr int LPR = G::N2 / 16;  // lines per row
+                const float2 *line = slot + (size_t)(part * G::GB + tid / LPR) * G::N2 + (tid % LPR) * 16;
+                asm volatile("discard.global.L2 [%0], 128;" ::"l"(line) : "memory");
+            }
             {   // later passes, lanes across the rows: thread (row tid % GB, butterfly index tid / GB)
                 const int r = tid % G::GB, j = tid / G::GB;
                 float2 *dst = out + frame * G::N + part * G::GB + r;
