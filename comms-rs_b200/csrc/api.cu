@@ -163,7 +163,15 @@ static bool is_pageable(const void *p)
     return a.type == cudaMemoryTypeUnregistered;
 }
 
-static const size_t STAGE_MIN_BYTES = (size_t)8 << 20;  // below this the driver's own staging of a pageable copy is fine
+// Pageable calls of at least this many bytes are staged through the handle's pinned slots.  Default 0: also the small
+// messages the reference's graphs pass around (a 4096-symbol BPSK message is 32 KiB in, 128 KiB out) -- the driver's own
+// path for a pageable copy blocks in the D2H call and costs 82 us per such message, a memcpy into / out of a pinned slot
+// around two asynchronous DMAs and one wait costs less than half (profiles/r03p_bench_graph.jsonl).  Pieces below 1 MiB
+// are copied by the calling thread, larger ones by the pool.  COMMS_B200_STAGE_MIN_BYTES overrides.
+static const size_t STAGE_MIN_BYTES = [] {
+    const char *e = getenv("COMMS_B200_STAGE_MIN_BYTES");
+    return e ? (size_t)atoll(e) : (size_t)0;
+}();
 
 // Two copy/compute lanes used by the host-pointer entry points: chunk i runs
 // H2D -> kernel -> D2H on lane i%2, so the copy engines and the SMs overlap.
