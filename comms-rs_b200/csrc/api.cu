@@ -168,6 +168,25 @@ static bool is_pageable(const void *p)
 // path for a pageable copy blocks in the D2H call and costs 82 us per such message, a memcpy into / out of a pinned slot
 // around two asynchronous DMAs and one wait costs less than half (profiles/r03p_bench_graph.jsonl).  Pieces below 1 MiB
 // are copied by the calling thread, larger ones by the pool.  COMMS_B200_STAGE_MIN_BYTES overrides.
+// device-side address of pinned / registered / managed host memory, or NULL (pageable, or not mapped)
+template <typename T>
+static const T *host_device_view(const T *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    if (a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged) return static_cast<const T *>(a.devicePointer);
+    return nullptr;
+}
+
+// host-pointer FIR calls whose input + output fit in this many bytes run as one kernel over pinned host memory
+static const size_t ZEROCOPY_MAX_BYTES = [] {
+    const char *e = getenv("COMMS_B200_ZEROCOPY_MAX_BYTES");
+    return e ? (size_t)atoll(e) : (size_t)1 << 20;
+}();
+
 static const size_t STAGE_MIN_BYTES = [] {
     const char *e = getenv("COMMS_B200_STAGE_MIN_BYTES");
     return e ? (size_t)atoll(e) : (size_t)0;
@@ -1250,6 +1269,29 @@ int cb_fir_run(cb_fir *h, const float *in, size_t n_in, float *out, size_t out_c
     rc = h->pipe.begin_call(in, n_in * sizeof(float2), (chunk + H) * sizeof(float2), out, no * sizeof(float2),
                             fir_out_len(h, chunk) * sizeof(float2));
     if (rc) return rc;
+    // Small messages (what the reference's graphs pass around: a 4096-symbol message is 32 KiB in, 128 KiB out): no
+    // copy engine at all -- the kernel reads the samples from, and writes the result to, pinned host memory (the
+    // caller's own when it is pinned, the handle's slots around a memcpy when it is pageable), one launch and one wait.
+    // Only the CUDA-core kernels take this path (plain loads and stores); history and carried state stay on the device.
+    if (chunk == n_in && (n_in + no) * sizeof(float2) <= ZEROCOPY_MAX_BYTES && !(h->tc_img && n_in >= h->tc.min_samples) &&
+        !(h->ols_hf != nullptr && n_in >= 8192)) {
+        const float2 *dx = h->pipe.stage_in ? nullptr : host_device_view(hin);
+        float2 *dy = h->pipe.stage_out ? nullptr : const_cast<float2 *>(host_device_view(hout));
+        const bool copy_in = dx == nullptr, copy_out = dy == nullptr;
+        if ((!copy_in || h->pipe.stage_in) && (!copy_out || h->pipe.stage_out)) {
+            if (copy_in) {
+                memcpy(h->pipe.pin_in[0], hin, n_in * sizeof(float2));
+                dx = reinterpret_cast<const float2 *>(h->pipe.pin_in[0]);
+            }
+            if (copy_out) dy = reinterpret_cast<float2 *>(h->pipe.pin_out[0]);
+            rc = fir_launch_segment(h, dx, n_in, h->hist[h->cur], h->hist[h->cur ^ 1], dy, h->pipe.lane[0], 0);
+            if (rc) return rc;
+            CB_CUDA(cudaStreamSynchronize(h->pipe.lane[0]));
+            if (copy_out) memcpy(hout, h->pipe.pin_out[0], no * sizeof(float2));
+            h->cur ^= 1;
+            return CB_OK;
+        }
+    }
     size_t done = 0, out_done = 0;
     for (int i = 0; done < n_in; ++i) {
         const int l = i & 1;
