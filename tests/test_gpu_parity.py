@@ -933,8 +933,8 @@ def test_handle_state_is_ordered_across_streams(cb):
 
 
 def test_large_pageable_host_call_is_staged_and_correct(cb):
-    # a Rust Vec is pageable memory: host-pointer calls of >= 8 MiB stage each chunk through pinned slots with the
-    # parallel copier (api.cu HostPipe::h2d / d2h); results must equal the pinned-buffer call bit for bit
+    # a Rust Vec is pageable memory: host-pointer calls stage each chunk through pinned slots (the parallel copier above
+    # 1 MiB; api.cu HostPipe::h2d / d2h); results must equal the pinned-buffer call bit for bit
     import ctypes as C
     import oracle
     import torch
@@ -963,6 +963,40 @@ def test_large_pageable_host_call_is_staged_and_correct(cb):
     m = cb.MixerNode(0.37, 0.5)
     cb._lib.check(cb.load().cb_mixer_run(m._h, xp.data_ptr(), n, mp.data_ptr()))
     assert gm.tobytes() == mp.numpy().tobytes()
+
+
+@pytest.mark.parametrize("interp,decim", [(1, 1), (4, 1), (1, 5)])
+def test_small_host_calls_run_over_pinned_host_memory(cb, oracle, interp, decim):
+    # cb_fir_run with input + output below 1 MiB: one kernel over pinned host memory, no copy engine (api.cu
+    # ZEROCOPY_MAX_BYTES) -- the caller's buffers in place when they are pinned, the handle's slots when pageable.
+    # Messages of both kinds, and one above the threshold (copy-engine path), interleaved on one handle: the carried
+    # state lives on the device across all of them, so the stream must equal one oracle pass over the concatenation.
+    import torch
+
+    rng = np.random.default_rng(50 + interp + decim)
+    taps = rnd_c32(rng, 64) if interp == 1 else rng.uniform(-1, 1, 32).astype(np.complex64)
+    sizes = [4096, 4095, 200_000, 1, 4096 * 5, 63, 8190]
+    sizes = [n - n % decim if n >= decim else decim for n in sizes]  # whole decimation periods: one oracle pass compares
+    x = rnd_c32(rng, sum(sizes))
+    node = cb.BatchFirNode(taps, None, interp=interp, decim=decim)
+    outs, pos = [], 0
+    for i, n in enumerate(sizes):
+        seg = x[pos:pos + n]
+        no = n * interp // decim
+        if i % 2 == 0:
+            outs.append(node.run(seg))  # numpy memory: pageable
+        else:
+            xp = torch.from_numpy(seg.copy()).pin_memory()
+            yp = torch.empty(max(no, 1), dtype=torch.complex64).pin_memory()
+            cb._lib.check(cb.load().cb_fir_run(node._h, xp.data_ptr(), n, yp.data_ptr(), max(no, 1), None))
+            outs.append(yp.numpy()[:no].copy())
+        assert len(outs[-1]) == no
+        pos += n
+    got = np.concatenate(outs)
+    want, _ = oracle.batch_fir(oracle.upsample(x, interp) if interp > 1 else x, taps, np.zeros(len(taps), np.complex64))
+    assert rel_l2(got, want[::decim]) <= FIR_TOL
+    one = cb.BatchFirNode(taps, None, interp=interp, decim=decim).run(x)  # a single large call: copy-engine or TC path
+    assert rel_l2(got, one) <= FIR_TOL
 
 
 def test_cpp_graph_message_rate_bench_runs(cb):
