@@ -50,6 +50,8 @@ WORKLOADS = {
     "fm_radio": ("graph", 1 << 28, 2.16, "examples/fm_radio.rs end to end, one stream per GPU: u8 IQ -> ConvertNode -> filt1 (63 taps) -> /5 -> "
                  "FMDemodNode -> Convert2Node -> filt2 (63 taps) -> Convert3Node -> /5 -> f32 audio; two kernels "
                  "(fused byte front end, fused real second stage), 2^28 IQ samples per step"),
+    "fft4096_iq16": ("fft16", 1 << 28, 12.0, "batched 4096-point FFT of i16 IQ samples (IQBatchInput -> FFT, src/io/raw_iq.rs:78-140; the cast is "
+                     "folded into the transform's first loads): 4 B in + 8 B out per sample, 2^28 samples per GPU"),
     "fft1024": ("fft", 1 << 28, 16.0, "batched 1024-point FFT over 2^28 complex-f32 samples per GPU"),
     "fft2048": ("fft", 1 << 28, 16.0, "batched 2048-point FFT over 2^28 complex-f32 samples per GPU"),
     "fft16384": ("fft", 1 << 28, 16.0, "batched 16384-point FFT over 2^28 complex-f32 samples per GPU"),
@@ -212,6 +214,8 @@ def cpu_rate(workload, samples, threads):
     if kind == "fft":
         n = int(workload.replace("ifft", "").replace("fft", ""))
         per = max(per // n, 1) * n
+    if kind == "fft16":
+        per = max(per // 4096, 1) * 4096
     jobs = []
     for i in range(threads):
         x = oracle.synth_uniform_c32(SEED, i * per, per)
@@ -227,6 +231,9 @@ def cpu_rate(workload, samples, threads):
             jobs.append(lambda x=x, t=t: oracle.batch_fir(x, t, np.zeros(len(t), np.complex64), literal=True, native=True))
         elif kind == "fft":
             jobs.append(lambda x=x: oracle.fft(x, n, workload.startswith("ifft")))
+        elif kind == "fft16":
+            iq = (x.view(np.float32) * np.float32(32767.0)).astype(np.int16)
+            jobs.append(lambda iq=iq: oracle.fft((iq.astype(np.float32) * np.float32(1.0 / 32767.0)).view(np.complex64), 4096, False))
         elif kind == "firdec":
             t = fm_radio_lowpass()
             jobs.append(lambda x=x, t=t: oracle.decimate(oracle.batch_fir(x, t, np.zeros(63, np.complex64), literal=True, native=True)[0], 5))
@@ -283,7 +290,7 @@ def run_reference(args, rank):
         return
     threads = os.cpu_count() or 1
     kind, _, _, desc = WORKLOADS[args.workload]
-    rate1 = {"fir16": 8e6, "fir": 8e6, "fft": 30e6, "chain": 20e6, "interp": 2e6, "mixer": 30e6, "fm": 60e6, "firdec": 8e6, "est": 3e6, "firreal": 8e6, "graph": 8e6}[kind]
+    rate1 = {"fir16": 8e6, "fft16": 30e6, "fir": 8e6, "fft": 30e6, "chain": 20e6, "interp": 2e6, "mixer": 30e6, "fm": 60e6, "firdec": 8e6, "est": 3e6, "firreal": 8e6, "graph": 8e6}[kind]
     if args.workload.startswith("poly8x1024"):
         rate1 = 1e4
     per_thread = int(min(max(150.0 * rate1 / (args.steps + args.warmup), 1 << 12), 1 << 23))
@@ -350,6 +357,17 @@ class Job:
             sc_in, sc_out = 1.0 / 32767.0, 8192.0
             self.step = lambda: self.node.run_dev_iq16(self.x16.data_ptr(), n, sc_in, sc_out, self.y.data_ptr(), n, self.stream)
             self.host_call = lambda hin, hout: cb.load().cb_fir_run_iq16(self.node._h, hin, n, sc_in, sc_out, hout, n, None)
+        elif self.kind == "fft16":
+            self.node = cb.FFTBatchNode(4096, False)
+            xr = torch.view_as_real(self.x)
+            self.x16 = (xr * 32767.0).to(torch.int16).contiguous()
+            self.x8 = self.x16  # (the e2e leg copies `x8` when present)
+            self.y = torch.empty(n, dtype=torch.complex64, device="cuda")
+            self.in_bytes_override = 4 * n
+            self.out_bytes = 8 * n
+            sc_in = 1.0 / 32767.0
+            self.step = lambda: self.node.run_dev_iq16(self.x16.data_ptr(), n, sc_in, self.y.data_ptr(), self.stream)
+            self.host_call = lambda hin, hout: cb.load().cb_fft_run_iq16(self.node._h, hin, n, sc_in, hout)
         elif self.kind == "firdec":
             self.taps = fm_radio_lowpass()
             self.node = cb.BatchFirNode(self.taps, None, decim=5)
@@ -757,7 +775,7 @@ def measure(cb, torch, dist, args, workload, rank, world, local_rank, steps, war
             line["gather"] = gather
         if world == 1 and not args.no_cpu:
             kind = job.kind
-            sample = {"fir16": 1 << 26, "fir": 1 << 26, "fft": 1 << 27, "chain": 1 << 26, "interp": 1 << 23, "mixer": 1 << 26, "fm": 1 << 27, "firdec": 1 << 26, "est": 1 << 24, "firreal": 1 << 26, "graph": 1 << 26}[kind]
+            sample = {"fir16": 1 << 26, "fft16": 1 << 27, "fir": 1 << 26, "fft": 1 << 27, "chain": 1 << 26, "interp": 1 << 23, "mixer": 1 << 26, "fm": 1 << 27, "firdec": 1 << 26, "est": 1 << 24, "firreal": 1 << 26, "graph": 1 << 26}[kind]
             if workload == "timing10x5":
                 sample = 1 << 22
             if workload.startswith("poly8x1024"):

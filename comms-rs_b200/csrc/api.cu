@@ -2045,6 +2045,23 @@ int cb_fft_run(cb_fft *h, const float *in, size_t n_in, float *out)
 }
 
 // i16 IQ frames in (IQBatchInput, src/io/raw_iq.rs:78-140), f32 spectra out: x = in_scale * (i16 as f32)
+// i16 IQ in: the transforms that read the samples themselves (single-kernel sizes, 65536 points) widen them in their
+// first loads; the others get a widening pass into the lane's scratch first
+static int fft_exec_iq16(cb_fft *h, const int16_t *d_in, float in_scale, float2 *d_out, size_t nframes, int lane, cudaStream_t s)
+{
+    if (h->plan.kind != FFT_BLUESTEIN) {
+        fft_prepare_scratch(h, nframes);
+        if (fft_fuses_iq16(h->plan, nframes)) return launch_fft_iq16(h->plan, d_in, in_scale, d_out, nframes, s);
+    }
+    const size_t n = nframes * h->plan.n;
+    int rc = h->pipe.reserve_aux(n * sizeof(float2), 0);
+    if (rc) return rc;
+    float2 *wide = reinterpret_cast<float2 *>(h->pipe.aux_in[lane]);
+    rc = launch_convert_i16(d_in, reinterpret_cast<float *>(wide), 2 * n, in_scale, s);
+    if (rc) return rc;
+    return fft_exec(h, wide, d_out, nframes, s);
+}
+
 int cb_fft_run_dev_iq16(cb_fft *h, const int16_t *d_in, size_t n_in, float in_scale, float *d_out, void *stream)
 {
     CB_REQUIRE(h, CB_ERR_INVALID_ARG, "handle is NULL");
@@ -2056,11 +2073,7 @@ int cb_fft_run_dev_iq16(cb_fft *h, const int16_t *d_in, size_t n_in, float in_sc
     cudaStream_t s = pick_stream(stream, h->stream);
     int rc = h->last.begin(s);  // the widened-input scratch is per handle
     if (rc) return rc;
-    rc = h->pipe.reserve_aux(n_in * sizeof(float2), 0);
-    if (rc) return rc;
-    float2 *wide = reinterpret_cast<float2 *>(h->pipe.aux_in[0]);
-    rc = launch_convert_i16(d_in, reinterpret_cast<float *>(wide), 2 * n_in, in_scale, s);
-    if (rc == CB_OK) rc = fft_exec(h, wide, reinterpret_cast<float2 *>(d_out), n_in / h->plan.n, s);
+    rc = fft_exec_iq16(h, d_in, in_scale, reinterpret_cast<float2 *>(d_out), n_in / h->plan.n, 0, s);
     if (rc) return rc;
     return h->last.end(s);
 }
@@ -2080,8 +2093,6 @@ int cb_fft_run_iq16(cb_fft *h, const int16_t *in, size_t n_in, float in_scale, f
     if (rc) return rc;
     rc = h->pipe.reserve(chunk * IQ, chunk * sizeof(float2));
     if (rc) return rc;
-    rc = h->pipe.reserve_aux(chunk * sizeof(float2), 0);
-    if (rc) return rc;
     rc = h->pipe.begin_call(in, n_in * IQ, chunk * IQ, out, n_in * sizeof(float2), chunk * sizeof(float2));
     if (rc) return rc;
     const char *hin = reinterpret_cast<const char *>(in);
@@ -2091,13 +2102,11 @@ int cb_fft_run_iq16(cb_fft *h, const int16_t *in, size_t n_in, float in_scale, f
         const int l = i & 1;
         const size_t m = n_in - done < chunk ? n_in - done : chunk;
         cudaStream_t s = h->pipe.lane[l];
-        float2 *wide = reinterpret_cast<float2 *>(h->pipe.aux_in[l]), *dout = reinterpret_cast<float2 *>(h->pipe.out[l]);
+        float2 *dout = reinterpret_cast<float2 *>(h->pipe.out[l]);
         rc = h->pipe.h2d(l, h->pipe.in[l], hin + done * IQ, m * IQ);
         if (rc) return rc;
-        rc = launch_convert_i16(reinterpret_cast<const int16_t *>(h->pipe.in[l]), reinterpret_cast<float *>(wide), 2 * m, in_scale, s);
-        if (rc) return rc;
         if ((h->plan.kind == FFT_FOURSTEP || h->plan.kind == FFT_BLUESTEIN) && i > 0) CB_CUDA(cudaStreamSynchronize(h->pipe.lane[l ^ 1]));
-        rc = fft_exec(h, wide, dout, m / N, s);
+        rc = fft_exec_iq16(h, reinterpret_cast<const int16_t *>(h->pipe.in[l]), in_scale, dout, m / N, l, s);
         if (rc) return rc;
         rc = h->pipe.d2h(l, hout + done, dout, m * sizeof(float2));
         if (rc) return rc;

@@ -218,6 +218,41 @@ fft2_frames_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, cons
     }
 }
 
+// i16 IQ input (src/io/raw_iq.rs:78-140): x = in_scale * (i16 as f32) folded into the first pass's loads -- half the
+// input bytes and no widening pass (convert_i16_kernel's arithmetic, so the spectra equal convert -> transform bit for bit)
+__device__ __forceinline__ float2 ldg_iq16(const uint32_t *p, float scale)
+{
+    uint32_t w;
+    asm volatile("ld.global.cs.b32 %0, [%1];" : "=r"(w) : "l"(p));
+    return make_float2(__fmul_rn(scale, (float)(int16_t)(w & 0xFFFFu)), __fmul_rn(scale, (float)(int16_t)(w >> 16)));
+}
+
+template <int LOG2N, bool INV>
+__global__ void __launch_bounds__(Fft2Cfg<LOG2N>::THREADS, Fft2Cfg<LOG2N>::MINB)
+fft2_frames_iq16_kernel(const uint32_t *__restrict__ in, float in_scale, float2 *__restrict__ out, const float2 *__restrict__ tw,
+                        size_t nframes)
+{
+    using PL = fft2::Plan<LOG2N>;
+    using CF = Fft2Cfg<LOG2N>;
+    extern __shared__ __align__(16) float2 fsm[];
+    const int f = threadIdx.x / PL::T, j = threadIdx.x % PL::T;
+    const size_t frame = (size_t)blockIdx.x * CF::FPB + f;
+    const bool live = frame < nframes;
+    const uint32_t *src = in + frame * PL::N;
+    float2 *dst = out + frame * PL::N;
+    float2 *b0 = fsm + f * PL::PADN;
+    float2 *b1 = CF::PINGPONG ? b0 + CF::FPB * PL::PADN : b0;
+    auto gld = [&](int i) { return live ? ldg_iq16(src + i, in_scale) : make_float2(0.f, 0.f); };
+    auto gst = [&](int i, float2 v) {
+        if (live) stg_stream2(dst + i, v);
+    };
+    if constexpr (CF::PINGPONG) {
+        fft2_passes<LOG2N, INV, 0>(j, tw, gld, gst, b0, b1);
+    } else {
+        fft2_passes<LOG2N, INV, 0>(j, tw, gld, gst, b0, b0);
+    }
+}
+
 // ---------------------------------------------------------------- four-step column kernels
 // Column batch: COLS adjacent columns of a (ROWS x ld) matrix, FFT along the rows
 // index.  Thread t: column f = t % COLS, butterfly index j = t / COLS.
@@ -518,6 +553,38 @@ static int launch_frames2_dir(int log2n, const float2 *in, float2 *out, const fl
     case 12: return launch_frames2<12, INV>(in, out, tw2, nframes, s);
     case 13: return launch_frames2<13, INV>(in, out, tw2, nframes, s);
     case 14: return launch_frames2<14, INV>(in, out, tw2, nframes, s);
+    default: set_error("fft: no v2 kernel for 2^%d", log2n); return CB_ERR_UNSUPPORTED;
+    }
+}
+
+template <int LOG2N, bool INV>
+static int launch_frames2_iq16(const uint32_t *in, float in_scale, float2 *out, const float2 *tw2, size_t nframes, cudaStream_t s)
+{
+    using CF = Fft2Cfg<LOG2N>;
+    auto kern = fft2_frames_iq16_kernel<LOG2N, INV>;
+    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM));
+    kern<<<(unsigned)ceil_div(nframes, (size_t)CF::FPB), CF::THREADS, CF::SMEM, s>>>(in, in_scale, out, tw2, nframes);
+    count_launch();
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+
+template <bool INV>
+static int launch_frames2_iq16_dir(int log2n, const uint32_t *in, float sc, float2 *out, const float2 *tw2, size_t nframes,
+                                   cudaStream_t s)
+{
+    switch (log2n) {
+    case 4: return launch_frames2_iq16<4, INV>(in, sc, out, tw2, nframes, s);
+    case 5: return launch_frames2_iq16<5, INV>(in, sc, out, tw2, nframes, s);
+    case 6: return launch_frames2_iq16<6, INV>(in, sc, out, tw2, nframes, s);
+    case 7: return launch_frames2_iq16<7, INV>(in, sc, out, tw2, nframes, s);
+    case 8: return launch_frames2_iq16<8, INV>(in, sc, out, tw2, nframes, s);
+    case 9: return launch_frames2_iq16<9, INV>(in, sc, out, tw2, nframes, s);
+    case 10: return launch_frames2_iq16<10, INV>(in, sc, out, tw2, nframes, s);
+    case 11: return launch_frames2_iq16<11, INV>(in, sc, out, tw2, nframes, s);
+    case 12: return launch_frames2_iq16<12, INV>(in, sc, out, tw2, nframes, s);
+    case 13: return launch_frames2_iq16<13, INV>(in, sc, out, tw2, nframes, s);
+    case 14: return launch_frames2_iq16<14, INV>(in, sc, out, tw2, nframes, s);
     default: set_error("fft: no v2 kernel for 2^%d", log2n); return CB_ERR_UNSUPPORTED;
     }
 }
@@ -854,6 +921,24 @@ int fft_plan_split(size_t n, int *log2n1, int *log2n2)
     *log2n1 = l / 2;
     *log2n2 = l - l / 2;
     return CB_OK;
+}
+
+// true when launch_fft_iq16 reads the i16 IQ samples itself (otherwise the caller widens them first)
+bool fft_fuses_iq16(const FftPlanDev &p, size_t nframes)
+{
+    if (p.kind == FFT_SINGLE && p.tw16 != nullptr && p.log2n >= 4) return true;
+    return p.kind == FFT_FOURSTEP && p.n == 65536 && p.cluster_tpt == 6 && p.flags != nullptr && p.flags_frames >= nframes &&
+           p.scratch_frames >= 4;
+}
+
+int launch_fft_iq16(const FftPlanDev &p, const int16_t *in, float in_scale, float2 *out, size_t nframes, cudaStream_t s)
+{
+    if (nframes == 0) return CB_OK;
+    const uint32_t *in32 = reinterpret_cast<const uint32_t *>(in);
+    if (p.kind == FFT_SINGLE)
+        return p.inverse ? launch_frames2_iq16_dir<true>(p.log2n, in32, in_scale, out, p.tw16, nframes, s)
+                         : launch_frames2_iq16_dir<false>(p.log2n, in32, in_scale, out, p.tw16, nframes, s);
+    return launch_fft65536_rows_iq16(p, in32, in_scale, out, nframes, s);
 }
 
 int launch_fft(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s)

@@ -37,6 +37,9 @@ int launch_fft65536_cluster(const float2 *in, float2 *out, const float2 *twN, si
                             cudaStream_t s);
 int launch_fft65536_cpipe(const float2 *in, float2 *out, const float2 *twN, size_t nframes, bool inverse, cudaStream_t s);
 int launch_fft65536_rows(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s);
+int launch_fft65536_rows_iq16(const FftPlanDev &p, const uint32_t *in, float in_scale, float2 *out, size_t nframes, cudaStream_t s);
+bool fft_fuses_iq16(const FftPlanDev &p, size_t nframes);
+int launch_fft_iq16(const FftPlanDev &p, const int16_t *in, float in_scale, float2 *out, size_t nframes, cudaStream_t s);
 bool fft_big_applicable(const FftPlanDev &p, size_t nframes);
 int launch_fft_big(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s);
 int launch_bluestein_fused(const float2 *x, const float2 *chirp, const float2 *bspec, float2 *spec, float2 *out, uint32_t N,

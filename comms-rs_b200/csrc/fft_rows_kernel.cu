@@ -172,11 +172,20 @@ __device__ __forceinline__ FusedItem fused_decode(unsigned long long item, unsig
 // two tickets, so the ring has to cover twice the items in flight: 96 frames (48 MiB) measured best, was 32.
 // (Looking at the next item's dependency counter ahead of time as well, or prefetching the next item's points with
 // the TMA engine -- K5-R2 below -- measured no better: profiles/r03h_fft65536_variants.txt.)
-template <bool INV>
+// IN16: the input is i16 IQ pairs (one 32-bit word per sample, src/io/raw_iq.rs:78-140), widened as in_scale * (i16 as
+// f32) in step A's loads
+__device__ __forceinline__ float2 ld_cs_iq16(const uint32_t *p, float scale)
+{
+    uint32_t w;
+    asm volatile("ld.global.cs.b32 %0, [%1];" : "=r"(w) : "l"(p));
+    return make_float2(__fmul_rn(scale, (float)(int16_t)(w & 0xFFFFu)), __fmul_rn(scale, (float)(int16_t)(w >> 16)));
+}
+
+template <bool INV, bool IN16 = false>
 __global__ void __launch_bounds__(256, 4)
 fft65536_fused_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, float2 *__restrict__ scratch,
                       const float2 *__restrict__ twN, unsigned *ticket, unsigned *flags_a, unsigned *flags_b,
-                      unsigned long long nframes, unsigned lag, unsigned ring)
+                      unsigned long long nframes, unsigned lag, unsigned ring, float in_scale = 1.f)
 {
     using namespace fft2;
     extern __shared__ __align__(16) float2 rsm[];
@@ -197,10 +206,16 @@ fft65536_fused_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, f
         float2 *slot = scratch + (frame % ring) * NF;
         float2 v[16];
         if (it.valid && it.is_a) {
-            const float2 *src = in + frame * NF + part16 + lo;
             float2 *row = rsm + lo * RP;
+            if constexpr (IN16) {
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(in) + frame * NF + part16 + lo;
 #pragma unroll
-            for (int m = 0; m < 16; ++m) v[m] = ld_cs(src + 256 * (hi + 16 * m));
+                for (int m = 0; m < 16; ++m) v[m] = ld_cs_iq16(src + 256 * (hi + 16 * m), in_scale);
+            } else {
+                const float2 *src = in + frame * NF + part16 + lo;
+#pragma unroll
+                for (int m = 0; m < 16; ++m) v[m] = ld_cs(src + 256 * (hi + 16 * m));
+            }
             if (threadIdx.x == 32 && pending != nullptr) red_release(pending);
             // the slot must have been consumed by its last reader before anything is stored into it: warp 0 polls
             // (all 32 lanes together) while the input loads are in flight; the block barrier below orders the
@@ -563,10 +578,10 @@ static int launch_fused_pf(const FftPlanDev &p, const float2 *in, float2 *out, s
     return CB_OK;
 }
 
-template <bool INV>
-static int launch_fused(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s)
+template <bool INV, bool IN16 = false>
+static int launch_fused(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s, float in_scale = 1.f)
 {
-    auto kf = fft65536_fused_kernel<INV>;
+    auto kf = fft65536_fused_kernel<INV, IN16>;
     CB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
@@ -580,7 +595,7 @@ static int launch_fused(const FftPlanDev &p, const float2 *in, float2 *out, size
     const unsigned long long cap = (unsigned long long)sms * per_sm;  // one CTA per resident slot
     const unsigned grid = (unsigned)(items < cap ? items : cap);
     CB_CUDA(cudaMemsetAsync(p.flags, 0, (4 + 2 * nframes) * sizeof(unsigned), s));
-    kf<<<grid, 256, SMEM, s>>>(in, out, p.scratch, p.tw, p.flags, p.flags + 4, p.flags + 4 + nframes, nframes, lag, ring);
+    kf<<<grid, 256, SMEM, s>>>(in, out, p.scratch, p.tw, p.flags, p.flags + 4, p.flags + 4 + nframes, nframes, lag, ring, in_scale);
     count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;
@@ -610,6 +625,14 @@ static int launch(const FftPlanDev &p, const float2 *in, float2 *out, size_t nfr
 }
 
 }  // namespace fftr
+
+int launch_fft65536_rows_iq16(const FftPlanDev &p, const uint32_t *in, float in_scale, float2 *out, size_t nframes, cudaStream_t s)
+{
+    if (nframes == 0) return CB_OK;
+    const float2 *in2 = reinterpret_cast<const float2 *>(in);  // the kernel reads it as 32-bit words
+    return p.inverse ? fftr::launch_fused<true, true>(p, in2, out, nframes, s, in_scale)
+                     : fftr::launch_fused<false, true>(p, in2, out, nframes, s, in_scale);
+}
 
 int launch_fft65536_rows(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s)
 {

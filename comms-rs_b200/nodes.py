@@ -336,7 +336,12 @@ def _fft_run_iq16(self, iq, in_scale: float = 1.0) -> np.ndarray:
     return out
 
 
+def _fft_run_dev_iq16(self, d_in: int, n_in: int, in_scale: float, d_out: int, stream: int = 0) -> None:
+    check(_lib.load().cb_fft_run_dev_iq16(self._h, d_in, n_in, float(in_scale), d_out, stream))
+
+
 FFTBatchNode.run_iq16 = _fft_run_iq16
+FFTBatchNode.run_dev_iq16 = _fft_run_dev_iq16
 
 
 class FFTSampleNode(FFTBatchNode):

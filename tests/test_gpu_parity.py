@@ -1056,6 +1056,21 @@ def test_fft_iq16_input_equals_cast_then_fft(cb):
     assert f2.run_iq16(iq2, 0.5).tobytes() == f2.run((iq2.astype(np.float32) * np.float32(0.5)).view(np.complex64).ravel()).tobytes()
     with pytest.raises(cb.NodeError):
         f.run_iq16(iq[:100])  # wrong length -> DataError, like the f32 entry
+    # every kind of plan: single-kernel sizes and 65536 points read the i16 samples in their first pass (fft_kernels.cu
+    # fft2_frames_iq16_kernel, fft_rows_kernel.cu IN16), the others widen first; all equal cast -> transform bit for bit
+    for n, frames, inverse in ((16, 700, False), (64, 33, True), (1024, 9, False), (8192, 3, True), (16384, 5, False),
+                               (32768, 3, False), (65536, 120, True), (1 << 17, 2, False), (1000, 7, False), (100, 3, True)):
+        iq3 = rng.integers(-32768, 32768, size=(frames * n, 2), dtype=np.int16)
+        sc = np.float32(1.0 / 1024)
+        node = cb.FFTBatchNode(n, inverse)
+        want = node.run((iq3.astype(np.float32) * sc).view(np.complex64).ravel())
+        assert node.run_iq16(iq3, float(sc)).tobytes() == want.tobytes(), (n, inverse)
+        import torch
+        d_iq = torch.from_numpy(iq3).cuda()
+        d_out = torch.empty(frames * n, dtype=torch.complex64, device="cuda")
+        node.run_dev_iq16(d_iq.data_ptr(), frames * n, float(sc), d_out.data_ptr(), 0)
+        torch.cuda.synchronize()
+        assert d_out.cpu().numpy().tobytes() == want.tobytes(), (n, inverse, "dev")
 
 
 # ------------------------------------------------------------------ buffer pool (back-pressure for unbounded channels)

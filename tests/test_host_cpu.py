@@ -223,7 +223,7 @@ def test_bench_cpu_leg_runs_for_every_workload_kind():
     kinds = {}
     for name, (kind, *_rest) in bench.WORKLOADS.items():
         kinds.setdefault(kind, name)
-    assert set(kinds) == {"fir", "fir16", "firdec", "firreal", "graph", "fft", "est", "mixer", "fm", "chain", "interp"}
+    assert set(kinds) == {"fir", "fir16", "fft16", "firdec", "firreal", "graph", "fft", "est", "mixer", "fm", "chain", "interp"}
     for kind, name in kinds.items():
         rate, dt, n = bench.cpu_rate(name, 1 << 15, 2)
         assert rate > 0 and n > 0, name
