@@ -1342,6 +1342,17 @@ static int fir_segment_to_i16(cb_fir *h, const float2 *x, size_t n, const float2
     return launch_quantize_i16(reinterpret_cast<const float *>(yscratch), y16, 2 * no, out_scale, s);
 }
 
+// Plain filters of up to 128 taps on a long enough batch: the tensor-core kernel reads the i16 IQ words itself and its
+// epilogue writes i16 IQ words (fir_tc_kernel.cu, IQ16) -- 4 + 4 bytes per sample, one launch.
+static bool fir_iq16_fused(const cb_fir *h, size_t n, const int16_t *x16, const int16_t *y16)
+{
+    if (!h->tc_img || n < h->tc.min_samples || h->interp != 1 || h->decim != 1 || h->k_eff == 0) return false;
+    if (const char *e = getenv("COMMS_B200_FIR_IQ16"))  // "split": cast, filter and quantiser as separate passes (for comparison)
+        if (strcmp(e, "split") == 0) return false;
+    FirSeg seg{nullptr, h->hist[0], nullptr, nullptr, n, n, h->hist_len, h->k_eff, h->interp, h->decim};
+    return fir_tc_iq16_applicable(seg, x16, y16);
+}
+
 int cb_fir_run_dev_iq16(cb_fir *h, const int16_t *d_in, size_t n_in, float in_scale, float out_scale, int16_t *d_out,
                         size_t out_cap, size_t *n_out, void *stream)
 {
@@ -1356,6 +1367,13 @@ int cb_fir_run_dev_iq16(cb_fir *h, const int16_t *d_in, size_t n_in, float in_sc
     cudaStream_t s = pick_stream(stream, h->stream);
     int rc = h->last.begin(s);
     if (rc) return rc;
+    if (fir_iq16_fused(h, n_in, d_in, d_out)) {
+        FirSeg seg{nullptr, h->hist[h->cur], h->hist[h->cur ^ 1], nullptr, n_in, no, h->hist_len, h->k_eff, h->interp, h->decim};
+        rc = launch_fir_tc_iq16(seg, d_in, in_scale, d_out, out_scale, h->tc.bimg_dev, h->tc.tap_inv_scale, s);
+        if (rc) return rc;
+        h->cur ^= 1;
+        return h->last.end(s);
+    }
     if (h->rscratch_len < n_in + no) {  // widened input followed by the f32 result
         if (h->rscratch) CB_CUDA(cudaFree(h->rscratch));
         h->rscratch = nullptr;
@@ -1405,6 +1423,29 @@ int cb_fir_run_iq16(cb_fir *h, const int16_t *in, size_t n_in, float in_scale, f
         char *slot16 = reinterpret_cast<char *>(h->pipe.in[l]);
         float2 *wide = reinterpret_cast<float2 *>(h->pipe.aux_in[l]);
         const float2 *hist_in;
+        if (fir_iq16_fused(h, n, reinterpret_cast<const int16_t *>(slot16 + H * IQ), reinterpret_cast<const int16_t *>(h->pipe.out[l]))) {
+            // the kernel reads and writes the i16 words itself; only a later chunk's halo (the tail of the previous
+            // chunk, re-sent with this one) is widened, because the kernel takes its history as f32
+            if (done == 0) {
+                hist_in = h->hist[h->cur];
+                rc = h->pipe.h2d(l, slot16 + H * IQ, hin, n * IQ);
+            } else {
+                hist_in = wide;
+                rc = h->pipe.h2d(l, slot16, hin + (done - H) * IQ, (n + H) * IQ);
+                if (rc == CB_OK) rc = launch_convert_i16(reinterpret_cast<const int16_t *>(slot16), reinterpret_cast<float *>(wide), 2 * H, in_scale, s);
+            }
+            if (rc) return rc;
+            int16_t *y16 = reinterpret_cast<int16_t *>(h->pipe.out[l]);
+            FirSeg seg{nullptr, hist_in, last ? h->hist[h->cur ^ 1] : nullptr, nullptr, n, n, h->hist_len, h->k_eff, h->interp, h->decim};
+            rc = launch_fir_tc_iq16(seg, reinterpret_cast<const int16_t *>(slot16 + H * IQ), in_scale, y16, out_scale, h->tc.bimg_dev,
+                                    h->tc.tap_inv_scale, s);
+            if (rc) return rc;
+            rc = h->pipe.d2h(l, hout + out_done * IQ, y16, n * IQ);
+            if (rc) return rc;
+            done += n;
+            out_done += n;
+            continue;
+        }
         if (done == 0) {  // the carried history is already f32
             hist_in = h->hist[h->cur];
             rc = h->pipe.h2d(l, slot16 + H * IQ, hin, n * IQ);

@@ -67,6 +67,9 @@ void fir_tc_build_image(const float2 *taps, uint32_t ntaps, unsigned char *img, 
 bool fir_tc_applicable(const FirSeg &seg);
 int launch_fir_tc(const FirSeg &seg, const void *bimg_dev, float tap_inv_scale, FirFix *fix, const float2 *taps_dev,
                   cudaStream_t stream);
+bool fir_tc_iq16_applicable(const FirSeg &seg, const int16_t *x16, const int16_t *y16);
+int launch_fir_tc_iq16(const FirSeg &seg, const int16_t *x16, float in_scale, int16_t *y16, float out_scale, const void *bimg_dev,
+                       float tap_inv_scale, cudaStream_t stream);
 
 // Polyphase tensor-core path (fir_ptc_kernel.cu): interp in {4, 8}, decim = 1, real or complex taps.
 // The plan's bimg_dev / tap_inv_scale then hold the polyphase tap image.

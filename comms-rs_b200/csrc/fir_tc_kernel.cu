@@ -69,7 +69,24 @@ struct Args {
     float tap_inv_scale;    // 2^-(14 - e_h)
     unsigned *fix_count;    // tiles flagged for the exact fall-back pass (FirFix), or NULL
     unsigned *fix_list;
+    // IQ16 (i16 IQ on both edges, src/io/raw_iq.rs:78-140, :185-223): one 32-bit word per sample
+    const uint32_t *x16;    // input: x = in_scale * (i16 as f32), widened by the converter warps (x unused)
+    uint32_t *y16;          // output: (out_scale * y) as i16, quantised by the epilogue warps (y unused)
+    float in_scale, out_scale;
 };
+
+// Rust `as i16`: truncate toward zero, saturate, NaN -> 0 (misc_kernels.cu quant_i16).  One conversion-pipe instruction
+// and a clamp per value: this epilogue is short of issue slots, not of conversion throughput
+__device__ __forceinline__ int quant_i16(float v, float scale)
+{
+    const int q = __float2int_rz(__fmul_rn(scale, v));
+    return min(max(q, -32768), 32767);
+}
+__device__ __forceinline__ uint32_t pack_i16(int lo, int hi) { return __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410); }
+__device__ __forceinline__ float2 widen_iq16(uint32_t w, float scale)
+{
+    return make_float2(__fmul_rn(scale, (float)(int16_t)(w & 0xFFFFu)), __fmul_rn(scale, (float)(int16_t)(w >> 16)));
+}
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
@@ -138,7 +155,11 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr)
 __device__ __forceinline__ uint32_t swz128(uint32_t o) { return o ^ (((o >> 7) & 7) << 4); }
 
 // NRAW raw f32 tiles are kept in flight by the TMA warp (2 when shared memory allows, i.e. up to 64 taps, else 1)
-template <int KB, int NRAW>
+__device__ __noinline__ float4 iq16_edge_pair(const Args &a, long long g, int halo);
+
+// IQ16: the raw tiles are i16 IQ words (half the bytes; the first tile's halo is read from the f32 history by the
+// converters, a tile of 16-bit samples never needs the exact fall-back) and the epilogue writes i16 IQ words.
+template <int KB, int NRAW, bool IQ16 = false>
 __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_constant__ Args a)
 {
     constexpr int HALO = RS * (KB - 1);            // complex samples of history per tile
@@ -153,7 +174,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
     unsigned char *sB = smem;                      // B image
     unsigned char *sA = smem + B_BYTES;            // 2 stages x (hi, lo)
     unsigned char *sOut = sA + 2 * A_STAGE;        // 4 warps x 32 rows x 272 B
-    constexpr int RAWB = (TILE + HALO) * 8;        // one raw f32 tile incl. halo
+    constexpr int RAWB = (TILE + HALO) * (IQ16 ? 4 : 8);  // one raw tile incl. halo
     unsigned char *sRaw = sOut + 4 * OUT_WARP;     // NRAW raw tiles (TMA destination)
     __shared__ __align__(8) uint64_t raw_full[NRAW], raw_empty[NRAW];
     __shared__ __align__(8) uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2], sc_ready[8];
@@ -207,10 +228,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
             const long long g0 = (long long)tile * TILE - HALO;
             const long long g_lo = g0 < 0 ? 0 : g0;
             long long g_hi = g0 + TILE + HALO;
-            if (g_hi > (long long)a.n) g_hi = (long long)a.n & ~1ll;
+            if (g_hi > (long long)a.n) g_hi = (long long)a.n & (IQ16 ? ~3ll : ~1ll);  // 16-byte copy granularity
             if (g_hi < g_lo) g_hi = g_lo;
             mbar_wait_long(&raw_empty[rs], ph ^ 1);
             unsigned char *dstb = sRaw + rs * RAWB;
+            if constexpr (IQ16) {
+                if (lane == 0) mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)((g_hi - g_lo) * 4));
+                __syncwarp();
+                for (long long g = g_lo + (long long)lane * 512; g < g_hi; g += 32 * 512) {  // 2 KiB pieces
+                    const long long n = g_hi - g < 512 ? g_hi - g : 512;
+                    tma_load_1d(dstb + (g - g0) * 4, a.x16 + g, (uint32_t)(n * 4), &raw_full[rs]);
+                }
+                continue;
+            }
             if (lane == 0) mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)((g_hi - g_lo) * 8 + (g0 < 0 ? -g0 * 8 : 0)));
             __syncwarp();
             if (g0 < 0 && lane == 31) tma_load_1d(dstb, a.halo + (HALO + g0), (uint32_t)(-g0 * 8), &raw_full[rs]);
@@ -226,7 +256,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
             const long long H = a.hist_len;
             for (long long i = gt; i < H; i += NCONV) {
                 const long long g = (long long)a.n - H + i;
-                a.hist_out[i] = g >= 0 ? a.x[g] : a.hist_in[H + g];
+                if constexpr (IQ16) a.hist_out[i] = g >= 0 ? widen_iq16(a.x16[g], a.in_scale) : a.hist_in[H + g];
+                else a.hist_out[i] = g >= 0 ? a.x[g] : a.hist_in[H + g];
             }
         }
         unsigned long long it = grp;
@@ -241,23 +272,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
             const int rs = (int)(it % NRAW);
             mbar_wait(&raw_full[rs], (uint32_t)((it / NRAW) & 1));
             const float4 *rawt = reinterpret_cast<const float4 *>(sRaw + rs * RAWB);
+            if constexpr (IQ16) {
+                // all the tile's words first (NLD loads in flight), widened branch-free; the first tile's halo (f32
+                // history) and the up to three trailing samples the 16-byte bulk copies leave out are patched afterwards,
+                // out of line, so that the loop every tile runs stays small
+                uint2 rw[NLD];
 #pragma unroll
-            for (int i = 0; i < NLD; ++i) {
-                const int q = gt + i * NCONV;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (q < NPAIR) {
-                    const long long g = t0 - HALO + 2 * q;  // even
-                    if (g < 0 || g + 1 < (long long)a.n) {
-                        v = rawt[q];
-                    } else if (g < (long long)a.n) {  // odd trailing sample: not covered by the 16-byte bulk copies
-                        const float2 t = a.x[g];
-                        v = make_float4(t.x, t.y, 0.f, 0.f);
+                for (int i = 0; i < NLD; ++i) {
+                    const int q = gt + i * NCONV;
+                    rw[i] = q < NPAIR ? reinterpret_cast<const uint2 *>(rawt)[q] : make_uint2(0u, 0u);
+                }
+#pragma unroll
+                for (int i = 0; i < NLD; ++i) {
+                    const float2 s0 = widen_iq16(rw[i].x, a.in_scale), s1 = widen_iq16(rw[i].y, a.in_scale);
+                    raw[i] = make_float4(s0.x, s0.y, s1.x, s1.y);
+                }
+                if (t0 < HALO || t0 + TILE > ((long long)a.n & ~3ll)) {
+#pragma unroll
+                    for (int i = 0; i < NLD; ++i) {
+                        const int q = gt + i * NCONV;
+                        const long long g = t0 - HALO + 2 * q;  // even
+                        if (q < NPAIR && (g < 0 || g + 1 >= ((long long)a.n & ~3ll))) raw[i] = iq16_edge_pair(a, g, HALO);
                     }
                 }
-                raw[i] = v;
-                const float pm = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
-                mx = fmaxf(mx, pm);
-                mnu = min(mnu, __float_as_uint(pm) - 1u);
+#pragma unroll
+                for (int i = 0; i < NLD; ++i) {
+                    const float4 v = raw[i];
+                    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NLD; ++i) {
+                    const int q = gt + i * NCONV;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (q < NPAIR) {
+                        const long long g = t0 - HALO + 2 * q;  // even
+                        if (g < 0 || g + 1 < (long long)a.n) {
+                            v = rawt[q];
+                        } else if (g < (long long)a.n) {  // odd trailing sample: not covered by the 16-byte bulk copies
+                            const float2 t = a.x[g];
+                            v = make_float4(t.x, t.y, 0.f, 0.f);
+                        }
+                    }
+                    raw[i] = v;
+                    const float pm = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+                    mx = fmaxf(mx, pm);
+                    mnu = min(mnu, __float_as_uint(pm) - 1u);
+                }
             }
             mbar_arrive(&raw_empty[rs]);  // tile is in registers: the TMA warp may refill the stage
 #pragma unroll
@@ -353,7 +414,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
         // ------------------------------------------------------------------ epilogue
         const int e = warp - W_EPI;  // TMEM sub-partition = warp % 4
         unsigned char *stage = sOut + e * OUT_WARP;
-        const bool direct = (reinterpret_cast<uintptr_t>(a.y) & 31) == 0;
+        const bool direct = IQ16 ? (reinterpret_cast<uintptr_t>(a.y16) & 31) == 0 : (reinterpret_cast<uintptr_t>(a.y) & 31) == 0;
         unsigned long long it = 0;
         for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int s = (int)(it & 1);
@@ -369,6 +430,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
             // transpose: the staging round trip was 16 B/sample of shared-memory traffic on the busiest pipe);
             // otherwise through the padded per-warp staging buffer and 128-bit coalesced stores.
             const long long row = t0 + (long long)(32 * e + lane) * RS;
+            if constexpr (IQ16) {
+                // 32 output samples = 128 bytes of i16 IQ per lane: 4 x 256-bit stores of 8 words (whole sectors) when
+                // y16 is 32-byte aligned, single words otherwise.  (out_scale * y) as i16 with y formed exactly as the
+                // f32 epilogue forms it, so the words equal quantising the f32 result.
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t p[32], r[32];
+                    tc_ld32(taddr + half * 32, p);
+                    tc_ld32(taddr + 64 + half * 32, r);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        float w[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const float vr = (__uint_as_float(p[16 * c + 2 * u]) + __uint_as_float(r[16 * c + 2 * u])) * k0 * k1;
+                            const float vi = (__uint_as_float(p[16 * c + 2 * u + 1]) + __uint_as_float(r[16 * c + 2 * u + 1])) * k0 * k1;
+                            w[u] = __uint_as_float(pack_i16(quant_i16(vr, a.out_scale), quant_i16(vi, a.out_scale)));
+                        }
+                        const long long sidx = row + 16 * half + 8 * c;  // 8 complex samples = 32 bytes
+                        if (direct && sidx + 7 < (long long)a.n) {
+                            stg_stream8(reinterpret_cast<float *>(a.y16 + sidx), w);
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                if (sidx + u < (long long)a.n) a.y16[sidx + u] = __float_as_uint(w[u]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&t_empty[s]);
+                continue;
+            }
             if (direct) {
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -436,6 +530,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
     }
 }
 
+// samples g, g + 1 of the stream seen by an IQ16 tile where they are not in its raw words: before the batch (f32 history)
+// or in the unaligned tail (read from the i16 words directly), zero past the end
+__device__ __noinline__ float4 iq16_edge_pair(const Args &a, long long g, int halo)
+{
+    float2 s0 = make_float2(0.f, 0.f), s1 = s0;
+    if (g < 0) {
+        s0 = a.halo[halo + g];
+        s1 = a.halo[halo + g + 1];
+    } else {
+        if (g < (long long)a.n) s0 = widen_iq16(a.x16[g], a.in_scale);
+        if (g + 1 < (long long)a.n) s1 = widen_iq16(a.x16[g + 1], a.in_scale);
+    }
+    return make_float4(s0.x, s0.y, s1.x, s1.y);
+}
+
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------ host side
@@ -488,15 +597,15 @@ void fir_tc_build_image(const float2 *taps, uint32_t ntaps, unsigned char *img, 
     }
 }
 
-template <int KB>
+template <int KB, bool IQ16 = false>
 static int launch_tc_kb(const tc::Args &a, cudaStream_t stream)
 {
-    constexpr int RAWB = (tc::TILE + tc::RS * (KB - 1)) * 8;
+    constexpr int RAWB = (tc::TILE + tc::RS * (KB - 1)) * (IQ16 ? 4 : 8);
     constexpr int BASE = KB * 16384 + 2 * tc::A_STAGE + 4 * tc::OUT_WARP + 1024;
     constexpr int NRAW = BASE + 2 * RAWB <= 227 * 1024 ? 2 : 1;
     constexpr int SMEM = BASE + NRAW * RAWB;
     static_assert(SMEM <= 227 * 1024, "fir_tc: shared memory budget");
-    auto kern = tc::fir_tc_kernel<KB, NRAW>;
+    auto kern = tc::fir_tc_kernel<KB, NRAW, IQ16>;
     CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const unsigned long long ntiles = (a.n + tc::TILE - 1) / tc::TILE;
     int dev = 0, sms = 148;
@@ -519,12 +628,48 @@ bool fir_tc_applicable(const FirSeg &seg)
     return ((reinterpret_cast<uintptr_t>(seg.x) | reinterpret_cast<uintptr_t>(seg.y) | reinterpret_cast<uintptr_t>(h)) & 15) == 0;
 }
 
+// i16 IQ on both edges: applicable like the f32 form, on 16-byte aligned word buffers
+bool fir_tc_iq16_applicable(const FirSeg &seg, const int16_t *x16, const int16_t *y16)
+{
+    if (seg.interp != 1 || seg.decim != 1 || seg.ntaps == 0 || seg.ntaps > 128) return false;
+    const int KB = fir_tc_kblocks(seg.ntaps);
+    const uint32_t halo = (uint32_t)tc::RS * (KB - 1);
+    if (seg.hist_len < halo) return false;
+    return (reinterpret_cast<uintptr_t>(x16) & 15) == 0 && (reinterpret_cast<uintptr_t>(y16) & 3) == 0;
+}
+
+int launch_fir_tc_iq16(const FirSeg &seg, const int16_t *x16, float in_scale, int16_t *y16, float out_scale, const void *bimg_dev,
+                       float tap_inv_scale, cudaStream_t stream)
+{
+    if (seg.n_in == 0) return CB_OK;
+    const int KB = fir_tc_kblocks(seg.ntaps);
+    tc::Args a = {};
+    a.halo = seg.hist_in + (seg.hist_len - (uint32_t)tc::RS * (KB - 1));
+    a.hist_in = seg.hist_in;
+    a.hist_out = seg.hist_out;
+    a.bimg = reinterpret_cast<const uint4 *>(bimg_dev);
+    a.n = seg.n_in;
+    a.hist_len = seg.hist_len;
+    a.tap_inv_scale = tap_inv_scale;
+    a.x16 = reinterpret_cast<const uint32_t *>(x16);
+    a.y16 = reinterpret_cast<uint32_t *>(y16);
+    a.in_scale = in_scale;
+    a.out_scale = out_scale;
+    switch (KB) {
+    case 2: return launch_tc_kb<2, true>(a, stream);
+    case 3: return launch_tc_kb<3, true>(a, stream);
+    case 4: return launch_tc_kb<4, true>(a, stream);
+    case 5: return launch_tc_kb<5, true>(a, stream);
+    default: set_error("fir_tc: unsupported tap count %u", seg.ntaps); return CB_ERR_UNSUPPORTED;
+    }
+}
+
 int launch_fir_tc(const FirSeg &seg, const void *bimg_dev, float tap_inv_scale, FirFix *fix, const float2 *taps_dev,
                   cudaStream_t stream)
 {
     if (seg.n_in == 0) return CB_OK;
     const int KB = fir_tc_kblocks(seg.ntaps);
-    tc::Args a;
+    tc::Args a = {};
     a.x = seg.x;
     a.halo = seg.hist_in + (seg.hist_len - (uint32_t)tc::RS * (KB - 1));
     a.y = seg.y;
