@@ -177,7 +177,9 @@ CB_API int cb_fir_run_i16(cb_fir *h, const float *in, size_t n_in, float scale, 
  * interleaved native-endian i16): x = in_scale * (i16 as f32) (in_scale = 1: the plain cast of a
  * Vec<Complex<i16>>), this filter, out = (out_scale * y) as i16 (truncating, saturating).  d_in / in: 2*n_in int16,
  * d_out / out: 2*n_out int16.  Results are identical to cb_convert_i16 -> cb_fir_run -> cb_quantize_i16; every edge
- * carries 4 instead of 8 bytes per sample (the host-pointer form is PCIe-bound: twice the samples per second). */
+ * carries 4 instead of 8 bytes per sample (the host-pointer form is PCIe-bound: twice the samples per second).
+ * Plain filters of up to 128 taps on long batches run as ONE kernel that reads and writes the i16 words itself
+ * (tensor-core FIR, fir_tc_kernel.cu IQ16; 16-byte aligned d_in); other shapes widen, filter and quantise in turn. */
 CB_API int cb_fir_run_dev_iq16(cb_fir *h, const int16_t *d_in, size_t n_in, float in_scale, float out_scale,
                                int16_t *d_out, size_t out_cap, size_t *n_out, void *stream);
 CB_API int cb_fir_run_iq16(cb_fir *h, const int16_t *in, size_t n_in, float in_scale, float out_scale, int16_t *out,
@@ -232,7 +234,9 @@ CB_API int cb_fft_destroy(cb_fft *h);
 CB_API int cb_fft_run(cb_fft *h, const float *in, size_t n_in, float *out);
 CB_API int cb_fft_run_dev(cb_fft *h, const float *d_in, size_t n_in, float *d_out, void *stream);
 CB_API int cb_fft_size(const cb_fft *h, size_t *fft_size, int *inverse);
-/* i16 IQ frames in (IQBatchInput, src/io/raw_iq.rs:78-140): x = in_scale * (i16 as f32); complex f32 spectra out. */
+/* i16 IQ frames in (IQBatchInput, src/io/raw_iq.rs:78-140): x = in_scale * (i16 as f32); complex f32 spectra out.
+ * Power-of-two sizes up to 2^14 and 65536 points widen the samples in the transform's first loads (no extra pass);
+ * spectra are bit-identical to cb_convert_i16 -> cb_fft_run. */
 CB_API int cb_fft_run_iq16(cb_fft *h, const int16_t *in, size_t n_in, float in_scale, float *out);
 CB_API int cb_fft_run_dev_iq16(cb_fft *h, const int16_t *d_in, size_t n_in, float in_scale, float *d_out, void *stream);
 
