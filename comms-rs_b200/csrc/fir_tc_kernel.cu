@@ -157,6 +157,25 @@ __device__ __forceinline__ uint32_t swz128(uint32_t o) { return o ^ (((o >> 7) &
 // NRAW raw f32 tiles are kept in flight by the TMA warp (2 when shared memory allows, i.e. up to 64 taps, else 1)
 __device__ __noinline__ float4 iq16_edge_pair(const Args &a, long long g, int halo);
 
+// scripts/ftc_timeline.cu compiles this file with CB_FTC_STATS: clock64 sums per phase of one thread of every role
+#ifdef CB_FTC_STATS
+__device__ unsigned long long *g_ftc_dbg = nullptr;
+#define FTC_DECL unsigned long long st_[8] = {0}; long long t_ = clock64()
+#define FTC_T(cond, k)                               \
+    if (cond) {                                      \
+        const long long now_ = clock64();            \
+        st_[k] += (unsigned long long)(now_ - t_);   \
+        t_ = now_;                                   \
+    }
+#define FTC_OUT(cond, role)                                                                            \
+    if ((cond) && g_ftc_dbg != nullptr)                                                                \
+        for (int k_ = 0; k_ < 8; ++k_) g_ftc_dbg[((size_t)blockIdx.x * 5 + (role)) * 8 + k_] = st_[k_]
+#else
+#define FTC_DECL
+#define FTC_T(cond, k)
+#define FTC_OUT(cond, role)
+#endif
+
 // IQ16: the raw tiles are i16 IQ words (half the bytes; the first tile's halo is read from the f32 history by the
 // converters, a tile of 16-bit samples never needs the exact fall-back) and the epilogue writes i16 IQ words.
 template <int KB, int NRAW, bool IQ16 = false>
@@ -222,6 +241,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
         // raw stage rs = it % NRAW holds samples g = t0 - HALO + e, e = 0 .. TILE + HALO - 1; the first tile's halo comes
         // from the history buffer; an odd trailing sample (16-byte copy granularity) is left to the converters
         unsigned long long it = 0;
+        FTC_DECL;
         for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int rs = (int)(it % NRAW);
             const uint32_t ph = (uint32_t)((it / NRAW) & 1);
@@ -230,12 +250,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
             long long g_hi = g0 + TILE + HALO;
             if (g_hi > (long long)a.n) g_hi = (long long)a.n & (IQ16 ? ~3ll : ~1ll);  // 16-byte copy granularity
             if (g_hi < g_lo) g_hi = g_lo;
+            FTC_T(lane == 0, 0);
             mbar_wait_long(&raw_empty[rs], ph ^ 1);
+            FTC_T(lane == 0, 1);
             unsigned char *dstb = sRaw + rs * RAWB;
+            // 2 KiB pieces, one per lane.  (Issuing a bulk copy costs the warp ~100 cycles whatever its size and the
+            // lanes' copies serialise: this warp is busy 1700 of a tile's 2800 cycles.  One 33 KiB copy per tile cuts the
+            // tile to 2450 cycles -- and the SM clock under this kernel's load sags from 1.77 to 1.5 GHz, so the time
+            // does not move: profiles/r03x_fir_tc_phases.txt.  Kept as pieces.)
             if constexpr (IQ16) {
                 if (lane == 0) mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)((g_hi - g_lo) * 4));
                 __syncwarp();
-                for (long long g = g_lo + (long long)lane * 512; g < g_hi; g += 32 * 512) {  // 2 KiB pieces
+                for (long long g = g_lo + (long long)lane * 512; g < g_hi; g += 32 * 512) {
                     const long long n = g_hi - g < 512 ? g_hi - g : 512;
                     tma_load_1d(dstb + (g - g0) * 4, a.x16 + g, (uint32_t)(n * 4), &raw_full[rs]);
                 }
@@ -244,11 +270,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
             if (lane == 0) mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)((g_hi - g_lo) * 8 + (g0 < 0 ? -g0 * 8 : 0)));
             __syncwarp();
             if (g0 < 0 && lane == 31) tma_load_1d(dstb, a.halo + (HALO + g0), (uint32_t)(-g0 * 8), &raw_full[rs]);
-            for (long long g = g_lo + (long long)lane * 256; g < g_hi; g += 32 * 256) {  // 2 KiB pieces
+            for (long long g = g_lo + (long long)lane * 256; g < g_hi; g += 32 * 256) {
                 const long long n = g_hi - g < 256 ? g_hi - g : 256;
                 tma_load_1d(dstb + (g - g0) * 8, a.x + g, (uint32_t)(n * 8), &raw_full[rs]);
             }
         }
+        FTC_OUT(lane == 0, 0);
     } else if (warp < W_EPI) {
         // ------------------------------------------------------------------ converters (two groups, even / odd tiles)
         const int grp = warp / NCW, gt = tid - grp * NCONV, gw = warp - grp * NCW;
@@ -261,6 +288,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
             }
         }
         unsigned long long it = grp;
+        FTC_DECL;
         for (unsigned long long tile = blockIdx.x + (unsigned long long)grp * gridDim.x; tile < ntiles;
              tile += 2ull * gridDim.x, it += 2) {
             const int s = grp;
@@ -270,7 +298,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
             float mx = 0.f;            // tile maximum
             uint32_t mnu = 0xffffffffu;  // bits of the smallest non-zero pair maximum, minus one (a zero pair wraps to the top)
             const int rs = (int)(it % NRAW);
+            FTC_T(gt == 0, 0);
             mbar_wait(&raw_full[rs], (uint32_t)((it / NRAW) & 1));
+            FTC_T(gt == 0, 1);
             const float4 *rawt = reinterpret_cast<const float4 *>(sRaw + rs * RAWB);
             if constexpr (IQ16) {
                 // all the tile's words first (NLD loads in flight), widened branch-free; the first tile's halo (f32
@@ -330,7 +360,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
                 red_max[s][gw] = mx;
                 red_min[s][gw] = mnu;
             }
+            FTC_T(gt == 0, 2);
             asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(NCONV) : "memory");
+            FTC_T(gt == 0, 3);
             mx = red_max[s][0];
             mnu = red_min[s][0];
 #pragma unroll
@@ -352,7 +384,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
                 mbar_arrive(&sc_ready[it & 7]);
             }
 
+            FTC_T(gt == 0, 4);
             mbar_wait(&a_empty[s], ph ^ 1);  // MMAs that read this stage two tiles ago are done
+            FTC_T(gt == 0, 5);
             unsigned char *hi = sA + s * A_STAGE, *lo = hi + A_PART;
             __half2 nanacc = __floats2half2_rn(0.f, 0.f);  // sum of the lo terms: NaN iff a sample of the tile is Inf / NaN
 #pragma unroll
@@ -377,10 +411,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
             }
             fence_proxy_async();
             mbar_arrive(&a_full[s]);
+            FTC_T(gt == 0, 6);
             if (a.fix_count != nullptr && (__hisnan(__low2half(nanacc)) || __hisnan(__high2half(nanacc))) &&
                 atomicExch(&fix_seen[s], (unsigned)tile + 1u) != (unsigned)tile + 1u)
                 a.fix_list[atomicAdd(a.fix_count, 1u)] = (unsigned)tile;  // non-finite sample: exact fall-back (FirFix)
         }
+        FTC_OUT(gt == 0, 1 + grp);
     } else if (warp == W_MMA) {
         // ------------------------------------------------------------------ MMA issuer
         // The whole warp runs the loop, one elected lane issues: inside `if (lane == 0)` the compiler cannot prove the
@@ -389,11 +425,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
         // (descriptor = base descriptor + (byte offset >> 4), one UIADD3.64 between two UTCHMMAs).
         unsigned long long it = 0;
         const uint64_t bd0 = tc_desc(smem_u32(sB)), ad0 = tc_desc(smem_u32(sA));
+        FTC_DECL;
         for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int s = (int)(it & 1);
             const uint32_t ph = (uint32_t)((it >> 1) & 1);
+            FTC_T(lane == 0, 0);
             mbar_wait_long(&t_empty[s], ph ^ 1);
+            FTC_T(lane == 0, 1);
             mbar_wait_long(&a_full[s], ph);
+            FTC_T(lane == 0, 2);
             tc_fence_after();
             const uint64_t ahi = ad0 + (uint64_t)((s * A_STAGE) >> 4), alo = ahi + (uint64_t)(A_PART >> 4);
             const uint32_t d = tmem_base + (uint32_t)s * 128u;
@@ -410,19 +450,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
             }
             __syncwarp();
         }
+        FTC_OUT(lane == 0, 3);
     } else {
         // ------------------------------------------------------------------ epilogue
         const int e = warp - W_EPI;  // TMEM sub-partition = warp % 4
         unsigned char *stage = sOut + e * OUT_WARP;
         const bool direct = IQ16 ? (reinterpret_cast<uintptr_t>(a.y16) & 31) == 0 : (reinterpret_cast<uintptr_t>(a.y) & 31) == 0;
         unsigned long long it = 0;
+        FTC_DECL;
         for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int s = (int)(it & 1);
             const uint32_t ph = (uint32_t)((it >> 1) & 1);
             const long long t0 = (long long)tile * TILE;
+            FTC_T(e == 0 && lane == 0, 0);
             mbar_wait(&sc_ready[it & 7], (uint32_t)((it >> 3) & 1));  // acquire the loaders' block scale
             const float k0 = inv_scale[it & 7], k1 = a.tap_inv_scale;
             mbar_wait_long(&t_full[s], ph);
+            FTC_T(e == 0 && lane == 0, 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * e) << 16) + (uint32_t)s * 128u;
             // Lane m of this warp owns row 32 e + m of the tile = 32 consecutive output samples (256 bytes).  With the
@@ -461,6 +505,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
                 }
                 tc_fence_before();
                 mbar_arrive(&t_empty[s]);
+                FTC_T(e == 0 && lane == 0, 2);
                 continue;
             }
             if (direct) {
@@ -488,6 +533,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
                 }
                 tc_fence_before();
                 mbar_arrive(&t_empty[s]);
+                FTC_T(e == 0 && lane == 0, 2);
                 continue;
             }
 #pragma unroll
@@ -520,7 +566,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
                 else if (sidx < (long long)a.n) a.y[sidx] = make_float2(v.x, v.y);
             }
             __syncwarp();
+            FTC_T(e == 0 && lane == 0, 2);
         }
+        FTC_OUT(e == 0 && lane == 0, 4);
     }
 
     tc_fence_before();

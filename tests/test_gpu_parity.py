@@ -790,7 +790,12 @@ def test_fir_full_size_windows_and_properties(cb, oracle):
         for b in range(0, n, B):
             node2.run_dev(x.data_ptr() + 8 * b, B, y2.data_ptr() + 8 * b, B, s)
         torch.cuda.synchronize()
-        assert torch.equal(y.view(torch.float32), y2.view(torch.float32))
+        if not torch.equal(y.view(torch.float32), y2.view(torch.float32)):  # say where: tile, offset, batch
+            bad = torch.nonzero((y.view(torch.int32) != y2.view(torch.int32)).view(-1, 2).any(dim=1)).flatten()
+            tiles = torch.unique(bad // 4096)
+            raise AssertionError(f"batched != one shot: {bad.numel()} samples in {tiles.numel()} tiles, first tiles {tiles[:8].tolist()} "
+                                 f"(tile % 256: {(tiles[:8] % 256).tolist()}), offsets in tile {(bad[:8] % 4096).tolist()}, "
+                                 f"values {y[int(bad[0])].item()} vs {y2[int(bad[0])].item()}")
         assert node.state.tobytes() == node2.state.tobytes()
         del y2
     # impulse response: x = delta at 1000 -> y[1000 + k] = h[k]
