@@ -1,3 +1,6 @@
+"""GPU stress: the 64-tap tensor-core FIR over 2^28 samples, alternately in one call and in 256 calls of 2^20 with carried
+state, N times; every result must equal the first bit for bit (one-shot == batched, run-to-run determinism).
+usage (on a GPU box, from the repo root): python scripts/fir_bitident_stress.py [iterations]"""
 import numpy as np, torch, sys
 sys.path.insert(0, ".")
 import comms_rs_b200 as cb
