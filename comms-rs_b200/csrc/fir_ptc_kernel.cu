@@ -156,17 +156,15 @@ struct Geo {
     static constexpr int NLD = NEL / 2 / NLOAD;        // float4 loads per loader thread per tile
 };
 
-// Rust `as i16` of a float: truncate toward zero, saturate, NaN -> 0 (examples/single_thread_bpsk.rs:40-48)
-// Rust `v as i16` (truncate toward zero, saturate, NaN -> 0) without F2I, which is a slow-pipe instruction
-// and was measured to make the 4 epilogue warps the bottleneck: clamp, add 2^23 to |v| rounding toward zero
-// (the mantissa then holds floor(|v|) <= 32768), restore the sign in two's complement.  Full-rate ALU / FMA ops only.
+// Rust `v as i16` of a float: truncate toward zero, saturate, NaN -> 0 (examples/single_thread_bpsk.rs:40-48): one F2I
+// (saturating to s32, NaN -> 0) and an integer clamp.  An ALU-only form (clamp, add 2^23 to |v| toward zero, restore
+// the sign: 9 full-rate instructions instead of 3) was faster while the epilogue had 4 warps and its conversions
+// queued on the quarter-rate pipe; with 8 epilogue warps the kernel is short of issue slots instead and the F2I form
+// takes pulse4_i16 from 0.389 to 0.298 ms (63 -> 83 % of its 24 B/symbol roof).
 __device__ __forceinline__ uint32_t trunc_i16(float v)
 {
-    v = v == v ? v : 0.f;
-    v = fminf(fmaxf(v, -32768.f), 32767.f);
-    const uint32_t m = __float_as_uint(__fadd_rz(fabsf(v), 8388608.f));  // 0x4B000000 + floor(|v|)
-    const uint32_t s = (uint32_t)((int)__float_as_uint(v) >> 31);         // 0 or 0xFFFFFFFF
-    return (((m & 0xFFFFu) ^ s) - s) & 0xFFFFu;
+    const int q = __float2int_rz(v);
+    return (uint32_t)min(max(q, -32768), 32767) & 0xFFFFu;
 }
 
 // OUT16: the example's quantiser `(8192 x) as i16` fused into the epilogue: 4 bytes written per output
