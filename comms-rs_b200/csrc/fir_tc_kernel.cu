@@ -198,8 +198,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
     __shared__ __align__(8) uint64_t raw_full[NRAW], raw_empty[NRAW];
     __shared__ __align__(8) uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2], sc_ready[8];
     __shared__ uint32_t tmem_slot;
-    __shared__ float red_max[2][NCW];  // [loader group][warp]
-    __shared__ uint32_t red_min[2][NCW];
+    // [loader group][tile parity of the group][warp]: a warp that races ahead writes its next tile's partial result into
+    // the other half, and cannot reach the tile after that before every warp of the group has passed the next
+    // tile's barrier, i.e. has read this tile's values
+    __shared__ float red_max[2][2][NCW];
+    __shared__ uint32_t red_min[2][2][NCW];
     __shared__ unsigned fix_seen[2];  // tile + 1 last appended to the fix-up list by each converter group
     __shared__ float inv_scale[8];
 
@@ -357,18 +360,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const __grid_consta
                 mnu = min(mnu, __shfl_xor_sync(0xffffffffu, mnu, o));
             }
             if (lane == 0) {
-                red_max[s][gw] = mx;
-                red_min[s][gw] = mnu;
+                red_max[s][ph][gw] = mx;
+                red_min[s][ph][gw] = mnu;
             }
             FTC_T(gt == 0, 2);
             asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(NCONV) : "memory");
             FTC_T(gt == 0, 3);
-            mx = red_max[s][0];
-            mnu = red_min[s][0];
+            mx = red_max[s][ph][0];
+            mnu = red_min[s][ph][0];
 #pragma unroll
             for (int w = 1; w < NCW; ++w) {
-                mx = fmaxf(mx, red_max[s][w]);
-                mnu = min(mnu, red_min[s][w]);
+                mx = fmaxf(mx, red_max[s][ph][w]);
+                mnu = min(mnu, red_min[s][ph][w]);
             }
             // a quiet stretch more than 2^20 below the tile maximum (its lo terms go denormal): this tile is recomputed
             // in plain f32 by the fix-up pass (FirFix); non-finite samples are caught in the conversion loop below
