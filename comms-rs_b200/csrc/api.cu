@@ -1374,14 +1374,15 @@ int cb_fir_run_dev_iq16(cb_fir *h, const int16_t *d_in, size_t n_in, float in_sc
         h->cur ^= 1;
         return h->last.end(s);
     }
-    if (h->rscratch_len < n_in + no) {  // widened input followed by the f32 result
+    const size_t res_off = round_up(n_in, (size_t)4);  // the f32 result 32-byte aligned like the input (tensor-core path)
+    if (h->rscratch_len < res_off + no) {  // widened input followed by the f32 result
         if (h->rscratch) CB_CUDA(cudaFree(h->rscratch));
         h->rscratch = nullptr;
         h->rscratch_len = 0;
-        CB_CUDA(cudaMalloc(&h->rscratch, (n_in + no) * sizeof(float2)));
-        h->rscratch_len = n_in + no;
+        CB_CUDA(cudaMalloc(&h->rscratch, (res_off + no) * sizeof(float2)));
+        h->rscratch_len = res_off + no;
     }
-    float2 *wide = h->rscratch, *res = h->rscratch + n_in;
+    float2 *wide = h->rscratch, *res = h->rscratch + res_off;
     rc = launch_convert_i16(d_in, reinterpret_cast<float *>(wide), 2 * n_in, in_scale, s);
     if (rc == CB_OK)
         rc = fir_segment_to_i16(h, wide, n_in, h->hist[h->cur], h->hist[h->cur ^ 1], out_scale, d_out, res, s, 0);

@@ -1050,6 +1050,40 @@ def test_fir_iq16_edges_equal_the_separate_nodes(cb, oracle, ntaps, interp, deci
         assert d.max() <= 1 and (d != 0).mean() < 2e-2  # same values up to the filter's rounding: rarely one LSB apart
 
 
+def test_fir_iq16_device_call_alignments_and_tails(cb, oracle):
+    # cb_fir_run_dev_iq16 on the tensor-core path (fir_tc_kernel IQ16): output buffers that are only 4-byte aligned take
+    # the single-word stores, inputs that are not 16-byte aligned fall back to cast -> filter -> quantise, batch lengths
+    # that are not multiples of four leave up to three samples to the converters -- all must give the same words
+    import torch
+
+    rng = np.random.default_rng(77)
+    taps = rnd_c32(rng, 64)
+    n = 262_144 + 3
+    iq = rng.integers(-32768, 32768, size=(n + 8, 2), dtype=np.int16)
+    d_iq = torch.from_numpy(iq).cuda()
+    d_out = torch.zeros((n + 16, 2), dtype=torch.int16, device="cuda")
+    in_scale, out_scale = 1.0 / 32768.0, 5000.0
+    x = (iq.astype(np.float32) * np.float32(in_scale)).view(np.complex64).ravel()
+    results = {}
+    for in_off, out_off, m in ((0, 0, n), (0, 1, n), (0, 3, n - 1), (1, 0, n), (4, 8, n - 2), (0, 0, n - 3)):
+        node = cb.BatchFirNode(taps)
+        node.state = rnd_c32(np.random.default_rng(5), 64)  # a non-zero history: the first tile's halo is f32, not i16
+        d_out.zero_()
+        got_n = node.run_dev_iq16(d_iq.data_ptr() + 4 * in_off, m, in_scale, out_scale, d_out.data_ptr() + 4 * out_off, m, 0)
+        torch.cuda.synchronize()
+        assert got_n == m
+        out = d_out.cpu().numpy()
+        assert not out[:out_off].any() and not out[out_off + m:].any()  # nothing outside the output range
+        ref = cb.BatchFirNode(taps)
+        ref.state = rnd_c32(np.random.default_rng(5), 64)
+        want = oracle.quantize_i16(ref.run(x[in_off:in_off + m]), out_scale).reshape(-1, 2)
+        d = np.abs(out[out_off:out_off + m].astype(np.int32) - want.astype(np.int32))
+        # aligned input: the fused kernel, bit-identical to quantising the f32 tensor-core result; the fall-back is
+        # identical as well (same three steps)
+        assert d.max() == 0, (in_off, out_off, m, int(d.max()))
+        assert node.state.tobytes() == ref.state.tobytes()
+
+
 def test_fft_iq16_input_equals_cast_then_fft(cb):
     rng = np.random.default_rng(9)
     iq = rng.integers(-32768, 32768, size=(8 * 4096, 2), dtype=np.int16)
