@@ -21,16 +21,20 @@
 // the accumulator), A_lo * B_hi one N=64 MMA into columns 0-63; the epilogue adds the halves.
 // Relative L2 error against the f32 sequential form ~3e-7 (tolerance 1e-5).
 //
-// Roles (416 threads, one persistent CTA per SM, tiles round-robin):
-//   warps 0-3 / 4-7  two loader groups, even / odd tiles of the CTA, each feeding its own A stage:
-//              coalesced LDG.128 of the raw f32 tile (17 in flight per thread) -> block max ->
-//              scale, split, st.shared (pre-swizzled) -> fence.proxy.async -> mbarrier a_full
-//   warp  12   one thread issues 4*KB x 2 tcgen05.mma per tile, tcgen05.commit -> a_empty, t_full
-//   warps 8-11 epilogue: tcgen05.ld (32 lanes x 32 columns) -> add halves, unscale -> padded
-//              shared staging -> coalesced 128-bit streaming stores
-// Two A stages and two TMEM accumulator stages keep the roles overlapped; the loads of tile i+1
-// are in flight while tile i is converted.
-// Algorithmic HBM traffic: 8 B read + 8 B written per sample (halo re-read: 64 B/KB... negligible).
+// Roles (576 threads, one persistent CTA per SM, tiles round-robin):
+//   warp  17     TMA producer: the raw tile (f32, or i16 IQ words with IQ16) HBM -> shared by bulk copies, NRAW stages
+//   warps 0-5 / 6-11  two converter groups, even / odd tiles of the CTA, each feeding its own A stage:
+//              raw tile -> registers (IQ16: widened there) -> block max -> exact power-of-two scale, hi / lo split,
+//              st.shared (pre-swizzled) -> fence.proxy.async -> mbarrier a_full; tiles whose quiet stretches or
+//              non-finite samples the two-term split cannot carry are appended to the exact fall-back's list
+//   warp  16     the whole warp runs the loop, one elected lane issues 4*KB x 2 tcgen05.mma per tile,
+//              tcgen05.commit -> a_empty, t_full
+//   warps 12-15  epilogue: tcgen05.ld (32 lanes x 32 columns) -> add halves, unscale -> 256-bit streaming stores
+//              (IQ16: (out_scale * y) as i16, packed words); a padded shared staging path for unaligned outputs
+// Two A stages and two TMEM accumulator stages keep the roles overlapped; the copies of the next tiles are in flight
+// while a tile is converted.  scripts/ftc_timeline.cu prints where every role's cycles go
+// (profiles/r03x_fir_tc_phases.txt).
+// Algorithmic HBM traffic: 8 B read + 8 B written per sample (IQ16: 4 + 4); the halo re-read is 1.5 %.
 #include <cuda_fp16.h>
 
 #include <vector>
