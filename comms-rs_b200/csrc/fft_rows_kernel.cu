@@ -181,8 +181,8 @@ __device__ __forceinline__ float2 ld_cs_iq16(const uint32_t *p, float scale)
     return make_float2(__fmul_rn(scale, (float)(int16_t)(w & 0xFFFFu)), __fmul_rn(scale, (float)(int16_t)(w >> 16)));
 }
 
-template <bool INV, bool IN16 = false>
-__global__ void __launch_bounds__(256, 4)
+template <bool INV, bool IN16 = false, int MINB = 4>
+__global__ void __launch_bounds__(256, MINB)
 fft65536_fused_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, float2 *__restrict__ scratch,
                       const float2 *__restrict__ twN, unsigned *ticket, unsigned *flags_a, unsigned *flags_b,
                       unsigned long long nframes, unsigned lag, unsigned ring, float in_scale = 1.f)
@@ -578,10 +578,10 @@ static int launch_fused_pf(const FftPlanDev &p, const float2 *in, float2 *out, s
     return CB_OK;
 }
 
-template <bool INV, bool IN16 = false>
-static int launch_fused(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s, float in_scale = 1.f)
+template <bool INV, bool IN16, int MINB>
+static int launch_fused_m(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s, float in_scale)
 {
-    auto kf = fft65536_fused_kernel<INV, IN16>;
+    auto kf = fft65536_fused_kernel<INV, IN16, MINB>;
     CB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
@@ -599,6 +599,18 @@ static int launch_fused(const FftPlanDev &p, const float2 *in, float2 *out, size
     count_launch();
     CB_CUDA(cudaGetLastError());
     return CB_OK;
+}
+
+// CTAs per SM: the kernel compiles to 48 registers without spills when asked to (64 when not), so five CTAs (40 warps)
+// fit beside their 35 KiB buffers -- and are slower (1.128 vs 1.086 ms; six spill: 1.81 ms): more warps in flight do not
+// help a kernel that waits for the memory system.  Four it is; COMMS_B200_FFT_CTAS = 4 | 5 | 6 for comparison.
+template <bool INV, bool IN16 = false>
+static int launch_fused(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s, float in_scale = 1.f)
+{
+    static const int ctas = [] { const char *e = getenv("COMMS_B200_FFT_CTAS"); return e ? atoi(e) : 4; }();
+    if (ctas == 5) return launch_fused_m<INV, IN16, 5>(p, in, out, nframes, s, in_scale);
+    if (ctas == 6) return launch_fused_m<INV, IN16, 6>(p, in, out, nframes, s, in_scale);
+    return launch_fused_m<INV, IN16, 4>(p, in, out, nframes, s, in_scale);
 }
 
 // Frames are processed in groups of p.scratch_frames (the caller sizes the scratch to the whole batch when it
