@@ -207,12 +207,18 @@ def test_fft_chirpz_fused_and_split_forms_agree(cb, oracle, n):
 
 
 @pytest.mark.timeout(300)
-def test_fft65536_two_handles_concurrently(cb, oracle):
+@pytest.mark.parametrize("path", ["default", "rowspf"])
+def test_fft65536_two_handles_concurrently(cb, oracle, path, monkeypatch):
     # two fused 65536-point kernels in flight on different streams share the SMs; the ticket-ordered work
-    # distribution must let both finish (a static item-to-CTA assignment could deadlock here) with right results
+    # distribution must let both finish (a static item-to-CTA assignment could deadlock here) with right results.
+    # rowspf: the prefetching form, whose ninth warp holds two tickets ahead and waits for a dependency only after it
+    # has released its own item
     import threading
 
     import torch
+
+    if path != "default":
+        monkeypatch.setenv("COMMS_B200_FFT_PATH", path)
 
     n, frames = 65536, 512
     xs = [torch.empty(frames * n, dtype=torch.complex64, device="cuda") for _ in range(2)]
