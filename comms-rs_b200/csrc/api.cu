@@ -1067,7 +1067,10 @@ static FirFix *fir_fix_for(cb_fir *h, size_t n, int lane)
         f.cap = 0;
         f.calls = 0;
         const size_t cap = need < 4096 ? 4096 : need * 2;
-        if (cudaMalloc(&f.dev, (cap + 2) * sizeof(unsigned)) != cudaSuccess || cudaMemset(f.dev, 0, 2 * sizeof(unsigned)) != cudaSuccess) {
+        // (the memset runs on the legacy default stream, which non-blocking streams do not wait for: make sure it has
+        // landed before a kernel on the caller's stream reads the counters -- this happens once per handle and growth)
+        if (cudaMalloc(&f.dev, (cap + 2) * sizeof(unsigned)) != cudaSuccess || cudaMemset(f.dev, 0, 2 * sizeof(unsigned)) != cudaSuccess ||
+            cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess) {
             (void)cudaGetLastError();
             if (f.dev) cudaFree(f.dev);
             f.dev = nullptr;
@@ -2174,6 +2177,7 @@ int cb_fm_create(cb_fm **out)
     if (e == cudaSuccess) e = cudaMalloc(&h->prev[1], sizeof(float2));
     if (e == cudaSuccess) e = cudaMemset(h->prev[0], 0, sizeof(float2));  // FM::default (analog.rs:43-47)
     if (e == cudaSuccess) e = cudaMemset(h->prev[1], 0, sizeof(float2));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);  // the handle's non-blocking stream does not wait for it
     if (e != cudaSuccess || h->pipe.init(h->stream)) {
         cb_fm_destroy(h);
         return e != cudaSuccess ? cuda_fail(e, "fm create", __FILE__, __LINE__) : CB_ERR_CUDA;
@@ -2293,6 +2297,7 @@ int cb_chain_create(size_t channels, const double *dphase, const double *phase, 
         if (e == cudaSuccess) e = cudaMalloc(&h->phase[i], channels * sizeof(double));
         if (e == cudaSuccess) e = cudaMemset(h->phase[i], 0, channels * sizeof(double));
     }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);  // the memsets above: non-blocking streams do not wait for them
     if (e == cudaSuccess) e = cudaMalloc(&h->dphase, channels * sizeof(double));
     if (e == cudaSuccess && h->mix) {
         std::vector<double> d(channels), p(channels, 0.0);
