@@ -1277,7 +1277,7 @@ int cb_fir_run(cb_fir *h, const float *in, size_t n_in, float *out, size_t out_c
     // caller's own when it is pinned, the handle's slots around a memcpy when it is pageable), one launch and one wait.
     // Only the CUDA-core kernels take this path (plain loads and stores); history and carried state stay on the device.
     if (chunk == n_in && (n_in + no) * sizeof(float2) <= ZEROCOPY_MAX_BYTES && !(h->tc_img && n_in >= h->tc.min_samples) &&
-        !(h->ols_hf != nullptr && n_in >= 8192)) {
+        !(h->ols_hf != nullptr && n_in >= 8192) && !ranges_overlap(hin, n_in * sizeof(float2), hout, no * sizeof(float2))) {
         const float2 *dx = h->pipe.stage_in ? nullptr : host_device_view(hin);
         float2 *dy = h->pipe.stage_out ? nullptr : const_cast<float2 *>(host_device_view(hout));
         const bool copy_in = dx == nullptr, copy_out = dy == nullptr;

@@ -1002,6 +1002,13 @@ def test_small_host_calls_run_over_pinned_host_memory(cb, oracle, interp, decim)
     assert rel_l2(got, want[::decim]) <= FIR_TOL
     one = cb.BatchFirNode(taps, None, interp=interp, decim=decim).run(x)  # a single large call: copy-engine or TC path
     assert rel_l2(got, one) <= FIR_TOL
+    if interp == 1 and decim == 1:
+        # a pinned buffer used as input AND output of a small host call: not run over host memory in place (the kernel
+        # would read samples it has already overwritten) but through the copy path, which tolerates it
+        buf = torch.from_numpy(x[:4096].copy()).pin_memory()
+        a, b = cb.BatchFirNode(taps), cb.BatchFirNode(taps)
+        cb._lib.check(cb.load().cb_fir_run(a._h, buf.data_ptr(), 4096, buf.data_ptr(), 4096, None))
+        assert buf.numpy().tobytes() == b.run(x[:4096]).tobytes()
 
 
 def test_cpp_graph_message_rate_bench_runs(cb):
