@@ -535,7 +535,7 @@ class Job:
         return sharding.halo_state(prev, nstate if nstate is not None else k, interp)
 
 
-ALSO_DEFAULT = ["fft1024", "fft4096", "ifft4096", "fft65536", "chain", "pulse4_b4096", "poly8x1024"]
+ALSO_DEFAULT = ["fft1024", "fft4096", "ifft4096", "fft65536", "chain", "pulse4_b4096", "poly8x1024", "fir64_iq16"]
 NVLINK_GBS_PER_DIR = 900.0  # NVLink 5, per GPU and direction (B200_PROFILING.md)
 
 
@@ -823,7 +823,8 @@ def run_b200(args, rank, world, local_rank):
         if also:
             line["also"] = also
             line["gpu_launches"] += sum(v.get("gpu_launches", 0) for v in also.values())
-            line["also_note"] = ("the other BASELINE.json configs, same protocol as the headline (CUDA events on the launch "
+            line["also_note"] = ("the other BASELINE.json configs (plus fir64_iq16: the headline filter with i16 IQ on both edges, "
+                                 "src/io/raw_iq.rs, half the PCIe bytes), same protocol as the headline (CUDA events on the launch "
                                  "stream, max over ranks; e2e through the host-pointer C-ABI call; CPU port on one thread on a "
                                  "smaller sample); top-level value / ms_per_step / roofline are the headline workload's alone")
         print(json.dumps(line), flush=True)
