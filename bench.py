@@ -52,6 +52,11 @@ WORKLOADS = {
                  "(fused byte front end, fused real second stage), 2^28 IQ samples per step"),
     "fft4096_iq16": ("fft16", 1 << 28, 12.0, "batched 4096-point FFT of i16 IQ samples (IQBatchInput -> FFT, src/io/raw_iq.rs:78-140; the cast is "
                      "folded into the transform's first loads): 4 B in + 8 B out per sample, 2^28 samples per GPU"),
+    "fft16": ("fft", 1 << 28, 16.0, "batched 16-point FFT over 2^28 complex-f32 samples per GPU"),
+    "fft32": ("fft", 1 << 28, 16.0, "batched 32-point FFT over 2^28 complex-f32 samples per GPU"),
+    "fft64": ("fft", 1 << 28, 16.0, "batched 64-point FFT over 2^28 complex-f32 samples per GPU"),
+    "fft128": ("fft", 1 << 28, 16.0, "batched 128-point FFT over 2^28 complex-f32 samples per GPU"),
+    "fft256": ("fft", 1 << 28, 16.0, "batched 256-point FFT over 2^28 complex-f32 samples per GPU"),
     "fft1024": ("fft", 1 << 28, 16.0, "batched 1024-point FFT over 2^28 complex-f32 samples per GPU"),
     "fft2048": ("fft", 1 << 28, 16.0, "batched 2048-point FFT over 2^28 complex-f32 samples per GPU"),
     "fft16384": ("fft", 1 << 28, 16.0, "batched 16384-point FFT over 2^28 complex-f32 samples per GPU"),

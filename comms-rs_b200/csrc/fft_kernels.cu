@@ -526,9 +526,15 @@ static int launch_frames(const float2 *in, float2 *out, const float2 *tw, size_t
     return CB_OK;
 }
 
+template <int LOG2N, bool INV, bool IN16>
+static int launch_small_frames(const void *in, float in_scale, float2 *out, const float2 *tw2, size_t nframes, cudaStream_t s);
+static bool small_frames_enabled(int log2n);
+
 template <int LOG2N, bool INV>
 static int launch_frames2(const float2 *in, float2 *out, const float2 *tw2, size_t nframes, cudaStream_t s)
 {
+    if constexpr (LOG2N <= 7)
+        if (small_frames_enabled(LOG2N)) return launch_small_frames<LOG2N, INV, false>(in, 1.f, out, tw2, nframes, s);
     using CF = Fft2Cfg<LOG2N>;
     auto kern = fft2_frames_kernel<LOG2N, INV>;
     CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM));
@@ -557,9 +563,99 @@ static int launch_frames2_dir(int log2n, const float2 *in, float2 *out, const fl
     }
 }
 
+// 16 and 32 points (selectable up to 128): the generic kernel gives every thread 16 points of ONE frame, so a warp's
+// accesses are 8 (N = 16) or 16 bytes per lane, a frame apart -- 27 % / 51 % of the HBM roof.  Here a CTA moves 4096 contiguous points
+// (256 / 64 / ... frames) with coalesced 16-byte accesses through a shared-memory image in the passes' padded layout
+// and transforms them in place there (a thread only ever overwrites points of its own frame; block barriers separate
+// the reads and the writes of a pass when a frame has more than one thread).
+template <int LOG2N, bool INV, bool IN16>
+__global__ void __launch_bounds__(256, 4)
+fft2_small_frames_kernel(const void *__restrict__ in_, float in_scale, float2 *__restrict__ out, const float2 *__restrict__ tw,
+                         size_t nframes)
+{
+    using PL = fft2::Plan<LOG2N>;
+    constexpr int N = PL::N, T = PL::T, PADN = PL::PADN, PTS = 4096;
+    static_assert(LOG2N >= 4 && LOG2N <= 7 && PL::P16 == 1, "one radix-16 pass plus at most a remainder pass");
+    extern __shared__ __align__(16) float2 fsm[];
+    const int tid = threadIdx.x;
+    const size_t base = (size_t)blockIdx.x * PTS, total = nframes * (size_t)N;
+    const int live = (int)(total - base < (size_t)PTS ? total - base : (size_t)PTS);  // whole frames: a multiple of N
+    const float2 zero = make_float2(0.f, 0.f);
+    if constexpr (IN16) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(in_) + base;
+        for (int i = tid; i < PTS; i += 256)
+            fsm[(i >> LOG2N) * PADN + fft2::pad16(i & (N - 1))] = i < live ? ldg_iq16(src + i, in_scale) : zero;
+    } else {
+        const float2 *src = reinterpret_cast<const float2 *>(in_) + base;
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            for (int i = 2 * tid; i < PTS; i += 512) {  // pairs never straddle a frame (N is even)
+                const float4 v = i < live ? ldg_stream(reinterpret_cast<const float4 *>(src + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float2 *fr = fsm + (i >> LOG2N) * PADN;
+                fr[fft2::pad16(i & (N - 1))] = make_float2(v.x, v.y);
+                fr[fft2::pad16((i & (N - 1)) + 1)] = make_float2(v.z, v.w);
+            }
+        } else {
+            for (int i = tid; i < PTS; i += 256)
+                fsm[(i >> LOG2N) * PADN + fft2::pad16(i & (N - 1))] = i < live ? ldg_stream2(src + i) : zero;
+        }
+    }
+    __syncthreads();
+    {
+        const int j = tid % T;
+        float2 *S = fsm + (tid / T) * PADN;
+        auto ld = [&](int m) { return S[fft2::pad16(j + m * T)]; };
+        auto st = [&](int idx, float2 v) { S[fft2::pad16(idx)] = v; };
+        auto bar = [] { __syncthreads(); };
+        auto nobar = [] {};
+        if constexpr (T == 1) {
+            fft2::pass16<LOG2N, INV, 0>(j, tw, ld, nobar, st);  // the thread owns its frame
+        } else {
+            fft2::pass16<LOG2N, INV, 0>(j, tw, ld, bar, st);
+            __syncthreads();
+            fft2::pass_rem<LOG2N, INV>(j, tw, ld, bar, st);
+        }
+    }
+    __syncthreads();
+    float2 *dst = out + base;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        for (int i = 2 * tid; i < live; i += 512) {
+            const float2 *fr = fsm + (i >> LOG2N) * PADN;
+            const float2 a = fr[fft2::pad16(i & (N - 1))], b = fr[fft2::pad16((i & (N - 1)) + 1)];
+            stg_stream(reinterpret_cast<float4 *>(dst + i), make_float4(a.x, a.y, b.x, b.y));
+        }
+    } else {
+        for (int i = tid; i < live; i += 256) stg_stream2(dst + i, fsm[(i >> LOG2N) * PADN + fft2::pad16(i & (N - 1))]);
+    }
+}
+
+template <int LOG2N, bool INV, bool IN16>
+static int launch_small_frames(const void *in, float in_scale, float2 *out, const float2 *tw2, size_t nframes, cudaStream_t s)
+{
+    using PL = fft2::Plan<LOG2N>;
+    constexpr int SMEM = (4096 / PL::N) * PL::PADN * (int)sizeof(float2);
+    auto kern = fft2_small_frames_kernel<LOG2N, INV, IN16>;
+    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    kern<<<(unsigned)ceil_div(nframes * (size_t)PL::N, (size_t)4096), 256, SMEM, s>>>(in, in_scale, out, tw2, nframes);
+    count_launch();
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+
+// Measured on 2^28 samples (% of the 16 B/sample roof, staged / generic): 16 points 83 / 27, 32 points 68 / 51,
+// 64 points 69 / 76, 128 points 69 / 107 -- the staged form pays four block barriers and three more shared-memory
+// passes, which only the two smallest sizes win back.  COMMS_B200_FFT_SMALL = generic (never) | staged (16 .. 128).
+static bool small_frames_enabled(int log2n)
+{
+    const char *e = getenv("COMMS_B200_FFT_SMALL");  // read per launch: a test switches it within one process
+    const int mode = (e && strcmp(e, "generic") == 0) ? 0 : ((e && strcmp(e, "staged") == 0) ? 2 : 1);
+    return mode == 2 || (mode == 1 && log2n <= 5);
+}
+
 template <int LOG2N, bool INV>
 static int launch_frames2_iq16(const uint32_t *in, float in_scale, float2 *out, const float2 *tw2, size_t nframes, cudaStream_t s)
 {
+    if constexpr (LOG2N <= 7)
+        if (small_frames_enabled(LOG2N)) return launch_small_frames<LOG2N, INV, true>(in, in_scale, out, tw2, nframes, s);
     using CF = Fft2Cfg<LOG2N>;
     auto kern = fft2_frames_iq16_kernel<LOG2N, INV>;
     CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM));

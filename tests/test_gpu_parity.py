@@ -353,6 +353,39 @@ def test_fft65536_pipelined_cluster_frame_counts(cb, oracle, frames, monkeypatch
         assert np.all(np.abs(e_out / (n * e_in) - 1) < 1e-5)  # every frame: Parseval
 
 
+@pytest.mark.parametrize("n", [16, 32, 64, 128])
+def test_fft_small_sizes_many_frames(cb, oracle, n, monkeypatch):
+    # 16 .. 128 points (fft2_small_frames_kernel; the default for 16 and 32 points, forced here for 64 and 128 as well):
+    # a CTA moves 4096 contiguous points through shared memory; frame
+    # counts that fill CTAs exactly, leave a ragged last CTA, or are smaller than one CTA; forward and inverse; device
+    # buffers that are only 8-byte aligned (scalar accesses instead of 16-byte ones) give the same bits
+    import os
+    import torch
+
+    monkeypatch.setenv("COMMS_B200_FFT_SMALL", "staged")
+    rng = np.random.default_rng(n)
+    per_cta = 4096 // n
+    for frames in (1, per_cta - 1, per_cta, per_cta + 1, 5 * per_cta + 3, 40 * per_cta):
+        x = rnd_c32(rng, frames * n)
+        for inverse in (False, True):
+            got = cb.FFTBatchNode(n, inverse).run(x)
+            want = oracle.fft(x, n, inverse)
+            assert rel_l2(got, want) <= FFT_TOL, (frames, inverse)
+            for f in sorted({0, frames // 2, frames - 1}):
+                assert rel_l2(got[f * n:(f + 1) * n], want[f * n:(f + 1) * n]) <= FFT_TOL, (frames, inverse, f)
+    frames = 3 * per_cta + 5
+    x = rnd_c32(rng, frames * n)
+    d = torch.zeros(frames * n + 1, dtype=torch.complex64, device="cuda")
+    d[1:] = torch.from_numpy(x).cuda()
+    o = torch.zeros(frames * n + 2, dtype=torch.complex64, device="cuda")
+    node = cb.FFTBatchNode(n, False)
+    node.run_dev(d.data_ptr() + 8, frames * n, o.data_ptr() + 8, 0)  # both pointers 8 mod 16
+    torch.cuda.synchronize()
+    res = o.cpu().numpy()
+    assert res[0] == 0 and res[-1] == 0
+    assert res[1:-1].tobytes() == node.run(x).tobytes()
+
+
 @pytest.mark.parametrize("path", ["rows", "rowspf"])
 @pytest.mark.parametrize("frames", [1, 2, 17, 40, 150, 700])
 def test_fft65536_ring_frame_counts(cb, oracle, frames, path, monkeypatch):
