@@ -563,11 +563,12 @@ static int launch_frames2_dir(int log2n, const float2 *in, float2 *out, const fl
     }
 }
 
-// 16 and 32 points (selectable up to 128): the generic kernel gives every thread 16 points of ONE frame, so a warp's
-// accesses are 8 (N = 16) or 16 bytes per lane, a frame apart -- 27 % / 51 % of the HBM roof.  Here a CTA moves 4096 contiguous points
+// 16 .. 128 points: the generic kernel gives every thread 16 points of ONE frame, so a warp's accesses are 8 (N = 16)
+// to 64 bytes per lane, a frame apart -- 27 % of the HBM roof at 16 points, 76 % at 64.  Here a CTA moves 4096 contiguous points
 // (256 / 64 / ... frames) with coalesced 16-byte accesses through a shared-memory image in the passes' padded layout
-// and transforms them in place there (a thread only ever overwrites points of its own frame; block barriers separate
-// the reads and the writes of a pass when a frame has more than one thread).
+// and transforms them in place there (a thread only ever overwrites points of its own frame; warp barriers separate
+// the reads and the writes of a pass when a frame has more than one thread -- a warp owns 512 contiguous points from
+// the first load to the last store, so the CTA never synchronises).
 template <int LOG2N, bool INV, bool IN16>
 __global__ void __launch_bounds__(256, 4)
 fft2_small_frames_kernel(const void *__restrict__ in_, float in_scale, float2 *__restrict__ out, const float2 *__restrict__ tw,
@@ -581,50 +582,60 @@ fft2_small_frames_kernel(const void *__restrict__ in_, float in_scale, float2 *_
     const size_t base = (size_t)blockIdx.x * PTS, total = nframes * (size_t)N;
     const int live = (int)(total - base < (size_t)PTS ? total - base : (size_t)PTS);  // whole frames: a multiple of N
     const float2 zero = make_float2(0.f, 0.f);
+    // every warp stages, transforms and writes back its own 512 contiguous points (32 / T whole frames): warp barriers
+    // only, the eight warps of the CTA never wait for each other
+    const int w0 = (tid >> 5) * 512, lane = tid & 31;
     if constexpr (IN16) {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(in_) + base;
-        for (int i = tid; i < PTS; i += 256)
+        for (int i = w0 + lane; i < w0 + 512; i += 32)
             fsm[(i >> LOG2N) * PADN + fft2::pad16(i & (N - 1))] = i < live ? ldg_iq16(src + i, in_scale) : zero;
     } else {
         const float2 *src = reinterpret_cast<const float2 *>(in_) + base;
         if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-            for (int i = 2 * tid; i < PTS; i += 512) {  // pairs never straddle a frame (N is even)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {  // pairs never straddle a frame (N is even)
+                const int i = w0 + 2 * lane + 64 * k;
                 const float4 v = i < live ? ldg_stream(reinterpret_cast<const float4 *>(src + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 float2 *fr = fsm + (i >> LOG2N) * PADN;
                 fr[fft2::pad16(i & (N - 1))] = make_float2(v.x, v.y);
                 fr[fft2::pad16((i & (N - 1)) + 1)] = make_float2(v.z, v.w);
             }
         } else {
-            for (int i = tid; i < PTS; i += 256)
+            for (int i = w0 + lane; i < w0 + 512; i += 32)
                 fsm[(i >> LOG2N) * PADN + fft2::pad16(i & (N - 1))] = i < live ? ldg_stream2(src + i) : zero;
         }
     }
-    __syncthreads();
+    __syncwarp();
     {
         const int j = tid % T;
         float2 *S = fsm + (tid / T) * PADN;
         auto ld = [&](int m) { return S[fft2::pad16(j + m * T)]; };
         auto st = [&](int idx, float2 v) { S[fft2::pad16(idx)] = v; };
-        auto bar = [] { __syncthreads(); };
+        auto bar = [] { __syncwarp(); };  // a frame's T <= 8 threads sit in one warp
         auto nobar = [] {};
         if constexpr (T == 1) {
             fft2::pass16<LOG2N, INV, 0>(j, tw, ld, nobar, st);  // the thread owns its frame
         } else {
             fft2::pass16<LOG2N, INV, 0>(j, tw, ld, bar, st);
-            __syncthreads();
+            __syncwarp();
             fft2::pass_rem<LOG2N, INV>(j, tw, ld, bar, st);
         }
     }
-    __syncthreads();
+    __syncwarp();
     float2 *dst = out + base;
     if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-        for (int i = 2 * tid; i < live; i += 512) {
-            const float2 *fr = fsm + (i >> LOG2N) * PADN;
-            const float2 a = fr[fft2::pad16(i & (N - 1))], b = fr[fft2::pad16((i & (N - 1)) + 1)];
-            stg_stream(reinterpret_cast<float4 *>(dst + i), make_float4(a.x, a.y, b.x, b.y));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = w0 + 2 * lane + 64 * k;
+            if (i < live) {
+                const float2 *fr = fsm + (i >> LOG2N) * PADN;
+                const float2 a = fr[fft2::pad16(i & (N - 1))], b = fr[fft2::pad16((i & (N - 1)) + 1)];
+                stg_stream(reinterpret_cast<float4 *>(dst + i), make_float4(a.x, a.y, b.x, b.y));
+            }
         }
     } else {
-        for (int i = tid; i < live; i += 256) stg_stream2(dst + i, fsm[(i >> LOG2N) * PADN + fft2::pad16(i & (N - 1))]);
+        for (int i = w0 + lane; i < w0 + 512 && i < live; i += 32)
+            stg_stream2(dst + i, fsm[(i >> LOG2N) * PADN + fft2::pad16(i & (N - 1))]);
     }
 }
 
@@ -641,14 +652,14 @@ static int launch_small_frames(const void *in, float in_scale, float2 *out, cons
     return CB_OK;
 }
 
-// Measured on 2^28 samples (% of the 16 B/sample roof, staged / generic): 16 points 83 / 27, 32 points 68 / 51,
-// 64 points 69 / 76, 128 points 69 / 107 -- the staged form pays four block barriers and three more shared-memory
-// passes, which only the two smallest sizes win back.  COMMS_B200_FFT_SMALL = generic (never) | staged (16 .. 128).
+// Measured on 2^28 samples (% of the 16 B/sample roof, this kernel / the generic one): 16 points 106 / 27, 32 points
+// 107 / 51, 64 points 106 / 76, 128 points 106 / 107.  (A first form with block barriers around the staging reached
+// only 83 / 68 / 69 / 69: what matters is that the warps never wait for each other.)
+// COMMS_B200_FFT_SMALL = generic: the generic frames kernel for these sizes too (for comparison).
 static bool small_frames_enabled(int log2n)
 {
     const char *e = getenv("COMMS_B200_FFT_SMALL");  // read per launch: a test switches it within one process
-    const int mode = (e && strcmp(e, "generic") == 0) ? 0 : ((e && strcmp(e, "staged") == 0) ? 2 : 1);
-    return mode == 2 || (mode == 1 && log2n <= 5);
+    return !(e && strcmp(e, "generic") == 0) && log2n <= 7;
 }
 
 template <int LOG2N, bool INV>

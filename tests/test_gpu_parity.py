@@ -355,14 +355,13 @@ def test_fft65536_pipelined_cluster_frame_counts(cb, oracle, frames, monkeypatch
 
 @pytest.mark.parametrize("n", [16, 32, 64, 128])
 def test_fft_small_sizes_many_frames(cb, oracle, n, monkeypatch):
-    # 16 .. 128 points (fft2_small_frames_kernel; the default for 16 and 32 points, forced here for 64 and 128 as well):
+    # 16 .. 128 points (fft2_small_frames_kernel):
     # a CTA moves 4096 contiguous points through shared memory; frame
     # counts that fill CTAs exactly, leave a ragged last CTA, or are smaller than one CTA; forward and inverse; device
     # buffers that are only 8-byte aligned (scalar accesses instead of 16-byte ones) give the same bits
     import os
     import torch
 
-    monkeypatch.setenv("COMMS_B200_FFT_SMALL", "staged")
     rng = np.random.default_rng(n)
     per_cta = 4096 // n
     for frames in (1, per_cta - 1, per_cta, per_cta + 1, 5 * per_cta + 3, 40 * per_cta):
