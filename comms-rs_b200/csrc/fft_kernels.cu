@@ -1030,6 +1030,114 @@ int fft_plan_split(size_t n, int *log2n1, int *log2n2)
     return CB_OK;
 }
 
+// ---------------------------------------------------------------- 8192 / 16384 points: two levels inside one CTA
+// N = 256 x N2 (N2 = 32 / 64), n = N2 a + b, k = k1 + 256 k2:
+//   X[k1 + 256 k2] = sum_b W_N2^{b k2} { W_N^{b k1} sum_a x[N2 a + b] W_256^{a k1} }
+// The generic kernel runs four radix passes over the whole frame with two block barriers each.  Here the frame is
+// transposed into shared memory while it is loaded (row b = the 256 points x[N2 a + b], pitch 273), the 256-point
+// transform of a row is done by 16 threads of ONE warp (two radix-16 passes, warp barriers), and after one block
+// barrier the N2-point transform of a column k1 is done by 2 / 4 adjacent threads (radix 16 + radix 2 / 4, warp
+// barriers) which store X[k1 + 256 k2] straight to global memory, 16 / 8 consecutive k1 per store instruction.
+// Two block barriers per frame instead of seven -- and slower all the same (see two_level_enabled below): kept selectable.
+template <int LOG2N, bool INV, bool IN16>
+__global__ void __launch_bounds__((1 << LOG2N) / 16, LOG2N == 13 ? 2 : 1)
+fft2_two_level_kernel(const void *__restrict__ in_, float in_scale, float2 *__restrict__ out, const float2 *__restrict__ twN,
+                      size_t nframes)
+{
+    using namespace fft2;
+    constexpr int N = 1 << LOG2N, L2 = LOG2N - 8, N2 = 1 << L2, NT = N / 16, T2 = N2 / 16, RP = 273;
+    using P2 = Plan<L2>;
+    extern __shared__ __align__(16) float2 fsm[];  // A[N2][RP], then twS[N2]
+    float2 *twS = fsm + N2 * RP;
+    const int tid = threadIdx.x;
+    const size_t frame = blockIdx.x;
+    if (frame >= nframes) return;
+    const float2 *src = reinterpret_cast<const float2 *>(in_) + frame * N;
+    float2 *dst = out + frame * N;
+    if (tid < N2) twS[tid] = __ldg(twN + 256 * tid);  // W_N2^s = W_N^{256 s}: the remainder pass's table
+    // coalesced load, transposed store: n = N2 a + b -> A[b][pad16(a)]
+    if constexpr (IN16) {  // i16 IQ words, widened here (src/io/raw_iq.rs:78-140)
+        const uint32_t *src16 = reinterpret_cast<const uint32_t *>(in_) + frame * N;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int n = tid + NT * k;
+            fsm[(n & (N2 - 1)) * RP + pad16(n >> L2)] = ldg_iq16(src16 + n, in_scale);
+        }
+    } else if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int n = 2 * tid + 2 * NT * k;
+            const float4 v = ldg_stream(reinterpret_cast<const float4 *>(src + n));
+            const int b = n & (N2 - 1), a = n >> L2;
+            fsm[b * RP + pad16(a)] = make_float2(v.x, v.y);
+            fsm[(b + 1) * RP + pad16(a)] = make_float2(v.z, v.w);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int n = tid + NT * k;
+            fsm[(n & (N2 - 1)) * RP + pad16(n >> L2)] = ldg_stream2(src + n);
+        }
+    }
+    __syncthreads();
+    {   // level 1: row b, 16 threads of one warp
+        const int b = tid >> 4, j = tid & 15;
+        float2 *row = fsm + b * RP;
+        float2 v[16];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) v[m] = row[pad16(j + 16 * m)];
+        __syncwarp();
+        bfly16<INV>(v);
+#pragma unroll
+        for (int sl = 0; sl < 16; ++sl) row[pad16(16 * j + q16(sl))] = v[sl];
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 16; ++m) v[m] = row[pad16(j + 16 * m)];
+        twiddle16(v, __ldg(twN + N2 * j));  // W_256^j
+        bfly16<INV>(v);
+#pragma unroll
+        for (int sl = 0; sl < 16; ++sl) row[pad16(j + 16 * q16(sl))] = v[sl];  // Y_b[k1] at k1: the slots this thread read
+    }
+    __syncthreads();
+    {   // level 2: column k1, T2 adjacent threads
+        const int k1 = tid / T2, j2 = tid % T2;
+        float2 *col = fsm + pad16(k1);
+        float2 v[16];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) v[m] = col[(j2 + T2 * m) * RP];
+        twiddle16c(v, __ldg(twN + k1 * j2), __ldg(twN + k1 * T2));  // W_N^{k1 b}, b = j2 + T2 m
+        auto ld0 = [&](int m) { return v[m]; };
+        auto ld = [&](int m) { return col[(j2 + T2 * m) * RP]; };
+        auto st = [&](int idx, float2 val) { col[idx * RP] = val; };
+        auto bar = [] { __syncwarp(); };
+        auto gst = [&](int idx, float2 val) { stg_stream2(dst + k1 + 256 * idx, val); };
+        pass16<L2, INV, 0>(j2, twS, ld0, bar, st);
+        __syncwarp();
+        pass_rem<L2, INV>(j2, twS, ld, bar, gst);
+    }
+}
+
+template <int LOG2N, bool INV, bool IN16 = false>
+static int launch_two_level(const void *in, float2 *out, const float2 *twN, size_t nframes, cudaStream_t s, float in_scale = 1.f)
+{
+    constexpr int N2 = 1 << (LOG2N - 8), SMEM = (N2 * 273 + N2) * (int)sizeof(float2);
+    auto kern = fft2_two_level_kernel<LOG2N, INV, IN16>;
+    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    kern<<<(unsigned)nframes, (1 << LOG2N) / 16, SMEM, s>>>(in, in_scale, out, twN, nframes);
+    count_launch();
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+
+// Measured (2^28 samples, % of the 16 B/sample roof, two-level / generic): 8192 points 58 / 77, 16384 points 39 / 58 --
+// the column accesses at a pitch of 273 and the transposing stores conflict two ways, a CTA does one frame and the
+// 16384-point stores are 64-byte pieces: the generic kernel stays the default.  COMMS_B200_FFT_8K16K = two selects this one.
+static bool two_level_enabled()
+{
+    const char *e = getenv("COMMS_B200_FFT_8K16K");  // read per launch: a test switches it within one process
+    return e && strcmp(e, "two") == 0;
+}
+
 // true when launch_fft_iq16 reads the i16 IQ samples itself (otherwise the caller widens them first)
 bool fft_fuses_iq16(const FftPlanDev &p, size_t nframes)
 {
@@ -1042,6 +1150,13 @@ int launch_fft_iq16(const FftPlanDev &p, const int16_t *in, float in_scale, floa
 {
     if (nframes == 0) return CB_OK;
     const uint32_t *in32 = reinterpret_cast<const uint32_t *>(in);
+    if (p.kind == FFT_SINGLE && p.tw != nullptr && (p.log2n == 13 || p.log2n == 14) && nframes < (1ull << 31) && two_level_enabled()) {
+        if (p.log2n == 13)
+            return p.inverse ? launch_two_level<13, true, true>(in, out, p.tw, nframes, s, in_scale)
+                             : launch_two_level<13, false, true>(in, out, p.tw, nframes, s, in_scale);
+        return p.inverse ? launch_two_level<14, true, true>(in, out, p.tw, nframes, s, in_scale)
+                         : launch_two_level<14, false, true>(in, out, p.tw, nframes, s, in_scale);
+    }
     if (p.kind == FFT_SINGLE)
         return p.inverse ? launch_frames2_iq16_dir<true>(p.log2n, in32, in_scale, out, p.tw16, nframes, s)
                          : launch_frames2_iq16_dir<false>(p.log2n, in32, in_scale, out, p.tw16, nframes, s);
@@ -1051,6 +1166,11 @@ int launch_fft_iq16(const FftPlanDev &p, const int16_t *in, float in_scale, floa
 int launch_fft(const FftPlanDev &p, const float2 *in, float2 *out, size_t nframes, cudaStream_t s)
 {
     if (nframes == 0) return CB_OK;
+    if (p.kind == FFT_SINGLE && p.tw != nullptr && (p.log2n == 13 || p.log2n == 14) && nframes < (1ull << 31) && two_level_enabled()) {
+        if (p.log2n == 13)
+            return p.inverse ? launch_two_level<13, true>(in, out, p.tw, nframes, s) : launch_two_level<13, false>(in, out, p.tw, nframes, s);
+        return p.inverse ? launch_two_level<14, true>(in, out, p.tw, nframes, s) : launch_two_level<14, false>(in, out, p.tw, nframes, s);
+    }
     if (p.kind == FFT_SINGLE && p.tw16 != nullptr && p.log2n >= 4) {
         return p.inverse ? launch_frames2_dir<true>(p.log2n, in, out, p.tw16, nframes, s)
                          : launch_frames2_dir<false>(p.log2n, in, out, p.tw16, nframes, s);

@@ -385,6 +385,39 @@ def test_fft_small_sizes_many_frames(cb, oracle, n, monkeypatch):
     assert res[1:-1].tobytes() == node.run(x).tobytes()
 
 
+@pytest.mark.parametrize("n", [8192, 16384])
+def test_fft_8192_16384_two_level_kernel(cb, oracle, n, monkeypatch):
+    # fft2_two_level_kernel: 256 x 32 / 256 x 64 inside one CTA (rows by half-warps, columns by 2 / 4 adjacent threads);
+    # several frame counts, both directions, 8-byte aligned device buffers (scalar loads), and agreement with the
+    # generic radix-16 kernel (the default)
+    import torch
+
+    monkeypatch.setenv("COMMS_B200_FFT_8K16K", "two")  # not the default: the generic kernel measured faster
+    rng = np.random.default_rng(n + 5)
+    for frames in (1, 5, 37):
+        x = rnd_c32(rng, frames * n)
+        x[(frames // 2) * n:(frames // 2 + 1) * n] = 0
+        x[(frames // 2) * n + 4321] = 1  # an impulse frame: every output has modulus 1 and a known phase
+        for inverse in (False, True):
+            got = cb.FFTBatchNode(n, inverse).run(x)
+            for f in sorted({0, frames // 2, frames - 1}):
+                want = oracle.fft(x[f * n:(f + 1) * n], n, inverse)
+                assert rel_l2(got[f * n:(f + 1) * n], want) <= FFT_TOL, (frames, inverse, f)
+    frames = 7
+    x = rnd_c32(rng, frames * n)
+    node = cb.FFTBatchNode(n, False)
+    ref = node.run(x)
+    d = torch.zeros(frames * n + 1, dtype=torch.complex64, device="cuda")
+    d[1:] = torch.from_numpy(x).cuda()
+    o = torch.zeros(frames * n + 2, dtype=torch.complex64, device="cuda")
+    node.run_dev(d.data_ptr() + 8, frames * n, o.data_ptr() + 8, 0)
+    torch.cuda.synchronize()
+    res = o.cpu().numpy()
+    assert res[0] == 0 and res[-1] == 0 and res[1:-1].tobytes() == ref.tobytes()
+    monkeypatch.setenv("COMMS_B200_FFT_8K16K", "generic")
+    assert rel_l2(cb.FFTBatchNode(n, False).run(x), ref) <= 2e-6
+
+
 @pytest.mark.parametrize("path", ["rows", "rowspf"])
 @pytest.mark.parametrize("frames", [1, 2, 17, 40, 150, 700])
 def test_fft65536_ring_frame_counts(cb, oracle, frames, path, monkeypatch):
