@@ -1034,7 +1034,7 @@ int fft_plan_split(size_t n, int *log2n1, int *log2n2)
 // N = 256 x N2 (N2 = 32 / 64), n = N2 a + b, k = k1 + 256 k2:
 //   X[k1 + 256 k2] = sum_b W_N2^{b k2} { W_N^{b k1} sum_a x[N2 a + b] W_256^{a k1} }
 // The generic kernel runs four radix passes over the whole frame with two block barriers each.  Here the frame is
-// transposed into shared memory while it is loaded (row b = the 256 points x[N2 a + b], pitch 273), the 256-point
+// transposed into shared memory while it is loaded (row b = the 256 points x[N2 a + b], pitch 304 + a rotation), the 256-point
 // transform of a row is done by 16 threads of ONE warp (two radix-16 passes, warp barriers), and after one block
 // barrier the N2-point transform of a column k1 is done by 2 / 4 adjacent threads (radix 16 + radix 2 / 4, warp
 // barriers) which store X[k1 + 256 k2] straight to global memory, 16 / 8 consecutive k1 per store instruction.
@@ -1045,7 +1045,12 @@ fft2_two_level_kernel(const void *__restrict__ in_, float in_scale, float2 *__re
                       size_t nframes)
 {
     using namespace fft2;
-    constexpr int N = 1 << LOG2N, L2 = LOG2N - 8, N2 = 1 << L2, NT = N / 16, T2 = N2 / 16, RP = 273;
+    constexpr int N = 1 << LOG2N, L2 = LOG2N - 8, N2 = 1 << L2, NT = N / 16, T2 = N2 / 16, RP = 304;
+    // row b starts at b * RP + (b / T2) + (16 / T2) * (b % T2): a multiple-of-16 pitch plus a rotation that puts the rows
+    // of one staging store (b = 2 i or 2 i + 1) AND the T2 rows of one column access (b = j2 + T2 m) into different
+    // banks -- with a plain odd pitch the 2 / 4 adjacent threads of a column sat one row = two banks apart and every
+    // half-warp access took two wavefronts (profiles/r04s_ncu_full_fft8192_two_level.csv)
+    auto rb = [](int b) { return b * RP + (b / T2) + (16 / T2) * (b % T2); };
     using P2 = Plan<L2>;
     extern __shared__ __align__(16) float2 fsm[];  // A[N2][RP], then twS[N2]
     float2 *twS = fsm + N2 * RP;
@@ -1061,7 +1066,7 @@ fft2_two_level_kernel(const void *__restrict__ in_, float in_scale, float2 *__re
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             const int n = tid + NT * k;
-            fsm[(n & (N2 - 1)) * RP + pad16(n >> L2)] = ldg_iq16(src16 + n, in_scale);
+            fsm[rb(n & (N2 - 1)) + pad16(n >> L2)] = ldg_iq16(src16 + n, in_scale);
         }
     } else if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
 #pragma unroll
@@ -1069,20 +1074,20 @@ fft2_two_level_kernel(const void *__restrict__ in_, float in_scale, float2 *__re
             const int n = 2 * tid + 2 * NT * k;
             const float4 v = ldg_stream(reinterpret_cast<const float4 *>(src + n));
             const int b = n & (N2 - 1), a = n >> L2;
-            fsm[b * RP + pad16(a)] = make_float2(v.x, v.y);
-            fsm[(b + 1) * RP + pad16(a)] = make_float2(v.z, v.w);
+            fsm[rb(b) + pad16(a)] = make_float2(v.x, v.y);
+            fsm[rb(b + 1) + pad16(a)] = make_float2(v.z, v.w);
         }
     } else {
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             const int n = tid + NT * k;
-            fsm[(n & (N2 - 1)) * RP + pad16(n >> L2)] = ldg_stream2(src + n);
+            fsm[rb(n & (N2 - 1)) + pad16(n >> L2)] = ldg_stream2(src + n);
         }
     }
     __syncthreads();
     {   // level 1: row b, 16 threads of one warp
         const int b = tid >> 4, j = tid & 15;
-        float2 *row = fsm + b * RP;
+        float2 *row = fsm + rb(b);
         float2 v[16];
 #pragma unroll
         for (int m = 0; m < 16; ++m) v[m] = row[pad16(j + 16 * m)];
@@ -1104,11 +1109,11 @@ fft2_two_level_kernel(const void *__restrict__ in_, float in_scale, float2 *__re
         float2 *col = fsm + pad16(k1);
         float2 v[16];
 #pragma unroll
-        for (int m = 0; m < 16; ++m) v[m] = col[(j2 + T2 * m) * RP];
+        for (int m = 0; m < 16; ++m) v[m] = col[rb(j2 + T2 * m)];
         twiddle16c(v, __ldg(twN + k1 * j2), __ldg(twN + k1 * T2));  // W_N^{k1 b}, b = j2 + T2 m
         auto ld0 = [&](int m) { return v[m]; };
-        auto ld = [&](int m) { return col[(j2 + T2 * m) * RP]; };
-        auto st = [&](int idx, float2 val) { col[idx * RP] = val; };
+        auto ld = [&](int m) { return col[rb(j2 + T2 * m)]; };
+        auto st = [&](int idx, float2 val) { col[rb(idx)] = val; };
         auto bar = [] { __syncwarp(); };
         auto gst = [&](int idx, float2 val) { stg_stream2(dst + k1 + 256 * idx, val); };
         pass16<L2, INV, 0>(j2, twS, ld0, bar, st);
@@ -1120,7 +1125,7 @@ fft2_two_level_kernel(const void *__restrict__ in_, float in_scale, float2 *__re
 template <int LOG2N, bool INV, bool IN16 = false>
 static int launch_two_level(const void *in, float2 *out, const float2 *twN, size_t nframes, cudaStream_t s, float in_scale = 1.f)
 {
-    constexpr int N2 = 1 << (LOG2N - 8), SMEM = (N2 * 273 + N2) * (int)sizeof(float2);
+    constexpr int N2 = 1 << (LOG2N - 8), SMEM = (N2 * 304 + N2) * (int)sizeof(float2);
     auto kern = fft2_two_level_kernel<LOG2N, INV, IN16>;
     CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     kern<<<(unsigned)nframes, (1 << LOG2N) / 16, SMEM, s>>>(in, in_scale, out, twN, nframes);
@@ -1129,9 +1134,10 @@ static int launch_two_level(const void *in, float2 *out, const float2 *twN, size
     return CB_OK;
 }
 
-// Measured (2^28 samples, % of the 16 B/sample roof, two-level / generic): 8192 points 58 / 77, 16384 points 39 / 58 --
-// the column accesses at a pitch of 273 and the transposing stores conflict two ways, a CTA does one frame and the
-// 16384-point stores are 64-byte pieces: the generic kernel stays the default.  COMMS_B200_FFT_8K16K = two selects this one.
+// Measured (2^28 samples, % of the 16 B/sample roof, two-level / generic): 8192 points 70 / 77, 16384 points 53 / 58
+// (58 / 39 before the rotated row layout removed the column accesses' bank conflicts).  Still behind: more shared-memory
+// passes per point than the four-pass kernel, one frame per CTA, 64-byte store pieces at 16384 points.  The generic
+// kernel stays the default; COMMS_B200_FFT_8K16K = two selects this one.
 static bool two_level_enabled()
 {
     const char *e = getenv("COMMS_B200_FFT_8K16K");  // read per launch: a test switches it within one process
