@@ -346,6 +346,115 @@ def test_two_step_fft_split_algebra(L1, L2):
         assert np.linalg.norm(got - want) <= 1e-11 * np.linalg.norm(want)
 
 
+@pytest.mark.parametrize("L2", [5, 6])
+def test_two_level_fft_layout_is_conflict_free_and_covers_the_frame(L2):
+    # fft2_two_level_kernel (fft_kernels.cu), 8192 / 16384 points = 256 x N2: element (b, a) of the transposed frame lives
+    # at rb(b) + pad16(a) with rb(b) = b * 304 + b // T2 + (16 // T2) * (b % T2).  (1) no two elements share a word;
+    # (2) the 16 lanes of a half-warp hit 16 different 8-byte banks in all three access patterns: the transposing store
+    # (b = 2 i resp. 2 i + 1, a fixed), the row accesses of level 1 (positions 17 m + j and 17 j + q of one row) and the
+    # column accesses of level 2 (k1 = k0 .. k0 + 16 / T2 - 1, b = j2 + T2 m, j2 < T2).
+    N2 = 1 << L2
+    T2, RP = N2 // 16, 304
+    pad16 = lambda i: i + (i >> 4)
+    rb = lambda b: b * RP + b // T2 + (16 // T2) * (b % T2)
+    cells = {rb(b) + pad16(a) for b in range(N2) for a in range(256)}
+    assert len(cells) == N2 * 256 and max(cells) < N2 * RP  # injective, inside the buffer (the table follows it)
+    bank = lambda addr: addr % 16
+    for a in (0, 1, 15, 16, 255):
+        for half in range(N2 // 32 if N2 >= 32 else 1):
+            for odd in (0, 1):
+                lanes = [rb(2 * i + odd + 32 * half) + pad16(a) for i in range(16)]
+                assert len({bank(x) for x in lanes}) == 16
+    for b in (0, 1, N2 - 1):
+        for m in range(16):
+            assert len({bank(rb(b) + pad16(j + 16 * m)) for j in range(16)}) == 16
+        for q in range(16):
+            assert len({bank(rb(b) + pad16(16 * j + q)) for j in range(16)}) == 16
+    per = 16 // T2
+    for k0 in range(0, 256, per):
+        for m in range(16):
+            lanes = [rb(j2 + T2 * m) + pad16(k0 + i) for i in range(per) for j2 in range(T2)]
+            assert len({bank(x) for x in lanes}) == 16, (k0, m)
+    # and the algebra: X[k1 + 256 k2] = sum_b W_N2^{b k2} { W_N^{b k1} sum_a x[N2 a + b] W_256^{a k1} }
+    N = 256 * N2
+    rng = np.random.default_rng(L2)
+    x = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    Y = np.fft.fft(x.reshape(256, N2), axis=0)                       # rows b (columns of this view): Y[k1][b]
+    k1, b = np.meshgrid(np.arange(256), np.arange(N2), indexing="ij")
+    X = np.fft.fft(Y * np.exp(-2j * np.pi * (k1 * b) / N), axis=1)    # X[k1][k2]
+    assert np.linalg.norm(X.T.reshape(-1) - np.fft.fft(x)) <= 1e-10 * np.linalg.norm(x) * np.sqrt(N)
+
+
+@pytest.mark.parametrize("log2n", [4, 5, 6, 7])
+def test_small_fft_staging_is_warp_local(log2n):
+    # fft2_small_frames_kernel: warp w of the CTA stages points [512 w, 512 w + 512) of the CTA's 4096, thread t transforms
+    # frame t // T with T = N / 16 threads per frame.  The frames a warp's threads transform must be exactly the frames
+    # whose points that warp staged (so that warp barriers suffice), and a pair of points loaded together never
+    # straddles two frames.
+    N = 1 << log2n
+    T = N // 16
+    for w in range(8):
+        staged = {i >> log2n for i in range(512 * w, 512 * w + 512)}
+        transformed = {t // T for t in range(32 * w, 32 * w + 32)}
+        assert staged == transformed
+    assert all((i >> log2n) == ((i + 1) >> log2n) for i in range(0, 4096, 2))
+
+
+@pytest.mark.parametrize("nframes,ring,ctas", [(40, 8, 3), (200, 96, 592), (9, 4, 1), (64, 16, 7)])
+def test_fused_fft_held_tickets_cannot_deadlock(nframes, ring, ctas):
+    # the 65536-point kernels of this round hold tickets ahead of the item they run: K5-R one (requested at the top of an
+    # item), K5-R2 two, and both release an item's counter only at the top of the NEXT item.  Simulate `ctas` CTAs with
+    # a two-ticket look-ahead and the deferred release: a CTA runs its item only when the item's dependency counter is
+    # complete; every schedule in which CTAs are picked round-robin must finish all items (no deadlock), because a CTA
+    # never waits while it still owes a release.
+    ITEMS = 16
+    lag = max(ring // 2, 1)
+    total = (lag + 2 * nframes) * ITEMS
+
+    def decode(item):
+        chunk = item // ITEMS
+        if chunk < lag:
+            return True, chunk
+        t = chunk - lag
+        return (t % 2 == 0), (lag + t // 2 if t % 2 == 0 else t // 2)
+
+    done_a, done_b = [0] * nframes, [0] * nframes
+    ticket = 0
+    state = []
+    for _ in range(ctas):  # each CTA: [current ticket, next ticket, owed release]
+        state.append([ticket, ticket + 1, None])
+        ticket += 2
+    finished = 0
+    idle_rounds = 0
+    while finished < ctas:
+        progressed = False
+        for st in state:
+            if st[0] is None:
+                continue
+            if st[2] is not None:  # top of an item: pay the previous item's release first
+                is_a, f = st[2]
+                (done_a if is_a else done_b)[f] += 1
+                st[2] = None
+                progressed = True
+            if st[0] >= total:
+                st[0] = None
+                finished += 1
+                progressed = True
+                continue
+            is_a, f = decode(st[0])
+            if f < nframes:
+                ready = (done_a[f] == ITEMS) if not is_a else (f < ring or done_b[f - ring] == ITEMS)
+                if not ready:
+                    continue  # blocking wait; nothing is owed
+                st[2] = (is_a, f)
+            st[0], st[1] = st[1], ticket
+            ticket += 1
+            progressed = True
+        idle_rounds = 0 if progressed else idle_rounds + 1
+        assert idle_rounds < 2, "deadlock"
+    assert all(v == ITEMS for v in done_a) and all(v == ITEMS for v in done_b)
+
+
 @pytest.mark.parametrize("nframes,ring", [(1, 4), (5, 4), (33, 32), (100, 8), (7, 2)])
 def test_fused_fft_ticket_order_cannot_wait_on_a_later_ticket(nframes, ring):
     # the work order of the fused two-step FFT kernels: A(0 .. lag-1), then A(lag + u), B(u) alternating, ITEMS items per
