@@ -551,3 +551,47 @@ def test_reference_arm_never_maps_the_product():
     assert p.returncode == 0, p.stderr[-2000:]
     line = json.loads(p.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["gpu_launches"] == 0
+
+
+def test_hot_kernels_keep_their_register_budgets_and_do_not_spill(cb):
+    # the occupancies DESIGN.md quotes rest on register counts: 64 registers x 256 threads x 4 CTAs per SM for the
+    # frame FFTs, 576 x 95 for the persistent tensor-core FIR, ... and on no local-memory spills.  Read them from the
+    # built library (cuobjdump --dump-resource-usage) so that a compiler or source change that breaks one is seen on
+    # the CPU box, not as a silent slowdown on the GPU.
+    import re
+    import shutil
+    import subprocess
+
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    lib = os.path.join(ROOT, "comms-rs_b200", "libcomms_b200.so")
+    out = subprocess.run(["cuobjdump", "--dump-resource-usage", lib], capture_output=True, text=True, check=True).stdout
+    usage = {}
+    for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", out):
+        usage[m.group(1)] = (int(m.group(2)), int(m.group(3)))
+    assert len(usage) > 100
+
+    def find(*parts):
+        hits = [(k, v) for k, v in usage.items() if all(p in k for p in parts)]
+        assert hits, parts
+        return hits
+
+    budgets = [  # (name fragments, max registers, threads, CTAs per SM the launch code counts on, max stack bytes)
+        (("fft2_frames_kernelILi12E",), 64, 256, 4, 0),
+        (("fft2_frames_kernelILi10E",), 64, 256, 4, 0),
+        (("fft2_small_frames_kernel",), 64, 256, 4, 0),
+        (("fft65536_fused_kernel", "ELi4EEE"), 64, 256, 4, 0),
+        (("fft65536_fused_kernel", "ELi5EEE"), 48, 256, 5, 0),
+        (("fft65536_pf_kernel",), 72, 288, 3, 0),
+        (("fft_big_fused_kernelILi7ELi8ELi256E",), 64, 256, 4, 0),
+        (("fir_tc_kernelILi3ELi2E",), 112, 576, 1, 0),
+        (("fir_ptc_kernel", "ELb0ELi"), 168, 320, 1, 0),   # f32 output: 4 epilogue warps
+        (("fir_ptc_kernel", "ELb1ELi"), 144, 448, 1, 0),   # i16 output: 8 epilogue warps
+        (("chain_tc_kernel",), 102, 640, 1, 0),
+        (("chain3_kernelILb1ELb1ELb0ELi10ELi3ELi128ELi2ELi3E",), 136, 160, 3, 64),  # (a 32-byte local array, no spills)
+    ]
+    for parts, max_regs, threads, ctas, max_stack in budgets:
+        for name, (regs, stack) in find(*parts):
+            assert stack <= max_stack, (name, "stack", stack)
+            assert regs <= max_regs, (name, regs)
+            assert regs * threads * ctas <= 65536, (name, regs, threads, ctas)
